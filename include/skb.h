@@ -1,0 +1,155 @@
+/* skb.h — C ABI of libskb.so: the B200-native sketch -> screen -> chain -> ANI path behind pyskani.
+ *
+ * Every entry point replaces one Rust-to-Rust call that the reference (althonos/pyskani,
+ * src/pyskani/_skani/lib.rs) makes into the crate `skani`; the call site is cited on each
+ * declaration.  The ABI is plain C: opaque handles, pointers and sizes, integer status codes.
+ * There is NO CPU fallback behind it: every function that computes launches sm_100a kernels and
+ * fails with SKB_ERR_CUDA if no device is usable.
+ *
+ * Ownership: input byte ranges are borrowed for the duration of the call only (the reference
+ * borrows them the same way, utils.rs:81-101); handles returned through an out-parameter are owned
+ * by the caller and released with the matching *_free / *_destroy; hit arrays are library-allocated
+ * and released with skb_hits_free.
+ * Threading: a context serialises its own calls with an internal mutex (the reference guards its
+ * state with RwLocks, lib.rs:135-136).  Use one context per GPU.
+ */
+#ifndef SKB_H
+#define SKB_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKB_OK            0
+#define SKB_ERR_ARG       1   /* -> ValueError   */
+#define SKB_ERR_CUDA      2   /* -> RuntimeError */
+#define SKB_ERR_NOMEM     3   /* -> MemoryError  */
+#define SKB_ERR_KEY       4   /* -> KeyError     */
+#define SKB_ERR_UNSUPPORTED 5 /* -> NotImplementedError / RuntimeError */
+
+#define SKB_MIN_LENGTH_CONTIG 500   /* skani::params::MIN_LENGTH_CONTIG, gate at lib.rs:156 */
+#define SKB_MARKER_K 21             /* skani::params::K_MARKER_DNA */
+
+typedef struct skb_ctx    skb_ctx_t;     /* one GPU: device id, streams, scratch arenas */
+typedef struct skb_sketch skb_sketch_t;  /* one sketched genome, resident in HBM (skani::types::Sketch) */
+typedef struct skb_db     skb_db_t;      /* ordered set of sketches queried together (Database.markers + Database.sketches) */
+
+/* SketchParams::new(marker_c, c, k, false, false) — lib.rs:416 */
+typedef struct {
+    int32_t k;          /* seed k-mer length, <= 16 (skani panics above 16)      */
+    int32_t c;          /* FracMinHash compression of seeds   (default 125)      */
+    int32_t marker_c;   /* FracMinHash compression of markers (default 1000)     */
+} skb_sketch_params_t;
+
+/* The part of CommandParams that pyskani lets the caller set — lib.rs:573-614 */
+typedef struct {
+    double  cutoff;        /* screen_val; 0.0 means "use SEARCH_ANI_CUTOFF_DEFAULT = 0.80" (lib.rs:603-609) */
+    int32_t learned_ani;   /* -1 = None, 0 = False, 1 = True (lib.rs:593,611-614)                          */
+    int32_t median;        /* lib.rs:582 */
+    int32_t robust;        /* lib.rs:581 */
+    int32_t faster_small;  /* rescue_small = !faster_small (lib.rs:597) */
+} skb_query_opts_t;
+
+/* AniEstResult fields that Hit exposes — hit.rs:77-104 */
+typedef struct {
+    uint32_t query_index;  /* index of the query in the call's query array  */
+    uint32_t ref_index;    /* index of the reference inside the database    */
+    float    ani;          /* Hit.identity            */
+    float    af_query;     /* Hit.query_fraction      */
+    float    af_ref;       /* Hit.reference_fraction  */
+    uint32_t n_windows;    /* diagnostics: 20 kb query windows that contributed */
+    uint32_t n_chains;     /* diagnostics: kept chains                          */
+    uint32_t n_anchors;    /* diagnostics: k-mer matches joined                 */
+} skb_hit_t;
+
+typedef struct {
+    uint64_t n_seeds, n_markers, total_len;
+    uint32_t n_contigs;    /* contigs that passed the MIN_LENGTH_CONTIG gate */
+    int32_t  k, c, marker_c;
+    int32_t  has_seeds;    /* sketched with seed=True */
+} skb_sketch_info_t;
+
+/* Timings of the last call on this context, measured with CUDA events on the context's stream. */
+typedef struct {
+    float h2d_ms, seed_ms, index_ms, screen_ms, chain_ms, total_ms;
+    uint64_t kernels_launched;   /* cumulative count of this library's kernel launches */
+} skb_stats_t;
+
+/* ---- context ---- */
+int  skb_ctx_create(int device, skb_ctx_t** out);
+void skb_ctx_destroy(skb_ctx_t* ctx);
+const char* skb_last_error(const skb_ctx_t* ctx);     /* message of the last failing call */
+int  skb_ctx_stats(const skb_ctx_t* ctx, skb_stats_t* out);
+int  skb_ctx_sync(skb_ctx_t* ctx);
+/* CUDA stream all work of this context is enqueued on (a cudaStream_t), for event timing by callers */
+void* skb_ctx_stream(skb_ctx_t* ctx);
+
+/* pinned host staging memory (so that callers can keep inputs where an async H2D copy can reach them) */
+int  skb_host_alloc(skb_ctx_t* ctx, size_t bytes, void** out);
+void skb_host_free(skb_ctx_t* ctx, void* p);
+/* device memory for device-resident inputs of skb_sketch_batch_device */
+int  skb_dev_alloc(skb_ctx_t* ctx, size_t bytes, void** out);
+void skb_dev_free(skb_ctx_t* ctx, void* p);
+int  skb_memcpy_h2d(skb_ctx_t* ctx, void* dst, const void* src, size_t bytes);
+
+/* ---- sketching: Database::_sketch (lib.rs:140-185) = Sketch::new + per-contig fmh_seeds (lib.rs:165-171) ----
+ * n_genomes genomes are sketched in one pass.  Genome g owns contigs
+ * [genome_contig_start[g], genome_contig_start[g+1]) of the flat arrays contigs[] / contig_lens[].
+ * Contigs shorter than SKB_MIN_LENGTH_CONTIG are skipped and do not consume a contig index.
+ * out[g] receives a new sketch handle.  Host version: contigs[i] are host pointers (pinned or pageable),
+ * the H2D copy happens inside the call. */
+int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t seed,
+                     uint32_t n_genomes, const uint32_t* genome_contig_start,
+                     const uint8_t* const* contigs, const uint64_t* contig_lens,
+                     skb_sketch_t** out);
+/* Device version: all contigs already sit in one device buffer `seq`; contig i occupies
+ * seq[contig_offsets[i] .. contig_offsets[i] + contig_lens[i]).  Offsets must be multiples of 16 and the
+ * buffer must extend 64 readable bytes before the first and after the last contig. */
+int skb_sketch_batch_device(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t seed,
+                            uint32_t n_genomes, const uint32_t* genome_contig_start,
+                            const uint8_t* seq, const uint64_t* contig_offsets, const uint64_t* contig_lens,
+                            skb_sketch_t** out);
+void skb_sketch_free(skb_sketch_t* s);
+int  skb_sketch_info(const skb_sketch_t* s, skb_sketch_info_t* out);
+/* Copy a sketch to host arrays (any pointer may be NULL).  Seeds come sorted by (kmer, contig, pos);
+ * canonical[i] = SeedPosition.canonical; markers sorted ascending and unique (the reference keeps both in
+ * hash containers whose order is arbitrary).  Used by save() and by the parity tests. */
+int  skb_sketch_export(const skb_sketch_t* s, uint64_t* kmer, uint32_t* pos, uint32_t* contig,
+                       uint8_t* canonical, uint64_t* markers, uint32_t* contig_lengths);
+/* Rebuild a device sketch from host arrays (Database.load / Database.open path, lib.rs:93-122).
+ * Seeds may come in any order. */
+int  skb_sketch_import(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t has_seeds,
+                       uint64_t n_seeds, const uint64_t* kmer, const uint32_t* pos, const uint32_t* contig,
+                       const uint8_t* canonical, uint64_t n_markers, const uint64_t* markers,
+                       uint32_t n_contigs, const uint32_t* contig_lengths, skb_sketch_t** out);
+
+/* ---- database: the (markers, sketches) pair a Database owns (lib.rs:132-137) ---- */
+int  skb_db_create(skb_ctx_t* ctx, skb_db_t** out);
+void skb_db_destroy(skb_db_t* db);
+/* Database.sketch's two pushes (lib.rs:501-508).  The database shares ownership of the sketch. */
+int  skb_db_add(skb_db_t* db, skb_sketch_t* s, uint32_t* index_out);
+uint64_t skb_db_size(const skb_db_t* db);
+
+/* ---- query: lib.rs:616-657 for n_queries queries at once ----
+ * For every (query, reference) pair: check_markers_quickly (lib.rs:623-628); for survivors
+ * map_params_from_sketch + chain_seeds (lib.rs:646-653); keep results with ani > 0.1 (lib.rs:654).
+ * Hits come back grouped by query, references in database order (the reference iterates a HashSet,
+ * lib.rs:640, so its order is arbitrary).  n_screened_in (may be NULL) = pairs that passed the screen. */
+int  skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
+                  const skb_query_opts_t* opts, skb_hit_t** hits, uint64_t* n_hits, uint64_t* n_screened_in);
+void skb_hits_free(skb_hit_t* hits);
+
+/* check_markers_quickly alone (lib.rs:623-628) for every (query, reference) pair:
+ * pass[q * db_size + r] = 1/0, shared[...] = marker intersection size (either may be NULL). */
+int  skb_db_screen(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
+                   double cutoff, int32_t rescue_small, uint8_t* pass, uint32_t* shared);
+
+/* Library build info */
+const char* skb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,262 @@
+"""ctypes binding of include/skb.h (libskb.so).
+
+This is the thinnest possible Python view of the C ABI: it is what bench.py and the parity tests call,
+and what the reference's maintainers would mirror as an `extern "C"` block on the Rust side
+(INTEGRATION.md).  It never computes anything itself and has no CPU fallback: if libskb.so is missing,
+or no CUDA device is usable, it raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libskb.so")
+
+SKB_OK, SKB_ERR_ARG, SKB_ERR_CUDA, SKB_ERR_NOMEM, SKB_ERR_KEY, SKB_ERR_UNSUPPORTED = range(6)
+
+
+class SketchParams(C.Structure):
+    _fields_ = [("k", C.c_int32), ("c", C.c_int32), ("marker_c", C.c_int32)]
+
+
+class QueryOpts(C.Structure):
+    _fields_ = [("cutoff", C.c_double), ("learned_ani", C.c_int32), ("median", C.c_int32),
+                ("robust", C.c_int32), ("faster_small", C.c_int32)]
+
+
+class Hit(C.Structure):
+    _fields_ = [("query_index", C.c_uint32), ("ref_index", C.c_uint32), ("ani", C.c_float),
+                ("af_query", C.c_float), ("af_ref", C.c_float), ("n_windows", C.c_uint32),
+                ("n_chains", C.c_uint32), ("n_anchors", C.c_uint32)]
+
+
+class SketchInfo(C.Structure):
+    _fields_ = [("n_seeds", C.c_uint64), ("n_markers", C.c_uint64), ("total_len", C.c_uint64),
+                ("n_contigs", C.c_uint32), ("k", C.c_int32), ("c", C.c_int32), ("marker_c", C.c_int32),
+                ("has_seeds", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("seed_ms", C.c_float), ("index_ms", C.c_float),
+                ("screen_ms", C.c_float), ("chain_ms", C.c_float), ("total_ms", C.c_float),
+                ("kernels_launched", C.c_uint64)]
+
+
+# every symbol include/skb.h declares (tests/test_abi.py checks the library exports all of them)
+SYMBOLS = [
+    "skb_ctx_create", "skb_ctx_destroy", "skb_last_error", "skb_ctx_stats", "skb_ctx_sync", "skb_ctx_stream",
+    "skb_host_alloc", "skb_host_free", "skb_dev_alloc", "skb_dev_free", "skb_memcpy_h2d",
+    "skb_sketch_batch", "skb_sketch_batch_device", "skb_sketch_free", "skb_sketch_info", "skb_sketch_export",
+    "skb_sketch_import", "skb_db_create", "skb_db_destroy", "skb_db_add", "skb_db_size", "skb_db_query",
+    "skb_hits_free", "skb_db_screen", "skb_version",
+]
+
+_lib = None
+
+
+class SkbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libskb error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(pyskani_b200 has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32
+        L.skb_version.restype = C.c_char_p
+        L.skb_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.skb_ctx_destroy.argtypes = [vp]
+        L.skb_last_error.restype = C.c_char_p
+        L.skb_last_error.argtypes = [vp]
+        L.skb_ctx_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.skb_ctx_sync.argtypes = [vp]
+        L.skb_ctx_stream.restype = vp
+        L.skb_ctx_stream.argtypes = [vp]
+        L.skb_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+        L.skb_host_free.argtypes = [vp, vp]
+        L.skb_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+        L.skb_dev_free.argtypes = [vp, vp]
+        L.skb_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
+        L.skb_sketch_batch.argtypes = [vp, C.POINTER(SketchParams), i32, u32, vp, vp, vp, vp]
+        L.skb_sketch_batch_device.argtypes = [vp, C.POINTER(SketchParams), i32, u32, vp, vp, vp, vp, vp]
+        L.skb_sketch_free.argtypes = [vp]
+        L.skb_sketch_info.argtypes = [vp, C.POINTER(SketchInfo)]
+        L.skb_sketch_export.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.skb_sketch_import.argtypes = [vp, C.POINTER(SketchParams), i32, u64, vp, vp, vp, vp, u64, vp, u32, vp,
+                                        C.POINTER(vp)]
+        L.skb_db_create.argtypes = [vp, C.POINTER(vp)]
+        L.skb_db_destroy.argtypes = [vp]
+        L.skb_db_add.argtypes = [vp, vp, C.POINTER(u32)]
+        L.skb_db_size.restype = u64
+        L.skb_db_size.argtypes = [vp]
+        L.skb_db_query.argtypes = [vp, u32, vp, C.POINTER(QueryOpts), C.POINTER(C.POINTER(Hit)), C.POINTER(u64),
+                                   C.POINTER(u64)]
+        L.skb_hits_free.argtypes = [C.POINTER(Hit)]
+        L.skb_db_screen.argtypes = [vp, u32, vp, C.c_double, i32, vp, vp]
+        _lib = L
+    return _lib
+
+
+class Context:
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().skb_ctx_create(device, C.byref(self._h))
+        if rc != SKB_OK:
+            self._h = None
+            raise SkbError(rc, f"cannot create a CUDA context on device {device} (pyskani_b200 has no CPU fallback)")
+
+    def check(self, rc):
+        if rc != SKB_OK:
+            raise SkbError(rc, lib().skb_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            lib().skb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        # sketches and databases hold their own reference to the device state; destroying the handle is safe
+        self.close()
+
+    def stats(self):
+        s = Stats()
+        self.check(lib().skb_ctx_stats(self._h, C.byref(s)))
+        return s
+
+    def sync(self):
+        self.check(lib().skb_ctx_sync(self._h))
+
+    @property
+    def stream(self):
+        return lib().skb_ctx_stream(self._h)
+
+    # ---- sketching
+    def sketch_batch(self, genomes, k=15, c=125, marker_c=1000, seed=True):
+        """genomes: list of lists of bytes-like contigs (host memory). Returns a list of Sketch."""
+        flat, starts = [], [0]
+        for g in genomes:
+            flat.extend(g)
+            starts.append(len(flat))
+        n = len(flat)
+        keep = [np.frombuffer(x, dtype=np.uint8) if len(x) else np.zeros(0, np.uint8) for x in flat]
+        ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data if a.size else None for a in keep])
+        lens = (C.c_uint64 * max(n, 1))(*[a.size for a in keep])
+        gs = (C.c_uint32 * len(starts))(*starts)
+        out = (C.c_void_p * max(len(genomes), 1))()
+        p = SketchParams(k, c, marker_c)
+        self.check(lib().skb_sketch_batch(self._h, C.byref(p), int(seed), len(genomes), gs, ptrs, lens, out))
+        return [Sketch(self, out[i]) for i in range(len(genomes))]
+
+    def sketch_batch_device(self, seq_dev_ptr, genome_contig_start, contig_offsets, contig_lens,
+                            k=15, c=125, marker_c=1000, seed=True):
+        gs = np.ascontiguousarray(genome_contig_start, np.uint32)
+        offs = np.ascontiguousarray(contig_offsets, np.uint64)
+        lens = np.ascontiguousarray(contig_lens, np.uint64)
+        ng = len(gs) - 1
+        out = (C.c_void_p * max(ng, 1))()
+        p = SketchParams(k, c, marker_c)
+        self.check(lib().skb_sketch_batch_device(self._h, C.byref(p), int(seed), ng, gs.ctypes.data, seq_dev_ptr,
+                                                 offs.ctypes.data, lens.ctypes.data, out))
+        return [Sketch(self, out[i]) for i in range(ng)]
+
+    def import_sketch(self, kmer, pos, contig, canonical, markers, contig_lengths, k=15, c=125, marker_c=1000,
+                      has_seeds=True):
+        kmer = np.ascontiguousarray(kmer, np.uint64); pos = np.ascontiguousarray(pos, np.uint32)
+        contig = np.ascontiguousarray(contig, np.uint32); canonical = np.ascontiguousarray(canonical, np.uint8)
+        markers = np.ascontiguousarray(markers, np.uint64); cl = np.ascontiguousarray(contig_lengths, np.uint32)
+        out = C.c_void_p()
+        p = SketchParams(k, c, marker_c)
+        self.check(lib().skb_sketch_import(self._h, C.byref(p), int(has_seeds), len(kmer), kmer.ctypes.data,
+                                           pos.ctypes.data, contig.ctypes.data, canonical.ctypes.data, len(markers),
+                                           markers.ctypes.data, len(cl), cl.ctypes.data, C.byref(out)))
+        return Sketch(self, out.value)
+
+    def host_alloc(self, nbytes):
+        p = C.c_void_p()
+        self.check(lib().skb_host_alloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def host_free(self, p):
+        lib().skb_host_free(self._h, p)
+
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        self.check(lib().skb_dev_alloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def dev_free(self, p):
+        lib().skb_dev_free(self._h, p)
+
+    def memcpy_h2d(self, dst, src, nbytes):
+        self.check(lib().skb_memcpy_h2d(self._h, dst, src, nbytes))
+
+
+class Sketch:
+    def __init__(self, ctx, handle):
+        self.ctx, self._h = ctx, handle
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().skb_sketch_free(self._h)
+            self._h = None
+
+    def info(self):
+        i = SketchInfo()
+        self.ctx.check(lib().skb_sketch_info(self._h, C.byref(i)))
+        return i
+
+    def export(self):
+        i = self.info()
+        kmer = np.empty(i.n_seeds, np.uint64); pos = np.empty(i.n_seeds, np.uint32)
+        contig = np.empty(i.n_seeds, np.uint32); canon = np.empty(i.n_seeds, np.uint8)
+        markers = np.empty(i.n_markers, np.uint64); cl = np.empty(i.n_contigs, np.uint32)
+        self.ctx.check(lib().skb_sketch_export(self._h, kmer.ctypes.data, pos.ctypes.data, contig.ctypes.data,
+                                               canon.ctypes.data, markers.ctypes.data, cl.ctypes.data))
+        return dict(kmer=kmer, pos=pos, contig=contig, canonical=canon, markers=markers, contig_lengths=cl)
+
+
+class Database:
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        ctx.check(lib().skb_db_create(ctx._h, C.byref(self._h)))
+        self._keep = []
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().skb_db_destroy(self._h)
+            self._h = None
+
+    def add(self, sketch):
+        idx = C.c_uint32()
+        self.ctx.check(lib().skb_db_add(self._h, sketch._h, C.byref(idx)))
+        self._keep.append(sketch)
+        return idx.value
+
+    def __len__(self):
+        return lib().skb_db_size(self._h)
+
+    def query(self, queries, cutoff=0.0, learned_ani=0, median=False, robust=False, faster_small=False):
+        n = len(queries)
+        qs = (C.c_void_p * max(n, 1))(*[q._h for q in queries])
+        o = QueryOpts(cutoff, learned_ani, int(median), int(robust), int(faster_small))
+        hits = C.POINTER(Hit)()
+        nh, ns = C.c_uint64(0), C.c_uint64(0)
+        self.ctx.check(lib().skb_db_query(self._h, n, qs, C.byref(o), C.byref(hits), C.byref(nh), C.byref(ns)))
+        out = [(hits[i].query_index, hits[i].ref_index, hits[i].ani, hits[i].af_query, hits[i].af_ref,
+                hits[i].n_windows, hits[i].n_chains, hits[i].n_anchors) for i in range(nh.value)]
+        lib().skb_hits_free(hits)
+        return out, ns.value
+
+    def screen(self, queries, cutoff=0.8, rescue_small=True):
+        n, nr = len(queries), len(self)
+        qs = (C.c_void_p * max(n, 1))(*[q._h for q in queries])
+        ok = np.zeros((n, nr), np.uint8); shared = np.zeros((n, nr), np.uint32)
+        self.ctx.check(lib().skb_db_screen(self._h, n, qs, cutoff, int(rescue_small), ok.ctypes.data, shared.ctypes.data))
+        return ok.astype(bool), shared

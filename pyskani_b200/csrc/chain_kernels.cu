@@ -1,0 +1,416 @@
+// chain_kernels.cu — anchor lookup, banded sparse chaining and ANI/AF on sm_100a.
+//
+// Replaces skani::chain::chain_seeds (reference lib.rs:652-653) for a whole batch of screened-in pairs.
+// The algorithm is the one frozen in oracle/skani_oracle.cpp (orc_chain_params_default):
+//   1. anchors   = every (query seed, reference seed) pair with equal k-mer, in
+//                  (q_contig, q_pos, r_contig, r_pos) order.  The query side is walked in position order and
+//                  each seed is looked up in the reference's k-mer-sorted array through its bucket table,
+//                  so the anchors come out already sorted: no per-pair sort.
+//   2. windows   : a window opens at the first anchor of a contig / the first anchor >= start + 20000 bp.
+//   3. DP        : inside a window, f[i] = max(20, max_j f[j] + 20 - |dr - dq|) over the <= 100 previous
+//                  anchors within 2500 bp on the query, same reference contig and strand, dq > 0, dr > 0,
+//                  |dr - dq| <= 300; ties go to the nearest predecessor.  One warp per window: lane l keeps
+//                  the last four anchors whose index is congruent to l (mod 32) in registers, so the 128
+//                  most recent anchors are scored against the current one without touching memory.
+//   4. chains    = components of the back-pointer forest; score = best f in the component, extent = root ..
+//                  best anchor, weight = component size; keep size >= 3 and score >= 45; greedy by score
+//                  without query overlap inside the window.
+//   5. window ANI = min(1, anchors / query seeds spanned)^(1/k); genome ANI = seed-weighted mean (or
+//                  10-90 % trimmed, or median); AF = sum of (chain span + 198) / genome length.
+// Scores are integers (20 per anchor minus integer gaps), so the int32 DP is bit-identical to skani's f64.
+#include "skb_internal.cuh"
+
+namespace skb {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr uint32_t AUX_PROCESSED = 0x80000000u, AUX_ACCEPTED = 0x40000000u, AUX_SIZE = 0x3FFFFFFFu;
+
+// first index in [lo, hi) whose key >= target, keys non-decreasing; all lanes of the warp cooperate
+template <typename KeyFn>
+__device__ __forceinline__ uint32_t warp_lower_bound(uint32_t lo, uint32_t hi, uint32_t target, int lane, KeyFn key) {
+    while (true) {
+        const uint32_t n = hi - lo;
+        if (n == 0) return lo;
+        if (n <= 32) {
+            const uint32_t idx = lo + lane;
+            const bool ge = idx >= hi || key(idx) >= target;
+            const uint32_t b = __ballot_sync(FULL, ge);
+            return lo + (uint32_t)(__ffs(b) - 1);   // lanes >= n always vote true, so b != 0
+        }
+        const uint32_t stride = (n + 31) / 32;
+        const uint32_t idx = lo + lane * stride;
+        const bool ge = idx >= hi || key(idx) >= target;
+        const uint32_t b = __ballot_sync(FULL, ge);
+        if (b == 0) {                       // every probe below target and inside the range
+            lo = lo + 31 * stride + 1;
+            continue;
+        }
+        const int f = __ffs(b) - 1;
+        if (f == 0) return lo;
+        const uint32_t new_lo = lo + (uint32_t)(f - 1) * stride + 1;
+        const uint32_t new_hi = min(lo + (uint32_t)f * stride, hi);
+        lo = new_lo; hi = new_hi;
+    }
+}
+
+// ------------------------------------------------------------------ 1a. match counts
+__global__ void match_count_kernel(const ChainBatch b) {
+    const PairDesc pd = b.pairs[blockIdx.y];
+    const GenomeView& Q = b.qviews[pd.q];
+    const GenomeView& R = b.rviews[pd.r];
+    const uint32_t nq = Q.n_seeds;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
+        const uint32_t km = __ldg(Q.kmer_p + i);
+        uint32_t first = 0, cnt = 0;
+        if (R.n_seeds) {
+            const uint32_t bk = km >> R.bucket_shift;
+            uint32_t lo = __ldg(R.bucket + bk), hi = __ldg(R.bucket + bk + 1);
+            while (lo < hi) {               // buckets hold ~8 seeds: a short search
+                uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(R.kmer_k + mid) < km) lo = mid + 1; else hi = mid;
+            }
+            first = lo;
+            const uint32_t end = __ldg(R.bucket + bk + 1);
+            while (lo < end && __ldg(R.kmer_k + lo) == km) lo++;
+            cnt = lo - first;
+        }
+        b.m_first[pd.seed_off + i] = first;
+        b.m_cnt[pd.seed_off + i] = cnt;
+    }
+}
+
+// ------------------------------------------------------------------ 1b. anchors
+__global__ void anchor_fill_kernel(const ChainBatch b) {
+    const PairDesc pd = b.pairs[blockIdx.y];
+    const GenomeView& Q = b.qviews[pd.q];
+    const GenomeView& R = b.rviews[pd.r];
+    const uint32_t nq = Q.n_seeds;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
+        const uint32_t cnt = b.m_cnt[pd.seed_off + i];
+        if (cnt == 0) continue;
+        const uint32_t first = b.m_first[pd.seed_off + i];
+        const uint32_t off = b.a_off[pd.seed_off + i];
+        const uint32_t qp = __ldg(Q.pos_p + i);
+        const uint32_t qm = __ldg(Q.meta_p + i);
+        for (uint32_t m = 0; m < cnt; m++) {
+            const uint32_t o = off + m;
+            if (o >= b.anchor_cap) break;
+            const uint32_t rm = __ldg(R.meta_k + first + m);
+            b.a_qi[o] = i;
+            b.a_qp[o] = qp;
+            b.a_rp[o] = __ldg(R.pos_k + first + m);
+            b.a_meta[o] = (rm & ~1u) | ((qm ^ rm) & 1u);    // ref contig << 1 | reverse_match
+        }
+    }
+}
+
+// ------------------------------------------------------------------ 2. windows
+// One warp per (pair, query contig).  Window j of contig c lands in slot win_off + contig_win_start[c] + j.
+__global__ void window_walk_kernel(const ChainBatch b, const uint32_t F) {
+    const PairDesc pd = b.pairs[blockIdx.x];
+    const GenomeView& Q = b.qviews[pd.q];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t* aoff = b.a_off + pd.seed_off;
+    for (uint32_t c = warp; c < Q.n_contigs; c += nwarps) {
+        const uint32_t cs = Q.contig_seed_start[c], ce = Q.contig_seed_start[c + 1];
+        // capacity of contig c: len / F + 1 windows, laid out contiguously in contig order
+        uint32_t slot = pd.win_off + Q.contig_win_start[c];
+        uint32_t s = cs;
+        while (s < ce) {
+            // first matched seed i >= s  <=>  first j in [s+1, ce] with aoff[j] > aoff[s]; i = j - 1
+            const uint32_t base = aoff[s];
+            const uint32_t j = warp_lower_bound(s + 1, ce + 1, base + 1, lane, [&](uint32_t x) { return aoff[x]; });
+            if (j > ce) break;
+            const uint32_t i = j - 1;
+            const uint32_t p0 = __ldg(Q.pos_p + i);
+            const uint32_t e = warp_lower_bound(i + 1, ce, p0 + F, lane, [&](uint32_t x) { return __ldg(Q.pos_p + x); });
+            if (lane == 0) {
+                b.win_start[slot] = i;
+                b.win_end[slot] = e;
+                b.win_contig[slot] = blockIdx.x;   // pair index, read back by the DP kernel
+            }
+            slot++;
+            s = e;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ 3+4. DP, chains, per-window record
+struct Gen { uint32_t qp, rp, meta; int32_t f; uint32_t root; };
+
+__device__ __forceinline__ void tuple_min(int32_t& sc, uint32_t& qs, uint32_t& rs, uint32_t& idx,
+                                          int32_t sc2, uint32_t qs2, uint32_t rs2, uint32_t idx2) {
+    // order: score desc, qs asc, rs asc, idx asc
+    bool take = sc2 > sc || (sc2 == sc && (qs2 < qs || (qs2 == qs && (rs2 < rs || (rs2 == rs && idx2 < idx)))));
+    if (take) { sc = sc2; qs = qs2; rs = rs2; idx = idx2; }
+}
+
+constexpr int DP_WARPS = 4;
+
+__global__ void __launch_bounds__(DP_WARPS * 32) chain_dp_kernel(const ChainBatch b, const ChainConsts C) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t slot = blockIdx.x * DP_WARPS + (threadIdx.x >> 5);
+    if (slot >= b.n_win_total) return;
+    const uint32_t ws = b.win_start[slot], we = b.win_end[slot];
+    if (we <= ws) return;                                   // unused slot
+    const PairDesc pd = b.pairs[b.win_contig[slot]];
+    const uint32_t A0 = b.a_off[pd.seed_off + ws], A1 = b.a_off[pd.seed_off + we];
+    const uint32_t n = A1 - A0;
+    const uint32_t* qp_a = b.a_qp + A0; const uint32_t* rp_a = b.a_rp + A0; const uint32_t* meta_a = b.a_meta + A0;
+    int32_t* f_a = b.a_f + A0; uint32_t* root_a = b.a_root + A0; uint32_t* aux_a = b.a_aux + A0;
+    unsigned long long* best_a = b.a_best + A0;
+
+    // ---------------- DP
+    Gen g0{0, 0, 0xFFFFFFFFu, 0, 0}, g1 = g0, g2 = g0, g3 = g0;     // meta 0xFFFFFFFF never matches
+    for (uint32_t sb = 0; sb < n; sb += 32) {
+        const uint32_t mine = sb + lane;
+        uint32_t sq = 0, sr = 0, sm = 0;
+        if (mine < n) { sq = qp_a[mine]; sr = rp_a[mine]; sm = meta_a[mine]; }
+        const uint32_t lim = min(32u, n - sb);
+        for (uint32_t u = 0; u < lim; u++) {
+            const uint32_t i = sb + u;                       // window-local anchor index; owner lane = u
+            const uint32_t cq = __shfl_sync(FULL, sq, u), cr = __shfl_sync(FULL, sr, u), cm = __shfl_sync(FULL, sm, u);
+            const bool rev = cm & 1u;
+            const int d0 = (int)((u - 1 - lane) & 31) + 1;  // distance of this lane's newest anchor from i
+            int32_t best = C.anchor_score; int bestd = 0;
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const Gen& G = g == 0 ? g0 : g == 1 ? g1 : g == 2 ? g2 : g3;
+                const int d = d0 + 32 * g;
+                const bool exists = (uint32_t)d <= i;
+                const bool inband = exists && d <= C.index_band && (cq - G.qp) <= (uint32_t)C.bp_band;
+                int32_t sc = INT32_MIN;
+                if (inband && G.meta == cm) {
+                    const int32_t dq = (int32_t)(cq - G.qp);
+                    const int32_t dr = rev ? (int32_t)(G.rp - cr) : (int32_t)(cr - G.rp);
+                    const int32_t gap = abs(dr - dq);
+                    if (dq > 0 && dr > 0 && gap <= C.max_gap) sc = G.f + C.anchor_score - gap;
+                }
+                const int32_t m = __reduce_max_sync(FULL, sc);
+                if (m > best) {                               // strictly better than anything nearer
+                    best = m;
+                    bestd = (int)__reduce_min_sync(FULL, sc == m ? (uint32_t)d : 0x7FFFFFFFu);
+                }
+                // the anchor at distance 32(g+1) is this generation's oldest: if it is out of band, so is the rest
+                const uint32_t ib = __ballot_sync(FULL, inband);
+                if (!((ib >> u) & 1u)) break;
+            }
+            // component root of i
+            uint32_t root = i;
+            if (bestd) {
+                const uint32_t j = i - (uint32_t)bestd;
+                const int L = (int)(j & 31);
+                const int dL = (int)((u - 1 - L) & 31) + 1;
+                const int gsel = (bestd - dL) >> 5;
+                const uint32_t rsel = gsel == 0 ? g0.root : gsel == 1 ? g1.root : gsel == 2 ? g2.root : g3.root;
+                root = __shfl_sync(FULL, rsel, L);
+            }
+            if (lane == (int)u) {
+                g3 = g2; g2 = g1; g1 = g0;
+                g0 = Gen{cq, cr, cm, best, root};
+            }
+        }
+        if (mine < n) { f_a[mine] = g0.f; root_a[mine] = g0.root; }
+    }
+
+    // ---------------- per-component size and best end
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t r = root_a[i];
+        atomicAdd(&aux_a[r], 1u);
+        atomicMax(&best_a[r], ((unsigned long long)(uint32_t)f_a[i] << 32) | (0xFFFFFFFFu - i));
+    }
+    __threadfence();
+    __syncwarp();
+
+    // ---------------- candidate chains -> compact list of roots in f_a[0..ncand)
+    uint32_t ncand = 0;
+    for (uint32_t sb = 0; sb < n; sb += 32) {
+        const uint32_t i = sb + lane;
+        bool cand = false;
+        if (i < n && root_a[i] == i) {
+            const uint32_t size = __ldcg(&aux_a[i]) & AUX_SIZE;
+            const int32_t score = (int32_t)(__ldcg(&best_a[i]) >> 32);
+            cand = size >= (uint32_t)C.min_anchors && score >= C.min_score;
+        }
+        const uint32_t bal = __ballot_sync(FULL, cand);
+        // f_a[0..ncand) is overwritten only at indices < i's strip start or by earlier lanes of the strip,
+        // whose f values are no longer needed (f lives on in best_a)
+        __syncwarp();
+        if (cand) f_a[ncand + __popc(bal & ((1u << lane) - 1u))] = (int32_t)i;
+        ncand += __popc(bal);
+        __syncwarp();
+    }
+
+    // ---------------- greedy selection without query overlap
+    uint32_t w_anchors = 0, w_lo = 0xFFFFFFFFu, w_hi = 0, w_lo_qi = 0, w_hi_qi = 0, w_covq = 0, w_covr = 0, w_chains = 0;
+    for (uint32_t round = 0; round < ncand; round++) {
+        int32_t sc = INT32_MIN; uint32_t qs = 0xFFFFFFFFu, rs = 0xFFFFFFFFu, idx = 0xFFFFFFFFu;
+        for (uint32_t t = lane; t < ncand; t += 32) {
+            const uint32_t r = (uint32_t)f_a[t];
+            if (__ldcg(&aux_a[r]) & AUX_PROCESSED) continue;
+            const unsigned long long bb = __ldcg(&best_a[r]);
+            const uint32_t bi = 0xFFFFFFFFu - (uint32_t)bb;
+            const bool rv = meta_a[r] & 1u;
+            const uint32_t rs2 = rv ? rp_a[bi] : rp_a[r];
+            tuple_min(sc, qs, rs, idx, (int32_t)(bb >> 32), qp_a[r], rs2, r);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int32_t sc2 = __shfl_xor_sync(FULL, sc, o);
+            const uint32_t qs2 = __shfl_xor_sync(FULL, qs, o), rs2 = __shfl_xor_sync(FULL, rs, o), idx2 = __shfl_xor_sync(FULL, idx, o);
+            tuple_min(sc, qs, rs, idx, sc2, qs2, rs2, idx2);
+        }
+        const uint32_t r = idx;                                 // uniform: the best unprocessed candidate
+        const unsigned long long bb = __ldcg(&best_a[r]);
+        const uint32_t bi = 0xFFFFFFFFu - (uint32_t)bb;
+        const uint32_t cqs = qp_a[r], cqe = qp_a[bi];
+        bool ov = false;
+        for (uint32_t t = lane; t < ncand; t += 32) {
+            const uint32_t r2 = (uint32_t)f_a[t];
+            if (!(__ldcg(&aux_a[r2]) & AUX_ACCEPTED)) continue;
+            const uint32_t bi2 = 0xFFFFFFFFu - (uint32_t)__ldcg(&best_a[r2]);
+            const uint32_t lo = max(cqs, qp_a[r2]), hi = min(cqe, qp_a[bi2]);
+            ov |= hi >= lo;
+        }
+        ov = __any_sync(FULL, ov);
+        const uint32_t size = __ldcg(&aux_a[r]) & AUX_SIZE;
+        if (lane == 0) aux_a[r] = size | AUX_PROCESSED | (ov ? 0u : AUX_ACCEPTED);
+        __threadfence_block();
+        __syncwarp();
+        if (!ov) {
+            const bool rv = meta_a[r] & 1u;
+            const uint32_t crs = rv ? rp_a[bi] : rp_a[r], cre = rv ? rp_a[r] : rp_a[bi];
+            w_anchors += size;
+            if (cqs < w_lo) { w_lo = cqs; w_lo_qi = b.a_qi[A0 + r]; }
+            if (cqe >= w_hi) { w_hi = cqe; w_hi_qi = b.a_qi[A0 + bi]; }
+            w_covq += (cqe - cqs) + (uint32_t)C.af_ext;
+            w_covr += (cre - crs) + (uint32_t)C.af_ext;
+            w_chains++;
+        }
+    }
+    if (lane == 0) {
+        WindowRec rec;
+        rec.anchors = w_anchors;
+        rec.seeds = w_chains ? (w_hi_qi - w_lo_qi + 1u) : 0u;
+        rec.cov_q = w_covq; rec.cov_r = w_covr; rec.n_chains = w_chains;
+        b.win_rec[slot] = rec;
+    }
+}
+
+// ------------------------------------------------------------------ 5a. sort keys: pair << 32 | floor(ratio * 2^32)
+__global__ void window_keys_kernel(const ChainBatch b) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= b.n_win_total) return;
+    uint64_t key = (uint64_t)b.n_pairs << 32;                // unused / chainless windows sort behind every pair
+    if (b.win_end[slot] > b.win_start[slot]) {
+        const WindowRec rec = b.win_rec[slot];
+        if (rec.n_chains && rec.seeds) {
+            uint64_t rk = ((uint64_t)rec.anchors << 32) / rec.seeds;     // exact order of the rationals (seeds < 2^15)
+            if (rk > 0xFFFFFFFFull) rk = 0xFFFFFFFFull;
+            key = ((uint64_t)b.win_contig[slot] << 32) | rk;
+        }
+    }
+    b.sort_keys[slot] = key;
+    b.sort_vals[slot] = slot;
+}
+
+// ------------------------------------------------------------------ 5b. per-pair ANI / AF
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+__global__ void ani_reduce_kernel(const ChainBatch b, const ChainConsts C, const uint64_t* __restrict__ keys,
+                                  const uint32_t* __restrict__ vals) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= b.n_pairs) return;
+    const PairDesc pd = b.pairs[p];
+    const GenomeView& Q = b.qviews[pd.q];
+    const GenomeView& R = b.rviews[pd.r];
+    // segment of this pair in the sorted key array
+    uint32_t lo = 0, hi = b.n_win_total;
+    {
+        uint32_t l = 0, h = b.n_win_total;
+        const uint64_t t0 = (uint64_t)p << 32, t1 = (uint64_t)(p + 1) << 32;
+        while (l < h) { uint32_t m = (l + h) >> 1; if (keys[m] < t0) l = m + 1; else h = m; }
+        lo = l; h = b.n_win_total;
+        while (l < h) { uint32_t m = (l + h) >> 1; if (keys[m] < t1) l = m + 1; else h = m; }
+        hi = l;
+    }
+    const uint32_t n = hi - lo;
+    PairResult res{-1.f, 0.f, 0.f, n, 0, b.a_off[pd.seed_off + Q.n_seeds] - b.a_off[pd.seed_off]};
+    if (n) {
+        uint32_t s_lo = 0, s_hi = n;
+        if (C.robust) { s_lo = n / 10; s_hi = n * 9 / 10; if (s_hi <= s_lo) { s_lo = 0; s_hi = n; } }
+        const double inv_k = 1.0 / (double)C.k;
+        double wsum = 0, ssum = 0, covq = 0, covr = 0, chains = 0;
+        for (uint32_t t = lane; t < n; t += 32) {
+            const WindowRec rec = b.win_rec[vals[lo + t]];
+            covq += rec.cov_q; covr += rec.cov_r; chains += rec.n_chains;
+            if (t >= s_lo && t < s_hi) {
+                double ratio = (double)rec.anchors / (double)rec.seeds;
+                if (ratio > 1.0) ratio = 1.0;
+                wsum += pow(ratio, inv_k) * (double)rec.seeds;
+                ssum += (double)rec.seeds;
+            }
+        }
+        wsum = warp_sum_f64(wsum); ssum = warp_sum_f64(ssum);
+        covq = warp_sum_f64(covq); covr = warp_sum_f64(covr); chains = warp_sum_f64(chains);
+        double ani = wsum / ssum;
+        if (C.median) {
+            const WindowRec rec = b.win_rec[vals[lo + n / 2]];
+            double ratio = (double)rec.anchors / (double)rec.seeds;
+            if (ratio > 1.0) ratio = 1.0;
+            ani = pow(ratio, inv_k);
+        }
+        double afq = covq / (double)Q.total_len, afr = covr / (double)R.total_len;
+        if (afq > 1.0) afq = 1.0;
+        if (afr > 1.0) afr = 1.0;
+        if (afq < C.frac_cover_cutoff && afr < C.frac_cover_cutoff) ani = -1.0;
+        res.ani = (float)ani; res.af_q = (float)afq; res.af_r = (float)afr;
+        res.n_chains = (uint32_t)chains;
+    }
+    if (lane == 0) b.results[p] = res;
+}
+
+}  // namespace
+
+void launch_match_count(const ChainBatch& b, cudaStream_t st) {
+    if (b.n_pairs == 0) return;
+    dim3 grid(32, b.n_pairs);
+    match_count_kernel<<<grid, 256, 0, st>>>(b);
+    g_kernel_launches++;
+}
+void launch_anchor_fill(const ChainBatch& b, cudaStream_t st) {
+    if (b.n_pairs == 0) return;
+    dim3 grid(32, b.n_pairs);
+    anchor_fill_kernel<<<grid, 256, 0, st>>>(b);
+    g_kernel_launches++;
+}
+void launch_window_walk(const ChainBatch& b, const ChainConsts& c, cudaStream_t st) {
+    if (b.n_pairs == 0) return;
+    window_walk_kernel<<<b.n_pairs, 128, 0, st>>>(b, c.fragment_length);
+    g_kernel_launches++;
+}
+void launch_chain_dp(const ChainBatch& b, const ChainConsts& c, cudaStream_t st) {
+    if (b.n_win_total == 0) return;
+    chain_dp_kernel<<<(b.n_win_total + DP_WARPS - 1) / DP_WARPS, DP_WARPS * 32, 0, st>>>(b, c);
+    g_kernel_launches++;
+}
+void launch_window_keys(const ChainBatch& b, cudaStream_t st) {
+    if (b.n_win_total == 0) return;
+    window_keys_kernel<<<(b.n_win_total + 255) / 256, 256, 0, st>>>(b);
+    g_kernel_launches++;
+}
+void launch_ani_reduce(const ChainBatch& b, const ChainConsts& c, const uint64_t* sorted_keys,
+                       const uint32_t* sorted_vals, cudaStream_t st) {
+    if (b.n_pairs == 0) return;
+    ani_reduce_kernel<<<(b.n_pairs + 3) / 4, 128, 0, st>>>(b, c, sorted_keys, sorted_vals);
+    g_kernel_launches++;
+}
+
+}  // namespace skb

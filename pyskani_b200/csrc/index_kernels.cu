@@ -1,0 +1,229 @@
+// index_kernels.cu — turns the seeding kernel's position-ordered output into the device-resident index.
+//
+// Replaces the hash containers skani fills inside fmh_seeds (reference lib.rs:165-171):
+//   kmer_seeds_k : FxHashMap<kmer, SmallVec<SeedPosition>>  ->  seeds sorted by (genome, kmer, contig, pos)
+//                                                                + a bucket table over the k-mer's top bits
+//   marker_seeds : FxHashSet<u64>                            ->  sorted unique 21-mers per genome
+// Sorting is CUB's device radix sort (library code, like cuBLAS for a GEMM); everything around it is ours.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+
+#include "skb_internal.cuh"
+
+namespace skb {
+
+namespace {
+
+__device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t* a, uint32_t n, uint32_t v) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] <= v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t n, uint32_t v) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* a, uint32_t n, uint64_t v) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// key = genome << 32 | kmer ; value = index in position order
+__global__ void make_seed_keys(uint32_t n, uint32_t n_genomes, const uint32_t* __restrict__ genome_seed_start,
+                               const uint32_t* __restrict__ kmer_p, uint64_t* __restrict__ keys,
+                               uint32_t* __restrict__ vals) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // genome g owns [start[g], start[g+1]); empty genomes are skipped by the upper bound
+    uint32_t g = upper_bound_u32(genome_seed_start, n_genomes + 1, i) - 1;
+    keys[i] = ((uint64_t)g << 32) | kmer_p[i];
+    vals[i] = i;
+}
+
+__global__ void gather_kmer_order(uint32_t n, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                  const uint32_t* __restrict__ pos_p, const uint32_t* __restrict__ meta_p,
+                                  uint32_t* __restrict__ kmer_k, uint32_t* __restrict__ pos_k,
+                                  uint32_t* __restrict__ meta_k) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t src = vals[i];
+    kmer_k[i] = (uint32_t)keys[i];
+    pos_k[i] = pos_p[src];
+    meta_k[i] = meta_p[src];
+}
+
+__global__ void strip_marker_keys(uint32_t n_in, const uint32_t* __restrict__ n_unique, const uint64_t* __restrict__ keys,
+                                  uint64_t* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_in || i >= *n_unique) return;
+    out[i] = keys[i] & ((1ull << 42) - 1);
+}
+
+__global__ void marker_genome_offsets(uint32_t n_genomes, const uint32_t* __restrict__ n_unique,
+                                      const uint64_t* __restrict__ keys, uint32_t* __restrict__ out) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n_genomes) return;
+    uint32_t n = *n_unique;
+    out[g] = g == n_genomes ? n : lower_bound_u64(keys, n, (uint64_t)g << 42);
+}
+
+__global__ void build_buckets_kernel(const GenomeView* __restrict__ views, uint32_t n_genomes) {
+    const GenomeView v = views[blockIdx.y];
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > v.n_buckets) return;
+    uint32_t* out = const_cast<uint32_t*>(v.bucket);
+    if (b == v.n_buckets) { out[b] = v.n_seeds; return; }
+    out[b] = lower_bound_u32(v.kmer_k, v.n_seeds, b << v.bucket_shift);
+}
+
+__global__ void contig_starts_kernel(const GenomeView* __restrict__ views, uint32_t n_genomes) {
+    const GenomeView v = views[blockIdx.y];
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > v.n_contigs) return;
+    uint32_t* out = const_cast<uint32_t*>(v.contig_seed_start);
+    // meta_p = contig << 1 | canonical, non-decreasing in contig
+    uint32_t lo = 0, hi = v.n_seeds;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if ((v.meta_p[mid] >> 1) < c) lo = mid + 1; else hi = mid;
+    }
+    out[c] = lo;
+}
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+size_t kmer_order_scratch_bytes(uint32_t n) {
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 64);
+    return align_up(cub_bytes) + 2 * align_up((size_t)n * 8) + 2 * align_up((size_t)n * 4) + 1024;
+}
+
+void build_kmer_order(const IndexBuildArgs& a, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    const uint32_t n = a.n_seeds_total;
+    if (n == 0) return;
+    char* p = (char*)scratch;
+    uint64_t* keys_in = (uint64_t*)p; p += align_up((size_t)n * 8);
+    uint64_t* keys_out = (uint64_t*)p; p += align_up((size_t)n * 8);
+    uint32_t* vals_in = (uint32_t*)p; p += align_up((size_t)n * 4);
+    uint32_t* vals_out = (uint32_t*)p; p += align_up((size_t)n * 4);
+    size_t cub_bytes = scratch_bytes - (size_t)(p - (char*)scratch);
+    const int T = 256;
+    make_seed_keys<<<(n + T - 1) / T, T, 0, st>>>(n, a.n_genomes, a.genome_seed_start, a.kmer_p, keys_in, vals_in);
+    g_kernel_launches++;
+    int gbits = 0;
+    while ((1ull << gbits) < (uint64_t)a.n_genomes) gbits++;
+    const int end_bit = 32 + gbits;   // k-mer bits above 2k are zero; sorting them is harmless for k < 16
+    cub::DeviceRadixSort::SortPairs(p, cub_bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0, end_bit, st);
+    g_kernel_launches += 1 + (end_bit + 7) / 8;
+    gather_kmer_order<<<(n + T - 1) / T, T, 0, st>>>(n, keys_out, vals_out, a.pos_p, a.meta_p, a.kmer_k, a.pos_k, a.meta_k);
+    g_kernel_launches++;
+}
+
+size_t marker_scratch_bytes(uint32_t n) {
+    size_t s1 = 0, s2 = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, s1, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int)n, 0, 64);
+    cub::DeviceSelect::Unique(nullptr, s2, (const uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (int)n);
+    return align_up(s1 > s2 ? s1 : s2) + 2 * align_up((size_t)n * 8 + 8) + 256 + 1024;
+}
+
+void build_marker_sets(uint32_t n_genomes, uint32_t n, uint64_t* marker_keys, uint64_t* markers_out,
+                       uint32_t* genome_marker_out, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    const int T = 256;
+    char* p = (char*)scratch;
+    uint64_t* sorted = (uint64_t*)p; p += align_up((size_t)n * 8 + 8);
+    uint64_t* uniq = (uint64_t*)p; p += align_up((size_t)n * 8 + 8);
+    uint32_t* n_unique = (uint32_t*)p; p += 256;
+    size_t cub_bytes = scratch_bytes - (size_t)(p - (char*)scratch);
+    if (n == 0) {
+        cudaMemsetAsync(genome_marker_out, 0, sizeof(uint32_t) * (n_genomes + 1), st);
+        return;
+    }
+    int gbits = 0;
+    while ((1ull << gbits) < (uint64_t)n_genomes) gbits++;
+    cub::DeviceRadixSort::SortKeys(p, cub_bytes, marker_keys, sorted, (int)n, 0, 42 + gbits, st);
+    g_kernel_launches += 1 + (42 + gbits + 7) / 8;
+    cub::DeviceSelect::Unique(p, cub_bytes, sorted, uniq, n_unique, (int)n, st);
+    g_kernel_launches += 2;
+    strip_marker_keys<<<(n + T - 1) / T, T, 0, st>>>(n, n_unique, uniq, markers_out);
+    marker_genome_offsets<<<(n_genomes + 1 + T - 1) / T, T, 0, st>>>(n_genomes, n_unique, uniq, genome_marker_out);
+    g_kernel_launches += 2;
+}
+
+void launch_build_buckets(const GenomeView* views_dev, uint32_t n_genomes, uint32_t max_buckets, cudaStream_t st) {
+    if (n_genomes == 0) return;
+    const int T = 256;
+    for (uint32_t g0 = 0; g0 < n_genomes; g0 += 65535) {
+        uint32_t ng = n_genomes - g0 < 65535 ? n_genomes - g0 : 65535;
+        dim3 grid((max_buckets + 1 + T - 1) / T, ng);
+        build_buckets_kernel<<<grid, T, 0, st>>>(views_dev + g0, ng);
+        g_kernel_launches++;
+    }
+}
+
+void launch_contig_starts(const GenomeView* views_dev, uint32_t n_genomes, uint32_t max_contigs, cudaStream_t st) {
+    if (n_genomes == 0) return;
+    const int T = 128;
+    for (uint32_t g0 = 0; g0 < n_genomes; g0 += 65535) {
+        uint32_t ng = n_genomes - g0 < 65535 ? n_genomes - g0 : 65535;
+        dim3 grid((max_contigs + 1 + T - 1) / T, ng);
+        contig_starts_kernel<<<grid, T, 0, st>>>(views_dev + g0, ng);
+        g_kernel_launches++;
+    }
+}
+
+// indices of the set flags, ascending, plus their count
+void select_passing(uint32_t n, const uint8_t* flags, uint32_t* out_idx, uint32_t* out_count, cudaStream_t st) {
+    cub::CountingInputIterator<uint32_t> it(0);
+    size_t bytes = 0;
+    cub::DeviceSelect::Flagged(nullptr, bytes, it, flags, out_idx, out_count, (int)n, st);
+    void* tmp = nullptr;
+    cudaMallocAsync(&tmp, bytes + 16, st);
+    cub::DeviceSelect::Flagged(tmp, bytes, it, flags, out_idx, out_count, (int)n, st);
+    cudaFreeAsync(tmp, st);
+    g_kernel_launches += 2;
+}
+
+size_t scan_scratch_bytes(uint32_t n) {
+    size_t s = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, s, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
+    return align_up(s) + 256;
+}
+
+size_t sort_pairs_scratch_bytes(uint32_t n) {
+    size_t s = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, s, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)n, 0, 64);
+    return align_up(s) + 256;
+}
+
+void sort_window_keys(uint32_t n, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in,
+                      uint32_t* vals_out, int end_bit, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    if (n == 0) return;
+    cub::DeviceRadixSort::SortPairs(scratch, scratch_bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0, end_bit, st);
+    g_kernel_launches += 1 + (end_bit + 7) / 8;
+}
+
+void scan_match_counts(const ChainBatch& b, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    // a_off[i] = sum of m_cnt[0..i); the trailing element m_cnt[n] is zero-initialised by the caller, so
+    // a_off[n] is the total number of anchors
+    cub::DeviceScan::ExclusiveSum(scratch, scratch_bytes, b.m_cnt, b.a_off, (int)b.n_qseeds_total + 1, st);
+    g_kernel_launches += 2;
+}
+
+}  // namespace skb

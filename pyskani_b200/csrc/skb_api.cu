@@ -1,0 +1,843 @@
+// skb_api.cu — host side of libskb.so: the C ABI declared in include/skb.h.
+//
+// Orchestrates the kernels of seed_kernels.cu / index_kernels.cu / screen_kernels.cu / chain_kernels.cu on one
+// CUDA stream per context.  All device memory comes from the stream-ordered allocator (cudaMallocAsync) with
+// an unbounded release threshold, so scratch is recycled between calls instead of hitting cudaMalloc.
+// There is deliberately no CPU implementation of any step in this file.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "skb_internal.cuh"
+
+namespace skb {
+
+void launch_screen_decide(const GenomeView*, uint32_t, const GenomeView*, uint32_t, const uint32_t*, double, int, int,
+                          uint8_t*, cudaStream_t);
+void select_passing(uint32_t n, const uint8_t* flags, uint32_t* out_idx, uint32_t* out_count, cudaStream_t st);
+
+struct Core {
+    int device = 0;
+    int n_sm = 148;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    skb_stats_t stats{};
+    cudaEvent_t ev[6]{};
+    void* pinned = nullptr;        // staging for small contigs / tables
+    size_t pinned_bytes = 0;
+    ~Core() {
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (pinned) cudaFreeHost(pinned);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+struct Fail {
+    int code;
+    std::string msg;
+};
+
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            throw Fail{_e == cudaErrorMemoryAllocation ? SKB_ERR_NOMEM : SKB_ERR_CUDA,              \
+                       std::string(#expr) + ": " + cudaGetErrorString(_e)};                        \
+    } while (0)
+
+// stream-ordered device buffer
+struct DevMem {
+    void* p = nullptr;
+    size_t bytes = 0;
+    std::shared_ptr<Core> core;
+    DevMem() = default;
+    DevMem(const std::shared_ptr<Core>& c, size_t n) : bytes(n), core(c) {
+        if (n) CU(cudaMallocAsync(&p, n, c->stream));
+    }
+    DevMem(const DevMem&) = delete;
+    DevMem& operator=(const DevMem&) = delete;
+    DevMem(DevMem&& o) noexcept { *this = std::move(o); }
+    DevMem& operator=(DevMem&& o) noexcept {
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; core = std::move(o.core); o.p = nullptr; o.bytes = 0; }
+        return *this;
+    }
+    void release() {
+        if (p && core) { cudaSetDevice(core->device); cudaFreeAsync(p, core->stream); }
+        p = nullptr; bytes = 0;
+    }
+    ~DevMem() { release(); }
+    template <typename T> T* as() const { return (T*)p; }
+};
+
+struct BatchStore {   // device arrays shared by the sketches that were produced together
+    DevMem kmer_p, pos_p, meta_p, kmer_k, pos_k, meta_k, bucket, contig_seed_start, contig_len, contig_win_start, markers;
+};
+
+struct SketchImpl {
+    std::shared_ptr<Core> core;
+    std::shared_ptr<BatchStore> store;
+    GenomeView view{};
+    skb_sketch_info_t info{};
+    std::vector<uint32_t> contig_len_host;
+};
+
+constexpr uint32_t FRAGMENT_LENGTH = 20000;   // skani::params::CHUNK_SIZE_DNA
+
+}  // namespace skb
+
+struct skb_ctx { std::shared_ptr<skb::Core> core; };
+struct skb_sketch { std::shared_ptr<skb::SketchImpl> impl; };
+struct skb_db {
+    std::shared_ptr<skb::Core> core;
+    std::vector<std::shared_ptr<skb::SketchImpl>> items;
+    skb::DevMem d_views;
+    bool dirty = true;
+};
+
+namespace skb {
+
+static void* ensure_pinned(Core& c, size_t bytes) {
+    if (c.pinned_bytes < bytes) {
+        if (c.pinned) cudaFreeHost(c.pinned);
+        c.pinned = nullptr; c.pinned_bytes = 0;
+        size_t want = std::max(bytes, (size_t)1 << 20);
+        CU(cudaHostAlloc(&c.pinned, want, cudaHostAllocDefault));
+        c.pinned_bytes = want;
+    }
+    return c.pinned;
+}
+
+template <typename T>
+static void upload(Core& c, T* dst, const T* src, size_t n) {
+    if (n) CU(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, c.stream));
+}
+template <typename T>
+static void download(Core& c, T* dst, const T* src, size_t n) {
+    if (n) CU(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, c.stream));
+}
+
+static inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// ------------------------------------------------------------------------------------------------ sketching
+struct KeptContig { uint64_t off; uint32_t len; };
+
+// Finishes a batch whose seeds/markers are described by per-genome contig tables; shared by the scan path
+// (seq on device) and the import path (arrays from the host).
+static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_params_t& P, int seed,
+                         uint32_t n_genomes, const std::vector<std::vector<uint32_t>>& contig_lens,
+                         std::shared_ptr<BatchStore> store, const std::vector<uint32_t>& seed_start,
+                         const std::vector<uint32_t>& marker_start, skb_sketch_t** out);
+
+static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_params_t& P, int seed, uint32_t n_genomes,
+                        const uint32_t* gstart, const uint8_t* seq_dev, const uint64_t* offs, const uint64_t* lens,
+                        skb_sketch_t** out) {
+    Core& c = *core;
+    cudaStream_t st = c.stream;
+    if (P.k < 1 || P.k > 16) throw Fail{SKB_ERR_ARG, "k must be in 1..16 for DNA (skani panics above 16)"};
+    if (P.c < 1 || P.marker_c < 1) throw Fail{SKB_ERR_ARG, "compression factors must be >= 1"};
+
+    // ---- contig gate + tile table (reference lib.rs:155-174)
+    std::vector<std::vector<uint32_t>> contig_lens(n_genomes);
+    std::vector<Tile> tiles;
+    uint64_t total_bases = 0;
+    for (uint32_t g = 0; g < n_genomes; g++) {
+        bool first = true;
+        uint32_t kept = 0;
+        for (uint32_t ci = gstart[g]; ci < gstart[g + 1]; ci++) {
+            if (lens[ci] < SKB_MIN_LENGTH_CONTIG) continue;
+            if (lens[ci] > 0x7FFFFFFFull) throw Fail{SKB_ERR_ARG, "contigs of 2^31 bases or more are not supported"};
+            if (offs[ci] & 15) throw Fail{SKB_ERR_ARG, "device contig offsets must be multiples of 16"};
+            contig_lens[g].push_back((uint32_t)lens[ci]);
+            total_bases += lens[ci];
+            for (uint64_t t0 = 0; t0 < lens[ci]; t0 += TILE_BASES) {
+                Tile t;
+                t.seq_off = offs[ci] + t0;
+                t.pos0 = (uint32_t)t0;
+                t.n = (uint32_t)std::min<uint64_t>(TILE_BASES, lens[ci] - t0);
+                t.contig = kept;
+                t.genome = g | (first ? 0x80000000u : 0u);
+                first = false;
+                tiles.push_back(t);
+            }
+            kept++;
+        }
+    }
+    if (total_bases >= 0x7FFFFFFFull) throw Fail{SKB_ERR_ARG, "a sketch batch is limited to 2^31 bases; split the call"};
+    if (n_genomes >= (1u << 22)) throw Fail{SKB_ERR_ARG, "a sketch batch is limited to 2^22 genomes"};
+    const uint32_t n_tiles = (uint32_t)tiles.size();
+
+    std::vector<uint32_t> seed_start(n_genomes + 1, 0), marker_start(n_genomes + 1, 0);
+    auto store = std::make_shared<BatchStore>();
+
+    if (n_tiles) {
+        DevMem d_tiles(core, sizeof(Tile) * n_tiles);
+        {
+            Tile* h = (Tile*)ensure_pinned(c, sizeof(Tile) * n_tiles);
+            std::memcpy(h, tiles.data(), sizeof(Tile) * n_tiles);
+            upload(c, d_tiles.as<Tile>(), h, n_tiles);
+        }
+        DevMem d_status(core, sizeof(uint64_t) * n_tiles + 64);
+        DevMem d_gs(core, sizeof(uint32_t) * (n_genomes + 1)), d_gm(core, sizeof(uint32_t) * (n_genomes + 1));
+        uint32_t* d_counter = (uint32_t*)((char*)d_status.p + sizeof(uint64_t) * n_tiles);
+        uint32_t* d_overflow = d_counter + 1;
+
+        uint64_t seed_cap = seed ? total_bases / P.c + total_bases / P.c / 4 + 65536 : 1;
+        uint64_t marker_cap = total_bases / P.marker_c + total_bases / P.marker_c / 4 + 65536;
+        seed_cap = std::min<uint64_t>(seed_cap, total_bases);
+        marker_cap = std::min<uint64_t>(marker_cap, total_bases);
+
+        DevMem t_kmer, t_pos, t_meta, t_mkeys;
+        uint32_t h_over = 0;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            t_kmer = DevMem(core, 4 * seed_cap); t_pos = DevMem(core, 4 * seed_cap); t_meta = DevMem(core, 4 * seed_cap);
+            t_mkeys = DevMem(core, 8 * marker_cap);
+            CU(cudaMemsetAsync(d_status.p, 0, d_status.bytes, st));
+            CU(cudaMemsetAsync(d_gs.p, 0xFF, d_gs.bytes, st));
+            CU(cudaMemsetAsync(d_gm.p, 0xFF, d_gm.bytes, st));
+            SeedScanArgs a{};
+            a.seq = seq_dev; a.tiles = d_tiles.as<Tile>(); a.n_tiles = n_tiles;
+            a.kmask = P.k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * P.k)) - 1u);
+            a.kshift = 42 - 2 * P.k;
+            a.thr_seed = seed ? UINT64_MAX / (uint64_t)P.c : 0;     // seed=False keeps markers only (A.4)
+            a.thr_marker = UINT64_MAX / (uint64_t)P.marker_c;
+            a.kmer_p = t_kmer.as<uint32_t>(); a.pos_p = t_pos.as<uint32_t>(); a.meta_p = t_meta.as<uint32_t>();
+            a.marker_keys = t_mkeys.as<uint64_t>();
+            a.seed_cap = (uint32_t)seed_cap; a.marker_cap = (uint32_t)marker_cap;
+            a.tile_status = d_status.as<uint64_t>(); a.tile_counter = d_counter;
+            a.genome_seed_start = d_gs.as<uint32_t>(); a.genome_marker_start = d_gm.as<uint32_t>();
+            a.n_genomes = n_genomes; a.overflow = d_overflow;
+            CU(cudaEventRecord(c.ev[1], st));
+            launch_seed_scan(a, c.n_sm, st);
+            CU(cudaEventRecord(c.ev[2], st));
+            download(c, seed_start.data(), d_gs.as<uint32_t>(), n_genomes + 1);
+            download(c, marker_start.data(), d_gm.as<uint32_t>(), n_genomes + 1);
+            download(c, &h_over, d_overflow, 1);
+            CU(cudaStreamSynchronize(st));
+            if (!h_over) break;
+            if (attempt == 1) throw Fail{SKB_ERR_CUDA, "seed buffers overflowed twice"};
+            seed_cap = std::max<uint64_t>(seed_start[n_genomes], 1);   // the totals are exact even when writes were dropped
+            marker_cap = std::max<uint64_t>(marker_start[n_genomes], 1);
+        }
+        // genomes without a tile never wrote their start: they are empty and begin where the next one begins
+        for (uint32_t g = n_genomes; g-- > 0;) {
+            if (seed_start[g] == 0xFFFFFFFFu) { seed_start[g] = seed_start[g + 1]; marker_start[g] = marker_start[g + 1]; }
+        }
+        const uint32_t ns = seed_start[n_genomes], nm = marker_start[n_genomes];
+
+        // ---- exact-size position-order arrays
+        store->kmer_p = DevMem(core, 4 * (size_t)ns); store->pos_p = DevMem(core, 4 * (size_t)ns);
+        store->meta_p = DevMem(core, 4 * (size_t)ns);
+        if (ns) {
+            CU(cudaMemcpyAsync(store->kmer_p.p, t_kmer.p, 4 * (size_t)ns, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(store->pos_p.p, t_pos.p, 4 * (size_t)ns, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(store->meta_p.p, t_meta.p, 4 * (size_t)ns, cudaMemcpyDeviceToDevice, st));
+        }
+        // ---- k-mer order
+        store->kmer_k = DevMem(core, 4 * (size_t)ns); store->pos_k = DevMem(core, 4 * (size_t)ns);
+        store->meta_k = DevMem(core, 4 * (size_t)ns);
+        if (ns) {
+            upload(c, d_gs.as<uint32_t>(), seed_start.data(), n_genomes + 1);   // repaired starts
+            DevMem scratch(core, kmer_order_scratch_bytes(ns));
+            IndexBuildArgs ib{};
+            ib.n_genomes = n_genomes; ib.n_seeds_total = ns; ib.genome_seed_start = d_gs.as<uint32_t>();
+            ib.kmer_p = store->kmer_p.as<uint32_t>(); ib.pos_p = store->pos_p.as<uint32_t>(); ib.meta_p = store->meta_p.as<uint32_t>();
+            ib.kmer_k = store->kmer_k.as<uint32_t>(); ib.pos_k = store->pos_k.as<uint32_t>(); ib.meta_k = store->meta_k.as<uint32_t>();
+            ib.k = P.k;
+            build_kmer_order(ib, scratch.p, scratch.bytes, st);
+        }
+        // ---- marker sets
+        store->markers = DevMem(core, 8 * (size_t)std::max<uint32_t>(nm, 1));
+        {
+            DevMem scratch(core, marker_scratch_bytes(nm));
+            build_marker_sets(n_genomes, nm, t_mkeys.as<uint64_t>(), store->markers.as<uint64_t>(), d_gm.as<uint32_t>(),
+                              scratch.p, scratch.bytes, st);
+            download(c, marker_start.data(), d_gm.as<uint32_t>(), n_genomes + 1);
+            CU(cudaStreamSynchronize(st));
+        }
+        CU(cudaEventRecord(c.ev[3], st));
+    } else {
+        CU(cudaEventRecord(c.ev[1], st)); CU(cudaEventRecord(c.ev[2], st)); CU(cudaEventRecord(c.ev[3], st));
+    }
+    finish_batch(core, P, seed, n_genomes, contig_lens, store, seed_start, marker_start, out);
+}
+
+static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_params_t& P, int seed,
+                         uint32_t n_genomes, const std::vector<std::vector<uint32_t>>& contig_lens,
+                         std::shared_ptr<BatchStore> store, const std::vector<uint32_t>& seed_start,
+                         const std::vector<uint32_t>& marker_start, skb_sketch_t** out) {
+    Core& c = *core;
+    cudaStream_t st = c.stream;
+    // ---- per-genome tables: buckets, contig seed starts, contig lengths, window capacities
+    std::vector<GenomeView> views(n_genomes);
+    std::vector<uint32_t> h_clen, h_cwin;
+    size_t bucket_total = 0, cstart_total = 0;
+    uint32_t max_buckets = 1, max_contigs = 0;
+    std::vector<size_t> bucket_off(n_genomes), cstart_off(n_genomes), clen_off(n_genomes);
+    for (uint32_t g = 0; g < n_genomes; g++) {
+        const uint32_t ns = seed_start[g + 1] - seed_start[g];
+        int B = 1;
+        while (B < 2 * P.k - 1 && B < 20 && ((uint64_t)8 << B) < ns) B++;   // ~8 seeds per bucket, shift <= 31
+        if (2 * P.k - B > 31) B = 2 * P.k - 31;
+        GenomeView& v = views[g];
+        v.n_buckets = 1u << B;
+        v.bucket_shift = (uint32_t)(2 * P.k - B);
+        max_buckets = std::max(max_buckets, v.n_buckets);
+        bucket_off[g] = bucket_total; bucket_total += v.n_buckets + 1;
+        const uint32_t nc = (uint32_t)contig_lens[g].size();
+        max_contigs = std::max(max_contigs, nc);
+        cstart_off[g] = cstart_total; cstart_total += nc + 1;
+        clen_off[g] = h_clen.size();
+        uint32_t wcap = 0; uint64_t tot = 0;
+        for (uint32_t ci = 0; ci < nc; ci++) {
+            h_clen.push_back(contig_lens[g][ci]);
+            h_cwin.push_back(wcap);
+            wcap += contig_lens[g][ci] / FRAGMENT_LENGTH + 1;
+            tot += contig_lens[g][ci];
+        }
+        h_cwin.push_back(wcap);
+        v.win_cap = wcap; v.total_len = tot; v.n_contigs = nc;
+        v.n_seeds = ns; v.n_markers = marker_start[g + 1] - marker_start[g];
+    }
+    store->bucket = DevMem(core, 4 * bucket_total);
+    store->contig_seed_start = DevMem(core, 4 * std::max<size_t>(cstart_total, 1));
+    store->contig_win_start = DevMem(core, 4 * std::max<size_t>(cstart_total, 1));
+    store->contig_len = DevMem(core, 4 * std::max<size_t>(h_clen.size(), 1));
+    for (uint32_t g = 0; g < n_genomes; g++) {
+        GenomeView& v = views[g];
+        const size_t so = seed_start[g];
+        v.kmer_p = store->kmer_p.as<uint32_t>() + so; v.pos_p = store->pos_p.as<uint32_t>() + so;
+        v.meta_p = store->meta_p.as<uint32_t>() + so; v.kmer_k = store->kmer_k.as<uint32_t>() + so;
+        v.pos_k = store->pos_k.as<uint32_t>() + so; v.meta_k = store->meta_k.as<uint32_t>() + so;
+        v.bucket = store->bucket.as<uint32_t>() + bucket_off[g];
+        v.contig_seed_start = store->contig_seed_start.as<uint32_t>() + cstart_off[g];
+        v.contig_win_start = store->contig_win_start.as<uint32_t>() + cstart_off[g];
+        v.contig_len = store->contig_len.as<uint32_t>() + clen_off[g];
+        v.markers = store->markers.as<uint64_t>() + marker_start[g];
+    }
+    {
+        // one pinned staging block: views | contig_len | contig_win_start
+        const size_t b_views = sizeof(GenomeView) * n_genomes, b_len = 4 * h_clen.size(), b_win = 4 * h_cwin.size();
+        char* h = (char*)ensure_pinned(c, b_views + b_len + b_win + 64);
+        std::memcpy(h, views.data(), b_views);
+        std::memcpy(h + b_views, h_clen.data(), b_len);
+        std::memcpy(h + b_views + b_len, h_cwin.data(), b_win);
+        DevMem d_views(core, b_views);
+        upload(c, (char*)d_views.p, h, b_views);
+        upload(c, (char*)store->contig_len.p, h + b_views, b_len);
+        upload(c, (char*)store->contig_win_start.p, h + b_views + b_len, b_win);
+        // per-genome layout of contig_win_start mirrors contig_seed_start (nc + 1 entries each)
+        launch_build_buckets(d_views.as<GenomeView>(), n_genomes, max_buckets, st);
+        launch_contig_starts(d_views.as<GenomeView>(), n_genomes, max_contigs, st);
+        CU(cudaStreamSynchronize(st));   // staging block is reused by the next call
+    }
+    for (uint32_t g = 0; g < n_genomes; g++) {
+        auto impl = std::make_shared<SketchImpl>();
+        impl->core = core; impl->store = store; impl->view = views[g];
+        impl->contig_len_host = contig_lens[g];
+        impl->info.n_seeds = views[g].n_seeds; impl->info.n_markers = views[g].n_markers;
+        impl->info.total_len = views[g].total_len; impl->info.n_contigs = views[g].n_contigs;
+        impl->info.k = P.k; impl->info.c = P.c; impl->info.marker_c = P.marker_c; impl->info.has_seeds = seed ? 1 : 0;
+        out[g] = new skb_sketch{impl};
+    }
+}
+
+}  // namespace skb
+
+// ================================================================================================ C ABI
+using namespace skb;
+
+namespace {
+
+template <typename F>
+int guarded(Core* core, F&& f) {
+    try {
+        if (core) { std::lock_guard<std::mutex> lk(core->mu); cudaSetDevice(core->device); return f(); }
+        return f();
+    } catch (const Fail& e) {
+        if (core) core->err = e.msg;
+        cudaGetLastError();
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        if (core) core->err = "host allocation failed";
+        return SKB_ERR_NOMEM;
+    } catch (const std::exception& e) {
+        if (core) core->err = e.what();
+        return SKB_ERR_CUDA;
+    }
+}
+
+float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+}  // namespace
+
+extern "C" {
+
+const char* skb_version(void) { return "pyskani_b200 libskb 0.1 (sm_100a)"; }
+
+int skb_ctx_create(int device, skb_ctx_t** out) {
+    if (!out) return SKB_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) { cudaGetLastError(); return SKB_ERR_CUDA; }
+    auto core = std::make_shared<Core>();
+    core->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) return SKB_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SKB_ERR_CUDA;
+    core->n_sm = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&core->stream, cudaStreamNonBlocking) != cudaSuccess) return SKB_ERR_CUDA;
+    for (auto& e : core->ev) if (cudaEventCreate(&e) != cudaSuccess) return SKB_ERR_CUDA;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = new skb_ctx{core};
+    return SKB_OK;
+}
+
+void skb_ctx_destroy(skb_ctx_t* ctx) { delete ctx; }
+const char* skb_last_error(const skb_ctx_t* ctx) { return ctx ? ctx->core->err.c_str() : "null context"; }
+int skb_ctx_stats(const skb_ctx_t* ctx, skb_stats_t* out) {
+    if (!ctx || !out) return SKB_ERR_ARG;
+    *out = ctx->core->stats;
+    out->kernels_launched = g_kernel_launches;
+    return SKB_OK;
+}
+int skb_ctx_sync(skb_ctx_t* ctx) {
+    if (!ctx) return SKB_ERR_ARG;
+    return guarded(ctx->core.get(), [&] { CU(cudaStreamSynchronize(ctx->core->stream)); return SKB_OK; });
+}
+void* skb_ctx_stream(skb_ctx_t* ctx) { return ctx ? (void*)ctx->core->stream : nullptr; }
+
+int skb_host_alloc(skb_ctx_t* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return SKB_ERR_ARG;
+    return guarded(ctx->core.get(), [&] { CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault)); return SKB_OK; });
+}
+void skb_host_free(skb_ctx_t* ctx, void* p) { if (ctx && p) { cudaSetDevice(ctx->core->device); cudaFreeHost(p); } }
+int skb_dev_alloc(skb_ctx_t* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return SKB_ERR_ARG;
+    return guarded(ctx->core.get(), [&] { CU(cudaMalloc(out, bytes)); return SKB_OK; });
+}
+void skb_dev_free(skb_ctx_t* ctx, void* p) { if (ctx && p) { cudaSetDevice(ctx->core->device); cudaFree(p); } }
+int skb_memcpy_h2d(skb_ctx_t* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return SKB_ERR_ARG;
+    return guarded(ctx->core.get(), [&] {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->core->stream));
+        CU(cudaStreamSynchronize(ctx->core->stream));
+        return SKB_OK;
+    });
+}
+
+int skb_sketch_batch_device(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t seed, uint32_t n_genomes,
+                            const uint32_t* genome_contig_start, const uint8_t* seq, const uint64_t* contig_offsets,
+                            const uint64_t* contig_lens, skb_sketch_t** out) {
+    if (!ctx || !params || !out || (n_genomes && (!genome_contig_start || !contig_lens || !contig_offsets))) return SKB_ERR_ARG;
+    return guarded(ctx->core.get(), [&] {
+        Core& c = *ctx->core;
+        CU(cudaEventRecord(c.ev[0], c.stream));
+        sketch_core(ctx->core, *params, seed, n_genomes, genome_contig_start, seq, contig_offsets, contig_lens, out);
+        CU(cudaEventRecord(c.ev[4], c.stream));
+        CU(cudaStreamSynchronize(c.stream));
+        c.stats.h2d_ms = 0; c.stats.seed_ms = elapsed(c.ev[1], c.ev[2]); c.stats.index_ms = elapsed(c.ev[2], c.ev[4]);
+        c.stats.total_ms = elapsed(c.ev[0], c.ev[4]);
+        return SKB_OK;
+    });
+}
+
+int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t seed, uint32_t n_genomes,
+                     const uint32_t* genome_contig_start, const uint8_t* const* contigs, const uint64_t* contig_lens,
+                     skb_sketch_t** out) {
+    if (!ctx || !params || !out || (n_genomes && (!genome_contig_start || !contig_lens || !contigs))) return SKB_ERR_ARG;
+    return guarded(ctx->core.get(), [&] {
+        Core& c = *ctx->core;
+        cudaStream_t st = c.stream;
+        const uint32_t n_contigs = n_genomes ? genome_contig_start[n_genomes] : 0;
+        // device layout: 64 B guard | contig 0 (16-aligned) | contig 1 | ... | 64 B guard.  Short contigs are
+        // dropped before the copy: they never reach the GPU (reference lib.rs:156).
+        std::vector<uint64_t> offs(n_contigs, 0);
+        uint64_t cur = 64;
+        for (uint32_t i = 0; i < n_contigs; i++) {
+            if (contig_lens[i] < SKB_MIN_LENGTH_CONTIG) continue;
+            offs[i] = cur;
+            cur += align16(contig_lens[i]) + 16;
+        }
+        cur += 64;
+        CU(cudaEventRecord(c.ev[0], st));
+        DevMem d_seq(ctx->core, cur);
+        // small contigs are packed through pinned staging; large ones are copied straight from the caller's memory
+        constexpr uint64_t DIRECT = 1 << 18;
+        constexpr size_t STAGE = (size_t)8 << 20;
+        char* stage = nullptr; size_t used = 0; uint64_t stage_dev0 = 0;
+        auto flush = [&] {
+            if (used) {
+                CU(cudaMemcpyAsync((char*)d_seq.p + stage_dev0, stage, used, cudaMemcpyHostToDevice, st));
+                CU(cudaStreamSynchronize(st));
+                used = 0;
+            }
+        };
+        for (uint32_t i = 0; i < n_contigs; i++) {
+            const uint64_t len = contig_lens[i];
+            if (len < SKB_MIN_LENGTH_CONTIG) continue;
+            if (len >= DIRECT) {
+                CU(cudaMemcpyAsync((char*)d_seq.p + offs[i], contigs[i], len, cudaMemcpyHostToDevice, st));
+            } else {
+                if (!stage) stage = (char*)ensure_pinned(c, STAGE);
+                const uint64_t span = align16(len) + 16;
+                if (used && (used + span > STAGE || stage_dev0 + used != offs[i])) flush();
+                if (!used) stage_dev0 = offs[i];
+                std::memcpy(stage + used, contigs[i], len);
+                used += span;
+            }
+        }
+        flush();
+        sketch_core(ctx->core, *params, seed, n_genomes, genome_contig_start, d_seq.as<uint8_t>(), offs.data(), contig_lens, out);
+        CU(cudaEventRecord(c.ev[4], st));
+        CU(cudaStreamSynchronize(st));
+        c.stats.h2d_ms = elapsed(c.ev[0], c.ev[1]); c.stats.seed_ms = elapsed(c.ev[1], c.ev[2]);
+        c.stats.index_ms = elapsed(c.ev[2], c.ev[4]); c.stats.total_ms = elapsed(c.ev[0], c.ev[4]);
+        return SKB_OK;
+    });
+}
+
+void skb_sketch_free(skb_sketch_t* s) {
+    if (!s) return;
+    std::shared_ptr<Core> core = s->impl ? s->impl->core : nullptr;   // outlives the lock below
+    if (core) {
+        std::lock_guard<std::mutex> lk(core->mu);
+        cudaSetDevice(core->device);
+        delete s;
+    } else {
+        delete s;
+    }
+}
+
+int skb_sketch_info(const skb_sketch_t* s, skb_sketch_info_t* out) {
+    if (!s || !out) return SKB_ERR_ARG;
+    *out = s->impl->info;
+    return SKB_OK;
+}
+
+int skb_sketch_export(const skb_sketch_t* s, uint64_t* kmer, uint32_t* pos, uint32_t* contig, uint8_t* canonical,
+                      uint64_t* markers, uint32_t* contig_lengths) {
+    if (!s) return SKB_ERR_ARG;
+    SketchImpl& I = *s->impl;
+    return guarded(I.core.get(), [&] {
+        Core& c = *I.core;
+        const uint32_t n = I.view.n_seeds;
+        std::vector<uint32_t> k32(n), p32(n), m32(n);
+        download(c, k32.data(), I.view.kmer_k, n); download(c, p32.data(), I.view.pos_k, n); download(c, m32.data(), I.view.meta_k, n);
+        if (markers) download(c, markers, I.view.markers, I.view.n_markers);
+        CU(cudaStreamSynchronize(c.stream));
+        for (uint32_t i = 0; i < n; i++) {
+            if (kmer) kmer[i] = k32[i];
+            if (pos) pos[i] = p32[i];
+            if (contig) contig[i] = m32[i] >> 1;
+            if (canonical) canonical[i] = (uint8_t)(m32[i] & 1u);
+        }
+        if (contig_lengths) std::memcpy(contig_lengths, I.contig_len_host.data(), 4 * I.contig_len_host.size());
+        return SKB_OK;
+    });
+}
+
+int skb_sketch_import(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t has_seeds, uint64_t n_seeds,
+                      const uint64_t* kmer, const uint32_t* pos, const uint32_t* contig, const uint8_t* canonical,
+                      uint64_t n_markers, const uint64_t* markers, uint32_t n_contigs, const uint32_t* contig_lengths,
+                      skb_sketch_t** out) {
+    if (!ctx || !params || !out) return SKB_ERR_ARG;
+    if (n_seeds && (!kmer || !pos || !contig || !canonical)) return SKB_ERR_ARG;
+    if (n_markers && !markers) return SKB_ERR_ARG;
+    if (n_contigs && !contig_lengths) return SKB_ERR_ARG;
+    return guarded(ctx->core.get(), [&] {
+        Core& c = *ctx->core;
+        cudaStream_t st = c.stream;
+        if (params->k < 1 || params->k > 16) throw Fail{SKB_ERR_ARG, "k must be in 1..16"};
+        if (n_seeds >= 0x7FFFFFFFull || n_markers >= 0x7FFFFFFFull) throw Fail{SKB_ERR_ARG, "sketch too large"};
+        // position order on the host (import is the Database.load path, not a hot path), then the same
+        // device index build as a fresh sketch
+        const uint32_t n = (uint32_t)n_seeds;
+        std::vector<uint32_t> ord(n);
+        for (uint32_t i = 0; i < n; i++) ord[i] = i;
+        std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) {
+            if (contig[a] != contig[b]) return contig[a] < contig[b];
+            return pos[a] < pos[b];
+        });
+        std::vector<uint32_t> hk(n), hp(n), hm(n);
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t s = ord[i];
+            if (contig[s] >= n_contigs) throw Fail{SKB_ERR_ARG, "seed refers to a contig that does not exist"};
+            if (kmer[s] >> (2 * params->k)) throw Fail{SKB_ERR_ARG, "k-mer wider than 2k bits"};
+            hk[i] = (uint32_t)kmer[s]; hp[i] = pos[s]; hm[i] = (contig[s] << 1) | (canonical[s] ? 1u : 0u);
+        }
+        std::vector<uint64_t> hmark(markers, markers + n_markers);
+        std::sort(hmark.begin(), hmark.end());
+        hmark.erase(std::unique(hmark.begin(), hmark.end()), hmark.end());
+        auto store = std::make_shared<BatchStore>();
+        store->kmer_p = DevMem(ctx->core, 4 * (size_t)n); store->pos_p = DevMem(ctx->core, 4 * (size_t)n);
+        store->meta_p = DevMem(ctx->core, 4 * (size_t)n); store->kmer_k = DevMem(ctx->core, 4 * (size_t)n);
+        store->pos_k = DevMem(ctx->core, 4 * (size_t)n); store->meta_k = DevMem(ctx->core, 4 * (size_t)n);
+        store->markers = DevMem(ctx->core, 8 * std::max<size_t>(hmark.size(), 1));
+        CU(cudaMemcpyAsync(store->kmer_p.p, hk.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(store->pos_p.p, hp.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(store->meta_p.p, hm.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(store->markers.p, hmark.data(), 8 * hmark.size(), cudaMemcpyHostToDevice, st));
+        std::vector<uint32_t> seed_start{0, n}, marker_start{0, (uint32_t)hmark.size()};
+        if (n) {
+            DevMem d_gs(ctx->core, 8);
+            CU(cudaMemcpyAsync(d_gs.p, seed_start.data(), 8, cudaMemcpyHostToDevice, st));
+            DevMem scratch(ctx->core, kmer_order_scratch_bytes(n));
+            IndexBuildArgs ib{};
+            ib.n_genomes = 1; ib.n_seeds_total = n; ib.genome_seed_start = d_gs.as<uint32_t>();
+            ib.kmer_p = store->kmer_p.as<uint32_t>(); ib.pos_p = store->pos_p.as<uint32_t>(); ib.meta_p = store->meta_p.as<uint32_t>();
+            ib.kmer_k = store->kmer_k.as<uint32_t>(); ib.pos_k = store->pos_k.as<uint32_t>(); ib.meta_k = store->meta_k.as<uint32_t>();
+            ib.k = params->k;
+            build_kmer_order(ib, scratch.p, scratch.bytes, st);
+            CU(cudaStreamSynchronize(st));   // host vectors above go out of scope after this call
+        }
+        CU(cudaStreamSynchronize(st));
+        std::vector<std::vector<uint32_t>> cl(1);
+        cl[0].assign(contig_lengths, contig_lengths + n_contigs);
+        finish_batch(ctx->core, *params, has_seeds, 1, cl, store, seed_start, marker_start, out);
+        return SKB_OK;
+    });
+}
+
+int skb_db_create(skb_ctx_t* ctx, skb_db_t** out) {
+    if (!ctx || !out) return SKB_ERR_ARG;
+    *out = new skb_db{ctx->core};
+    return SKB_OK;
+}
+void skb_db_destroy(skb_db_t* db) {
+    if (!db) return;
+    auto core = db->core;
+    std::lock_guard<std::mutex> lk(core->mu);
+    cudaSetDevice(core->device);
+    delete db;
+}
+int skb_db_add(skb_db_t* db, skb_sketch_t* s, uint32_t* index_out) {
+    if (!db || !s) return SKB_ERR_ARG;
+    return guarded(db->core.get(), [&] {
+        if (s->impl->core != db->core) throw Fail{SKB_ERR_ARG, "sketch belongs to another context"};
+        if (!db->items.empty()) {
+            const auto& a = db->items[0]->info; const auto& b = s->impl->info;
+            if (a.k != b.k || a.c != b.c || a.marker_c != b.marker_c) throw Fail{SKB_ERR_ARG, "sketch parameters differ from the database's"};
+        }
+        if (index_out) *index_out = (uint32_t)db->items.size();
+        db->items.push_back(s->impl);
+        db->dirty = true;
+        return SKB_OK;
+    });
+}
+uint64_t skb_db_size(const skb_db_t* db) { return db ? db->items.size() : 0; }
+
+void skb_hits_free(skb_hit_t* hits) { delete[] hits; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ query
+namespace {
+
+const GenomeView* db_views(skb_db& db) {
+    Core& c = *db.core;
+    if (db.dirty) {
+        const size_t n = db.items.size();
+        db.d_views = DevMem(db.core, sizeof(GenomeView) * std::max<size_t>(n, 1));
+        std::vector<GenomeView> h(n);
+        for (size_t i = 0; i < n; i++) h[i] = db.items[i]->view;
+        CU(cudaMemcpyAsync(db.d_views.p, h.data(), sizeof(GenomeView) * n, cudaMemcpyHostToDevice, c.stream));
+        CU(cudaStreamSynchronize(c.stream));
+        db.dirty = false;
+    }
+    return db.d_views.as<GenomeView>();
+}
+
+struct ScreenOut {
+    std::vector<uint32_t> pass_idx;   // q * n_refs + r, ascending
+};
+
+double pow21(double x) { double p = 1.0; for (int i = 0; i < SKB_MARKER_K; i++) p *= x; return p; }
+
+// runs the screen for all (query, ref) pairs; optionally returns the dense arrays
+void run_screen(skb_db& db, const std::vector<std::shared_ptr<SketchImpl>>& queries, const GenomeView* d_q,
+                double screen_val, int rescue_small, ScreenOut* out, uint8_t* pass_host, uint32_t* shared_host) {
+    Core& c = *db.core;
+    cudaStream_t st = c.stream;
+    const uint32_t nq = (uint32_t)queries.size(), nr = (uint32_t)db.items.size();
+    const size_t n = (size_t)nq * nr;
+    if (n == 0) return;
+    if (n >= 0x7FFFFFFFull) throw Fail{SKB_ERR_ARG, "more than 2^31 pairs in one call; split the queries"};
+    const GenomeView* d_r = db_views(db);
+    DevMem d_count(db.core, 4 * n), d_pass(db.core, n);
+    launch_marker_screen(d_q, nq, d_r, nr, d_count.as<uint32_t>(), st);
+    launch_screen_decide(d_q, nq, d_r, nr, d_count.as<uint32_t>(), pow21(screen_val), screen_val == 0.0, rescue_small,
+                         d_pass.as<uint8_t>(), st);
+    if (pass_host) download(c, pass_host, d_pass.as<uint8_t>(), n);
+    if (shared_host) download(c, shared_host, d_count.as<uint32_t>(), n);
+    if (out) {
+        DevMem d_idx(db.core, 4 * n + 4);
+        uint32_t* d_cnt = d_idx.as<uint32_t>() + n;
+        select_passing((uint32_t)n, d_pass.as<uint8_t>(), d_idx.as<uint32_t>(), d_cnt, st);
+        uint32_t cnt = 0;
+        download(c, &cnt, d_cnt, 1);
+        CU(cudaStreamSynchronize(st));
+        out->pass_idx.resize(cnt);
+        download(c, out->pass_idx.data(), d_idx.as<uint32_t>(), cnt);
+    }
+    CU(cudaStreamSynchronize(st));
+}
+
+}  // namespace
+
+extern "C" {
+
+int skb_db_screen(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries, double cutoff, int32_t rescue_small,
+                  uint8_t* pass, uint32_t* shared) {
+    if (!db || (n_queries && !queries)) return SKB_ERR_ARG;
+    return guarded(db->core.get(), [&] {
+        std::vector<std::shared_ptr<SketchImpl>> qs;
+        std::vector<GenomeView> hv;
+        for (uint32_t i = 0; i < n_queries; i++) { qs.push_back(queries[i]->impl); hv.push_back(queries[i]->impl->view); }
+        DevMem d_q(db->core, sizeof(GenomeView) * std::max<uint32_t>(n_queries, 1));
+        CU(cudaMemcpyAsync(d_q.p, hv.data(), sizeof(GenomeView) * n_queries, cudaMemcpyHostToDevice, db->core->stream));
+        run_screen(*db, qs, d_q.as<GenomeView>(), cutoff, rescue_small, nullptr, pass, shared);
+        return SKB_OK;
+    });
+}
+
+int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries, const skb_query_opts_t* opts,
+                 skb_hit_t** hits, uint64_t* n_hits, uint64_t* n_screened_in) {
+    if (!db || !opts || !hits || !n_hits || (n_queries && !queries)) return SKB_ERR_ARG;
+    *hits = nullptr; *n_hits = 0;
+    if (n_screened_in) *n_screened_in = 0;
+    return guarded(db->core.get(), [&] {
+        Core& c = *db->core;
+        cudaStream_t st = c.stream;
+        if (opts->learned_ani == 1)
+            throw Fail{SKB_ERR_UNSUPPORTED,
+                       "learned_ani=True needs skani's embedded GBDT model, whose weights are not part of pyskani's "
+                       "sources; pass learned_ani=False (or None) for the uncorrected estimate"};
+        const uint32_t nr = (uint32_t)db->items.size();
+        if (nr == 0 || n_queries == 0) return SKB_OK;
+        const skb_sketch_info_t& dbi = db->items[0]->info;
+        std::vector<std::shared_ptr<SketchImpl>> qs;
+        std::vector<GenomeView> hv;
+        for (uint32_t i = 0; i < n_queries; i++) {
+            if (!queries[i]) throw Fail{SKB_ERR_ARG, "null query sketch"};
+            const auto& qi = queries[i]->impl->info;
+            if (qi.k != dbi.k || qi.c != dbi.c || qi.marker_c != dbi.marker_c) throw Fail{SKB_ERR_ARG, "query sketch parameters differ from the database's"};
+            qs.push_back(queries[i]->impl); hv.push_back(queries[i]->impl->view);
+        }
+        CU(cudaEventRecord(c.ev[0], st));
+        DevMem d_q(db->core, sizeof(GenomeView) * n_queries);
+        CU(cudaMemcpyAsync(d_q.p, hv.data(), sizeof(GenomeView) * n_queries, cudaMemcpyHostToDevice, st));
+        const GenomeView* d_r = db_views(*db);
+
+        // ---- screen (reference lib.rs:603-637)
+        const double screen_val = opts->cutoff != 0.0 ? opts->cutoff : 0.80;   // SEARCH_ANI_CUTOFF_DEFAULT
+        ScreenOut so;
+        run_screen(*db, qs, d_q.as<GenomeView>(), screen_val, opts->faster_small ? 0 : 1, &so, nullptr, nullptr);
+        CU(cudaEventRecord(c.ev[1], st));
+        if (n_screened_in) *n_screened_in = so.pass_idx.size();
+
+        // ---- chain survivors in batches (reference lib.rs:640-657)
+        ChainConsts C{};
+        C.fragment_length = FRAGMENT_LENGTH; C.anchor_score = 20; C.min_anchors = 3; C.min_score = 45; C.max_gap = 300;
+        C.index_band = 100; C.bp_band = 2500; C.af_ext = 198; C.frac_cover_cutoff = 0.15;   // D_FRAC_COVER_CUTOFF / 100 (lib.rs:589)
+        C.robust = opts->robust; C.median = opts->median; C.k = dbi.k;
+
+        std::vector<skb_hit_t> all_hits;
+        const size_t n_pass = so.pass_idx.size();
+        constexpr uint64_t MAX_BATCH_SEEDS = 48ull << 20;
+        size_t p0 = 0;
+        while (p0 < n_pass) {
+            std::vector<PairDesc> pairs;
+            uint64_t seeds = 0, wins = 0;
+            size_t p1 = p0;
+            while (p1 < n_pass) {
+                const uint32_t q = so.pass_idx[p1] / nr, r = so.pass_idx[p1] % nr;
+                const GenomeView& qv = qs[q]->view;
+                if (!pairs.empty() && (seeds + qv.n_seeds > MAX_BATCH_SEEDS || pairs.size() >= 65535)) break;
+                pairs.push_back(PairDesc{q, r, (uint32_t)seeds, (uint32_t)wins});
+                seeds += qv.n_seeds; wins += qv.win_cap;
+                p1++;
+            }
+            if (seeds >= 0x7FFFFFFFull) throw Fail{SKB_ERR_ARG, "query sketch too large for one chaining batch"};
+            const uint32_t np = (uint32_t)pairs.size();
+            ChainBatch B{};
+            B.qviews = d_q.as<GenomeView>(); B.rviews = d_r; B.n_pairs = np;
+            B.n_qseeds_total = (uint32_t)seeds; B.n_win_total = (uint32_t)wins;
+            DevMem d_pairs(db->core, sizeof(PairDesc) * np);
+            CU(cudaMemcpyAsync(d_pairs.p, pairs.data(), sizeof(PairDesc) * np, cudaMemcpyHostToDevice, st));
+            B.pairs = d_pairs.as<PairDesc>();
+            DevMem d_first(db->core, 4 * (seeds + 1)), d_cnt(db->core, 4 * (seeds + 1)), d_aoff(db->core, 4 * (seeds + 2));
+            B.m_first = d_first.as<uint32_t>(); B.m_cnt = d_cnt.as<uint32_t>(); B.a_off = d_aoff.as<uint32_t>();
+            CU(cudaMemsetAsync(B.m_cnt + seeds, 0, 4, st));
+            launch_match_count(B, st);
+            {
+                DevMem scratch(db->core, scan_scratch_bytes((uint32_t)seeds + 1));
+                scan_match_counts(B, scratch.p, scratch.bytes, st);
+            }
+            uint32_t n_anchors = 0;
+            download(c, &n_anchors, B.a_off + seeds, 1);
+            CU(cudaStreamSynchronize(st));   // also keeps `pairs` alive until its upload has finished
+            const size_t na = std::max<uint32_t>(n_anchors, 1);
+            B.anchor_cap = n_anchors;
+            DevMem d_a(db->core, na * 4 * 7), d_best(db->core, na * 8);
+            B.a_qi = d_a.as<uint32_t>(); B.a_qp = B.a_qi + na; B.a_rp = B.a_qp + na; B.a_meta = B.a_rp + na;
+            B.a_f = (int32_t*)(B.a_meta + na); B.a_root = (uint32_t*)(B.a_f + na); B.a_aux = B.a_root + na;
+            B.a_best = d_best.as<unsigned long long>();
+            CU(cudaMemsetAsync(B.a_aux, 0, 4 * na, st));
+            CU(cudaMemsetAsync(B.a_best, 0, 8 * na, st));
+            const size_t nw = std::max<uint64_t>(wins, 1);
+            DevMem d_w(db->core, nw * 4 * 3 + 4 * (size_t)np), d_rec(db->core, nw * sizeof(WindowRec));
+            B.win_start = d_w.as<uint32_t>(); B.win_end = B.win_start + nw; B.win_contig = B.win_end + nw; B.pair_nwin = B.win_contig + nw;
+            B.win_rec = d_rec.as<WindowRec>();
+            CU(cudaMemsetAsync(B.win_start, 0, 8 * nw, st));   // start == end == 0 marks an unused slot
+            DevMem d_keys(db->core, nw * 8 * 2), d_vals(db->core, nw * 4 * 2), d_res(db->core, sizeof(PairResult) * np);
+            B.sort_keys = d_keys.as<uint64_t>(); B.sort_vals = d_vals.as<uint32_t>();
+            uint64_t* keys_sorted = B.sort_keys + nw; uint32_t* vals_sorted = B.sort_vals + nw;
+            B.results = d_res.as<PairResult>();
+
+            launch_anchor_fill(B, st);
+            launch_window_walk(B, C, st);
+            launch_chain_dp(B, C, st);
+            launch_window_keys(B, st);
+            {
+                int pbits = 1;
+                while ((1ull << pbits) <= (uint64_t)np) pbits++;
+                DevMem scratch(db->core, sort_pairs_scratch_bytes((uint32_t)wins));
+                sort_window_keys((uint32_t)wins, B.sort_keys, keys_sorted, B.sort_vals, vals_sorted, 32 + pbits, scratch.p,
+                                 scratch.bytes, st);
+            }
+            launch_ani_reduce(B, C, keys_sorted, vals_sorted, st);
+            std::vector<PairResult> res(np);
+            download(c, res.data(), B.results, np);
+            CU(cudaStreamSynchronize(st));
+            for (uint32_t i = 0; i < np; i++) {
+                if (res[i].ani > 0.1f) {   // reference lib.rs:654
+                    skb_hit_t h{};
+                    h.query_index = pairs[i].q; h.ref_index = pairs[i].r;
+                    h.ani = res[i].ani; h.af_query = res[i].af_q; h.af_ref = res[i].af_r;
+                    h.n_windows = res[i].n_windows; h.n_chains = res[i].n_chains; h.n_anchors = res[i].n_anchors;
+                    all_hits.push_back(h);
+                }
+            }
+            p0 = p1;
+        }
+        CU(cudaEventRecord(c.ev[2], st));
+        CU(cudaStreamSynchronize(st));
+        c.stats.screen_ms = elapsed(c.ev[0], c.ev[1]); c.stats.chain_ms = elapsed(c.ev[1], c.ev[2]);
+        c.stats.total_ms = elapsed(c.ev[0], c.ev[2]);
+        if (!all_hits.empty()) {
+            *hits = new skb_hit_t[all_hits.size()];
+            std::memcpy(*hits, all_hits.data(), sizeof(skb_hit_t) * all_hits.size());
+        }
+        *n_hits = all_hits.size();
+        return SKB_OK;
+    });
+}
+
+}  // extern "C"

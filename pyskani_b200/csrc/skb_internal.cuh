@@ -1,0 +1,181 @@
+// skb_internal.cuh — shared declarations of libskb's translation units (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/skb.h"
+
+namespace skb {
+
+// ---------------------------------------------------------------- device-side views
+// One sketched genome as the kernels see it.  Two orders of the same seeds:
+//   *_p : position order  (contig, pos)        — emitted directly by the seeding kernel
+//   *_k : k-mer order     (kmer, contig, pos)  — the "device-sorted hash->position array" that replaces
+//                                                 skani's FxHashMap seed index
+// meta = contig_index << 1 | canonical.
+struct GenomeView {
+    const uint32_t* kmer_p;
+    const uint32_t* pos_p;
+    const uint32_t* meta_p;
+    const uint32_t* kmer_k;
+    const uint32_t* pos_k;
+    const uint32_t* meta_k;
+    const uint32_t* bucket;        // [n_buckets + 1] offsets into *_k by top bits of the k-mer
+    const uint32_t* contig_seed_start;  // [n_contigs + 1] offsets into *_p
+    const uint32_t* contig_len;    // [n_contigs]
+    const uint32_t* contig_win_start;   // [n_contigs + 1] prefix sums of per-contig window capacity (len / 20000 + 1)
+    const uint64_t* markers;       // sorted unique canonical 21-mers
+    uint64_t total_len;
+    uint32_t n_seeds;
+    uint32_t n_markers;
+    uint32_t n_contigs;
+    uint32_t bucket_shift;         // bucket id = kmer >> bucket_shift
+    uint32_t n_buckets;
+    uint32_t win_cap;              // upper bound on 20 kb windows when this genome is the query
+};
+
+// ---------------------------------------------------------------- seeding
+constexpr int TILE_BASES = 4096;          // bases per tile = 256 threads x 16
+constexpr int SEED_THREADS = 256;
+
+struct Tile {
+    uint64_t seq_off;   // byte offset of the tile's first base in the device sequence buffer (16-aligned)
+    uint32_t pos0;      // position of that base inside its contig (multiple of 16)
+    uint32_t n;         // bases in the tile, 1..TILE_BASES
+    uint32_t contig;    // index among the genome's kept contigs
+    uint32_t genome;    // genome index inside the batch; bit 31 set on the first tile of a genome
+};
+
+struct SeedScanArgs {
+    const uint8_t* seq;
+    const Tile* tiles;
+    uint32_t n_tiles;
+    uint32_t kmask, kshift;
+    uint64_t thr_seed, thr_marker;
+    // outputs, position order over the whole batch
+    uint32_t* kmer_p;
+    uint32_t* pos_p;
+    uint32_t* meta_p;
+    uint64_t* marker_keys;       // genome << 42 | canonical 21-mer
+    uint32_t seed_cap, marker_cap;
+    uint64_t* tile_status;       // [n_tiles] decoupled look-back words, zero-initialised
+    uint32_t* tile_counter;      // zero-initialised
+    uint32_t* genome_seed_start;   // [n_genomes + 1]
+    uint32_t* genome_marker_start; // [n_genomes + 1]
+    uint32_t n_genomes;
+    uint32_t* overflow;          // set to 1 when a capacity was exceeded
+};
+
+void launch_seed_scan(const SeedScanArgs& a, int n_sm, cudaStream_t st);
+
+// ---------------------------------------------------------------- index build (sort by k-mer, buckets, marker sets)
+struct IndexBuildArgs {
+    uint32_t n_genomes;
+    uint32_t n_seeds_total, n_markers_total;
+    const uint32_t* genome_seed_start;    // device [n_genomes+1]
+    const uint32_t* kmer_p; const uint32_t* pos_p; const uint32_t* meta_p;
+    uint32_t* kmer_k; uint32_t* pos_k; uint32_t* meta_k;
+    int k;
+};
+
+// sorts (genome,kmer) keys carrying the position-order index, then gathers the *_k arrays
+void build_kmer_order(const IndexBuildArgs& a, void* scratch, size_t scratch_bytes, cudaStream_t st);
+size_t kmer_order_scratch_bytes(uint32_t n_seeds_total);
+
+// sorts marker keys and removes duplicates per genome; writes marker values (42-bit) to markers_out and the
+// per-genome offsets [n_genomes+1] to genome_marker_out (device)
+void build_marker_sets(uint32_t n_genomes, uint32_t n_markers_total, uint64_t* marker_keys, uint64_t* markers_out,
+                       uint32_t* genome_marker_out, void* scratch, size_t scratch_bytes, cudaStream_t st);
+size_t marker_scratch_bytes(uint32_t n_markers_total);
+
+// bucket offsets + per-contig seed starts for a set of genomes described by views
+void launch_build_buckets(const GenomeView* views_dev, uint32_t n_genomes, uint32_t max_buckets, cudaStream_t st);
+void launch_contig_starts(const GenomeView* views_dev, uint32_t n_genomes, uint32_t max_contigs, cudaStream_t st);
+
+// ---------------------------------------------------------------- screen
+// count[q * n_refs + r] = | markers(q) ∩ markers(r) |
+void launch_marker_screen(const GenomeView* queries, uint32_t n_queries, const GenomeView* refs, uint32_t n_refs,
+                          uint32_t* count, cudaStream_t st);
+void launch_screen_decide(const GenomeView* queries, uint32_t n_queries, const GenomeView* refs, uint32_t n_refs,
+                          const uint32_t* count, double p21, int always, int rescue_small, uint8_t* pass,
+                          cudaStream_t st);
+
+// ---------------------------------------------------------------- chain
+struct ChainConsts {           // skani::chain::map_params_from_sketch (reference lib.rs:646-651), frozen per DESIGN.md
+    uint32_t fragment_length;  // 20000
+    int32_t anchor_score;      // 20
+    int32_t min_anchors;       // 3
+    int32_t min_score;         // 45
+    int32_t max_gap;           // 300
+    int32_t index_band;        // 100
+    int32_t bp_band;           // 2500
+    int32_t af_ext;            // 198
+    double frac_cover_cutoff;  // 0.15
+    int32_t robust, median;
+    int32_t k;
+};
+
+struct PairDesc {
+    uint32_t q, r;             // indices into the query / reference view arrays
+    uint32_t seed_off;         // offset of this pair's slice in the per-query-seed scratch arrays
+    uint32_t win_off;          // offset of this pair's slice in the window arrays
+};
+
+struct WindowRec {             // one 20 kb query window of one pair
+    uint32_t anchors;          // anchors in kept chains (component sizes)
+    uint32_t seeds;            // query seeds between the first and the last kept chain coordinate
+    uint32_t cov_q, cov_r;     // sum over kept chains of (span + af_ext)
+    uint32_t n_chains;
+};
+
+struct PairResult {
+    float ani, af_q, af_r;
+    uint32_t n_windows, n_chains, n_anchors;
+};
+
+struct ChainBatch {            // device pointers of one batch of pairs
+    const GenomeView* qviews; const GenomeView* rviews;
+    const PairDesc* pairs; uint32_t n_pairs;
+    uint32_t n_qseeds_total;   // sum of query seeds over pairs
+    uint32_t n_win_total;      // sum of window capacities over pairs
+    // per query seed of each pair
+    uint32_t* m_first;         // first matching index in the reference's k-mer order
+    uint32_t* m_cnt;           // number of matches
+    uint32_t* a_off;           // exclusive scan of m_cnt (+1 trailing element = total)
+    // anchors
+    uint32_t anchor_cap;
+    uint32_t* a_qi; uint32_t* a_qp; uint32_t* a_rp; uint32_t* a_meta;   // meta = ref contig << 1 | reverse
+    int32_t* a_f; uint32_t* a_root; uint32_t* a_aux;                    // DP score, component root, per-root size
+    unsigned long long* a_best;                                         // per-root best (score << 32 | ~index)
+    // windows
+    uint32_t* win_start;       // [n_win_total] first query-seed index (pair-local) of each window
+    uint32_t* win_end;         // [n_win_total] one past the last query-seed index
+    uint32_t* win_contig;      // query contig
+    uint32_t* pair_nwin;       // [n_pairs]
+    WindowRec* win_rec;        // [n_win_total]
+    uint64_t* sort_keys; uint32_t* sort_vals;   // [n_win_total]
+    PairResult* results;       // [n_pairs]
+};
+
+void launch_match_count(const ChainBatch& b, cudaStream_t st);
+void launch_anchor_fill(const ChainBatch& b, cudaStream_t st);
+void launch_window_walk(const ChainBatch& b, const ChainConsts& c, cudaStream_t st);
+void launch_chain_dp(const ChainBatch& b, const ChainConsts& c, cudaStream_t st);
+void launch_window_keys(const ChainBatch& b, cudaStream_t st);
+void launch_ani_reduce(const ChainBatch& b, const ChainConsts& c, const uint64_t* sorted_keys,
+                       const uint32_t* sorted_vals, cudaStream_t st);
+// exclusive scan of m_cnt into a_off (n+1 outputs); sort of window keys
+void scan_match_counts(const ChainBatch& b, void* scratch, size_t scratch_bytes, cudaStream_t st);
+size_t scan_scratch_bytes(uint32_t n);
+void sort_window_keys(uint32_t n, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in,
+                      uint32_t* vals_out, int end_bit, void* scratch, size_t scratch_bytes, cudaStream_t st);
+size_t sort_pairs_scratch_bytes(uint32_t n);
+
+extern unsigned long long g_kernel_launches;   // incremented by every launch_* wrapper
+
+}  // namespace skb

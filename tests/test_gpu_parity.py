@@ -1,0 +1,267 @@
+"""GPU parity: libskb (through its C ABI) against the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): sketches (seed k-mers, positions, strands, contigs; marker sets) and the
+set of pairs passing the screen are bit-exact; ANI within 1e-4 (0.01 pp) and AF within 1e-3.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from pyskani_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ANI_TOL = 1e-4
+AF_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from pyskani_b200 import capi
+    c = capi.Context(0)
+    yield c
+
+
+def assert_sketch_equal(gs, osk):
+    e = gs.export()
+    ok, op, oc, ocan = osk.seeds()
+    assert len(e["kmer"]) == len(ok)
+    assert np.array_equal(e["kmer"], ok)
+    assert np.array_equal(e["pos"], op)
+    assert np.array_equal(e["contig"], oc)
+    assert np.array_equal(e["canonical"], ocan)
+    assert np.array_equal(e["markers"], osk.markers())
+    assert np.array_equal(e["contig_lengths"], osk.contig_lengths())
+    i = gs.info()
+    assert i.total_len == osk.total_len
+
+
+def rand(n, seed):
+    return synth.random_genome(n, seed).tobytes()
+
+
+# ------------------------------------------------------------------ sketches
+@pytest.mark.parametrize("n,seed", [(500, 1), (521, 2), (4096, 3), (4097, 4), (4112, 5), (100_000, 6), (1_000_003, 7)])
+def test_sketch_single_contig(ctx, n, seed):
+    s = rand(n, seed)
+    (g,) = ctx.sketch_batch([[s]])
+    assert_sketch_equal(g, oracle.Sketch([s]))
+
+
+def test_sketch_ecoli(ctx, ecoli):
+    ec, k12, _ = ecoli
+    g1, g2 = ctx.sketch_batch([[ec], [k12]])
+    assert_sketch_equal(g1, oracle.Sketch([ec]))
+    assert_sketch_equal(g2, oracle.Sketch([k12]))
+    assert (g1.info().n_seeds, g1.info().n_markers) == (37237, 4539)
+
+
+def test_sketch_ragged_batch(ctx):
+    # empty genome, genome of only short contigs, many small contigs, big + small mix
+    rng = np.random.default_rng(5)
+    genomes = [
+        [],
+        [rand(499, 1), rand(10, 2), b""],
+        [rand(int(l), 100 + i) for i, l in enumerate(rng.integers(400, 9000, 40))],
+        [rand(300_000, 7), rand(499, 8), rand(500, 9), rand(70_001, 10)],
+        [rand(5000, 11)],
+    ]
+    gs = ctx.sketch_batch(genomes)
+    for g, contigs in zip(gs, genomes):
+        assert_sketch_equal(g, oracle.Sketch(contigs))
+    assert gs[0].info().n_seeds == 0 and gs[1].info().n_contigs == 0
+
+
+def test_sketch_junk_and_lowercase(ctx):
+    rng = np.random.default_rng(3)
+    alpha = np.frombuffer(b"ACGTacgtNnRYKM-*", np.uint8)
+    s = alpha[rng.integers(0, len(alpha), 200_000)].tobytes()
+    (g,) = ctx.sketch_batch([[s]])
+    assert_sketch_equal(g, oracle.Sketch([s]))
+
+
+@pytest.mark.parametrize("k,c,mc", [(15, 125, 1000), (13, 30, 200), (16, 70, 500), (12, 1, 1), (15, 200, 3000)])
+def test_sketch_params(ctx, k, c, mc):
+    s = rand(60_000, 17)
+    (g,) = ctx.sketch_batch([[s]], k=k, c=c, marker_c=mc)
+    assert_sketch_equal(g, oracle.Sketch([s], k=k, c=c, marker_c=mc))
+
+
+def test_sketch_seed_false(ctx):
+    s = rand(80_000, 19)
+    (g,) = ctx.sketch_batch([[s]], seed=False)
+    o = oracle.Sketch([s], seed=False)
+    assert g.info().n_seeds == 0 and g.info().has_seeds == 0
+    assert np.array_equal(g.export()["markers"], o.markers())
+
+
+def test_sketch_low_complexity_overflow_path(ctx):
+    # poly-A and short tandem repeats: seed density far from 1/c exercises the capacity retry
+    s = (b"A" * 300_000) + (b"ACGTTGCA" * 20_000) + rand(50_000, 23)
+    for c in (1, 125):
+        (g,) = ctx.sketch_batch([[s]], c=c, marker_c=max(1, c * 8))
+        assert_sketch_equal(g, oracle.Sketch([s], c=c, marker_c=max(1, c * 8)))
+
+
+def test_import_roundtrip(ctx):
+    contigs = [rand(120_000, 31), rand(30_000, 32)]
+    (g,) = ctx.sketch_batch([contigs])
+    e = g.export()
+    perm = np.random.default_rng(1).permutation(len(e["kmer"]))
+    g2 = ctx.import_sketch(e["kmer"][perm], e["pos"][perm], e["contig"][perm], e["canonical"][perm],
+                           e["markers"][::-1].copy(), e["contig_lengths"])
+    e2 = g2.export()
+    for key in e:
+        assert np.array_equal(e[key], e2[key]), key
+
+
+# ------------------------------------------------------------------ screen
+def make_family(n_mut, length, seed, divs):
+    base = synth.random_genome(length, seed)
+    return [base] + [synth.mutate(base, d, seed * 1000 + i + 1) for i, d in zip(range(n_mut), divs)]
+
+
+def test_screen_matches_oracle(ctx):
+    from pyskani_b200 import capi
+    fams = []
+    for f in range(3):
+        fams += make_family(4, 400_000, 40 + f, [0.01, 0.05, 0.12, 0.22])
+    fams.append(synth.random_genome(5_000, 99))      # < 20 markers: exercises the small-genome rescue
+    contigs = [[g.tobytes()] for g in fams]
+    gs = ctx.sketch_batch(contigs)
+    os_ = [oracle.Sketch(c) for c in contigs]
+    db = capi.Database(ctx)
+    for g in gs:
+        db.add(g)
+    for cutoff, rescue in ((0.8, True), (0.8, False), (0.9, True), (0.95, False)):
+        ok, shared = db.screen(gs, cutoff, rescue)
+        for i, qo in enumerate(os_):
+            for j, ro in enumerate(os_):
+                want_ok, want_shared = oracle.screen(qo, ro, cutoff, rescue)
+                assert shared[i, j] == want_shared, (i, j)
+                assert ok[i, j] == want_ok, (i, j, cutoff, rescue)
+
+
+# ------------------------------------------------------------------ chain / ANI
+def check_hits(hits, oq, orefs, cutoff=0.8, rescue=True, **flags):
+    idx, res, n_in = oracle.query(oq, orefs, cutoff, rescue, oracle.default_params(**flags))
+    got = {h[1]: h for h in hits}
+    assert sorted(got) == sorted(int(i) for i in idx)
+    for i, r in zip(idx, res):
+        h = got[int(i)]
+        assert abs(h[2] - r.ani) <= ANI_TOL, (i, h[2], r.ani)
+        assert abs(h[3] - r.af_query) <= AF_TOL and abs(h[4] - r.af_ref) <= AF_TOL, (i, h, r.af_query, r.af_ref)
+        assert h[7] == r.n_anchors and h[6] == r.n_chains and h[5] == r.n_windows, (i, h, r.n_anchors, r.n_chains, r.n_windows)
+    return n_in
+
+
+def test_ecoli_goldens_through_gpu(ctx, ecoli):
+    """reference tests/test_ani.py:28-61 — the same assertions, through the CUDA path."""
+    from pyskani_b200 import capi
+    ec, k12, gold = ecoli
+    ref, qry = ctx.sketch_batch([[ec], [k12]])
+    db = capi.Database(ctx)
+    db.add(ref)
+    for flags, key in (({}, "ani_no_learned"), ({"robust": True}, "ani_robust"), ({"median": True}, "ani_median")):
+        hits, n_in = db.query([qry], **flags)
+        assert len(hits) == 1 and n_in == 1
+        h = hits[0]
+        assert round(abs(h[4] - gold["af_ref"]), 4) == 0
+        assert round(abs(h[3] - gold["af_query"]), 4) == 0
+        assert round(abs(h[2] - gold[key]), 4) == 0, (key, h[2])
+    oq, orf = oracle.Sketch([k12]), oracle.Sketch([ec])
+    check_hits(db.query([qry])[0], oq, [orf])
+    check_hits(db.query([qry], robust=True)[0], oq, [orf], robust=1)
+    check_hits(db.query([qry], median=True)[0], oq, [orf], median=1)
+
+
+def test_learned_ani_true_is_refused(ctx):
+    from pyskani_b200 import capi
+    s = rand(50_000, 3)
+    (g,) = ctx.sketch_batch([[s]])
+    db = capi.Database(ctx)
+    db.add(g)
+    with pytest.raises(capi.SkbError) as e:
+        db.query([g], learned_ani=1)
+    assert e.value.code == capi.SKB_ERR_UNSUPPORTED
+
+
+def test_mutant_series_vs_oracle(ctx):
+    """BASELINE.json config 2 at reduced size: one genome vs mutated copies, 1-15 % divergence + indels."""
+    from pyskani_b200 import capi
+    base = synth.random_genome(1_000_000, 7)
+    divs = np.linspace(0.01, 0.15, 12)
+    refs = [synth.mutate(base, d, 700 + i) for i, d in enumerate(divs)]
+    gs = ctx.sketch_batch([[r.tobytes()] for r in refs] + [[base.tobytes()]])
+    db = capi.Database(ctx)
+    for g in gs[:-1]:
+        db.add(g)
+    oq = oracle.Sketch([base.tobytes()])
+    orefs = [oracle.Sketch([r.tobytes()]) for r in refs]
+    for flags in ({}, {"robust": 1}, {"median": 1}):
+        hits, n_in = db.query([gs[-1]], robust=bool(flags.get("robust")), median=bool(flags.get("median")))
+        n_in_o = check_hits(hits, oq, orefs, **flags)
+        assert n_in == n_in_o
+    # sanity of the estimate itself: ANI tracks 1 - d for the close mutants
+    hits, _ = db.query([gs[-1]])
+    for h in hits:
+        if divs[h[1]] <= 0.08:
+            assert abs(h[2] - (1 - divs[h[1]])) < 0.01
+
+
+def test_fragmented_query_vs_oracle(ctx):
+    """BASELINE.json config 4 at reduced size: contigs of 1-50 kbp, shuffled, half reverse-complemented."""
+    from pyskani_b200 import capi
+    base = synth.random_genome(800_000, 11)
+    refs = [synth.mutate(base, d, 1100 + i) for i, d in enumerate((0.02, 0.06, 0.1))] + [synth.random_genome(500_000, 12)]
+    qcontigs = [c.tobytes() for c in synth.fragment(synth.mutate(base, 0.03, 1199), 5, lo=400, hi=50_000)]
+    rcontigs = [[c.tobytes() for c in synth.fragment(r, 50 + i, lo=2000, hi=200_000)] for i, r in enumerate(refs)]
+    gs = ctx.sketch_batch(rcontigs + [qcontigs])
+    db = capi.Database(ctx)
+    for g in gs[:-1]:
+        db.add(g)
+    oq = oracle.Sketch(qcontigs)
+    orefs = [oracle.Sketch(c) for c in rcontigs]
+    for g, o in zip(gs, orefs + [oq]):
+        assert_sketch_equal(g, o)
+    hits, n_in = db.query([gs[-1]])
+    assert check_hits(hits, oq, orefs) == n_in
+    assert len(hits) == 3
+
+
+def test_all_vs_all_small(ctx):
+    """BASELINE.json config 3 at reduced size: families of related genomes, every ordered pair."""
+    from pyskani_b200 import capi
+    genomes = []
+    for f in range(4):
+        genomes += make_family(3, 300_000, 60 + f, [0.02, 0.07, 0.13])
+    contigs = [[g.tobytes()] for g in genomes]
+    gs = ctx.sketch_batch(contigs)
+    db = capi.Database(ctx)
+    for g in gs:
+        db.add(g)
+    os_ = [oracle.Sketch(c) for c in contigs]
+    hits, n_in = db.query(gs)
+    total_in = 0
+    for qi, oq in enumerate(os_):
+        total_in += check_hits([h for h in hits if h[0] == qi], oq, os_)
+    assert total_in == n_in
+    # only intra-family pairs can pass the screen
+    assert all(h[0] // 4 == h[1] // 4 for h in hits)
+
+
+def test_empty_and_degenerate_queries(ctx):
+    from pyskani_b200 import capi
+    s = rand(100_000, 77)
+    full, empty, unrelated = ctx.sketch_batch([[s], [b"ATGC" * 100], [rand(100_000, 78)]])
+    db = capi.Database(ctx)
+    assert db.query([full])[0] == []          # empty database
+    db.add(full)
+    hits, n_in = db.query([empty])             # reference tests/test_database.py input: below the contig gate
+    assert hits == [] and n_in == 1            # rescue_small lets it through the screen, chaining finds nothing
+    hits, n_in = db.query([empty], faster_small=True)
+    assert hits == [] and n_in == 0
+    hits, n_in = db.query([unrelated])
+    assert hits == [] and n_in == 0
+    hits, n_in = db.query([full])
+    assert len(hits) == 1 and abs(hits[0][2] - 1.0) < 1e-6 and hits[0][3] > 0.99
