@@ -52,6 +52,7 @@ def lib():
         L.orc_sketch_new.restype = vp
         L.orc_sketch_new.argtypes = [C.POINTER(C.c_char_p), C.POINTER(u64), u32, i32, i32, i32, i32]
         L.orc_sketch_free.argtypes = [vp]
+        L.orc_sketch_batch.argtypes = [vp, vp, vp, u32, i32, i32, i32, i32, i32, vp]
         for name, rt in (("orc_sketch_n_seeds", u64), ("orc_sketch_n_markers", u64),
                          ("orc_sketch_n_contigs", u32), ("orc_sketch_total_len", u64)):
             getattr(L, name).restype = rt
@@ -126,6 +127,27 @@ class Sketch:
         out = np.empty(lib().orc_sketch_n_contigs(self._h), np.uint32)
         lib().orc_sketch_contig_lengths(self._h, out.ctypes.data)
         return out
+
+
+def sketch_batch(genomes, k=15, c=125, marker_c=1000, seed=True, threads=0):
+    """genomes: list of lists of contiguous uint8 numpy arrays / bytes. OpenMP over genomes."""
+    flat, starts = [], [0]
+    for g in genomes:
+        flat.extend(g)
+        starts.append(len(flat))
+    keep = [np.frombuffer(x, dtype=np.uint8) for x in flat]
+    n = len(keep)
+    ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in keep])
+    lens = (C.c_uint64 * max(n, 1))(*[a.size for a in keep])
+    gs = (C.c_uint32 * len(starts))(*starts)
+    out = (C.c_void_p * max(len(genomes), 1))()
+    lib().orc_sketch_batch(ptrs, lens, gs, len(genomes), k, c, marker_c, int(seed), threads, out)
+    res = []
+    for i in range(len(genomes)):
+        s = Sketch.__new__(Sketch)
+        s._h, s.k, s.c, s.marker_c = out[i], k, c, marker_c
+        res.append(s)
+    return res
 
 
 def screen(query, ref, screen_val=0.8, rescue_small=True):

@@ -476,6 +476,20 @@ orc_sketch_t* orc_sketch_new(const uint8_t* const* contigs, const uint64_t* lens
     return s;
 }
 
+// CPU-baseline helper: sketch many genomes, one OpenMP task per genome (the axis skani's own rayon driver uses)
+void orc_sketch_batch(const uint8_t* const* contigs, const uint64_t* lens, const uint32_t* genome_contig_start,
+                      uint32_t n_genomes, int32_t k, int32_t c, int32_t marker_c, int32_t seed, int32_t threads,
+                      orc_sketch_t** out) {
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t g = 0; g < (int64_t)n_genomes; g++) {
+        const uint32_t a = genome_contig_start[g], b = genome_contig_start[g + 1];
+        out[g] = orc_sketch_new(contigs + a, lens + a, b - a, k, c, marker_c, seed);
+    }
+}
+
 void orc_sketch_free(orc_sketch_t* s) { delete s; }
 uint64_t orc_sketch_n_seeds(const orc_sketch_t* s) { return s->seeds.size(); }
 uint64_t orc_sketch_n_markers(const orc_sketch_t* s) { return s->markers.size(); }

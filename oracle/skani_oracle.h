@@ -83,6 +83,9 @@ void orc_chain_params_default(orc_chain_params_t* p);
  * are skipped; contig_index counts kept contigs only. */
 orc_sketch_t* orc_sketch_new(const uint8_t* const* contigs, const uint64_t* lens, uint32_t n,
                              int32_t k, int32_t c, int32_t marker_c, int32_t seed);
+void     orc_sketch_batch(const uint8_t* const* contigs, const uint64_t* lens, const uint32_t* genome_contig_start,
+                          uint32_t n_genomes, int32_t k, int32_t c, int32_t marker_c, int32_t seed, int32_t threads,
+                          orc_sketch_t** out);
 void     orc_sketch_free(orc_sketch_t*);
 uint64_t orc_sketch_n_seeds(const orc_sketch_t*);
 uint64_t orc_sketch_n_markers(const orc_sketch_t*);

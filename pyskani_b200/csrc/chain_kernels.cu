@@ -37,7 +37,7 @@ __device__ __forceinline__ uint32_t warp_lower_bound(uint32_t lo, uint32_t hi, u
             const uint32_t idx = lo + lane;
             const bool ge = idx >= hi || key(idx) >= target;
             const uint32_t b = __ballot_sync(FULL, ge);
-            return lo + (uint32_t)(__ffs(b) - 1);   // lanes >= n always vote true, so b != 0
+            return b ? lo + (uint32_t)(__ffs(b) - 1) : hi;   // n == 32 with no hit leaves b == 0
         }
         const uint32_t stride = (n + 31) / 32;
         const uint32_t idx = lo + lane * stride;
