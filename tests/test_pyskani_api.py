@@ -1,0 +1,195 @@
+"""The reference's own test-suite (src/pyskani/tests/test_ani.py, test_database.py) against pyskani_b200,
+plus the storage round trips the reference never tests.  Runs on the GPU box."""
+import os
+import pathlib
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pyskani():
+    import pyskani_b200
+    return pyskani_b200
+
+
+@pytest.fixture(scope="module")
+def ec590_db(pyskani, ecoli):
+    db = pyskani.Database()
+    db.sketch("EC590", ecoli[0])
+    return db
+
+
+class TestAniEC590:
+    """reference tests/test_ani.py:14-61 (assertAlmostEqual(places=4) == abs diff rounds to 0 at 4 decimals)."""
+
+    @staticmethod
+    def close(a, b):
+        return round(abs(a - b), 4) == 0
+
+    def test_no_learned_ani(self, ec590_db, ecoli):
+        hits = ec590_db.query("K12", ecoli[1], learned_ani=False)
+        assert len(hits) == 1
+        assert self.close(hits[0].reference_fraction, 0.9246)
+        assert self.close(hits[0].query_fraction, 0.9189)
+        assert self.close(hits[0].identity, 0.9946)
+        assert hits[0].query_name == "K12" and hits[0].reference_name == "EC590"
+
+    def test_robust(self, ec590_db, ecoli):
+        hits = ec590_db.query("K12", ecoli[1], robust=True)
+        assert len(hits) == 1
+        assert self.close(hits[0].reference_fraction, 0.9246)
+        assert self.close(hits[0].query_fraction, 0.9189)
+        assert self.close(hits[0].identity, 0.9977)
+
+    def test_median(self, ec590_db, ecoli):
+        hits = ec590_db.query("K12", ecoli[1], median=True)
+        assert len(hits) == 1
+        assert self.close(hits[0].reference_fraction, 0.9246)
+        assert self.close(hits[0].query_fraction, 0.9189)
+        assert self.close(hits[0].identity, 0.9995)
+
+    def test_basic_returns_uncorrected_estimate(self, ec590_db, ecoli):
+        # The reference's default applies skani's learned regression (0.9939, test_ani.py:28-33).  Its weights are
+        # embedded in the skani crate and unavailable here: the default returns the uncorrected estimate.
+        hits = ec590_db.query("K12", ecoli[1])
+        assert len(hits) == 1
+        assert self.close(hits[0].reference_fraction, 0.9246)
+        assert self.close(hits[0].query_fraction, 0.9189)
+        assert self.close(hits[0].identity, 0.9946)
+
+    def test_learned_ani_true_is_refused(self, ec590_db, ecoli):
+        with pytest.raises(RuntimeError):
+            ec590_db.query("K12", ecoli[1], learned_ani=True)
+
+    def test_input_types(self, ec590_db, ecoli):
+        k12 = ecoli[1]
+        want = ec590_db.query("K12", k12, learned_ani=False)[0].identity
+        for seq in (k12.decode("ascii"), bytearray(k12), memoryview(k12)):
+            assert ec590_db.query("K12", seq, learned_ani=False)[0].identity == want
+
+    def test_cutoff_and_seed_flag(self, ec590_db, ecoli):
+        assert ec590_db.query("K12", ecoli[1], cutoff=0.9999999) == []      # screen rejects at an absurd cutoff
+        assert ec590_db.query("K12", ecoli[1], seed=False) == []             # markers only: passes the screen, no anchors
+
+
+class TestDatabase:
+    """reference tests/test_database.py:9-42"""
+
+    def test_memory(self, pyskani):
+        database = pyskani.Database()
+        database.sketch("test genome", b"ATGC" * 100)
+        assert database.path is None
+
+    def test_folder_separated(self, pyskani, tmp_path):
+        tmpdir = str(tmp_path)
+        database = pyskani.Database(tmpdir, format="separated")
+        database.sketch("test1", b"ATGC" * 100)
+        database.sketch("test2", b"TTGC" * 100)
+        assert os.path.exists(os.path.join(tmpdir, "test1.sketch"))
+        assert os.path.exists(os.path.join(tmpdir, "test2.sketch"))
+        assert not os.path.exists(os.path.join(tmpdir, "markers.bin"))
+        database.flush()
+        assert os.path.exists(os.path.join(tmpdir, "test1.sketch"))
+        assert os.path.exists(os.path.join(tmpdir, "test2.sketch"))
+        assert os.path.exists(os.path.join(tmpdir, "markers.bin"))
+        assert database.path == pathlib.Path(tmpdir)
+
+    def test_folder_consolidated(self, pyskani, tmp_path):
+        tmpdir = str(tmp_path)
+        database = pyskani.Database(tmpdir, format="consolidated")
+        database.sketch("test1", b"ATGC" * 100)
+        database.sketch("test2", b"TTGC" * 100)
+        assert os.path.exists(os.path.join(tmpdir, "sketches.db"))
+        assert not os.path.exists(os.path.join(tmpdir, "index.db"))
+        assert not os.path.exists(os.path.join(tmpdir, "markers.bin"))
+        database.flush()
+        assert os.path.exists(os.path.join(tmpdir, "sketches.db"))
+        assert os.path.exists(os.path.join(tmpdir, "index.db"))
+        assert os.path.exists(os.path.join(tmpdir, "markers.bin"))
+        assert database.path == pathlib.Path(tmpdir)
+
+    def test_constructor_errors(self, pyskani, tmp_path):
+        with pytest.raises(ValueError):
+            pyskani.Database(str(tmp_path / "a"), format="bogus")
+        with pyskani.Database(str(tmp_path / "b")) as db:
+            db.sketch("x", b"ATGC" * 100)
+        with pytest.raises(FileExistsError):
+            pyskani.Database(str(tmp_path / "b"))
+        with pytest.raises(ValueError):
+            pyskani.Database(k=17)
+        db = pyskani.Database(compression=30, marker_compression=200)
+        assert (db.compression, db.marker_compression) == (30, 200)
+
+    def test_duplicate_name_in_consolidated(self, pyskani, tmp_path):
+        db = pyskani.Database(str(tmp_path), format="consolidated")
+        db.sketch("dup", b"ATGC" * 100)
+        with pytest.raises(ValueError):
+            db.sketch("dup", b"ATGC" * 100)
+
+
+class TestStorageRoundTrip:
+    """Not covered by the reference: what is written can be read back and gives the same answers."""
+
+    @pytest.fixture(scope="class")
+    def genomes(self):
+        from pyskani_b200 import synth
+        base = synth.random_genome(400_000, 5)
+        return {"base": base.tobytes(), "m3": synth.mutate(base, 0.03, 6).tobytes(), "m9": synth.mutate(base, 0.09, 7).tobytes(),
+                "frag": [c.tobytes() for c in synth.fragment(synth.mutate(base, 0.05, 8), 9, lo=300, hi=60_000)]}
+
+    def expected(self, pyskani, genomes):
+        db = pyskani.Database()
+        db.sketch("m3", genomes["m3"]); db.sketch("m9", genomes["m9"]); db.sketch("frag", *genomes["frag"])
+        return db, {h.reference_name: (h.identity, h.query_fraction, h.reference_fraction) for h in db.query("base", genomes["base"])}
+
+    @pytest.mark.parametrize("fmt", ["consolidated", "separated"])
+    def test_context_manager_then_open_and_load(self, pyskani, genomes, tmp_path, fmt):
+        _, want = self.expected(pyskani, genomes)
+        assert set(want) == {"m3", "m9", "frag"}
+        folder = str(tmp_path / fmt)
+        with pyskani.Database(folder, format=fmt) as db:
+            db.sketch("m3", genomes["m3"]); db.sketch("m9", genomes["m9"]); db.sketch("frag", *genomes["frag"])
+        for opener in (pyskani.Database.open, pyskani.Database.load):
+            db2 = opener(folder)
+            got = {h.reference_name: (h.identity, h.query_fraction, h.reference_fraction) for h in db2.query("base", genomes["base"])}
+            assert got == want
+            assert (db2.compression, db2.marker_compression) == (125, 1000)
+        assert pyskani.Database.load(folder).path is None
+        assert pyskani.Database.open(folder).path == pathlib.Path(folder)
+
+    @pytest.mark.parametrize("fmt", [None, "consolidated", "separated"])
+    def test_save(self, pyskani, genomes, tmp_path, fmt):
+        db, want = self.expected(pyskani, genomes)
+        folder = str(tmp_path / "saved")
+        db.save(folder, format=fmt)
+        with pytest.raises(FileExistsError):
+            db.save(folder, format=fmt)
+        db.save(folder, overwrite=True, format=fmt)
+        files = set(os.listdir(folder))
+        if fmt == "separated":
+            assert {"markers.bin", "m3.sketch", "m9.sketch", "frag.sketch"} <= files
+        else:
+            assert {"markers.bin", "sketches.db", "index.db"} <= files
+        got = {h.reference_name: (h.identity, h.query_fraction, h.reference_fraction)
+               for h in pyskani.Database.load(folder).query("base", genomes["base"])}
+        assert got == want
+
+    def test_open_appends(self, pyskani, genomes, tmp_path):
+        folder = str(tmp_path / "grow")
+        with pyskani.Database(folder) as db:
+            db.sketch("m3", genomes["m3"])
+        with pyskani.Database.open(folder) as db:
+            db.sketch("m9", genomes["m9"])
+        names = {h.reference_name for h in pyskani.Database.load(folder).query("base", genomes["base"])}
+        assert names == {"m3", "m9"}
+
+    def test_missing_and_corrupt_files(self, pyskani, tmp_path):
+        with pytest.raises(OSError):
+            pyskani.Database.open(str(tmp_path / "nowhere"))
+        folder = tmp_path / "bad"
+        folder.mkdir()
+        (folder / "markers.bin").write_bytes(b"\x01\x02\x03")
+        with pytest.raises(ValueError):
+            pyskani.Database.load(str(folder))
