@@ -141,8 +141,8 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
 
     // ---- contig gate + tile table (reference lib.rs:155-174)
     std::vector<std::vector<uint32_t>> contig_lens(n_genomes);
-    std::vector<Tile> tiles;
-    uint64_t total_bases = 0;
+    std::vector<ContigDesc> descs;
+    uint64_t total_bases = 0, tile_count = 0;
     for (uint32_t g = 0; g < n_genomes; g++) {
         bool first = true;
         uint32_t kept = 0;
@@ -152,32 +152,31 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             if (offs[ci] & 15) throw Fail{SKB_ERR_ARG, "device contig offsets must be multiples of 16"};
             contig_lens[g].push_back((uint32_t)lens[ci]);
             total_bases += lens[ci];
-            for (uint64_t t0 = 0; t0 < lens[ci]; t0 += TILE_BASES) {
-                Tile t;
-                t.seq_off = offs[ci] + t0;
-                t.pos0 = (uint32_t)t0;
-                t.n = (uint32_t)std::min<uint64_t>(TILE_BASES, lens[ci] - t0);
-                t.contig = kept;
-                t.genome = g | (first ? 0x80000000u : 0u);
-                first = false;
-                tiles.push_back(t);
-            }
+            ContigDesc d;
+            d.seq_off = offs[ci];
+            d.len = (uint32_t)lens[ci];
+            d.contig = kept;
+            d.genome = g | (first ? 0x80000000u : 0u);
+            d.tile_start = (uint32_t)tile_count;
+            tile_count += (lens[ci] + TILE_BASES - 1) / TILE_BASES;
+            first = false;
+            descs.push_back(d);
             kept++;
         }
     }
     if (total_bases >= 0x7FFFFFFFull) throw Fail{SKB_ERR_ARG, "a sketch batch is limited to 2^31 bases; split the call"};
     if (n_genomes >= (1u << 22)) throw Fail{SKB_ERR_ARG, "a sketch batch is limited to 2^22 genomes"};
-    const uint32_t n_tiles = (uint32_t)tiles.size();
+    const uint32_t n_tiles = (uint32_t)tile_count;
 
     std::vector<uint32_t> seed_start(n_genomes + 1, 0), marker_start(n_genomes + 1, 0);
     auto store = std::make_shared<BatchStore>();
 
     if (n_tiles) {
-        DevMem d_tiles(core, sizeof(Tile) * n_tiles);
+        DevMem d_descs(core, sizeof(ContigDesc) * descs.size());
         {
-            Tile* h = (Tile*)ensure_pinned(c, sizeof(Tile) * n_tiles);
-            std::memcpy(h, tiles.data(), sizeof(Tile) * n_tiles);
-            upload(c, d_tiles.as<Tile>(), h, n_tiles);
+            ContigDesc* h = (ContigDesc*)ensure_pinned(c, sizeof(ContigDesc) * descs.size());
+            std::memcpy(h, descs.data(), sizeof(ContigDesc) * descs.size());
+            upload(c, d_descs.as<ContigDesc>(), h, descs.size());
         }
         DevMem d_status(core, sizeof(uint64_t) * n_tiles + 64);
         DevMem d_gs(core, sizeof(uint32_t) * (n_genomes + 1)), d_gm(core, sizeof(uint32_t) * (n_genomes + 1));
@@ -198,7 +197,7 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             CU(cudaMemsetAsync(d_gs.p, 0xFF, d_gs.bytes, st));
             CU(cudaMemsetAsync(d_gm.p, 0xFF, d_gm.bytes, st));
             SeedScanArgs a{};
-            a.seq = seq_dev; a.tiles = d_tiles.as<Tile>(); a.n_tiles = n_tiles;
+            a.seq = seq_dev; a.contigs = d_descs.as<ContigDesc>(); a.n_contigs = (uint32_t)descs.size(); a.n_tiles = n_tiles;
             a.kmask = P.k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * P.k)) - 1u);
             a.kshift = 42 - 2 * P.k;
             a.thr_seed = seed ? UINT64_MAX / (uint64_t)P.c : 0;     // seed=False keeps markers only (A.4)

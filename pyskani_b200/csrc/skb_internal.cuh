@@ -40,20 +40,25 @@ struct GenomeView {
 };
 
 // ---------------------------------------------------------------- seeding
-constexpr int TILE_BASES = 4096;          // bases per tile = 256 threads x 16
 constexpr int SEED_THREADS = 256;
+constexpr int WORDS_PER_THREAD = 4;                                   // 16-base words each thread evaluates per tile
+constexpr int TILE_WORDS = SEED_THREADS * WORDS_PER_THREAD;          // 1024
+constexpr int TILE_BASES = TILE_WORDS * 16;                          // 16384 bases per tile
 
-struct Tile {
-    uint64_t seq_off;   // byte offset of the tile's first base in the device sequence buffer (16-aligned)
-    uint32_t pos0;      // position of that base inside its contig (multiple of 16)
-    uint32_t n;         // bases in the tile, 1..TILE_BASES
-    uint32_t contig;    // index among the genome's kept contigs
-    uint32_t genome;    // genome index inside the batch; bit 31 set on the first tile of a genome
+// One kept contig of the batch.  Tiles are numbered contig after contig; tile t of a contig covers its bases
+// [t * TILE_BASES, min(len, (t + 1) * TILE_BASES)).
+struct ContigDesc {
+    uint64_t seq_off;    // byte offset of the contig's first base in the device sequence buffer (16-aligned)
+    uint32_t len;
+    uint32_t contig;     // index among the genome's kept contigs
+    uint32_t genome;     // genome index inside the batch; bit 31 set on the genome's first kept contig
+    uint32_t tile_start; // id of the contig's first tile
 };
 
 struct SeedScanArgs {
     const uint8_t* seq;
-    const Tile* tiles;
+    const ContigDesc* contigs;
+    uint32_t n_contigs;
     uint32_t n_tiles;
     uint32_t kmask, kshift;
     uint64_t thr_seed, thr_marker;
