@@ -59,38 +59,78 @@ def make_family(genome_len, n_refs, rank):
 
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons during the timed regions.  NVML is polled from a thread (two cheap queries per
+    sample); `nvidia-smi -lms` is only the fallback because each of its polls stalls PCIe traffic for milliseconds,
+    which distorts the host->device leg of the e2e measurement."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, uuid=None, period_s=0.01):
+        self.index, self.uuid, self.period = index, uuid, period_s
+        self.sm, self.mask, self.max_mhz, self.mode = [], 0, None, None
+        self._stop = threading.Event()
+        self.proc = None
 
     def start(self):
+        if os.environ.get("BENCH_NO_SAMPLER"):
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thr = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(self.uuid)).encode() if not str(self.uuid).startswith("GPU-") else str(self.uuid).encode())
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        self.mask |= int(reasons(h))
+                    except Exception:
+                        pass
+                    self._stop.wait(self.period)
+            self.thr = threading.Thread(target=loop, daemon=True)
             self.thr.start()
+            self.mode = "nvml"
+            return
+        except Exception:
+            pass
+        try:
+            fields = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                      "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.rows = []
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={fields}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=lambda: [self.rows.append([x.strip() for x in l.split(",")]) for l in self.proc.stdout], daemon=True)
+            self.thr.start()
+            self.mode = "nvidia-smi"
         except OSError:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        self.thr.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        if self.mode == "nvml":
+            self._stop.set()
+            self.thr.join(timeout=2)
+            reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": reasons, "samples": len(self.sm), "source": "nvml, %.0f ms period" % (1e3 * self.period)}
+        if self.mode == "nvidia-smi" and self.proc:
+            self.proc.terminate()
+            self.thr.join(timeout=2)
+            sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+            mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                    "reasons": reasons, "samples": len(sm), "source": "nvidia-smi -lms 200"}
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
 
 
 def cpu_step(base, refs, threads):
@@ -218,7 +258,12 @@ def main():
         barrier()
         t0 = time.perf_counter()
         e0.record(stream)
-        outs = [fn() for _ in range(steps)]
+        outs, per_step = [], []
+        for _ in range(steps):
+            ts = time.perf_counter()
+            outs.append(fn())
+            per_step.append(1e3 * (time.perf_counter() - ts))
+        timed.last_per_step = per_step
         e1.record(stream)
         barrier()
         wall_ms = 1e3 * (time.perf_counter() - t0)
@@ -228,14 +273,13 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms[0]), float(ms[1]), outs
 
+    sampler = ClockSampler(local_rank, uuid=getattr(torch.cuda.get_device_properties(local_rank), 'uuid', None))
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     k0 = ctx.stats().kernels_launched
     dev_ms, wall_ms, outs = timed(step_device, args.steps)
     k1 = ctx.stats().kernels_launched
-    clocks = sampler.stop()
     n_hits = outs[-1][0]
     seed_ms = float(np.mean([o[1] for o in outs]))
     sketch_ms = float(np.mean([o[2] for o in outs]))
@@ -244,6 +288,12 @@ def main():
     for _ in range(max(1, args.warmup // 2)):
         step_host()
     e2e_dev_ms, e2e_wall_ms, outs_h = timed(step_host, args.steps)
+    e2e_per_step = list(timed.last_per_step)
+    clocks = sampler.stop()      # sampled from the first warm-up step to the end of the e2e region
+    # plain pinned-host -> device copy of the same bytes, for context (the e2e floor on this box)
+    t0 = time.perf_counter()
+    ctx.memcpy_h2d(d_ptr, h_ptr, buf_bytes)
+    h2d_gbs = buf_bytes / (time.perf_counter() - t0) / 1e9
 
     pairs_total = args.n_refs * world
     ms_per_step = dev_ms / args.steps
@@ -273,7 +323,8 @@ def main():
             "query_pairs_per_s": pairs_total / (query_ms / 1e3),
             "phase_ms": {"seed_kernel": seed_ms, "sketch_total": sketch_ms, "query_total": query_ms, "wall_per_step": wall_ms / args.steps},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": total_bases,
-                    "d2h_bytes_per_step": int(n_hits) * C.sizeof(capi.Hit), "ms_per_step": e2e_ms},
+                    "d2h_bytes_per_step": int(n_hits) * C.sizeof(capi.Hit), "ms_per_step": e2e_ms,
+                    "pinned_h2d_copy_gbs": h2d_gbs, "per_step_wall_ms": [round(x, 3) for x in e2e_per_step]},
             "gpu_launches": int(k1 - k0),
             "roofline": {"bound": "hbm", "kernel": "seed_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

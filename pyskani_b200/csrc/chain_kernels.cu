@@ -107,15 +107,23 @@ __global__ void anchor_fill_kernel(const ChainBatch b) {
 }
 
 // ------------------------------------------------------------------ 2. windows
-// One warp per (pair, query contig).  Window j of contig c lands in slot win_off + contig_win_start[c] + j.
-__global__ void window_walk_kernel(const ChainBatch b, const uint32_t F) {
+// A window opens at the first matched query seed of a contig and then at the first matched seed whose position is
+// >= the previous opening position + F.  That is a serial chain per contig (~230 links for a 5 Mbp contig), so the
+// cost is the latency of one link.  Window j of contig c lands in slot win_off + contig_win_start[c] + j.
+//
+// Fast path (window_walk_smem_kernel): one CTA per pair stages the query's seed positions and a "has a match" bitmask
+// in shared memory (4 B + 1 bit per seed; <= WALK_SMEM_SEEDS seeds), then one warp per contig follows the chain with
+// every link resolved on chip.  Fallback (window_walk_kernel): same walk with 32-ary searches in global memory.
+constexpr uint32_t WALK_SMEM_SEEDS = 49152;     // 192 KB of positions + 6 KB of bits
+
+__global__ void window_walk_kernel(const ChainBatch b, const uint32_t F, const int only_large) {
     const PairDesc pd = b.pairs[blockIdx.x];
     const GenomeView& Q = b.qviews[pd.q];
+    if (only_large && Q.n_seeds <= WALK_SMEM_SEEDS) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const uint32_t* aoff = b.a_off + pd.seed_off;
     for (uint32_t c = warp; c < Q.n_contigs; c += nwarps) {
         const uint32_t cs = Q.contig_seed_start[c], ce = Q.contig_seed_start[c + 1];
-        // capacity of contig c: len / F + 1 windows, laid out contiguously in contig order
         uint32_t slot = pd.win_off + Q.contig_win_start[c];
         uint32_t s = cs;
         while (s < ce) {
@@ -130,6 +138,73 @@ __global__ void window_walk_kernel(const ChainBatch b, const uint32_t F) {
                 b.win_start[slot] = i;
                 b.win_end[slot] = e;
                 b.win_contig[slot] = blockIdx.x;   // pair index, read back by the DP kernel
+            }
+            slot++;
+            s = e;
+        }
+    }
+}
+
+// first set bit at index >= from in bits[0..n), or n
+__device__ __forceinline__ uint32_t next_set_bit(const uint32_t* bits, uint32_t from, uint32_t n) {
+    uint32_t w = from >> 5;
+    const uint32_t nw = (n + 31) >> 5;
+    if (w >= nw) return n;
+    uint32_t cur = bits[w] & (0xFFFFFFFFu << (from & 31));
+    while (cur == 0) {
+        if (++w >= nw) return n;
+        cur = bits[w];
+    }
+    const uint32_t r = (w << 5) + (uint32_t)__ffs(cur) - 1u;
+    return r < n ? r : n;
+}
+
+__global__ void __launch_bounds__(256) window_walk_smem_kernel(const ChainBatch b, const uint32_t F) {
+    extern __shared__ uint32_t sm[];
+    const PairDesc pd = b.pairs[blockIdx.x];
+    const GenomeView& Q = b.qviews[pd.q];
+    const uint32_t n = Q.n_seeds;
+    if (n > WALK_SMEM_SEEDS) return;                  // handled by the global-memory kernel
+    uint32_t* s_pos = sm;                             // [n]
+    uint32_t* s_bits = sm + n;                        // [(n + 31) / 32]
+    const uint32_t* cnt = b.m_cnt + pd.seed_off;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (uint32_t i0 = warp * 32; i0 < n; i0 += nwarps * 32) {
+        const uint32_t i = i0 + lane;
+        const bool m = i < n && cnt[i] != 0;
+        if (i < n) s_pos[i] = __ldg(Q.pos_p + i);
+        const uint32_t bal = __ballot_sync(FULL, m);
+        if (lane == 0) s_bits[i0 >> 5] = bal;
+    }
+    __syncthreads();
+    for (uint32_t c = warp; c < Q.n_contigs; c += nwarps) {
+        const uint32_t cs = Q.contig_seed_start[c], ce = Q.contig_seed_start[c + 1];
+        uint32_t slot = pd.win_off + Q.contig_win_start[c];
+        uint32_t s = cs;
+        while (s < ce) {
+            // first matched seed at or after s (uniform across the warp: every lane runs the same scan)
+            const uint32_t i = next_set_bit(s_bits, s, ce);
+            if (i >= ce) break;
+            const uint32_t target = s_pos[i] + F;
+            // gallop: 32 probes, 8 seeds apart, then resolve inside the 8-seed bracket
+            uint32_t lo = i + 1, e;
+            while (true) {
+                const uint32_t idx = lo + (uint32_t)lane * 8u;
+                const bool ge = idx >= ce || s_pos[idx] >= target;
+                const uint32_t bal = __ballot_sync(FULL, ge);
+                if (bal == 0) { lo += 32u * 8u - 7u; continue; }      // all 32 probes below target: restart after the last one
+                const int f = __ffs(bal) - 1;
+                const uint32_t blo = f == 0 ? lo : lo + (uint32_t)(f - 1) * 8u + 1u;
+                const uint32_t bhi = min(lo + (uint32_t)f * 8u, ce);  // answer in [blo, bhi]
+                const uint32_t j = blo + (uint32_t)lane;
+                const bool ge2 = j >= bhi || s_pos[j] >= target;       // lanes >= 8 are past bhi: vote true
+                e = blo + (uint32_t)(__ffs(__ballot_sync(FULL, ge2)) - 1);
+                break;
+            }
+            if (lane == 0) {
+                b.win_start[slot] = i;
+                b.win_end[slot] = e;
+                b.win_contig[slot] = blockIdx.x;
             }
             slot++;
             s = e;
@@ -391,10 +466,19 @@ void launch_anchor_fill(const ChainBatch& b, cudaStream_t st) {
     anchor_fill_kernel<<<grid, 256, 0, st>>>(b);
     g_kernel_launches++;
 }
-void launch_window_walk(const ChainBatch& b, const ChainConsts& c, cudaStream_t st) {
+void launch_window_walk(const ChainBatch& b, const ChainConsts& c, uint32_t max_query_seeds, cudaStream_t st) {
     if (b.n_pairs == 0) return;
-    window_walk_kernel<<<b.n_pairs, 128, 0, st>>>(b, c.fragment_length);
+    // shared-memory walk for every pair whose query fits, global-memory walk for the rest
+    const size_t cap_bytes = (size_t)WALK_SMEM_SEEDS * 4 + ((WALK_SMEM_SEEDS + 31) / 32) * 4 + 16;
+    cudaFuncSetAttribute(window_walk_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap_bytes);
+    const uint32_t n = max_query_seeds < WALK_SMEM_SEEDS ? max_query_seeds : WALK_SMEM_SEEDS;
+    const size_t bytes = (size_t)n * 4 + ((n + 31) / 32) * 4 + 16;
+    window_walk_smem_kernel<<<b.n_pairs, 256, bytes, st>>>(b, c.fragment_length);
     g_kernel_launches++;
+    if (max_query_seeds > WALK_SMEM_SEEDS) {
+        window_walk_kernel<<<b.n_pairs, 128, 0, st>>>(b, c.fragment_length, 1);
+        g_kernel_launches++;
+    }
 }
 void launch_chain_dp(const ChainBatch& b, const ChainConsts& c, cudaStream_t st) {
     if (b.n_win_total == 0) return;

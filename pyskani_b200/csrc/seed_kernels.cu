@@ -141,16 +141,17 @@ __global__ void __launch_bounds__(SEED_THREADS, 3) seed_scan_kernel(const SeedSc
     while (true) {
         if (t == 0) s_tile = atomicAdd(a.tile_counter, 1u);
         __syncthreads();
-        const uint32_t tile_id = s_tile;
+        const uint32_t tile_id = s_tile;                 // local to this launch
         if (tile_id >= a.n_tiles) break;
-        // contig of this tile: last descriptor whose tile_start <= tile_id (uniform search, L1-resident table)
+        const uint32_t gtile = a.tile_base + tile_id;    // id within the batch (descriptors hold batch-wide tile ids)
+        // contig of this tile: last descriptor whose tile_start <= gtile (uniform search, L1-resident table)
         uint32_t lo = 0, hi = a.n_contigs;
         while (hi - lo > 1) {
             const uint32_t mid = (lo + hi) >> 1;
-            if (__ldg(&a.contigs[mid].tile_start) <= tile_id) lo = mid; else hi = mid;
+            if (__ldg(&a.contigs[mid].tile_start) <= gtile) lo = mid; else hi = mid;
         }
         const ContigDesc cd = a.contigs[lo];
-        const uint32_t pos0 = (tile_id - cd.tile_start) * (uint32_t)TILE_BASES;   // contig position of the tile's first base
+        const uint32_t pos0 = (gtile - cd.tile_start) * (uint32_t)TILE_BASES;   // contig position of the tile's first base
         const uint32_t n = min((uint32_t)TILE_BASES, cd.len - pos0);             // bases in the tile
         const uint8_t* base = a.seq + cd.seq_off + pos0;
         const bool first_of_genome = (cd.genome & 0x80000000u) && pos0 == 0;
@@ -237,7 +238,10 @@ __global__ void __launch_bounds__(SEED_THREADS, 3) seed_scan_kernel(const SeedSc
             const uint64_t agg = (uint64_t)acc_s | ((uint64_t)acc_m << 31);
             uint64_t excl = 0;
             if (tile_id == 0) {
-                if (lane == 0) st_relaxed(&a.tile_status[0], ST_INC | agg);
+                // the first tile of a launch continues from the running total of the previous launch of the batch
+                // (chunked host->device pipelining); it publishes an inclusive prefix directly, never an aggregate
+                excl = a.base_in ? ld_relaxed(a.base_in) : 0ull;
+                if (lane == 0) st_relaxed(&a.tile_status[0], ST_INC | (excl + agg));
             } else {
                 if (lane == 0) st_relaxed(&a.tile_status[tile_id], ST_AGG | agg);
                 int64_t j0 = (int64_t)tile_id - 1;
@@ -269,8 +273,11 @@ __global__ void __launch_bounds__(SEED_THREADS, 3) seed_scan_kernel(const SeedSc
                 }
                 if (tile_id == a.n_tiles - 1) {
                     const uint64_t inc = excl + agg;
-                    a.genome_seed_start[a.n_genomes] = (uint32_t)(inc & CNT_MASK);
-                    a.genome_marker_start[a.n_genomes] = (uint32_t)((inc >> 31) & CNT_MASK);
+                    if (a.base_out) st_relaxed(a.base_out, inc);
+                    if (a.is_last) {
+                        a.genome_seed_start[a.n_genomes] = (uint32_t)(inc & CNT_MASK);
+                        a.genome_marker_start[a.n_genomes] = (uint32_t)((inc >> 31) & CNT_MASK);
+                    }
                 }
             }
         }

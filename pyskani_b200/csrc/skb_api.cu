@@ -5,6 +5,8 @@
 // an unbounded release threshold, so scratch is recycled between calls instead of hitting cudaMalloc.
 // There is deliberately no CPU implementation of any step in this file.
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 
@@ -23,15 +25,45 @@ struct Core {
     std::mutex mu;
     std::string err;
     skb_stats_t stats{};
-    cudaEvent_t ev[6]{};
+    cudaEvent_t ev[8]{};
     void* pinned = nullptr;        // staging for small contigs / tables
     size_t pinned_bytes = 0;
+    // grow-only scratch blocks reused by every call on this context (calls are serialised by `mu`): keeps the big
+    // transient buffers out of the allocator so that repeated batches never re-map device memory
+    struct Block { void* p = nullptr; size_t bytes = 0; };
+    Block arena[12];
+    void* scratch(int slot, size_t bytes);
+    cudaStream_t copy_stream = nullptr;       // host->device copies of skb_sketch_batch run here, ahead of the kernels
+    std::vector<cudaEvent_t> ev_pool;         // "chunk is on the device" events (timing disabled)
+    cudaEvent_t pool_event(size_t i) {
+        while (ev_pool.size() <= i) {
+            cudaEvent_t e;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            ev_pool.push_back(e);
+        }
+        return ev_pool[i];
+    }
     ~Core() {
         cudaSetDevice(device);
+        if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+        if (stream) cudaStreamSynchronize(stream);
+        for (auto& b : arena) if (b.p) cudaFree(b.p);
+        for (auto& e : ev_pool) cudaEventDestroy(e);
         if (stream) cudaStreamSynchronize(stream);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (pinned) cudaFreeHost(pinned);
         if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+// SKB_TRACE=1 prints host-side wall-clock marks (debug aid, stderr)
+struct Trace {
+    bool on; std::chrono::steady_clock::time_point t0; const char* what;
+    explicit Trace(const char* w) : on(std::getenv("SKB_TRACE") != nullptr), t0(std::chrono::steady_clock::now()), what(w) {}
+    void mark(const char* label) {
+        if (!on) return;
+        auto t = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[skb] %s: %-28s %8.3f ms\n", what, label, std::chrono::duration<double, std::milli>(t - t0).count());
     }
 };
 
@@ -47,6 +79,18 @@ struct Fail {
             throw Fail{_e == cudaErrorMemoryAllocation ? SKB_ERR_NOMEM : SKB_ERR_CUDA,              \
                        std::string(#expr) + ": " + cudaGetErrorString(_e)};                        \
     } while (0)
+
+void* Core::scratch(int slot, size_t bytes) {
+    Block& b = arena[slot];
+    if (b.bytes < bytes) {
+        if (b.p) { CU(cudaStreamSynchronize(stream)); CU(cudaStreamSynchronize(copy_stream)); CU(cudaFree(b.p)); b.p = nullptr; b.bytes = 0; }
+        const size_t want = bytes + bytes / 8 + 4096;
+        CU(cudaMalloc(&b.p, want));
+        b.bytes = want;
+    }
+    return b.p;
+}
+enum { SLOT_SEQ = 0, SLOT_KMER, SLOT_POS, SLOT_META, SLOT_MKEYS, SLOT_STATUS, SLOT_SORT, SLOT_MARK, SLOT_GS, SLOT_GM, SLOT_DESC };
 
 // stream-ordered device buffer
 struct DevMem {
@@ -131,9 +175,13 @@ static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_par
                          std::shared_ptr<BatchStore> store, const std::vector<uint32_t>& seed_start,
                          const std::vector<uint32_t>& marker_start, skb_sketch_t** out);
 
+// A chunk of the batch whose bytes become available on the device when `ready` fires (host->device pipelining):
+// flat contigs [previous contig_end, contig_end).
+struct ChunkPlan { uint32_t contig_end; cudaEvent_t ready; };
+
 static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_params_t& P, int seed, uint32_t n_genomes,
                         const uint32_t* gstart, const uint8_t* seq_dev, const uint64_t* offs, const uint64_t* lens,
-                        skb_sketch_t** out) {
+                        skb_sketch_t** out, const std::vector<ChunkPlan>* plan = nullptr) {
     Core& c = *core;
     cudaStream_t st = c.stream;
     if (P.k < 1 || P.k > 16) throw Fail{SKB_ERR_ARG, "k must be in 1..16 for DNA (skani panics above 16)"};
@@ -142,11 +190,14 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
     // ---- contig gate + tile table (reference lib.rs:155-174)
     std::vector<std::vector<uint32_t>> contig_lens(n_genomes);
     std::vector<ContigDesc> descs;
+    std::vector<uint32_t> chunk_desc_end;      // descriptor index at which each planned chunk ends
+    size_t plan_i = 0;
     uint64_t total_bases = 0, tile_count = 0;
     for (uint32_t g = 0; g < n_genomes; g++) {
         bool first = true;
         uint32_t kept = 0;
         for (uint32_t ci = gstart[g]; ci < gstart[g + 1]; ci++) {
+            while (plan && plan_i < plan->size() && (*plan)[plan_i].contig_end <= ci) { chunk_desc_end.push_back((uint32_t)descs.size()); plan_i++; }
             if (lens[ci] < SKB_MIN_LENGTH_CONTIG) continue;
             if (lens[ci] > 0x7FFFFFFFull) throw Fail{SKB_ERR_ARG, "contigs of 2^31 bases or more are not supported"};
             if (offs[ci] & 15) throw Fail{SKB_ERR_ARG, "device contig offsets must be multiples of 16"};
@@ -164,6 +215,7 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             kept++;
         }
     }
+    while (plan && plan_i < plan->size()) { chunk_desc_end.push_back((uint32_t)descs.size()); plan_i++; }
     if (total_bases >= 0x7FFFFFFFull) throw Fail{SKB_ERR_ARG, "a sketch batch is limited to 2^31 bases; split the call"};
     if (n_genomes >= (1u << 22)) throw Fail{SKB_ERR_ARG, "a sketch batch is limited to 2^22 genomes"};
     const uint32_t n_tiles = (uint32_t)tile_count;
@@ -172,47 +224,80 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
     auto store = std::make_shared<BatchStore>();
 
     if (n_tiles) {
-        DevMem d_descs(core, sizeof(ContigDesc) * descs.size());
+        ContigDesc* d_descs = (ContigDesc*)c.scratch(SLOT_DESC, sizeof(ContigDesc) * descs.size());
         {
             ContigDesc* h = (ContigDesc*)ensure_pinned(c, sizeof(ContigDesc) * descs.size());
             std::memcpy(h, descs.data(), sizeof(ContigDesc) * descs.size());
-            upload(c, d_descs.as<ContigDesc>(), h, descs.size());
+            upload(c, d_descs, h, descs.size());
         }
-        DevMem d_status(core, sizeof(uint64_t) * n_tiles + 64);
-        DevMem d_gs(core, sizeof(uint32_t) * (n_genomes + 1)), d_gm(core, sizeof(uint32_t) * (n_genomes + 1));
-        uint32_t* d_counter = (uint32_t*)((char*)d_status.p + sizeof(uint64_t) * n_tiles);
-        uint32_t* d_overflow = d_counter + 1;
+        const size_t n_chunks = plan ? plan->size() : 0;
+        // status words | running totals [n_chunks + 2] | tile counters [n_chunks + 1] | overflow flag
+        const size_t status_bytes = sizeof(uint64_t) * (n_tiles + n_chunks + 2) + sizeof(uint32_t) * (n_chunks + 2) + 64;
+        uint64_t* d_status = (uint64_t*)c.scratch(SLOT_STATUS, status_bytes);
+        const size_t g_bytes = sizeof(uint32_t) * (n_genomes + 1);
+        uint32_t* d_gs = (uint32_t*)c.scratch(SLOT_GS, g_bytes);
+        uint32_t* d_gm = (uint32_t*)c.scratch(SLOT_GM, g_bytes);
+        uint64_t* d_totals = d_status + n_tiles;
+        uint32_t* d_counter = (uint32_t*)(d_totals + n_chunks + 2);
+        uint32_t* d_overflow = d_counter + n_chunks + 1;
 
         uint64_t seed_cap = seed ? total_bases / P.c + total_bases / P.c / 4 + 65536 : 1;
         uint64_t marker_cap = total_bases / P.marker_c + total_bases / P.marker_c / 4 + 65536;
         seed_cap = std::min<uint64_t>(seed_cap, total_bases);
         marker_cap = std::min<uint64_t>(marker_cap, total_bases);
 
-        DevMem t_kmer, t_pos, t_meta, t_mkeys;
+        uint32_t *t_kmer = nullptr, *t_pos = nullptr, *t_meta = nullptr;
+        uint64_t* t_mkeys = nullptr;
         uint32_t h_over = 0;
         for (int attempt = 0; attempt < 2; attempt++) {
-            t_kmer = DevMem(core, 4 * seed_cap); t_pos = DevMem(core, 4 * seed_cap); t_meta = DevMem(core, 4 * seed_cap);
-            t_mkeys = DevMem(core, 8 * marker_cap);
-            CU(cudaMemsetAsync(d_status.p, 0, d_status.bytes, st));
-            CU(cudaMemsetAsync(d_gs.p, 0xFF, d_gs.bytes, st));
-            CU(cudaMemsetAsync(d_gm.p, 0xFF, d_gm.bytes, st));
+            t_kmer = (uint32_t*)c.scratch(SLOT_KMER, 4 * seed_cap); t_pos = (uint32_t*)c.scratch(SLOT_POS, 4 * seed_cap);
+            t_meta = (uint32_t*)c.scratch(SLOT_META, 4 * seed_cap); t_mkeys = (uint64_t*)c.scratch(SLOT_MKEYS, 8 * marker_cap);
+            CU(cudaMemsetAsync(d_status, 0, status_bytes, st));
+            CU(cudaMemsetAsync(d_gs, 0xFF, g_bytes, st));
+            CU(cudaMemsetAsync(d_gm, 0xFF, g_bytes, st));
             SeedScanArgs a{};
-            a.seq = seq_dev; a.contigs = d_descs.as<ContigDesc>(); a.n_contigs = (uint32_t)descs.size(); a.n_tiles = n_tiles;
+            a.seq = seq_dev; a.contigs = d_descs; a.n_contigs = (uint32_t)descs.size(); a.n_tiles = n_tiles;
             a.kmask = P.k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * P.k)) - 1u);
             a.kshift = 42 - 2 * P.k;
             a.thr_seed = seed ? UINT64_MAX / (uint64_t)P.c : 0;     // seed=False keeps markers only (A.4)
             a.thr_marker = UINT64_MAX / (uint64_t)P.marker_c;
-            a.kmer_p = t_kmer.as<uint32_t>(); a.pos_p = t_pos.as<uint32_t>(); a.meta_p = t_meta.as<uint32_t>();
-            a.marker_keys = t_mkeys.as<uint64_t>();
+            a.kmer_p = t_kmer; a.pos_p = t_pos; a.meta_p = t_meta;
+            a.marker_keys = t_mkeys;
             a.seed_cap = (uint32_t)seed_cap; a.marker_cap = (uint32_t)marker_cap;
-            a.tile_status = d_status.as<uint64_t>(); a.tile_counter = d_counter;
-            a.genome_seed_start = d_gs.as<uint32_t>(); a.genome_marker_start = d_gm.as<uint32_t>();
+            a.tile_status = d_status; a.tile_counter = d_counter;
+            a.genome_seed_start = d_gs; a.genome_marker_start = d_gm;
             a.n_genomes = n_genomes; a.overflow = d_overflow;
+            a.tile_base = 0; a.base_in = nullptr; a.base_out = nullptr; a.is_last = 1;
             CU(cudaEventRecord(c.ev[1], st));
-            launch_seed_scan(a, c.n_sm, st);
+            if (attempt == 0 && n_chunks > 1) {
+                // one launch per chunk, each gated on its copy; the look-back prefix is carried through d_totals
+                uint32_t d0 = 0, launch_i = 0, last_nonempty = 0;
+                for (size_t ch = 0; ch < n_chunks; ch++) if (chunk_desc_end[ch] > (ch ? chunk_desc_end[ch - 1] : 0)) last_nonempty = (uint32_t)ch;
+                for (size_t ch = 0; ch < n_chunks; ch++) {
+                    const uint32_t d1 = chunk_desc_end[ch];
+                    CU(cudaStreamWaitEvent(st, (*plan)[ch].ready, 0));
+                    if (d1 > d0) {
+                        SeedScanArgs b = a;
+                        b.contigs = a.contigs + d0; b.n_contigs = d1 - d0;
+                        b.tile_base = descs[d0].tile_start;
+                        b.n_tiles = (d1 < descs.size() ? descs[d1].tile_start : n_tiles) - b.tile_base;
+                        b.tile_status = a.tile_status + b.tile_base;
+                        b.tile_counter = d_counter + ch;
+                        b.base_in = d_totals + launch_i; b.base_out = d_totals + launch_i + 1;
+                        b.is_last = ch == last_nonempty;
+                        launch_seed_scan(b, c.n_sm, st);
+                        launch_i++;
+                    }
+                    d0 = d1;
+                }
+            } else {
+                if (plan) for (auto& pc : *plan) CU(cudaStreamWaitEvent(st, pc.ready, 0));
+                launch_seed_scan(a, c.n_sm, st);
+            }
             CU(cudaEventRecord(c.ev[2], st));
-            download(c, seed_start.data(), d_gs.as<uint32_t>(), n_genomes + 1);
-            download(c, marker_start.data(), d_gm.as<uint32_t>(), n_genomes + 1);
+            { Trace t2("sketch_core"); t2.mark("seed launches enqueued"); }
+            download(c, seed_start.data(), d_gs, n_genomes + 1);
+            download(c, marker_start.data(), d_gm, n_genomes + 1);
             download(c, &h_over, d_overflow, 1);
             CU(cudaStreamSynchronize(st));
             if (!h_over) break;
@@ -230,30 +315,31 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
         store->kmer_p = DevMem(core, 4 * (size_t)ns); store->pos_p = DevMem(core, 4 * (size_t)ns);
         store->meta_p = DevMem(core, 4 * (size_t)ns);
         if (ns) {
-            CU(cudaMemcpyAsync(store->kmer_p.p, t_kmer.p, 4 * (size_t)ns, cudaMemcpyDeviceToDevice, st));
-            CU(cudaMemcpyAsync(store->pos_p.p, t_pos.p, 4 * (size_t)ns, cudaMemcpyDeviceToDevice, st));
-            CU(cudaMemcpyAsync(store->meta_p.p, t_meta.p, 4 * (size_t)ns, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(store->kmer_p.p, t_kmer, 4 * (size_t)ns, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(store->pos_p.p, t_pos, 4 * (size_t)ns, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(store->meta_p.p, t_meta, 4 * (size_t)ns, cudaMemcpyDeviceToDevice, st));
         }
         // ---- k-mer order
         store->kmer_k = DevMem(core, 4 * (size_t)ns); store->pos_k = DevMem(core, 4 * (size_t)ns);
         store->meta_k = DevMem(core, 4 * (size_t)ns);
         if (ns) {
-            upload(c, d_gs.as<uint32_t>(), seed_start.data(), n_genomes + 1);   // repaired starts
-            DevMem scratch(core, kmer_order_scratch_bytes(ns));
+            upload(c, d_gs, seed_start.data(), n_genomes + 1);   // repaired starts
+            const size_t sort_bytes = kmer_order_scratch_bytes(ns);
+            void* sort_scratch = c.scratch(SLOT_SORT, sort_bytes);
             IndexBuildArgs ib{};
-            ib.n_genomes = n_genomes; ib.n_seeds_total = ns; ib.genome_seed_start = d_gs.as<uint32_t>();
+            ib.n_genomes = n_genomes; ib.n_seeds_total = ns; ib.genome_seed_start = d_gs;
             ib.kmer_p = store->kmer_p.as<uint32_t>(); ib.pos_p = store->pos_p.as<uint32_t>(); ib.meta_p = store->meta_p.as<uint32_t>();
             ib.kmer_k = store->kmer_k.as<uint32_t>(); ib.pos_k = store->pos_k.as<uint32_t>(); ib.meta_k = store->meta_k.as<uint32_t>();
             ib.k = P.k;
-            build_kmer_order(ib, scratch.p, scratch.bytes, st);
+            build_kmer_order(ib, sort_scratch, sort_bytes, st);
         }
         // ---- marker sets
         store->markers = DevMem(core, 8 * (size_t)std::max<uint32_t>(nm, 1));
         {
-            DevMem scratch(core, marker_scratch_bytes(nm));
-            build_marker_sets(n_genomes, nm, t_mkeys.as<uint64_t>(), store->markers.as<uint64_t>(), d_gm.as<uint32_t>(),
-                              scratch.p, scratch.bytes, st);
-            download(c, marker_start.data(), d_gm.as<uint32_t>(), n_genomes + 1);
+            const size_t mark_bytes = marker_scratch_bytes(nm);
+            void* mark_scratch = c.scratch(SLOT_MARK, mark_bytes);
+            build_marker_sets(n_genomes, nm, t_mkeys, store->markers.as<uint64_t>(), d_gm, mark_scratch, mark_bytes, st);
+            download(c, marker_start.data(), d_gm, n_genomes + 1);
             CU(cudaStreamSynchronize(st));
         }
         CU(cudaEventRecord(c.ev[3], st));
@@ -388,6 +474,7 @@ int skb_ctx_create(int device, skb_ctx_t** out) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SKB_ERR_CUDA;
     core->n_sm = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&core->stream, cudaStreamNonBlocking) != cudaSuccess) return SKB_ERR_CUDA;
+    if (cudaStreamCreateWithFlags(&core->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return SKB_ERR_CUDA;
     for (auto& e : core->ev) if (cudaEventCreate(&e) != cudaSuccess) return SKB_ERR_CUDA;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -465,24 +552,43 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
             cur += align16(contig_lens[i]) + 16;
         }
         cur += 64;
+        Trace tr("sketch_batch");
         CU(cudaEventRecord(c.ev[0], st));
-        DevMem d_seq(ctx->core, cur);
-        // small contigs are packed through pinned staging; large ones are copied straight from the caller's memory
+        uint8_t* d_seq = (uint8_t*)c.scratch(SLOT_SEQ, cur);
+        tr.mark("alloc d_seq");
+        // The copies run on their own stream in chunks of ~CHUNK bytes; each chunk records an event, and the seeding
+        // launch of that chunk waits on it, so the kernels of chunk i overlap the PCIe transfer of chunk i+1.
+        // Large contigs are copied straight from the caller's memory (true DMA when it is pinned); small ones are
+        // packed through pinned staging first.
+        cudaStream_t cs = c.copy_stream;
+        CU(cudaEventRecord(c.ev[5], st));
+        CU(cudaStreamWaitEvent(cs, c.ev[5], 0));          // d_seq's allocation is ordered on `st`
         constexpr uint64_t DIRECT = 1 << 18;
         constexpr size_t STAGE = (size_t)8 << 20;
+        constexpr uint64_t CHUNK = (uint64_t)16 << 20;
+        std::vector<ChunkPlan> plan;
         char* stage = nullptr; size_t used = 0; uint64_t stage_dev0 = 0;
         auto flush = [&] {
             if (used) {
-                CU(cudaMemcpyAsync((char*)d_seq.p + stage_dev0, stage, used, cudaMemcpyHostToDevice, st));
-                CU(cudaStreamSynchronize(st));
+                CU(cudaMemcpyAsync((char*)d_seq + stage_dev0, stage, used, cudaMemcpyHostToDevice, cs));
+                CU(cudaStreamSynchronize(cs));            // the staging block is reused
                 used = 0;
             }
+        };
+        uint64_t in_chunk = 0;
+        auto close_chunk = [&](uint32_t contig_end) {
+            flush();
+            cudaEvent_t e = c.pool_event(plan.size());
+            if (!e) throw Fail{SKB_ERR_CUDA, "cannot create an event"};
+            CU(cudaEventRecord(e, cs));
+            plan.push_back(ChunkPlan{contig_end, e});
+            in_chunk = 0;
         };
         for (uint32_t i = 0; i < n_contigs; i++) {
             const uint64_t len = contig_lens[i];
             if (len < SKB_MIN_LENGTH_CONTIG) continue;
             if (len >= DIRECT) {
-                CU(cudaMemcpyAsync((char*)d_seq.p + offs[i], contigs[i], len, cudaMemcpyHostToDevice, st));
+                CU(cudaMemcpyAsync((char*)d_seq + offs[i], contigs[i], len, cudaMemcpyHostToDevice, cs));
             } else {
                 if (!stage) stage = (char*)ensure_pinned(c, STAGE);
                 const uint64_t span = align16(len) + 16;
@@ -491,11 +597,16 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
                 std::memcpy(stage + used, contigs[i], len);
                 used += span;
             }
+            in_chunk += len;
+            if (in_chunk >= CHUNK) close_chunk(i + 1);
         }
-        flush();
-        sketch_core(ctx->core, *params, seed, n_genomes, genome_contig_start, d_seq.as<uint8_t>(), offs.data(), contig_lens, out);
+        close_chunk(n_contigs);
+        tr.mark("copies enqueued");
+        sketch_core(ctx->core, *params, seed, n_genomes, genome_contig_start, d_seq, offs.data(), contig_lens, out, &plan);
+        tr.mark("sketch_core done");
         CU(cudaEventRecord(c.ev[4], st));
         CU(cudaStreamSynchronize(st));
+        tr.mark("final sync");
         c.stats.h2d_ms = elapsed(c.ev[0], c.ev[1]); c.stats.seed_ms = elapsed(c.ev[1], c.ev[2]);
         c.stats.index_ms = elapsed(c.ev[2], c.ev[4]); c.stats.total_ms = elapsed(c.ev[0], c.ev[4]);
         return SKB_OK;
@@ -670,7 +781,9 @@ void run_screen(skb_db& db, const std::vector<std::shared_ptr<SketchImpl>>& quer
     if (n >= 0x7FFFFFFFull) throw Fail{SKB_ERR_ARG, "more than 2^31 pairs in one call; split the queries"};
     const GenomeView* d_r = db_views(db);
     DevMem d_count(db.core, 4 * n), d_pass(db.core, n);
-    launch_marker_screen(d_q, nq, d_r, nr, d_count.as<uint32_t>(), st);
+    uint32_t max_qm = 0;
+    for (auto& q : queries) max_qm = std::max(max_qm, q->view.n_markers);
+    launch_marker_screen(d_q, nq, d_r, nr, d_count.as<uint32_t>(), max_qm, c.n_sm, st);
     launch_screen_decide(d_q, nq, d_r, nr, d_count.as<uint32_t>(), pow21(screen_val), screen_val == 0.0, rescue_small,
                          d_pass.as<uint8_t>(), st);
     if (pass_host) download(c, pass_host, d_pass.as<uint8_t>(), n);
@@ -754,6 +867,7 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
         while (p0 < n_pass) {
             std::vector<PairDesc> pairs;
             uint64_t seeds = 0, wins = 0;
+            uint32_t max_qseeds = 0;
             size_t p1 = p0;
             while (p1 < n_pass) {
                 const uint32_t q = so.pass_idx[p1] / nr, r = so.pass_idx[p1] % nr;
@@ -761,6 +875,7 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
                 if (!pairs.empty() && (seeds + qv.n_seeds > MAX_BATCH_SEEDS || pairs.size() >= 65535)) break;
                 pairs.push_back(PairDesc{q, r, (uint32_t)seeds, (uint32_t)wins});
                 seeds += qv.n_seeds; wins += qv.win_cap;
+                max_qseeds = std::max(max_qseeds, qv.n_seeds);
                 p1++;
             }
             if (seeds >= 0x7FFFFFFFull) throw Fail{SKB_ERR_ARG, "query sketch too large for one chaining batch"};
@@ -801,7 +916,7 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
             B.results = d_res.as<PairResult>();
 
             launch_anchor_fill(B, st);
-            launch_window_walk(B, C, st);
+            launch_window_walk(B, C, max_qseeds, st);
             launch_chain_dp(B, C, st);
             launch_window_keys(B, st);
             {

@@ -57,9 +57,13 @@ struct ContigDesc {
 
 struct SeedScanArgs {
     const uint8_t* seq;
-    const ContigDesc* contigs;
+    const ContigDesc* contigs;   // descriptors of THIS launch (a contiguous slice of the batch's table)
     uint32_t n_contigs;
-    uint32_t n_tiles;
+    uint32_t n_tiles;            // tiles of this launch
+    uint32_t tile_base;          // batch-wide id of this launch's first tile
+    const uint64_t* base_in;     // running (seeds | markers << 31) total before this launch, or NULL for 0
+    uint64_t* base_out;          // receives the running total after this launch, or NULL
+    uint32_t is_last;            // last launch of the batch: also writes the batch totals
     uint32_t kmask, kshift;
     uint64_t thr_seed, thr_marker;
     // outputs, position order over the whole batch
@@ -105,7 +109,7 @@ void launch_contig_starts(const GenomeView* views_dev, uint32_t n_genomes, uint3
 // ---------------------------------------------------------------- screen
 // count[q * n_refs + r] = | markers(q) ∩ markers(r) |
 void launch_marker_screen(const GenomeView* queries, uint32_t n_queries, const GenomeView* refs, uint32_t n_refs,
-                          uint32_t* count, cudaStream_t st);
+                          uint32_t* count, uint32_t max_query_markers, int n_sm, cudaStream_t st);
 void launch_screen_decide(const GenomeView* queries, uint32_t n_queries, const GenomeView* refs, uint32_t n_refs,
                           const uint32_t* count, double p21, int always, int rescue_small, uint8_t* pass,
                           cudaStream_t st);
@@ -169,7 +173,7 @@ struct ChainBatch {            // device pointers of one batch of pairs
 
 void launch_match_count(const ChainBatch& b, cudaStream_t st);
 void launch_anchor_fill(const ChainBatch& b, cudaStream_t st);
-void launch_window_walk(const ChainBatch& b, const ChainConsts& c, cudaStream_t st);
+void launch_window_walk(const ChainBatch& b, const ChainConsts& c, uint32_t max_query_seeds, cudaStream_t st);
 void launch_chain_dp(const ChainBatch& b, const ChainConsts& c, cudaStream_t st);
 void launch_window_keys(const ChainBatch& b, cudaStream_t st);
 void launch_ani_reduce(const ChainBatch& b, const ChainConsts& c, const uint64_t* sorted_keys,
