@@ -1,18 +1,19 @@
 // seed_kernels.cu — FracMinHash seeding on sm_100a.
 //
 // Replaces skani::seeding::fmh_seeds (one call per contig at reference lib.rs:165-171) for a whole batch
-// of genomes in ONE launch.  Work unit: a tile of TILE_BASES (16 384) consecutive bases of one contig.
-//   * each thread loads 4 x 16 ASCII bytes with 128-bit read-only loads (warp-contiguous 512 B each) and packs
-//     them to 2-bit words in shared memory
+// of genomes in ONE launch.  Work unit: a tile of TILE_BASES (2 048) consecutive bases of one contig, owned by
+// one WARP; every warp owns a contiguous run of tiles and a private, ordered output region.
+//   * each lane loads 4 x 16 ASCII bytes with 128-bit read-only loads (warp-contiguous 512 B each) and packs
+//     them to 2-bit words in the warp's slice of shared memory
 //   * k-mers are cut out of three consecutive words with funnel shifts (no rolling dependency chain)
 //   * both hashes (k-mer and 21-mer marker) are evaluated for all 16 positions of a word in 32-bit halves:
-//     multiplies go to the FMA pipe (IMAD.WIDE / IMAD), xor-shifts to the ALU pipe, so both pipes issue
-//   * popcounts are scanned over the CTA, and the CTA obtains its global output offset with a
-//     single-pass decoupled look-back over tile status words, so seeds leave the kernel already ordered
-//     by (genome, contig, position) — no atomics on the data path, no second pass over the sequence
-//   * hit positions are re-extracted and written to their exact slot.
-// The kernel is persistent: CTAs draw tile ids from an atomic counter, which also gives the look-back
-// its forward-progress guarantee (a CTA only ever waits on tiles that were claimed before its own).
+//     multiplies go to the FMA pipe (IMAD.WIDE / IMAD), xor-shifts and compares to the ALU pipe
+//   * popcounts are scanned over the warp with shuffles; hit positions are re-extracted and written to their
+//     exact slot of the warp's region, so a region is ordered by (genome, contig, position)
+//   * there is no block barrier, no atomic and no inter-warp dependency anywhere: warps never wait on each other.
+// A one-CTA scan over the region counts and a gather (which doubles as the copy into exact-size arrays) stitch
+// the regions together in tile order, so seeds come out ordered without a sort and without a second pass over
+// the sequence.
 #include "kmer_bits.cuh"
 #include "skb_internal.cuh"
 
@@ -22,31 +23,12 @@ unsigned long long g_kernel_launches = 0;
 
 namespace {
 
-constexpr uint64_t ST_AGG = 1ull << 62;     // tile aggregate published
-constexpr uint64_t ST_INC = 2ull << 62;     // inclusive prefix published
-constexpr uint64_t ST_MASK = 3ull << 62;
-constexpr uint64_t CNT_MASK = 0x7FFFFFFFull;   // seeds in bits 0..30, markers in bits 31..61
-
-__device__ __forceinline__ uint64_t ld_relaxed(const uint64_t* p) {
-    uint64_t v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed(uint64_t* p, uint64_t v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 __device__ __forceinline__ uint4 ld_stream16(const uint8_t* p) {
     uint4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
-__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
 // ---- mm_hash64 in 32-bit halves (see kmer_bits.cuh::mm_hash64 for the reference form) -------------------
 struct U64 { uint32_t lo, hi; };
 
@@ -97,7 +79,7 @@ __device__ __forceinline__ bool hash_below(U64 x, uint32_t thr_lo, uint32_t thr_
     b = mul_c(b, 21u);
     b = xorshr<28>(b);
     b = mul_c(b, 0x80000001u);                                        // x + (x << 31)
-    return b.hi < thr_hi || (b.hi == thr_hi && b.lo < thr_lo);
+    return (((uint64_t)b.hi << 32) | b.lo) < (((uint64_t)thr_hi << 32) | thr_lo);
 }
 
 struct WordCtx { uint32_t w0, w1, w2, r0, r1, r2; };
@@ -122,220 +104,251 @@ __device__ __forceinline__ void eval_word(const WordCtx& c, uint32_t kmask, uint
         const uint32_t km = min(fk, rk);
         if (hash_below(U64{km, 0u}, ts_lo, ts_hi)) smask |= 1u << e;
         // marker 21-mer: canonical = min of the two 42-bit values
-        const bool fsmall = fhi < rhi || (fhi == rhi && flo < rlo);
+        const bool fsmall = (((uint64_t)fhi << 32) | flo) < (((uint64_t)rhi << 32) | rlo);
         const U64 mk{fsmall ? flo : rlo, fsmall ? fhi : rhi};
         if (hash_below(mk, tm_lo, tm_hi)) mmask |= 1u << e;
     }
 }
 
 __global__ void __launch_bounds__(SEED_THREADS, 3) seed_scan_kernel(const SeedScanArgs a) {
-    __shared__ uint32_t s_pk[TILE_WORDS + 2];
-    __shared__ uint32_t s_masks[TILE_WORDS];      // smask | mmask << 16 per word
-    __shared__ uint64_t s_wseed[SEED_THREADS / 32], s_wmark[SEED_THREADS / 32];
-    __shared__ uint32_t s_tile;
-    __shared__ uint64_t s_base;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    // Warps are independent: private packed-word and mask buffers, private output region, no block barriers.
+    __shared__ uint32_t s_pk[SEED_WARPS][TILE_WORDS + 2];
+    __shared__ uint32_t s_masks[SEED_WARPS][TILE_WORDS];      // smask | mmask << 16 per word
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t W = blockIdx.x * SEED_WARPS + warp;        // warp id inside the launch
+    if (W >= a.n_warps) return;
     const uint32_t ts_lo = (uint32_t)a.thr_seed, ts_hi = (uint32_t)(a.thr_seed >> 32);
     const uint32_t tm_lo = (uint32_t)a.thr_marker, tm_hi = (uint32_t)(a.thr_marker >> 32);
+    uint32_t* pk = s_pk[warp];
+    uint32_t* masks = s_masks[warp];
 
-    while (true) {
-        if (t == 0) s_tile = atomicAdd(a.tile_counter, 1u);
-        __syncthreads();
-        const uint32_t tile_id = s_tile;                 // local to this launch
-        if (tile_id >= a.n_tiles) break;
-        const uint32_t gtile = a.tile_base + tile_id;    // id within the batch (descriptors hold batch-wide tile ids)
-        // contig of this tile: last descriptor whose tile_start <= gtile (uniform search, L1-resident table)
-        uint32_t lo = 0, hi = a.n_contigs;
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (__ldg(&a.contigs[mid].tile_start) <= gtile) lo = mid; else hi = mid;
-        }
-        const ContigDesc cd = a.contigs[lo];
-        const uint32_t pos0 = (gtile - cd.tile_start) * (uint32_t)TILE_BASES;   // contig position of the tile's first base
-        const uint32_t n = min((uint32_t)TILE_BASES, cd.len - pos0);             // bases in the tile
-        const uint8_t* base = a.seq + cd.seq_off + pos0;
-        const bool first_of_genome = (cd.genome & 0x80000000u) && pos0 == 0;
+    // contiguous tile range and output region of this warp
+    const uint32_t t0 = (uint32_t)((uint64_t)W * a.n_tiles / a.n_warps);
+    const uint32_t t1 = (uint32_t)((uint64_t)(W + 1) * a.n_tiles / a.n_warps);
+    const uint32_t region = a.region_base + W;
+    uint32_t seed_off, seed_cap, marker_off, marker_cap;
+    if (a.region_seed_off) {
+        seed_off = a.region_seed_off[region]; seed_cap = a.region_seed_off[region + 1] - seed_off;
+        marker_off = a.region_marker_off[region]; marker_cap = a.region_marker_off[region + 1] - marker_off;
+    } else {
+        seed_off = (a.tile_base + t0) * a.seed_tile_cap; seed_cap = (t1 - t0) * a.seed_tile_cap;
+        marker_off = (a.tile_base + t0) * a.marker_tile_cap; marker_cap = (t1 - t0) * a.marker_tile_cap;
+    }
+    uint32_t cur_s = 0, cur_m = 0;                             // records written so far (warp-uniform)
 
-        // ---- load + pack: word j*256 + t for j = 0..3 (each warp load covers 512 contiguous bytes)
-        uint4 v[WORDS_PER_THREAD];
-#pragma unroll
-        for (int j = 0; j < WORDS_PER_THREAD; j++) {
-            const uint32_t w = j * SEED_THREADS + t;
-            v[j] = make_uint4(0, 0, 0, 0);
-            if (16u * w < n) v[j] = ld_stream16(base + 16u * w);
-        }
-#pragma unroll
-        for (int j = 0; j < WORDS_PER_THREAD; j++) s_pk[2 + j * SEED_THREADS + t] = pack16(v[j].x, v[j].y, v[j].z, v[j].w);
-        if (t < 2) {
-            uint32_t h = 0;
-            if (pos0 > 0) {   // the two words before the tile belong to the same contig
-                uint4 q = ld_stream16(base - 32 + 16 * t);
-                h = pack16(q.x, q.y, q.z, q.w);
+    if (t0 < t1) {
+        // descriptor of the first tile: last one whose tile_start <= tile_base + t0
+        uint32_t ci = 0;
+        {
+            uint32_t lo = 0, hi = a.n_contigs;
+            const uint32_t g0 = a.tile_base + t0;
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(&a.contigs[mid].tile_start) <= g0) lo = mid; else hi = mid;
             }
-            s_pk[t] = h;
+            ci = lo;
         }
-        __syncthreads();
+        ContigDesc cd = a.contigs[ci];
+        uint32_t next_start = ci + 1 < a.n_contigs ? __ldg(&a.contigs[ci + 1].tile_start) : 0xFFFFFFFFu;
 
-        // ---- evaluate
-        uint64_t cs = 0, cm = 0;                   // per sub-tile counts, 16 bits each
+        for (uint32_t tile = t0; tile < t1; tile++) {
+            const uint32_t gtile = a.tile_base + tile;
+            while (gtile >= next_start) {                      // uniform: move on to the next contig
+                ci++;
+                cd = a.contigs[ci];
+                next_start = ci + 1 < a.n_contigs ? __ldg(&a.contigs[ci + 1].tile_start) : 0xFFFFFFFFu;
+            }
+            const uint32_t pos0 = (gtile - cd.tile_start) * (uint32_t)TILE_BASES;   // contig position of the tile's first base
+            const uint32_t n = min((uint32_t)TILE_BASES, cd.len - pos0);             // bases in the tile
+            const uint8_t* base = a.seq + cd.seq_off + pos0;
+            const uint32_t genome = cd.genome & 0x7FFFFFFFu;
+            if ((cd.genome & 0x80000000u) && pos0 == 0 && lane == 0) {               // first tile of a genome
+                a.genome_region[genome] = region;
+                a.genome_seed_local[genome] = cur_s;
+                a.genome_marker_local[genome] = cur_m;
+            }
+
+            // ---- load + pack: word j*32 + lane for j = 0..3 (each warp load covers 512 contiguous bytes)
+            uint4 v[WORDS_PER_LANE];
+#pragma unroll
+            for (int j = 0; j < WORDS_PER_LANE; j++) {
+                const uint32_t w = j * 32 + lane;
+                v[j] = make_uint4(0, 0, 0, 0);
+                if (16u * w < n) v[j] = ld_stream16(base + 16u * w);
+            }
+            uint4 hv = make_uint4(0, 0, 0, 0);
+            if (lane < 2 && pos0 > 0) hv = ld_stream16(base - 32 + 16 * lane);      // the two words before the tile
+#pragma unroll
+            for (int j = 0; j < WORDS_PER_LANE; j++) pk[2 + j * 32 + lane] = pack16(v[j].x, v[j].y, v[j].z, v[j].w);
+            if (lane < 2) pk[lane] = pos0 > 0 ? pack16(hv.x, hv.y, hv.z, hv.w) : 0u;
+            __syncwarp();
+
+            // ---- evaluate
+            uint64_t cs = 0, cm = 0;                   // per sub-tile counts, 16 bits each
 #pragma unroll 1
-        for (int j = 0; j < WORDS_PER_THREAD; j++) {
-            const uint32_t w = j * SEED_THREADS + t;
-            uint32_t mk = 0;
-            if (16u * w < n) {
-                WordCtx c;
-                c.w2 = s_pk[w]; c.w1 = s_pk[w + 1]; c.w0 = s_pk[w + 2];
-                c.r0 = revcomp_word(c.w0); c.r1 = revcomp_word(c.w1); c.r2 = revcomp_word(c.w2);
-                uint32_t sm, mm;
-                eval_word(c, a.kmask, a.kshift, ts_lo, ts_hi, tm_lo, tm_hi, sm, mm);
-                const uint32_t left = n - 16u * w;
-                uint32_t valid = left >= 16 ? 0xFFFFu : ((1u << left) - 1u);
-                const uint32_t p0 = pos0 + 16u * w;
-                if (p0 < SKB_MARKER_K - 1) {                  // the first window ends at position 20
-                    const uint32_t skip = SKB_MARKER_K - 1 - p0;
-                    valid &= skip >= 16 ? 0u : ~((1u << skip) - 1u);
-                }
-                sm &= valid; mm &= valid;
-                mk = sm | (mm << 16);
-                cs |= (uint64_t)__popc(sm) << (16 * j);
-                cm |= (uint64_t)__popc(mm) << (16 * j);
-            }
-            s_masks[w] = mk;
-        }
-
-        // ---- CTA scan: four sub-tiles at once, 16-bit lanes inside a u64 (a sub-tile holds <= 4096 hits)
-        uint64_t is = cs, im = cm;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint64_t ns = __shfl_up_sync(0xffffffffu, is, o), nm = __shfl_up_sync(0xffffffffu, im, o);
-            if (lane >= o) { is += ns; im += nm; }
-        }
-        if (lane == 31) { s_wseed[warp] = is; s_wmark[warp] = im; }
-        __syncthreads();
-
-        if (warp == 0) {
-            constexpr int NW = SEED_THREADS / 32;
-            const uint64_t ws = lane < NW ? s_wseed[lane] : 0ull, wm = lane < NW ? s_wmark[lane] : 0ull;
-            uint64_t wis = ws, wim = wm;
-#pragma unroll
-            for (int o = 1; o < NW; o <<= 1) {
-                const uint64_t ns = __shfl_up_sync(0xffffffffu, wis, o), nm = __shfl_up_sync(0xffffffffu, wim, o);
-                if (lane >= o) { wis += ns; wim += nm; }
-            }
-            const uint64_t tot_s = __shfl_sync(0xffffffffu, wis, NW - 1), tot_m = __shfl_sync(0xffffffffu, wim, NW - 1);
-            // sub-tile bases: base_j = sum of totals of sub-tiles < j; fold them into the per-warp exclusive offsets
-            uint64_t sub_s = 0, sub_m = 0;
-            uint32_t acc_s = 0, acc_m = 0;
-#pragma unroll
-            for (int j = 0; j < WORDS_PER_THREAD; j++) {
-                sub_s |= (uint64_t)acc_s << (16 * j); sub_m |= (uint64_t)acc_m << (16 * j);
-                acc_s += (uint32_t)(tot_s >> (16 * j)) & 0xFFFFu; acc_m += (uint32_t)(tot_m >> (16 * j)) & 0xFFFFu;
-            }
-            // acc_* can reach 16384 (< 2^16): every 16-bit lane stays in range
-            if (lane < NW) { s_wseed[lane] = (wis - ws) + sub_s; s_wmark[lane] = (wim - wm) + sub_m; }
-
-            // ---- decoupled look-back
-            const uint64_t agg = (uint64_t)acc_s | ((uint64_t)acc_m << 31);
-            uint64_t excl = 0;
-            if (tile_id == 0) {
-                // the first tile of a launch continues from the running total of the previous launch of the batch
-                // (chunked host->device pipelining); it publishes an inclusive prefix directly, never an aggregate
-                excl = a.base_in ? ld_relaxed(a.base_in) : 0ull;
-                if (lane == 0) st_relaxed(&a.tile_status[0], ST_INC | (excl + agg));
-            } else {
-                if (lane == 0) st_relaxed(&a.tile_status[tile_id], ST_AGG | agg);
-                int64_t j0 = (int64_t)tile_id - 1;
-                while (true) {
-                    const int64_t j = j0 - lane;
-                    uint64_t s;
-                    do {
-                        s = j >= 0 ? ld_relaxed(&a.tile_status[j]) : ST_INC;
-                    } while (__any_sync(0xffffffffu, (s & ST_MASK) == 0));
-                    const uint32_t inc_mask = __ballot_sync(0xffffffffu, (s & ST_MASK) == ST_INC);
-                    uint64_t val = s & ~ST_MASK;
-                    if (inc_mask) {
-                        const int first = __ffs(inc_mask) - 1;   // nearest predecessor holding an inclusive prefix
-                        if (lane > first) val = 0;
-                        excl += warp_sum_u64(val);
-                        break;
+            for (int j = 0; j < WORDS_PER_LANE; j++) {
+                const uint32_t w = j * 32 + lane;
+                uint32_t mk = 0;
+                if (16u * w < n) {
+                    WordCtx c;
+                    c.w2 = pk[w]; c.w1 = pk[w + 1]; c.w0 = pk[w + 2];
+                    c.r0 = revcomp_word(c.w0); c.r1 = revcomp_word(c.w1); c.r2 = revcomp_word(c.w2);
+                    uint32_t sm, mm;
+                    eval_word(c, a.kmask, a.kshift, ts_lo, ts_hi, tm_lo, tm_hi, sm, mm);
+                    const uint32_t left = n - 16u * w;
+                    uint32_t valid = left >= 16 ? 0xFFFFu : ((1u << left) - 1u);
+                    const uint32_t p0 = pos0 + 16u * w;
+                    if (p0 < SKB_MARKER_K - 1) {                  // the first window ends at position 20
+                        const uint32_t skip = SKB_MARKER_K - 1 - p0;
+                        valid &= skip >= 16 ? 0u : ~((1u << skip) - 1u);
                     }
-                    excl += warp_sum_u64(val);
-                    j0 -= 32;
+                    sm &= valid; mm &= valid;
+                    mk = sm | (mm << 16);
+                    cs |= (uint64_t)__popc(sm) << (16 * j);
+                    cm |= (uint64_t)__popc(mm) << (16 * j);
                 }
-                if (lane == 0) st_relaxed(&a.tile_status[tile_id], ST_INC | (excl + agg));
+                masks[w] = mk;
             }
-            if (lane == 0) {
-                s_base = excl;
-                if (first_of_genome) {
-                    const uint32_t g = cd.genome & 0x7FFFFFFFu;
-                    a.genome_seed_start[g] = (uint32_t)(excl & CNT_MASK);
-                    a.genome_marker_start[g] = (uint32_t)((excl >> 31) & CNT_MASK);
-                }
-                if (tile_id == a.n_tiles - 1) {
-                    const uint64_t inc = excl + agg;
-                    if (a.base_out) st_relaxed(a.base_out, inc);
-                    if (a.is_last) {
-                        a.genome_seed_start[a.n_genomes] = (uint32_t)(inc & CNT_MASK);
-                        a.genome_marker_start[a.n_genomes] = (uint32_t)((inc >> 31) & CNT_MASK);
-                    }
-                }
-            }
-        }
-        __syncthreads();
 
-        // ---- ordered write-out
-        if (cs | cm) {
-            const uint64_t ex_s = (is - cs) + s_wseed[warp], ex_m = (im - cm) + s_wmark[warp];
-            const uint64_t b = s_base;
-            const uint32_t base_s = (uint32_t)(b & CNT_MASK), base_m = (uint32_t)((b >> 31) & CNT_MASK);
-            const uint64_t gkey = (uint64_t)(cd.genome & 0x7FFFFFFFu) << 42;
+            // ---- warp scan: four sub-tiles at once, 16-bit lanes inside a u64 (a sub-tile holds <= 512 hits)
+            uint64_t is = cs, im = cm;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint64_t ns = __shfl_up_sync(0xffffffffu, is, o), nm = __shfl_up_sync(0xffffffffu, im, o);
+                if (lane >= o) { is += ns; im += nm; }
+            }
+            const uint64_t tot_s = __shfl_sync(0xffffffffu, is, 31), tot_m = __shfl_sync(0xffffffffu, im, 31);
+            if (tot_s | tot_m) {
+                // sub-tile bases: base_j = sum of the totals of sub-tiles < j
+                uint64_t sub_s = 0, sub_m = 0;
+                uint32_t acc_s = 0, acc_m = 0;
+#pragma unroll
+                for (int j = 0; j < WORDS_PER_LANE; j++) {
+                    sub_s |= (uint64_t)acc_s << (16 * j); sub_m |= (uint64_t)acc_m << (16 * j);
+                    acc_s += (uint32_t)(tot_s >> (16 * j)) & 0xFFFFu; acc_m += (uint32_t)(tot_m >> (16 * j)) & 0xFFFFu;
+                }
+                // ---- ordered write-out into the warp's region
+                if (cs | cm) {
+                    const uint64_t ex_s = (is - cs) + sub_s, ex_m = (im - cm) + sub_m;   // <= 2048 per 16-bit lane
+                    const uint64_t gkey = (uint64_t)genome << 42;
 #pragma unroll 1
-            for (int j = 0; j < WORDS_PER_THREAD; j++) {
-                const uint32_t w = j * SEED_THREADS + t;
-                const uint32_t mk = s_masks[w];
-                uint32_t both = (mk | (mk >> 16)) & 0xFFFFu;
-                if (!both) continue;
-                const uint32_t w2 = s_pk[w], w1 = s_pk[w + 1], w0 = s_pk[w + 2];
-                const uint32_t r0 = revcomp_word(w0), r1 = revcomp_word(w1), r2 = revcomp_word(w2);
-                uint32_t so = base_s + ((uint32_t)(ex_s >> (16 * j)) & 0xFFFFu);
-                uint32_t mo = base_m + ((uint32_t)(ex_m >> (16 * j)) & 0xFFFFu);
-                const uint32_t p0 = pos0 + 16u * w;
-                while (both) {
-                    const int e = __ffs(both) - 1;
-                    both &= both - 1;
-                    const KmerPair kp = kmers_at(w2, w1, w0, r2, r1, r0, e);
-                    if ((mk >> e) & 1u) {
-                        const uint32_t fk = (uint32_t)kp.f21 & a.kmask;
-                        const uint32_t rk = (uint32_t)(kp.r21 >> a.kshift);
-                        const bool canon = fk < rk;
-                        if (so < a.seed_cap) {
-                            a.kmer_p[so] = canon ? fk : rk;
-                            a.pos_p[so] = p0 + e;
-                            a.meta_p[so] = (cd.contig << 1) | (uint32_t)canon;
-                        } else {
-                            *a.overflow = 1u;
+                    for (int j = 0; j < WORDS_PER_LANE; j++) {
+                        const uint32_t w = j * 32 + lane;
+                        const uint32_t mk = masks[w];
+                        uint32_t both = (mk | (mk >> 16)) & 0xFFFFu;
+                        if (!both) continue;
+                        const uint32_t w2 = pk[w], w1 = pk[w + 1], w0 = pk[w + 2];
+                        const uint32_t r0 = revcomp_word(w0), r1 = revcomp_word(w1), r2 = revcomp_word(w2);
+                        uint32_t so = cur_s + ((uint32_t)(ex_s >> (16 * j)) & 0xFFFFu);
+                        uint32_t mo = cur_m + ((uint32_t)(ex_m >> (16 * j)) & 0xFFFFu);
+                        const uint32_t p0 = pos0 + 16u * w;
+                        while (both) {
+                            const int e = __ffs(both) - 1;
+                            both &= both - 1;
+                            const KmerPair kp = kmers_at(w2, w1, w0, r2, r1, r0, e);
+                            if ((mk >> e) & 1u) {
+                                const uint32_t fk = (uint32_t)kp.f21 & a.kmask;
+                                const uint32_t rk = (uint32_t)(kp.r21 >> a.kshift);
+                                const bool canon = fk < rk;
+                                if (so < seed_cap) {
+                                    a.kmer_r[seed_off + so] = canon ? fk : rk;
+                                    a.pos_r[seed_off + so] = p0 + e;
+                                    a.meta_r[seed_off + so] = (cd.contig << 1) | (uint32_t)canon;
+                                } else {
+                                    *a.overflow = 1u;
+                                }
+                                so++;
+                            }
+                            if ((mk >> (16 + e)) & 1u) {
+                                if (mo < marker_cap) a.marker_r[marker_off + mo] = gkey | (kp.f21 < kp.r21 ? kp.f21 : kp.r21);
+                                else *a.overflow = 1u;
+                                mo++;
+                            }
                         }
-                        so++;
-                    }
-                    if ((mk >> (16 + e)) & 1u) {
-                        if (mo < a.marker_cap) a.marker_keys[mo] = gkey | (kp.f21 < kp.r21 ? kp.f21 : kp.r21);
-                        else *a.overflow = 1u;
-                        mo++;
                     }
                 }
+                cur_s += acc_s; cur_m += acc_m;
             }
+            __syncwarp();     // the next tile overwrites pk / masks
         }
-        // the next iteration's first __syncthreads separates these reads of shared state from its writes
+    }
+    if (lane == 0) {
+        a.region_seed_cnt[region] = cur_s; a.region_marker_cnt[region] = cur_m;
+        a.region_seed_src[region] = seed_off; a.region_marker_src[region] = marker_off;
+    }
+}
+
+// single CTA: exclusive scans of the region counts, then the per-genome starts
+__global__ void __launch_bounds__(1024) region_scan_kernel(uint32_t n_regions, const uint32_t* __restrict__ seed_cnt,
+                                                           const uint32_t* __restrict__ marker_cnt, uint32_t* __restrict__ seed_start,
+                                                           uint32_t* __restrict__ marker_start, uint32_t n_genomes,
+                                                           const uint32_t* __restrict__ genome_region,
+                                                           const uint32_t* __restrict__ genome_seed_local,
+                                                           const uint32_t* __restrict__ genome_marker_local,
+                                                           uint32_t* __restrict__ genome_seed_start,
+                                                           uint32_t* __restrict__ genome_marker_start) {
+    __shared__ uint32_t s_s[1024], s_m[1024];
+    const uint32_t t = threadIdx.x;
+    const uint32_t chunk = (n_regions + 1023) / 1024;
+    const uint32_t b = min(t * chunk, n_regions), e = min(b + chunk, n_regions);
+    uint32_t ss = 0, sm = 0;
+    for (uint32_t i = b; i < e; i++) { ss += seed_cnt[i]; sm += marker_cnt[i]; }
+    s_s[t] = ss; s_m[t] = sm;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024; o <<= 1) {       // Hillis-Steele inclusive scan over the 1024 chunk sums
+        const uint32_t vs = t >= o ? s_s[t - o] : 0u, vm = t >= o ? s_m[t - o] : 0u;
+        __syncthreads();
+        s_s[t] += vs; s_m[t] += vm;
+        __syncthreads();
+    }
+    uint32_t ps = s_s[t] - ss, pm = s_m[t] - sm;
+    for (uint32_t i = b; i < e; i++) { seed_start[i] = ps; marker_start[i] = pm; ps += seed_cnt[i]; pm += marker_cnt[i]; }
+    if (t == 1023) { seed_start[n_regions] = s_s[1023]; marker_start[n_regions] = s_m[1023]; }
+    __syncthreads();
+    for (uint32_t g = t; g <= n_genomes; g += 1024) {
+        if (g == n_genomes) { genome_seed_start[g] = s_s[1023]; genome_marker_start[g] = s_m[1023]; continue; }
+        const uint32_t r = genome_region[g];
+        if (r == 0xFFFFFFFFu) { genome_seed_start[g] = 0xFFFFFFFFu; genome_marker_start[g] = 0xFFFFFFFFu; }
+        else { genome_seed_start[g] = seed_start[r] + genome_seed_local[g]; genome_marker_start[g] = marker_start[r] + genome_marker_local[g]; }
+    }
+}
+
+__global__ void __launch_bounds__(256) region_gather_kernel(const RegionGatherArgs a) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= a.n_regions) return;
+    {
+        const uint32_t dst = a.seed_start[r], n = a.seed_start[r + 1] - dst, src = a.seed_src[r];
+        for (uint32_t i = lane; i < n; i += 32) {
+            a.kmer_p[dst + i] = a.kmer_r[src + i]; a.pos_p[dst + i] = a.pos_r[src + i]; a.meta_p[dst + i] = a.meta_r[src + i];
+        }
+    }
+    {
+        const uint32_t dst = a.marker_start[r], n = a.marker_start[r + 1] - dst, src = a.marker_src[r];
+        for (uint32_t i = lane; i < n; i += 32) a.marker_keys[dst + i] = a.marker_r[src + i];
     }
 }
 
 }  // namespace
 
 void launch_seed_scan(const SeedScanArgs& a, int n_sm, cudaStream_t st) {
-    if (a.n_tiles == 0) return;
-    uint32_t grid = (uint32_t)n_sm * 3u;
-    if (grid > a.n_tiles) grid = a.n_tiles;
-    seed_scan_kernel<<<grid, SEED_THREADS, 0, st>>>(a);
+    if (a.n_warps == 0) return;
+    seed_scan_kernel<<<a.n_warps / SEED_WARPS, SEED_THREADS, 0, st>>>(a);
+    g_kernel_launches++;
+}
+
+void launch_region_scan(uint32_t n_regions, const uint32_t* seed_cnt, const uint32_t* marker_cnt, uint32_t* seed_start,
+                        uint32_t* marker_start, uint32_t n_genomes, const uint32_t* genome_region,
+                        const uint32_t* genome_seed_local, const uint32_t* genome_marker_local, uint32_t* genome_seed_start,
+                        uint32_t* genome_marker_start, cudaStream_t st) {
+    region_scan_kernel<<<1, 1024, 0, st>>>(n_regions, seed_cnt, marker_cnt, seed_start, marker_start, n_genomes, genome_region,
+                                           genome_seed_local, genome_marker_local, genome_seed_start, genome_marker_start);
+    g_kernel_launches++;
+}
+
+void launch_region_gather(const RegionGatherArgs& a, cudaStream_t st) {
+    if (a.n_regions == 0) return;
+    region_gather_kernel<<<(a.n_regions + 7) / 8, 256, 0, st>>>(a);
     g_kernel_launches++;
 }
 

@@ -31,7 +31,7 @@ struct Core {
     // grow-only scratch blocks reused by every call on this context (calls are serialised by `mu`): keeps the big
     // transient buffers out of the allocator so that repeated batches never re-map device memory
     struct Block { void* p = nullptr; size_t bytes = 0; };
-    Block arena[12];
+    Block arena[16];
     void* scratch(int slot, size_t bytes);
     cudaStream_t copy_stream = nullptr;       // host->device copies of skb_sketch_batch run here, ahead of the kernels
     std::vector<cudaEvent_t> ev_pool;         // "chunk is on the device" events (timing disabled)
@@ -90,7 +90,7 @@ void* Core::scratch(int slot, size_t bytes) {
     }
     return b.p;
 }
-enum { SLOT_SEQ = 0, SLOT_KMER, SLOT_POS, SLOT_META, SLOT_MKEYS, SLOT_STATUS, SLOT_SORT, SLOT_MARK, SLOT_GS, SLOT_GM, SLOT_DESC };
+enum { SLOT_SEQ = 0, SLOT_KMER, SLOT_POS, SLOT_META, SLOT_MKEYS, SLOT_STATUS, SLOT_SORT, SLOT_MARK, SLOT_GS, SLOT_GM, SLOT_DESC, SLOT_MKEYS2 };
 
 // stream-ordered device buffer
 struct DevMem {
@@ -230,94 +230,102 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             std::memcpy(h, descs.data(), sizeof(ContigDesc) * descs.size());
             upload(c, d_descs, h, descs.size());
         }
-        const size_t n_chunks = plan ? plan->size() : 0;
-        // status words | running totals [n_chunks + 2] | tile counters [n_chunks + 1] | overflow flag
-        const size_t status_bytes = sizeof(uint64_t) * (n_tiles + n_chunks + 2) + sizeof(uint32_t) * (n_chunks + 2) + 64;
-        uint64_t* d_status = (uint64_t*)c.scratch(SLOT_STATUS, status_bytes);
+        // ---- launch plan: one launch per copy chunk (or one for everything); every warp of a launch owns a region
+        struct Launch { uint32_t d0, d1, tile_base, n_tiles, n_warps, region_base; cudaEvent_t ready; };
+        std::vector<Launch> launches;
+        uint32_t n_regions = 0;
+        auto add_launch = [&](uint32_t d0, uint32_t d1, cudaEvent_t ready) {
+            if (d1 <= d0) return;
+            Launch L{};
+            L.d0 = d0; L.d1 = d1; L.tile_base = descs[d0].tile_start;
+            L.n_tiles = (d1 < descs.size() ? descs[d1].tile_start : n_tiles) - L.tile_base;
+            uint32_t grid = std::min<uint32_t>((uint32_t)c.n_sm * 3u, (L.n_tiles + SEED_WARPS - 1) / SEED_WARPS);
+            L.n_warps = grid * SEED_WARPS; L.region_base = n_regions; L.ready = ready;
+            n_regions += L.n_warps;
+            launches.push_back(L);
+        };
+        if (plan && plan->size() > 1) {
+            uint32_t d0 = 0;
+            for (size_t ch = 0; ch < plan->size(); ch++) { add_launch(d0, chunk_desc_end[ch], (*plan)[ch].ready); d0 = chunk_desc_end[ch]; }
+        } else {
+            add_launch(0, (uint32_t)descs.size(), nullptr);
+        }
+
+        // ---- region bookkeeping (device): counts, storage offsets, scans, per-genome records, overflow flag
         const size_t g_bytes = sizeof(uint32_t) * (n_genomes + 1);
+        const size_t book_words = (size_t)n_regions * 4 + 2 * ((size_t)n_regions + 1) + 3 * (size_t)n_genomes + 16;
+        uint32_t* book = (uint32_t*)c.scratch(SLOT_STATUS, 4 * book_words);
+        uint32_t* r_scnt = book; uint32_t* r_mcnt = r_scnt + n_regions; uint32_t* r_ssrc = r_mcnt + n_regions;
+        uint32_t* r_msrc = r_ssrc + n_regions; uint32_t* r_sstart = r_msrc + n_regions; uint32_t* r_mstart = r_sstart + n_regions + 1;
+        uint32_t* g_region = r_mstart + n_regions + 1; uint32_t* g_slocal = g_region + n_genomes; uint32_t* g_mlocal = g_slocal + n_genomes;
+        uint32_t* d_overflow = g_mlocal + n_genomes;
         uint32_t* d_gs = (uint32_t*)c.scratch(SLOT_GS, g_bytes);
         uint32_t* d_gm = (uint32_t*)c.scratch(SLOT_GM, g_bytes);
-        uint64_t* d_totals = d_status + n_tiles;
-        uint32_t* d_counter = (uint32_t*)(d_totals + n_chunks + 2);
-        uint32_t* d_overflow = d_counter + n_chunks + 1;
 
-        uint64_t seed_cap = seed ? total_bases / P.c + total_bases / P.c / 4 + 65536 : 1;
-        uint64_t marker_cap = total_bases / P.marker_c + total_bases / P.marker_c / 4 + 65536;
-        seed_cap = std::min<uint64_t>(seed_cap, total_bases);
-        marker_cap = std::min<uint64_t>(marker_cap, total_bases);
-
+        // per-tile capacities of the region storage: generous multiples of the expected hit counts; a region that
+        // still overflows (low-complexity sequence) triggers one retry with the exact layout
+        uint32_t seed_tile_cap = seed ? std::min<uint32_t>(TILE_BASES, TILE_BASES / P.c + TILE_BASES / P.c / 2 + 24) : 0;
+        uint32_t marker_tile_cap = std::min<uint32_t>(TILE_BASES, 2 * (TILE_BASES / P.marker_c) + 16);
         uint32_t *t_kmer = nullptr, *t_pos = nullptr, *t_meta = nullptr;
-        uint64_t* t_mkeys = nullptr;
+        uint64_t* t_mreg = nullptr;
         uint32_t h_over = 0;
         for (int attempt = 0; attempt < 2; attempt++) {
-            t_kmer = (uint32_t*)c.scratch(SLOT_KMER, 4 * seed_cap); t_pos = (uint32_t*)c.scratch(SLOT_POS, 4 * seed_cap);
-            t_meta = (uint32_t*)c.scratch(SLOT_META, 4 * seed_cap); t_mkeys = (uint64_t*)c.scratch(SLOT_MKEYS, 8 * marker_cap);
-            CU(cudaMemsetAsync(d_status, 0, status_bytes, st));
-            CU(cudaMemsetAsync(d_gs, 0xFF, g_bytes, st));
-            CU(cudaMemsetAsync(d_gm, 0xFF, g_bytes, st));
+            const size_t seed_store = attempt == 0 ? (size_t)n_tiles * seed_tile_cap : (size_t)seed_start[n_genomes];
+            const size_t marker_store = attempt == 0 ? (size_t)n_tiles * marker_tile_cap : (size_t)marker_start[n_genomes];
+            if (seed_store >= 0xFFFFFFFFull || marker_store >= 0xFFFFFFFFull) throw Fail{SKB_ERR_ARG, "sketch batch too large for 32-bit seed offsets; split the call"};
+            t_kmer = (uint32_t*)c.scratch(SLOT_KMER, 4 * seed_store + 16); t_pos = (uint32_t*)c.scratch(SLOT_POS, 4 * seed_store + 16);
+            t_meta = (uint32_t*)c.scratch(SLOT_META, 4 * seed_store + 16); t_mreg = (uint64_t*)c.scratch(SLOT_MKEYS, 8 * marker_store + 16);
+            CU(cudaMemsetAsync(g_region, 0xFF, 4 * (size_t)n_genomes, st));
+            CU(cudaMemsetAsync(d_overflow, 0, 4, st));
             SeedScanArgs a{};
-            a.seq = seq_dev; a.contigs = d_descs; a.n_contigs = (uint32_t)descs.size(); a.n_tiles = n_tiles;
+            a.seq = seq_dev;
             a.kmask = P.k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * P.k)) - 1u);
             a.kshift = 42 - 2 * P.k;
             a.thr_seed = seed ? UINT64_MAX / (uint64_t)P.c : 0;     // seed=False keeps markers only (A.4)
             a.thr_marker = UINT64_MAX / (uint64_t)P.marker_c;
-            a.kmer_p = t_kmer; a.pos_p = t_pos; a.meta_p = t_meta;
-            a.marker_keys = t_mkeys;
-            a.seed_cap = (uint32_t)seed_cap; a.marker_cap = (uint32_t)marker_cap;
-            a.tile_status = d_status; a.tile_counter = d_counter;
-            a.genome_seed_start = d_gs; a.genome_marker_start = d_gm;
-            a.n_genomes = n_genomes; a.overflow = d_overflow;
-            a.tile_base = 0; a.base_in = nullptr; a.base_out = nullptr; a.is_last = 1;
+            a.seed_tile_cap = seed_tile_cap; a.marker_tile_cap = marker_tile_cap;
+            a.region_seed_off = attempt == 0 ? nullptr : r_sstart; a.region_marker_off = attempt == 0 ? nullptr : r_mstart;
+            a.kmer_r = t_kmer; a.pos_r = t_pos; a.meta_r = t_meta; a.marker_r = t_mreg;
+            a.region_seed_src = r_ssrc; a.region_marker_src = r_msrc; a.region_seed_cnt = r_scnt; a.region_marker_cnt = r_mcnt;
+            a.genome_region = g_region; a.genome_seed_local = g_slocal; a.genome_marker_local = g_mlocal;
+            a.overflow = d_overflow;
             CU(cudaEventRecord(c.ev[1], st));
-            if (attempt == 0 && n_chunks > 1) {
-                // one launch per chunk, each gated on its copy; the look-back prefix is carried through d_totals
-                uint32_t d0 = 0, launch_i = 0, last_nonempty = 0;
-                for (size_t ch = 0; ch < n_chunks; ch++) if (chunk_desc_end[ch] > (ch ? chunk_desc_end[ch - 1] : 0)) last_nonempty = (uint32_t)ch;
-                for (size_t ch = 0; ch < n_chunks; ch++) {
-                    const uint32_t d1 = chunk_desc_end[ch];
-                    CU(cudaStreamWaitEvent(st, (*plan)[ch].ready, 0));
-                    if (d1 > d0) {
-                        SeedScanArgs b = a;
-                        b.contigs = a.contigs + d0; b.n_contigs = d1 - d0;
-                        b.tile_base = descs[d0].tile_start;
-                        b.n_tiles = (d1 < descs.size() ? descs[d1].tile_start : n_tiles) - b.tile_base;
-                        b.tile_status = a.tile_status + b.tile_base;
-                        b.tile_counter = d_counter + ch;
-                        b.base_in = d_totals + launch_i; b.base_out = d_totals + launch_i + 1;
-                        b.is_last = ch == last_nonempty;
-                        launch_seed_scan(b, c.n_sm, st);
-                        launch_i++;
-                    }
-                    d0 = d1;
-                }
-            } else {
-                if (plan) for (auto& pc : *plan) CU(cudaStreamWaitEvent(st, pc.ready, 0));
-                launch_seed_scan(a, c.n_sm, st);
+            for (const Launch& L : launches) {
+                if (L.ready) CU(cudaStreamWaitEvent(st, L.ready, 0));
+                SeedScanArgs b2 = a;
+                b2.contigs = d_descs + L.d0; b2.n_contigs = L.d1 - L.d0;
+                b2.tile_base = L.tile_base; b2.n_tiles = L.n_tiles; b2.n_warps = L.n_warps; b2.region_base = L.region_base;
+                launch_seed_scan(b2, c.n_sm, st);
             }
             CU(cudaEventRecord(c.ev[2], st));
-            { Trace t2("sketch_core"); t2.mark("seed launches enqueued"); }
-            download(c, seed_start.data(), d_gs, n_genomes + 1);
-            download(c, marker_start.data(), d_gm, n_genomes + 1);
+            if (attempt == 0) {
+                // the retry reads its layout from r_sstart / r_mstart, so the scan must not run again after it
+                launch_region_scan(n_regions, r_scnt, r_mcnt, r_sstart, r_mstart, n_genomes, g_region, g_slocal, g_mlocal, d_gs, d_gm, st);
+                download(c, seed_start.data(), d_gs, n_genomes + 1);
+                download(c, marker_start.data(), d_gm, n_genomes + 1);
+            }
             download(c, &h_over, d_overflow, 1);
             CU(cudaStreamSynchronize(st));
             if (!h_over) break;
-            if (attempt == 1) throw Fail{SKB_ERR_CUDA, "seed buffers overflowed twice"};
-            seed_cap = std::max<uint64_t>(seed_start[n_genomes], 1);   // the totals are exact even when writes were dropped
-            marker_cap = std::max<uint64_t>(marker_start[n_genomes], 1);
+            if (attempt == 1) throw Fail{SKB_ERR_CUDA, "seed regions overflowed twice"};
         }
-        // genomes without a tile never wrote their start: they are empty and begin where the next one begins
+        // genomes without a tile never recorded a start: they are empty and begin where the next one begins
         for (uint32_t g = n_genomes; g-- > 0;) {
             if (seed_start[g] == 0xFFFFFFFFu) { seed_start[g] = seed_start[g + 1]; marker_start[g] = marker_start[g + 1]; }
         }
         const uint32_t ns = seed_start[n_genomes], nm = marker_start[n_genomes];
 
-        // ---- exact-size position-order arrays
+        // ---- exact-size position-order arrays + contiguous marker keys: the gather is also the compaction copy
         store->kmer_p = DevMem(core, 4 * (size_t)ns); store->pos_p = DevMem(core, 4 * (size_t)ns);
         store->meta_p = DevMem(core, 4 * (size_t)ns);
-        if (ns) {
-            CU(cudaMemcpyAsync(store->kmer_p.p, t_kmer, 4 * (size_t)ns, cudaMemcpyDeviceToDevice, st));
-            CU(cudaMemcpyAsync(store->pos_p.p, t_pos, 4 * (size_t)ns, cudaMemcpyDeviceToDevice, st));
-            CU(cudaMemcpyAsync(store->meta_p.p, t_meta, 4 * (size_t)ns, cudaMemcpyDeviceToDevice, st));
+        uint64_t* t_mkeys = (uint64_t*)c.scratch(SLOT_MKEYS2, 8 * (size_t)nm + 16);
+        {
+            RegionGatherArgs ga{};
+            ga.n_regions = n_regions; ga.seed_src = r_ssrc; ga.marker_src = r_msrc; ga.seed_start = r_sstart; ga.marker_start = r_mstart;
+            ga.kmer_r = t_kmer; ga.pos_r = t_pos; ga.meta_r = t_meta; ga.marker_r = t_mreg;
+            ga.kmer_p = store->kmer_p.as<uint32_t>(); ga.pos_p = store->pos_p.as<uint32_t>(); ga.meta_p = store->meta_p.as<uint32_t>();
+            ga.marker_keys = t_mkeys;
+            launch_region_gather(ga, st);
         }
         // ---- k-mer order
         store->kmer_k = DevMem(core, 4 * (size_t)ns); store->pos_k = DevMem(core, 4 * (size_t)ns);

@@ -41,9 +41,10 @@ struct GenomeView {
 
 // ---------------------------------------------------------------- seeding
 constexpr int SEED_THREADS = 256;
-constexpr int WORDS_PER_THREAD = 4;                                   // 16-base words each thread evaluates per tile
-constexpr int TILE_WORDS = SEED_THREADS * WORDS_PER_THREAD;          // 1024
-constexpr int TILE_BASES = TILE_WORDS * 16;                          // 16384 bases per tile
+constexpr int SEED_WARPS = SEED_THREADS / 32;
+constexpr int WORDS_PER_LANE = 4;                                     // 16-base words each lane evaluates per tile
+constexpr int TILE_WORDS = 32 * WORDS_PER_LANE;                       // 128 words per warp tile
+constexpr int TILE_BASES = TILE_WORDS * 16;                           // 2048 bases per warp tile
 
 // One kept contig of the batch.  Tiles are numbered contig after contig; tile t of a contig covers its bases
 // [t * TILE_BASES, min(len, (t + 1) * TILE_BASES)).
@@ -52,33 +53,48 @@ struct ContigDesc {
     uint32_t len;
     uint32_t contig;     // index among the genome's kept contigs
     uint32_t genome;     // genome index inside the batch; bit 31 set on the genome's first kept contig
-    uint32_t tile_start; // id of the contig's first tile
+    uint32_t tile_start; // batch-wide id of the contig's first tile
 };
 
+// Every warp of a seeding launch owns a contiguous range of tiles and a private, ordered output region; regions are
+// numbered launch after launch, warp after warp, i.e. in tile order.
 struct SeedScanArgs {
     const uint8_t* seq;
     const ContigDesc* contigs;   // descriptors of THIS launch (a contiguous slice of the batch's table)
     uint32_t n_contigs;
     uint32_t n_tiles;            // tiles of this launch
     uint32_t tile_base;          // batch-wide id of this launch's first tile
-    const uint64_t* base_in;     // running (seeds | markers << 31) total before this launch, or NULL for 0
-    uint64_t* base_out;          // receives the running total after this launch, or NULL
-    uint32_t is_last;            // last launch of the batch: also writes the batch totals
+    uint32_t region_base;        // id of the region of this launch's warp 0
+    uint32_t n_warps;            // warps of this launch (grid * SEED_WARPS)
     uint32_t kmask, kshift;
     uint64_t thr_seed, thr_marker;
-    // outputs, position order over the whole batch
-    uint32_t* kmer_p;
-    uint32_t* pos_p;
-    uint32_t* meta_p;
-    uint64_t* marker_keys;       // genome << 42 | canonical 21-mer
-    uint32_t seed_cap, marker_cap;
-    uint64_t* tile_status;       // [n_tiles] decoupled look-back words, zero-initialised
-    uint32_t* tile_counter;      // zero-initialised
-    uint32_t* genome_seed_start;   // [n_genomes + 1]
-    uint32_t* genome_marker_start; // [n_genomes + 1]
-    uint32_t n_genomes;
-    uint32_t* overflow;          // set to 1 when a capacity was exceeded
+    // region storage: the region of a warp whose first tile is T starts at T * seed_tile_cap (resp. marker_tile_cap)
+    // and may hold (tiles of the warp) * cap records, unless explicit tables are given (retry after an overflow)
+    uint32_t seed_tile_cap, marker_tile_cap;
+    const uint32_t* region_seed_off; const uint32_t* region_marker_off;   // optional [n_regions + 1] exact layouts
+    uint32_t* kmer_r; uint32_t* pos_r; uint32_t* meta_r;                 // region storage, seeds
+    uint64_t* marker_r;                                                  // region storage, genome << 42 | 21-mer
+    uint32_t* region_seed_src; uint32_t* region_marker_src;              // [n_regions] where each region's storage begins
+    uint32_t* region_seed_cnt; uint32_t* region_marker_cnt;              // [n_regions] exact counts (also on overflow)
+    uint32_t* genome_region;     // [n_genomes] region in which the genome's first tile lies (0xFFFFFFFF = no tile)
+    uint32_t* genome_seed_local; uint32_t* genome_marker_local;          // [n_genomes] cursor of that region at that tile
+    uint32_t* overflow;          // set to 1 when a region was too small
 };
+
+// exclusive scan of the region counts into *_start[n_regions + 1], and per-genome starts [n_genomes + 1]
+void launch_region_scan(uint32_t n_regions, const uint32_t* seed_cnt, const uint32_t* marker_cnt, uint32_t* seed_start,
+                        uint32_t* marker_start, uint32_t n_genomes, const uint32_t* genome_region,
+                        const uint32_t* genome_seed_local, const uint32_t* genome_marker_local, uint32_t* genome_seed_start,
+                        uint32_t* genome_marker_start, cudaStream_t st);
+// copies every region's records to their final, contiguous place (warp per region)
+struct RegionGatherArgs {
+    uint32_t n_regions;
+    const uint32_t* seed_src; const uint32_t* marker_src;       // [n_regions] region storage offsets
+    const uint32_t* seed_start; const uint32_t* marker_start;   // [n_regions + 1] destinations (exclusive scans)
+    const uint32_t* kmer_r; const uint32_t* pos_r; const uint32_t* meta_r; const uint64_t* marker_r;
+    uint32_t* kmer_p; uint32_t* pos_p; uint32_t* meta_p; uint64_t* marker_keys;
+};
+void launch_region_gather(const RegionGatherArgs& a, cudaStream_t st);
 
 void launch_seed_scan(const SeedScanArgs& a, int n_sm, cudaStream_t st);
 
