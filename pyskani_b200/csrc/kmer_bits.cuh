@@ -41,20 +41,20 @@ SKB_HD uint64_t mm_hash64(uint64_t x) {
 }
 
 // 4 ASCII bytes (little-endian in v: first base in the low byte) -> 8 bits, first base in bits 7..6.
+// code = ((b >> 1) & 3) ^ ((b >> 2) & 1) maps A/a C/c G/g T/t to 0..3.  Validity is checked by rebuilding the
+// upper-case letter each code stands for (0x41 + 2*b0 + 6*b1 + 11*b0*b1 per byte: A C G T) and comparing it with
+// the input; only words that contain a foreign byte take the masking path.
 SKB_HD uint32_t pack4(uint32_t v) {
     uint32_t code = ((v >> 1) & 0x03030303u) ^ ((v >> 2) & 0x01010101u);
-    // validity: (byte & 0xDF) in {'A','C','G','T'}; every other byte must encode as 0
-    uint32_t u = v & 0xDFDFDFDFu;
-    // per-byte equality via the zero-byte trick on (u ^ pattern): z = byte==0 ? 0x80 : 0
-    auto eq = [](uint32_t x) -> uint32_t {
-        // exact zero-byte detector: high bit of each byte set iff that byte of x is 0
-        uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-        return ~(t | x | 0x7F7F7F7Fu);
-    };
-    uint32_t ok = eq(u ^ 0x41414141u) | eq(u ^ 0x43434343u) | eq(u ^ 0x47474747u) | eq(u ^ 0x54545454u);
-    // 0x80 per valid byte -> 0x03 per valid byte
-    uint32_t m = (ok >> 7) * 3u;
-    code &= m;
+    const uint32_t b0 = code & 0x01010101u, b1 = (code >> 1) & 0x01010101u;
+    const uint32_t expect = 0x41414141u + b0 * 2u + b1 * 6u + (b0 & b1) * 11u;    // no carries between bytes
+    const uint32_t x = (v & 0xDFDFDFDFu) ^ expect;                                  // zero byte <=> valid base
+    if (x != 0u) {
+        // high bit of each byte set iff that byte of x is 0
+        const uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+        const uint32_t ok = ~(t | x | 0x7F7F7F7Fu);
+        code &= (ok >> 7) * 3u;                                                     // every other byte encodes as 0
+    }
     return (code * 0x40100401u) >> 24;
 }
 

@@ -110,22 +110,29 @@ __device__ __forceinline__ void eval_word(const WordCtx& c, uint32_t kmask, uint
     }
 }
 
-__global__ void __launch_bounds__(SEED_THREADS, 3) seed_scan_kernel(const SeedScanArgs a) {
+#ifndef SKB_SEED_MINBLOCKS
+#define SKB_SEED_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(SEED_THREADS, SKB_SEED_MINBLOCKS) seed_scan_kernel(const SeedScanArgs a) {
     // Warps are independent: private packed-word and mask buffers, private output region, no block barriers.
     __shared__ uint32_t s_pk[SEED_WARPS][TILE_WORDS + 2];
     __shared__ uint32_t s_masks[SEED_WARPS][TILE_WORDS];      // smask | mmask << 16 per word
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t W = blockIdx.x * SEED_WARPS + warp;        // warp id inside the launch
-    if (W >= a.n_warps) return;
     const uint32_t ts_lo = (uint32_t)a.thr_seed, ts_hi = (uint32_t)(a.thr_seed >> 32);
     const uint32_t tm_lo = (uint32_t)a.thr_marker, tm_hi = (uint32_t)(a.thr_marker >> 32);
     uint32_t* pk = s_pk[warp];
     uint32_t* masks = s_masks[warp];
 
-    // contiguous tile range and output region of this warp
-    const uint32_t t0 = (uint32_t)((uint64_t)W * a.n_tiles / a.n_warps);
-    const uint32_t t1 = (uint32_t)((uint64_t)(W + 1) * a.n_tiles / a.n_warps);
-    const uint32_t region = a.region_base + W;
+    // Regions are claimed dynamically (one atomic per CHUNK_TILES tiles) so that no warp idles while another still
+    // has a long static range in front of it; a region's place in the output depends only on its id.
+    while (true) {
+    uint32_t chunk = 0;
+    if (lane == 0) chunk = atomicAdd(a.chunk_counter, 1u);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    if (chunk >= a.n_chunks) break;
+    const uint32_t t0 = chunk * CHUNK_TILES;
+    const uint32_t t1 = min(t0 + CHUNK_TILES, a.n_tiles);
+    const uint32_t region = a.region_base + chunk;
     uint32_t seed_off, seed_cap, marker_off, marker_cap;
     if (a.region_seed_off) {
         seed_off = a.region_seed_off[region]; seed_cap = a.region_seed_off[region + 1] - seed_off;
@@ -276,6 +283,7 @@ __global__ void __launch_bounds__(SEED_THREADS, 3) seed_scan_kernel(const SeedSc
         a.region_seed_cnt[region] = cur_s; a.region_marker_cnt[region] = cur_m;
         a.region_seed_src[region] = seed_off; a.region_marker_src[region] = marker_off;
     }
+    }   // next region
 }
 
 // single CTA: exclusive scans of the region counts, then the per-genome starts

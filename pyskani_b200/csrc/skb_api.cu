@@ -231,7 +231,7 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             upload(c, d_descs, h, descs.size());
         }
         // ---- launch plan: one launch per copy chunk (or one for everything); every warp of a launch owns a region
-        struct Launch { uint32_t d0, d1, tile_base, n_tiles, n_warps, region_base; cudaEvent_t ready; };
+        struct Launch { uint32_t d0, d1, tile_base, n_tiles, n_warps, n_chunks, region_base; cudaEvent_t ready; };
         std::vector<Launch> launches;
         uint32_t n_regions = 0;
         auto add_launch = [&](uint32_t d0, uint32_t d1, cudaEvent_t ready) {
@@ -239,9 +239,10 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             Launch L{};
             L.d0 = d0; L.d1 = d1; L.tile_base = descs[d0].tile_start;
             L.n_tiles = (d1 < descs.size() ? descs[d1].tile_start : n_tiles) - L.tile_base;
-            uint32_t grid = std::min<uint32_t>((uint32_t)c.n_sm * 3u, (L.n_tiles + SEED_WARPS - 1) / SEED_WARPS);
+            L.n_chunks = (L.n_tiles + CHUNK_TILES - 1) / CHUNK_TILES;
+            uint32_t grid = std::min<uint32_t>((uint32_t)c.n_sm * 4u, (L.n_chunks + SEED_WARPS - 1) / SEED_WARPS);
             L.n_warps = grid * SEED_WARPS; L.region_base = n_regions; L.ready = ready;
-            n_regions += L.n_warps;
+            n_regions += L.n_chunks;
             launches.push_back(L);
         };
         if (plan && plan->size() > 1) {
@@ -253,12 +254,13 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
 
         // ---- region bookkeeping (device): counts, storage offsets, scans, per-genome records, overflow flag
         const size_t g_bytes = sizeof(uint32_t) * (n_genomes + 1);
-        const size_t book_words = (size_t)n_regions * 4 + 2 * ((size_t)n_regions + 1) + 3 * (size_t)n_genomes + 16;
+        const size_t book_words = (size_t)n_regions * 4 + 2 * ((size_t)n_regions + 1) + 3 * (size_t)n_genomes + 16 + launches.size();
         uint32_t* book = (uint32_t*)c.scratch(SLOT_STATUS, 4 * book_words);
         uint32_t* r_scnt = book; uint32_t* r_mcnt = r_scnt + n_regions; uint32_t* r_ssrc = r_mcnt + n_regions;
         uint32_t* r_msrc = r_ssrc + n_regions; uint32_t* r_sstart = r_msrc + n_regions; uint32_t* r_mstart = r_sstart + n_regions + 1;
         uint32_t* g_region = r_mstart + n_regions + 1; uint32_t* g_slocal = g_region + n_genomes; uint32_t* g_mlocal = g_slocal + n_genomes;
         uint32_t* d_overflow = g_mlocal + n_genomes;
+        uint32_t* d_claim = d_overflow + 1;     // one claim counter per launch
         uint32_t* d_gs = (uint32_t*)c.scratch(SLOT_GS, g_bytes);
         uint32_t* d_gm = (uint32_t*)c.scratch(SLOT_GM, g_bytes);
 
@@ -276,7 +278,7 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             t_kmer = (uint32_t*)c.scratch(SLOT_KMER, 4 * seed_store + 16); t_pos = (uint32_t*)c.scratch(SLOT_POS, 4 * seed_store + 16);
             t_meta = (uint32_t*)c.scratch(SLOT_META, 4 * seed_store + 16); t_mreg = (uint64_t*)c.scratch(SLOT_MKEYS, 8 * marker_store + 16);
             CU(cudaMemsetAsync(g_region, 0xFF, 4 * (size_t)n_genomes, st));
-            CU(cudaMemsetAsync(d_overflow, 0, 4, st));
+            CU(cudaMemsetAsync(d_overflow, 0, 4 * (1 + launches.size()), st));
             SeedScanArgs a{};
             a.seq = seq_dev;
             a.kmask = P.k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * P.k)) - 1u);
@@ -290,9 +292,11 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             a.genome_region = g_region; a.genome_seed_local = g_slocal; a.genome_marker_local = g_mlocal;
             a.overflow = d_overflow;
             CU(cudaEventRecord(c.ev[1], st));
-            for (const Launch& L : launches) {
+            for (size_t li = 0; li < launches.size(); li++) {
+                const Launch& L = launches[li];
                 if (L.ready) CU(cudaStreamWaitEvent(st, L.ready, 0));
                 SeedScanArgs b2 = a;
+                b2.n_chunks = L.n_chunks; b2.chunk_counter = d_claim + li;
                 b2.contigs = d_descs + L.d0; b2.n_contigs = L.d1 - L.d0;
                 b2.tile_base = L.tile_base; b2.n_tiles = L.n_tiles; b2.n_warps = L.n_warps; b2.region_base = L.region_base;
                 launch_seed_scan(b2, c.n_sm, st);

@@ -45,6 +45,7 @@ constexpr int SEED_WARPS = SEED_THREADS / 32;
 constexpr int WORDS_PER_LANE = 4;                                     // 16-base words each lane evaluates per tile
 constexpr int TILE_WORDS = 32 * WORDS_PER_LANE;                       // 128 words per warp tile
 constexpr int TILE_BASES = TILE_WORDS * 16;                           // 2048 bases per warp tile
+constexpr int CHUNK_TILES = 8;                                        // tiles per dynamically claimed region (16 kbp)
 
 // One kept contig of the batch.  Tiles are numbered contig after contig; tile t of a contig covers its bases
 // [t * TILE_BASES, min(len, (t + 1) * TILE_BASES)).
@@ -56,15 +57,17 @@ struct ContigDesc {
     uint32_t tile_start; // batch-wide id of the contig's first tile
 };
 
-// Every warp of a seeding launch owns a contiguous range of tiles and a private, ordered output region; regions are
-// numbered launch after launch, warp after warp, i.e. in tile order.
+// A seeding launch is cut into regions of CHUNK_TILES consecutive tiles; warps claim regions from an atomic counter and
+// fill the region's private, ordered storage.  Regions are numbered launch after launch in tile order.
 struct SeedScanArgs {
     const uint8_t* seq;
     const ContigDesc* contigs;   // descriptors of THIS launch (a contiguous slice of the batch's table)
     uint32_t n_contigs;
     uint32_t n_tiles;            // tiles of this launch
     uint32_t tile_base;          // batch-wide id of this launch's first tile
-    uint32_t region_base;        // id of the region of this launch's warp 0
+    uint32_t region_base;        // id of this launch's first region
+    uint32_t n_chunks;           // regions of this launch = ceil(n_tiles / CHUNK_TILES)
+    uint32_t* chunk_counter;     // zero-initialised claim counter of this launch
     uint32_t n_warps;            // warps of this launch (grid * SEED_WARPS)
     uint32_t kmask, kshift;
     uint64_t thr_seed, thr_marker;
