@@ -169,12 +169,25 @@ __global__ void __launch_bounds__(256) window_walk_smem_kernel(const ChainBatch 
     uint32_t* s_bits = sm + n;                        // [(n + 31) / 32]
     const uint32_t* cnt = b.m_cnt + pd.seed_off;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (uint32_t i0 = warp * 32; i0 < n; i0 += nwarps * 32) {
-        const uint32_t i = i0 + lane;
-        const bool m = i < n && cnt[i] != 0;
-        if (i < n) s_pos[i] = __ldg(Q.pos_p + i);
-        const uint32_t bal = __ballot_sync(FULL, m);
-        if (lane == 0) s_bits[i0 >> 5] = bal;
+    // staging: 8 independent loads in flight per lane (the loop is latency-bound otherwise)
+    constexpr int U = 4;
+    for (uint32_t i0 = warp * 32; i0 < n; i0 += nwarps * 32 * U) {
+        uint32_t p[U], cv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t i = i0 + u * nwarps * 32 + lane;
+            p[u] = i < n ? __ldg(Q.pos_p + i) : 0u;
+            cv[u] = i < n ? __ldg(cnt + i) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t ib = i0 + u * nwarps * 32;       // warp-uniform
+            if (ib >= n) break;
+            const uint32_t i = ib + lane;
+            if (i < n) s_pos[i] = p[u];
+            const uint32_t bal = __ballot_sync(FULL, i < n && cv[u] != 0);
+            if (lane == 0) s_bits[ib >> 5] = bal;
+        }
     }
     __syncthreads();
     for (uint32_t c = warp; c < Q.n_contigs; c += nwarps) {

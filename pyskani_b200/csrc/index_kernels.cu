@@ -199,6 +199,20 @@ void select_passing(uint32_t n, const uint8_t* flags, uint32_t* out_idx, uint32_
     g_kernel_launches += 2;
 }
 
+size_t region_scan_scratch_bytes(uint32_t n) {
+    size_t s = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, s, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int)n + 1);
+    return align_up(s) + 256;
+}
+
+void scan_region_counts(uint32_t n_regions, const uint64_t* region_cnt, uint64_t* region_start, void* scratch, size_t scratch_bytes,
+                        cudaStream_t st) {
+    // region_cnt[n_regions] is zero, so region_start[n_regions] is the batch total; 32-bit halves cannot carry into each
+    // other because both totals are < 2^32
+    cub::DeviceScan::ExclusiveSum(scratch, scratch_bytes, region_cnt, region_start, (int)n_regions + 1, st);
+    g_kernel_launches += 2;
+}
+
 size_t scan_scratch_bytes(uint32_t n) {
     size_t s = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, s, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);

@@ -134,9 +134,10 @@ __global__ void __launch_bounds__(SEED_THREADS, SKB_SEED_MINBLOCKS) seed_scan_ke
     const uint32_t t1 = min(t0 + CHUNK_TILES, a.n_tiles);
     const uint32_t region = a.region_base + chunk;
     uint32_t seed_off, seed_cap, marker_off, marker_cap;
-    if (a.region_seed_off) {
-        seed_off = a.region_seed_off[region]; seed_cap = a.region_seed_off[region + 1] - seed_off;
-        marker_off = a.region_marker_off[region]; marker_cap = a.region_marker_off[region + 1] - marker_off;
+    if (a.region_off) {       // exact layout (retry): exclusive scan of the packed counts
+        const uint64_t o0 = a.region_off[region], o1 = a.region_off[region + 1];
+        seed_off = (uint32_t)o0; seed_cap = (uint32_t)o1 - seed_off;
+        marker_off = (uint32_t)(o0 >> 32); marker_cap = (uint32_t)(o1 >> 32) - marker_off;
     } else {
         seed_off = (a.tile_base + t0) * a.seed_tile_cap; seed_cap = (t1 - t0) * a.seed_tile_cap;
         marker_off = (a.tile_base + t0) * a.marker_tile_cap; marker_cap = (t1 - t0) * a.marker_tile_cap;
@@ -280,59 +281,44 @@ __global__ void __launch_bounds__(SEED_THREADS, SKB_SEED_MINBLOCKS) seed_scan_ke
         }
     }
     if (lane == 0) {
-        a.region_seed_cnt[region] = cur_s; a.region_marker_cnt[region] = cur_m;
+        a.region_cnt[region] = (uint64_t)cur_s | ((uint64_t)cur_m << 32);
         a.region_seed_src[region] = seed_off; a.region_marker_src[region] = marker_off;
     }
     }   // next region
 }
 
-// single CTA: exclusive scans of the region counts, then the per-genome starts
-__global__ void __launch_bounds__(1024) region_scan_kernel(uint32_t n_regions, const uint32_t* __restrict__ seed_cnt,
-                                                           const uint32_t* __restrict__ marker_cnt, uint32_t* __restrict__ seed_start,
-                                                           uint32_t* __restrict__ marker_start, uint32_t n_genomes,
-                                                           const uint32_t* __restrict__ genome_region,
-                                                           const uint32_t* __restrict__ genome_seed_local,
-                                                           const uint32_t* __restrict__ genome_marker_local,
-                                                           uint32_t* __restrict__ genome_seed_start,
-                                                           uint32_t* __restrict__ genome_marker_start) {
-    __shared__ uint32_t s_s[1024], s_m[1024];
-    const uint32_t t = threadIdx.x;
-    const uint32_t chunk = (n_regions + 1023) / 1024;
-    const uint32_t b = min(t * chunk, n_regions), e = min(b + chunk, n_regions);
-    uint32_t ss = 0, sm = 0;
-    for (uint32_t i = b; i < e; i++) { ss += seed_cnt[i]; sm += marker_cnt[i]; }
-    s_s[t] = ss; s_m[t] = sm;
-    __syncthreads();
-    for (uint32_t o = 1; o < 1024; o <<= 1) {       // Hillis-Steele inclusive scan over the 1024 chunk sums
-        const uint32_t vs = t >= o ? s_s[t - o] : 0u, vm = t >= o ? s_m[t - o] : 0u;
-        __syncthreads();
-        s_s[t] += vs; s_m[t] += vm;
-        __syncthreads();
+// per-genome starts from the scanned region offsets (region_start[r] = seeds | markers << 32 before region r)
+__global__ void genome_starts_kernel(uint32_t n_regions, const uint64_t* __restrict__ region_start, uint32_t n_genomes,
+                                     const uint32_t* __restrict__ genome_region, const uint32_t* __restrict__ genome_seed_local,
+                                     const uint32_t* __restrict__ genome_marker_local, uint32_t* __restrict__ genome_seed_start,
+                                     uint32_t* __restrict__ genome_marker_start) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n_genomes) return;
+    if (g == n_genomes) {
+        const uint64_t tot = region_start[n_regions];
+        genome_seed_start[g] = (uint32_t)tot; genome_marker_start[g] = (uint32_t)(tot >> 32);
+        return;
     }
-    uint32_t ps = s_s[t] - ss, pm = s_m[t] - sm;
-    for (uint32_t i = b; i < e; i++) { seed_start[i] = ps; marker_start[i] = pm; ps += seed_cnt[i]; pm += marker_cnt[i]; }
-    if (t == 1023) { seed_start[n_regions] = s_s[1023]; marker_start[n_regions] = s_m[1023]; }
-    __syncthreads();
-    for (uint32_t g = t; g <= n_genomes; g += 1024) {
-        if (g == n_genomes) { genome_seed_start[g] = s_s[1023]; genome_marker_start[g] = s_m[1023]; continue; }
-        const uint32_t r = genome_region[g];
-        if (r == 0xFFFFFFFFu) { genome_seed_start[g] = 0xFFFFFFFFu; genome_marker_start[g] = 0xFFFFFFFFu; }
-        else { genome_seed_start[g] = seed_start[r] + genome_seed_local[g]; genome_marker_start[g] = marker_start[r] + genome_marker_local[g]; }
-    }
+    const uint32_t r = genome_region[g];
+    if (r == 0xFFFFFFFFu) { genome_seed_start[g] = 0xFFFFFFFFu; genome_marker_start[g] = 0xFFFFFFFFu; return; }
+    const uint64_t st = region_start[r];
+    genome_seed_start[g] = (uint32_t)st + genome_seed_local[g];
+    genome_marker_start[g] = (uint32_t)(st >> 32) + genome_marker_local[g];
 }
 
 __global__ void __launch_bounds__(256) region_gather_kernel(const RegionGatherArgs a) {
     const int lane = threadIdx.x & 31;
     const uint32_t r = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= a.n_regions) return;
+    const uint64_t st0 = a.region_start[r], st1 = a.region_start[r + 1];
     {
-        const uint32_t dst = a.seed_start[r], n = a.seed_start[r + 1] - dst, src = a.seed_src[r];
+        const uint32_t dst = (uint32_t)st0, n = (uint32_t)st1 - dst, src = a.seed_src[r];
         for (uint32_t i = lane; i < n; i += 32) {
             a.kmer_p[dst + i] = a.kmer_r[src + i]; a.pos_p[dst + i] = a.pos_r[src + i]; a.meta_p[dst + i] = a.meta_r[src + i];
         }
     }
     {
-        const uint32_t dst = a.marker_start[r], n = a.marker_start[r + 1] - dst, src = a.marker_src[r];
+        const uint32_t dst = (uint32_t)(st0 >> 32), n = (uint32_t)(st1 >> 32) - dst, src = a.marker_src[r];
         for (uint32_t i = lane; i < n; i += 32) a.marker_keys[dst + i] = a.marker_r[src + i];
     }
 }
@@ -345,12 +331,12 @@ void launch_seed_scan(const SeedScanArgs& a, int n_sm, cudaStream_t st) {
     g_kernel_launches++;
 }
 
-void launch_region_scan(uint32_t n_regions, const uint32_t* seed_cnt, const uint32_t* marker_cnt, uint32_t* seed_start,
-                        uint32_t* marker_start, uint32_t n_genomes, const uint32_t* genome_region,
-                        const uint32_t* genome_seed_local, const uint32_t* genome_marker_local, uint32_t* genome_seed_start,
-                        uint32_t* genome_marker_start, cudaStream_t st) {
-    region_scan_kernel<<<1, 1024, 0, st>>>(n_regions, seed_cnt, marker_cnt, seed_start, marker_start, n_genomes, genome_region,
-                                           genome_seed_local, genome_marker_local, genome_seed_start, genome_marker_start);
+void launch_genome_starts(uint32_t n_regions, const uint64_t* region_start, uint32_t n_genomes, const uint32_t* genome_region,
+                          const uint32_t* genome_seed_local, const uint32_t* genome_marker_local, uint32_t* genome_seed_start,
+                          uint32_t* genome_marker_start, cudaStream_t st) {
+    genome_starts_kernel<<<(n_genomes + 1 + 255) / 256, 256, 0, st>>>(n_regions, region_start, n_genomes, genome_region,
+                                                                       genome_seed_local, genome_marker_local, genome_seed_start,
+                                                                       genome_marker_start);
     g_kernel_launches++;
 }
 

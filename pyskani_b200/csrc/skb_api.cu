@@ -90,7 +90,7 @@ void* Core::scratch(int slot, size_t bytes) {
     }
     return b.p;
 }
-enum { SLOT_SEQ = 0, SLOT_KMER, SLOT_POS, SLOT_META, SLOT_MKEYS, SLOT_STATUS, SLOT_SORT, SLOT_MARK, SLOT_GS, SLOT_GM, SLOT_DESC, SLOT_MKEYS2 };
+enum { SLOT_SEQ = 0, SLOT_KMER, SLOT_POS, SLOT_META, SLOT_MKEYS, SLOT_STATUS, SLOT_SORT, SLOT_MARK, SLOT_GS, SLOT_GM, SLOT_DESC, SLOT_MKEYS2, SLOT_RSCAN };
 
 // stream-ordered device buffer
 struct DevMem {
@@ -254,13 +254,16 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
 
         // ---- region bookkeeping (device): counts, storage offsets, scans, per-genome records, overflow flag
         const size_t g_bytes = sizeof(uint32_t) * (n_genomes + 1);
-        const size_t book_words = (size_t)n_regions * 4 + 2 * ((size_t)n_regions + 1) + 3 * (size_t)n_genomes + 16 + launches.size();
-        uint32_t* book = (uint32_t*)c.scratch(SLOT_STATUS, 4 * book_words);
-        uint32_t* r_scnt = book; uint32_t* r_mcnt = r_scnt + n_regions; uint32_t* r_ssrc = r_mcnt + n_regions;
-        uint32_t* r_msrc = r_ssrc + n_regions; uint32_t* r_sstart = r_msrc + n_regions; uint32_t* r_mstart = r_sstart + n_regions + 1;
-        uint32_t* g_region = r_mstart + n_regions + 1; uint32_t* g_slocal = g_region + n_genomes; uint32_t* g_mlocal = g_slocal + n_genomes;
+        // layout: u64 region_cnt[n+1] | u64 region_start[n+1] | u32 src offsets 2n | u32 genome records 3g | overflow | claims
+        const size_t book_bytes = 16 * ((size_t)n_regions + 1) + 4 * ((size_t)n_regions * 2 + 3 * (size_t)n_genomes + 16 + launches.size());
+        char* book = (char*)c.scratch(SLOT_STATUS, book_bytes);
+        uint64_t* r_cnt = (uint64_t*)book; uint64_t* r_start = r_cnt + n_regions + 1;
+        uint32_t* r_ssrc = (uint32_t*)(r_start + n_regions + 1); uint32_t* r_msrc = r_ssrc + n_regions;
+        uint32_t* g_region = r_msrc + n_regions; uint32_t* g_slocal = g_region + n_genomes; uint32_t* g_mlocal = g_slocal + n_genomes;
         uint32_t* d_overflow = g_mlocal + n_genomes;
         uint32_t* d_claim = d_overflow + 1;     // one claim counter per launch
+        const size_t rscan_bytes = region_scan_scratch_bytes(n_regions);
+        void* rscan_scratch = c.scratch(SLOT_RSCAN, rscan_bytes);
         uint32_t* d_gs = (uint32_t*)c.scratch(SLOT_GS, g_bytes);
         uint32_t* d_gm = (uint32_t*)c.scratch(SLOT_GM, g_bytes);
 
@@ -279,6 +282,7 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             t_meta = (uint32_t*)c.scratch(SLOT_META, 4 * seed_store + 16); t_mreg = (uint64_t*)c.scratch(SLOT_MKEYS, 8 * marker_store + 16);
             CU(cudaMemsetAsync(g_region, 0xFF, 4 * (size_t)n_genomes, st));
             CU(cudaMemsetAsync(d_overflow, 0, 4 * (1 + launches.size()), st));
+            CU(cudaMemsetAsync(r_cnt + n_regions, 0, 8, st));
             SeedScanArgs a{};
             a.seq = seq_dev;
             a.kmask = P.k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * P.k)) - 1u);
@@ -286,9 +290,9 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             a.thr_seed = seed ? UINT64_MAX / (uint64_t)P.c : 0;     // seed=False keeps markers only (A.4)
             a.thr_marker = UINT64_MAX / (uint64_t)P.marker_c;
             a.seed_tile_cap = seed_tile_cap; a.marker_tile_cap = marker_tile_cap;
-            a.region_seed_off = attempt == 0 ? nullptr : r_sstart; a.region_marker_off = attempt == 0 ? nullptr : r_mstart;
+            a.region_off = attempt == 0 ? nullptr : r_start;
             a.kmer_r = t_kmer; a.pos_r = t_pos; a.meta_r = t_meta; a.marker_r = t_mreg;
-            a.region_seed_src = r_ssrc; a.region_marker_src = r_msrc; a.region_seed_cnt = r_scnt; a.region_marker_cnt = r_mcnt;
+            a.region_seed_src = r_ssrc; a.region_marker_src = r_msrc; a.region_cnt = r_cnt;
             a.genome_region = g_region; a.genome_seed_local = g_slocal; a.genome_marker_local = g_mlocal;
             a.overflow = d_overflow;
             CU(cudaEventRecord(c.ev[1], st));
@@ -304,7 +308,8 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             CU(cudaEventRecord(c.ev[2], st));
             if (attempt == 0) {
                 // the retry reads its layout from r_sstart / r_mstart, so the scan must not run again after it
-                launch_region_scan(n_regions, r_scnt, r_mcnt, r_sstart, r_mstart, n_genomes, g_region, g_slocal, g_mlocal, d_gs, d_gm, st);
+                scan_region_counts(n_regions, r_cnt, r_start, rscan_scratch, rscan_bytes, st);
+                launch_genome_starts(n_regions, r_start, n_genomes, g_region, g_slocal, g_mlocal, d_gs, d_gm, st);
                 download(c, seed_start.data(), d_gs, n_genomes + 1);
                 download(c, marker_start.data(), d_gm, n_genomes + 1);
             }
@@ -325,7 +330,7 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
         uint64_t* t_mkeys = (uint64_t*)c.scratch(SLOT_MKEYS2, 8 * (size_t)nm + 16);
         {
             RegionGatherArgs ga{};
-            ga.n_regions = n_regions; ga.seed_src = r_ssrc; ga.marker_src = r_msrc; ga.seed_start = r_sstart; ga.marker_start = r_mstart;
+            ga.n_regions = n_regions; ga.seed_src = r_ssrc; ga.marker_src = r_msrc; ga.region_start = r_start;
             ga.kmer_r = t_kmer; ga.pos_r = t_pos; ga.meta_r = t_meta; ga.marker_r = t_mreg;
             ga.kmer_p = store->kmer_p.as<uint32_t>(); ga.pos_p = store->pos_p.as<uint32_t>(); ga.meta_p = store->meta_p.as<uint32_t>();
             ga.marker_keys = t_mkeys;

@@ -74,26 +74,28 @@ struct SeedScanArgs {
     // region storage: the region of a warp whose first tile is T starts at T * seed_tile_cap (resp. marker_tile_cap)
     // and may hold (tiles of the warp) * cap records, unless explicit tables are given (retry after an overflow)
     uint32_t seed_tile_cap, marker_tile_cap;
-    const uint32_t* region_seed_off; const uint32_t* region_marker_off;   // optional [n_regions + 1] exact layouts
+    const uint64_t* region_off;                                          // optional [n_regions + 1] exact layout (seeds | markers << 32)
     uint32_t* kmer_r; uint32_t* pos_r; uint32_t* meta_r;                 // region storage, seeds
     uint64_t* marker_r;                                                  // region storage, genome << 42 | 21-mer
     uint32_t* region_seed_src; uint32_t* region_marker_src;              // [n_regions] where each region's storage begins
-    uint32_t* region_seed_cnt; uint32_t* region_marker_cnt;              // [n_regions] exact counts (also on overflow)
+    uint64_t* region_cnt;                                                // [n_regions + 1] exact counts, seeds | markers << 32 (also on overflow)
     uint32_t* genome_region;     // [n_genomes] region in which the genome's first tile lies (0xFFFFFFFF = no tile)
     uint32_t* genome_seed_local; uint32_t* genome_marker_local;          // [n_genomes] cursor of that region at that tile
     uint32_t* overflow;          // set to 1 when a region was too small
 };
 
-// exclusive scan of the region counts into *_start[n_regions + 1], and per-genome starts [n_genomes + 1]
-void launch_region_scan(uint32_t n_regions, const uint32_t* seed_cnt, const uint32_t* marker_cnt, uint32_t* seed_start,
-                        uint32_t* marker_start, uint32_t n_genomes, const uint32_t* genome_region,
-                        const uint32_t* genome_seed_local, const uint32_t* genome_marker_local, uint32_t* genome_seed_start,
-                        uint32_t* genome_marker_start, cudaStream_t st);
+// region_start[n_regions + 1] = exclusive scan of region_cnt (u64 lanes: seeds | markers << 32)
+void scan_region_counts(uint32_t n_regions, const uint64_t* region_cnt, uint64_t* region_start, void* scratch, size_t scratch_bytes,
+                        cudaStream_t st);
+size_t region_scan_scratch_bytes(uint32_t n_regions);
+void launch_genome_starts(uint32_t n_regions, const uint64_t* region_start, uint32_t n_genomes, const uint32_t* genome_region,
+                          const uint32_t* genome_seed_local, const uint32_t* genome_marker_local, uint32_t* genome_seed_start,
+                          uint32_t* genome_marker_start, cudaStream_t st);
 // copies every region's records to their final, contiguous place (warp per region)
 struct RegionGatherArgs {
     uint32_t n_regions;
     const uint32_t* seed_src; const uint32_t* marker_src;       // [n_regions] region storage offsets
-    const uint32_t* seed_start; const uint32_t* marker_start;   // [n_regions + 1] destinations (exclusive scans)
+    const uint64_t* region_start;                               // [n_regions + 1] destinations (seeds | markers << 32)
     const uint32_t* kmer_r; const uint32_t* pos_r; const uint32_t* meta_r; const uint64_t* marker_r;
     uint32_t* kmer_p; uint32_t* pos_p; uint32_t* meta_p; uint64_t* marker_keys;
 };
