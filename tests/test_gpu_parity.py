@@ -265,3 +265,29 @@ def test_empty_and_degenerate_queries(ctx):
     assert hits == [] and n_in == 0
     hits, n_in = db.query([full])
     assert len(hits) == 1 and abs(hits[0][2] - 1.0) < 1e-6 and hits[0][3] > 0.99
+
+
+def test_all_vs_all_driver_single_rank(ctx):
+    """pyskani_b200.parallel.all_vs_all with the CUDA backend (world size 1) against the oracle's query loop,
+    including the export -> import path every other rank's sketches take in a multi-GPU run."""
+    from pyskani_b200 import parallel
+    genomes = []
+    for f in range(3):
+        base = synth.random_genome(200_000, 900 + f)
+        genomes += [[base.tobytes()], [synth.mutate(base, 0.04, 950 + f).tobytes()]]
+    be = parallel.CudaBackend(0)
+    table = parallel.all_vs_all(genomes, be)
+    os_ = [oracle.Sketch(g) for g in genomes]
+    want = []
+    for qi, oq in enumerate(os_):
+        idx, res, _ = oracle.query(oq, os_)
+        want += [(qi, int(i), r.ani, r.af_query, r.af_ref) for i, r in zip(idx, res)]
+    want = np.asarray(want, np.float64)
+    assert table.shape == want.shape and np.array_equal(table[:, :2], want[:, :2])
+    assert np.abs(table[:, 2] - want[:, 2]).max() <= ANI_TOL and np.abs(table[:, 3:] - want[:, 3:]).max() <= AF_TOL
+    # imported sketches behave exactly like freshly sketched ones
+    local = be.sketch(genomes)
+    imported = [be.import_(be.export(s)) for s in local]
+    a = be.query(imported, local)
+    b = be.query(local, local)
+    assert a == b
