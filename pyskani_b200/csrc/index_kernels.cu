@@ -105,6 +105,12 @@ __global__ void contig_starts_kernel(const GenomeView* __restrict__ views, uint3
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+// small table "upload" done by the SMs: the source is pinned host memory mapped into the device address space, so the
+// transfer does not queue behind bulk copies on the host->device copy engine
+__global__ void pull_copy_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t n_words) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 }  // namespace
 
 size_t kmer_order_scratch_bytes(uint32_t n) {
@@ -197,6 +203,15 @@ void select_passing(uint32_t n, const uint8_t* flags, uint32_t* out_idx, uint32_
     cub::DeviceSelect::Flagged(tmp, bytes, it, flags, out_idx, out_count, (int)n, st);
     cudaFreeAsync(tmp, st);
     g_kernel_launches += 2;
+}
+
+void launch_pull_copy(void* dst, const void* src_pinned, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return;
+    const size_t n = (bytes + 3) / 4;
+    unsigned grid = (unsigned)((n + 255) / 256);
+    if (grid > 1024) grid = 1024;
+    pull_copy_kernel<<<grid, 256, 0, st>>>((uint32_t*)dst, (const uint32_t*)src_pinned, n);
+    g_kernel_launches++;
 }
 
 size_t region_scan_scratch_bytes(uint32_t n) {

@@ -123,6 +123,9 @@ void build_marker_sets(uint32_t n_genomes, uint32_t n_markers_total, uint64_t* m
                        uint32_t* genome_marker_out, void* scratch, size_t scratch_bytes, cudaStream_t st);
 size_t marker_scratch_bytes(uint32_t n_markers_total);
 
+// copies `bytes` (rounded up to 4) from pinned, device-mapped host memory to device memory with a kernel
+void launch_pull_copy(void* dst, const void* src_pinned, size_t bytes, cudaStream_t st);
+
 // bucket offsets + per-contig seed starts for a set of genomes described by views
 void launch_build_buckets(const GenomeView* views_dev, uint32_t n_genomes, uint32_t max_buckets, cudaStream_t st);
 void launch_contig_starts(const GenomeView* views_dev, uint32_t n_genomes, uint32_t max_contigs, cudaStream_t st);
