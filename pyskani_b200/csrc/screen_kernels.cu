@@ -14,43 +14,106 @@ namespace {
 
 constexpr int SCREEN_WARPS = 8;
 
-constexpr uint32_t SCREEN_SMEM_MARKERS = 24576;   // 192 KB of u64: query marker lists up to ~24 Mbp genomes
+constexpr uint32_t SCREEN_SMEM_BYTES = 200 * 1024;   // shared memory the fast path may use per CTA
+constexpr int SCREEN_QT = 4;                         // queries staged together per CTA (each streamed reference serves all)
 
-// Fast path: the CTA stages the query's sorted marker list in shared memory once, then walks references; all 256
-// threads stride one reference's list (coalesced 8-byte loads) and binary-search the staged list on chip.
+// bytes of shared memory one staged query of n markers needs: sorted list + membership bitmap (>= 16 bits / marker)
+__host__ __device__ inline uint32_t screen_bitmap_bits(uint32_t n) {
+    uint32_t b = 1024;
+    while (b < 16u * n && b < (1u << 22)) b <<= 1;
+    return b;
+}
+__host__ __device__ inline uint32_t screen_query_bytes(uint32_t n) { return 8u * n + screen_bitmap_bits(n) / 8u; }
+
+__device__ __forceinline__ uint32_t marker_slot(uint64_t v, uint32_t mask) {
+    return (uint32_t)((v * 0x9E3779B97F4A7C15ull) >> 40) & mask;
+}
+
+// Fast path.  A CTA stages up to SCREEN_QT queries: each query's sorted marker list plus a bitmap over a hash of its
+// markers.  References are then streamed once for all staged queries: 256 threads stride a reference's list with
+// coalesced 8-byte loads; a marker is first tested against the bitmap (one shared-memory word; ~93 % of the probes of
+// an unrelated pair end here) and only on a hit binary-searched in the staged list.  The count is exact.
 __global__ void __launch_bounds__(SCREEN_WARPS * 32)
 marker_screen_smem_kernel(const GenomeView* __restrict__ queries, uint32_t n_queries,
                           const GenomeView* __restrict__ refs, uint32_t n_refs, uint32_t* __restrict__ count) {
-    extern __shared__ uint64_t s_q[];
-    __shared__ uint32_t s_part[SCREEN_WARPS];
-    const uint32_t q = blockIdx.y;
-    const uint64_t* qm = queries[q].markers;
-    const uint32_t nq = queries[q].n_markers;
-    if (nq > SCREEN_SMEM_MARKERS) return;           // handled by marker_screen_kernel
-    for (uint32_t i = threadIdx.x; i < nq; i += blockDim.x) s_q[i] = __ldg(qm + i);
+    extern __shared__ uint64_t s_mem[];
+    __shared__ uint32_t s_part[SCREEN_WARPS][SCREEN_QT];
+    __shared__ uint32_t s_off[SCREEN_QT + 1];      // byte offsets of each staged query inside s_mem
+    const uint32_t q0 = blockIdx.y * SCREEN_QT;
+    const uint32_t nqt = min((uint32_t)SCREEN_QT, n_queries - q0);
+    uint32_t nq[SCREEN_QT], bmask[SCREEN_QT];
+    const uint64_t* list[SCREEN_QT];
+    uint32_t* bits[SCREEN_QT];
+    bool fits = true;
+    {
+        uint32_t off = 0;
+#pragma unroll
+        for (int t = 0; t < SCREEN_QT; t++) {
+            nq[t] = (uint32_t)t < nqt ? queries[q0 + t].n_markers : 0u;
+            const uint32_t bb = screen_bitmap_bits(nq[t]);
+            bmask[t] = bb - 1u;
+            list[t] = (const uint64_t*)((const char*)s_mem + off);
+            bits[t] = (uint32_t*)((char*)s_mem + off + 8u * nq[t]);
+            off += 8u * nq[t] + bb / 8u;
+        }
+        fits = off <= SCREEN_SMEM_BYTES;
+    }
+    if (!fits) return;                              // this group is handled by marker_screen_kernel
+    (void)s_off;
+#pragma unroll
+    for (int t = 0; t < SCREEN_QT; t++) {
+        uint32_t* bt = bits[t];
+        for (uint32_t i = threadIdx.x; i <= bmask[t] / 32u; i += blockDim.x) bt[i] = 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < SCREEN_QT; t++) {
+        if ((uint32_t)t >= nqt) break;
+        const uint64_t* qm = queries[q0 + t].markers;
+        uint64_t* lt = const_cast<uint64_t*>(list[t]);
+        for (uint32_t i = threadIdx.x; i < nq[t]; i += blockDim.x) {
+            const uint64_t v = __ldg(qm + i);
+            lt[i] = v;
+            const uint32_t sl = marker_slot(v, bmask[t]);
+            atomicOr(&bits[t][sl >> 5], 1u << (sl & 31u));
+        }
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t r = blockIdx.x; r < n_refs; r += gridDim.x) {
         const uint64_t* b = refs[r].markers;
         const uint32_t nb = refs[r].n_markers;
-        uint32_t c = 0;
+        uint32_t c[SCREEN_QT];
+#pragma unroll
+        for (int t = 0; t < SCREEN_QT; t++) c[t] = 0;
         for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
             const uint64_t v = __ldg(b + i);
-            uint32_t lo = 0, hi = nq;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (s_q[mid] < v) lo = mid + 1; else hi = mid;
-            }
-            c += (lo < nq && s_q[lo] == v) ? 1u : 0u;
-        }
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (lane == 0) s_part[warp] = c;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t t = 0;
+            const uint32_t h = (uint32_t)((v * 0x9E3779B97F4A7C15ull) >> 40);
 #pragma unroll
-            for (int w = 0; w < SCREEN_WARPS; w++) t += s_part[w];
-            count[(size_t)q * n_refs + r] = t;
+            for (int t = 0; t < SCREEN_QT; t++) {
+                const uint32_t sl = h & bmask[t];
+                if ((bits[t][sl >> 5] >> (sl & 31u)) & 1u) {
+                    uint32_t lo = 0, hi = nq[t];
+                    const uint64_t* lt = list[t];
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (lt[mid] < v) lo = mid + 1; else hi = mid;
+                    }
+                    c[t] += (lo < nq[t] && lt[lo] == v) ? 1u : 0u;
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < SCREEN_QT; t++) {
+            const uint32_t w = __reduce_add_sync(0xffffffffu, c[t]);
+            if (lane == 0) s_part[warp][t] = w;
+        }
+        __syncthreads();
+        if (threadIdx.x < nqt) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < SCREEN_WARPS; w++) tot += s_part[w][threadIdx.x];
+            count[(size_t)(q0 + threadIdx.x) * n_refs + r] = tot;
         }
         __syncthreads();
     }
@@ -64,7 +127,12 @@ marker_screen_kernel(const GenomeView* __restrict__ queries, uint32_t n_queries,
     const uint32_t q = blockIdx.y;
     const uint32_t r = blockIdx.x * SCREEN_WARPS + warp;
     if (r >= n_refs) return;
-    if (queries[q].n_markers <= SCREEN_SMEM_MARKERS) return;   // done by the shared-memory kernel
+    {   // done by the shared-memory kernel when the query's group of SCREEN_QT fits
+        const uint32_t g0 = q / SCREEN_QT * SCREEN_QT;
+        uint32_t off = 0;
+        for (uint32_t t = g0; t < g0 + SCREEN_QT; t++) off += screen_query_bytes(t < n_queries ? queries[t].n_markers : 0u);
+        if (off <= SCREEN_SMEM_BYTES) return;
+    }
     const uint64_t* a = queries[q].markers; uint32_t na = queries[q].n_markers;
     const uint64_t* b = refs[r].markers;    uint32_t nb = refs[r].n_markers;
     if (na > nb) { const uint64_t* t = a; a = b; b = t; uint32_t tn = na; na = nb; nb = tn; }
@@ -98,26 +166,36 @@ __global__ void screen_decide_kernel(const GenomeView* __restrict__ queries, uin
 }  // namespace
 
 void launch_marker_screen(const GenomeView* queries, uint32_t n_queries, const GenomeView* refs, uint32_t n_refs,
-                          uint32_t* count, uint32_t max_query_markers, int n_sm, cudaStream_t st) {
+                          uint32_t* count, const uint32_t* query_markers_host, int n_sm, cudaStream_t st) {
     if (n_queries == 0 || n_refs == 0) return;
-    const uint32_t staged = max_query_markers < SCREEN_SMEM_MARKERS ? max_query_markers : SCREEN_SMEM_MARKERS;
-    const size_t smem = (size_t)staged * 8 + 16;
-    cudaFuncSetAttribute(marker_screen_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)((size_t)SCREEN_SMEM_MARKERS * 8 + 16));
+    // shared memory of the largest group of SCREEN_QT consecutive queries that fits; groups that do not fit go to the fallback
+    size_t smem = 0; bool any_big = false;
+    for (uint32_t g0 = 0; g0 < n_queries; g0 += SCREEN_QT) {
+        size_t off = 0;
+        for (uint32_t t = g0; t < g0 + SCREEN_QT; t++) off += screen_query_bytes(t < n_queries ? query_markers_host[t] : 0u);   // empty slots still own a minimal bitmap
+        if (off <= SCREEN_SMEM_BYTES) smem = off > smem ? off : smem; else any_big = true;
+    }
+    smem += 64;
+    cudaFuncSetAttribute(marker_screen_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SCREEN_SMEM_BYTES + 64));
     const uint32_t per_sm = smem > 100 * 1024 ? 1u : (smem > 48 * 1024 ? 2u : 4u);   // resident CTAs per SM at this footprint
-    for (uint32_t q0 = 0; q0 < n_queries; q0 += 65535) {
-        const uint32_t nq = n_queries - q0 < 65535 ? n_queries - q0 : 65535;
+    const uint32_t n_groups = (n_queries + SCREEN_QT - 1) / SCREEN_QT;
+    for (uint32_t g0 = 0; g0 < n_groups; g0 += 65535) {
+        const uint32_t ng = n_groups - g0 < 65535 ? n_groups - g0 : 65535;
+        const uint32_t qb = g0 * SCREEN_QT, nq = n_queries - qb < ng * SCREEN_QT ? n_queries - qb : ng * SCREEN_QT;
         // enough CTAs to fill the machine; each CTA walks references with stride gridDim.x
-        uint32_t gx = ((uint32_t)n_sm * per_sm + nq - 1) / nq;
+        uint32_t gx = ((uint32_t)n_sm * per_sm + ng - 1) / ng;
         if (gx > n_refs) gx = n_refs;
         if (gx == 0) gx = 1;
-        marker_screen_smem_kernel<<<dim3(gx, nq), SCREEN_WARPS * 32, smem, st>>>(queries + q0, nq, refs, n_refs,
-                                                                                 count + (size_t)q0 * n_refs);
+        marker_screen_smem_kernel<<<dim3(gx, ng), SCREEN_WARPS * 32, smem, st>>>(queries + qb, nq, refs, n_refs,
+                                                                                 count + (size_t)qb * n_refs);
         g_kernel_launches++;
-        if (max_query_markers > SCREEN_SMEM_MARKERS) {
+    }
+    if (any_big) {
+        for (uint32_t q0 = 0; q0 < n_queries; q0 += 65535 / SCREEN_QT * SCREEN_QT) {
+            const uint32_t step = 65535 / SCREEN_QT * SCREEN_QT;
+            const uint32_t nq = n_queries - q0 < step ? n_queries - q0 : step;
             dim3 grid((n_refs + SCREEN_WARPS - 1) / SCREEN_WARPS, nq);
-            marker_screen_kernel<<<grid, SCREEN_WARPS * 32, 0, st>>>(queries + q0, nq, refs, n_refs,
-                                                                      count + (size_t)q0 * n_refs);
+            marker_screen_kernel<<<grid, SCREEN_WARPS * 32, 0, st>>>(queries + q0, nq, refs, n_refs, count + (size_t)q0 * n_refs);
             g_kernel_launches++;
         }
     }

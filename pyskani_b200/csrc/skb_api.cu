@@ -833,9 +833,9 @@ void run_screen(skb_db& db, const std::vector<std::shared_ptr<SketchImpl>>& quer
     if (n >= 0x7FFFFFFFull) throw Fail{SKB_ERR_ARG, "more than 2^31 pairs in one call; split the queries"};
     const GenomeView* d_r = db_views(db);
     DevMem d_count(db.core, 4 * n), d_pass(db.core, n);
-    uint32_t max_qm = 0;
-    for (auto& q : queries) max_qm = std::max(max_qm, q->view.n_markers);
-    launch_marker_screen(d_q, nq, d_r, nr, d_count.as<uint32_t>(), max_qm, c.n_sm, st);
+    std::vector<uint32_t> qm(nq);
+    for (uint32_t i = 0; i < nq; i++) qm[i] = queries[i]->view.n_markers;
+    launch_marker_screen(d_q, nq, d_r, nr, d_count.as<uint32_t>(), qm.data(), c.n_sm, st);
     launch_screen_decide(d_q, nq, d_r, nr, d_count.as<uint32_t>(), pow21(screen_val), screen_val == 0.0, rescue_small,
                          d_pass.as<uint8_t>(), st);
     if (pass_host) download(c, pass_host, d_pass.as<uint8_t>(), n);

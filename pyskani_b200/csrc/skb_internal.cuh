@@ -133,7 +133,7 @@ void launch_contig_starts(const GenomeView* views_dev, uint32_t n_genomes, uint3
 // ---------------------------------------------------------------- screen
 // count[q * n_refs + r] = | markers(q) ∩ markers(r) |
 void launch_marker_screen(const GenomeView* queries, uint32_t n_queries, const GenomeView* refs, uint32_t n_refs,
-                          uint32_t* count, uint32_t max_query_markers, int n_sm, cudaStream_t st);
+                          uint32_t* count, const uint32_t* query_markers_host, int n_sm, cudaStream_t st);
 void launch_screen_decide(const GenomeView* queries, uint32_t n_queries, const GenomeView* refs, uint32_t n_refs,
                           const uint32_t* count, double p21, int always, int rescue_small, uint8_t* pass,
                           cudaStream_t st);
