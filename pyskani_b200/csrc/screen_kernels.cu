@@ -6,6 +6,8 @@
 // binary-search the larger one.  The kernel produces the exact intersection size; the pass/fail
 // decision (count > screen_val^21 * |smaller|, or the small-genome rescue) is a second tiny kernel so
 // that the comparison is one IEEE multiply + compare, identical to the oracle's.
+#include <cstdlib>
+
 #include "skb_internal.cuh"
 
 namespace skb {
@@ -17,10 +19,10 @@ constexpr int SCREEN_WARPS = 8;
 constexpr uint32_t SCREEN_SMEM_BYTES = 200 * 1024;   // shared memory the fast path may use per CTA
 constexpr int SCREEN_QT = 4;                         // queries staged together per CTA (each streamed reference serves all)
 
-// bytes of shared memory one staged query of n markers needs: sorted list + membership bitmap (>= 16 bits / marker)
+// bytes of shared memory one staged query of n markers needs: sorted list + membership bitmap (>= 8 bits / marker)
 __host__ __device__ inline uint32_t screen_bitmap_bits(uint32_t n) {
     uint32_t b = 1024;
-    while (b < 16u * n && b < (1u << 22)) b <<= 1;
+    while (b < 8u * n && b < (1u << 22)) b <<= 1;
     return b;
 }
 __host__ __device__ inline uint32_t screen_query_bytes(uint32_t n) { return 8u * n + screen_bitmap_bits(n) / 8u; }
@@ -33,12 +35,15 @@ __device__ __forceinline__ uint32_t marker_slot(uint64_t v, uint32_t mask) {
 // markers.  References are then streamed once for all staged queries: 256 threads stride a reference's list with
 // coalesced 8-byte loads; a marker is first tested against the bitmap (one shared-memory word; ~93 % of the probes of
 // an unrelated pair end here) and only on a hit binary-searched in the staged list.  The count is exact.
-__global__ void __launch_bounds__(SCREEN_WARPS * 32)
+constexpr int SCREEN_MAX_WARPS = 32;             // the fast path runs 8, 16 or 32 warps per CTA depending on its smem footprint
+
+__global__ void __launch_bounds__(SCREEN_MAX_WARPS * 32)
 marker_screen_smem_kernel(const GenomeView* __restrict__ queries, uint32_t n_queries,
                           const GenomeView* __restrict__ refs, uint32_t n_refs, uint32_t* __restrict__ count) {
     extern __shared__ uint64_t s_mem[];
-    __shared__ uint32_t s_part[SCREEN_WARPS][SCREEN_QT];
-    __shared__ uint32_t s_off[SCREEN_QT + 1];      // byte offsets of each staged query inside s_mem
+    __shared__ uint32_t s_part[SCREEN_MAX_WARPS][SCREEN_QT];
+    __shared__ uint64_t s_qv[SCREEN_MAX_WARPS][64];    // per-warp queue of bitmap hits: marker value ...
+    __shared__ uint8_t s_qt[SCREEN_MAX_WARPS][64];     // ... and staged-query slot
     const uint32_t q0 = blockIdx.y * SCREEN_QT;
     const uint32_t nqt = min((uint32_t)SCREEN_QT, n_queries - q0);
     uint32_t nq[SCREEN_QT], bmask[SCREEN_QT];
@@ -59,7 +64,6 @@ marker_screen_smem_kernel(const GenomeView* __restrict__ queries, uint32_t n_que
         fits = off <= SCREEN_SMEM_BYTES;
     }
     if (!fits) return;                              // this group is handled by marker_screen_kernel
-    (void)s_off;
 #pragma unroll
     for (int t = 0; t < SCREEN_QT; t++) {
         uint32_t* bt = bits[t];
@@ -80,39 +84,70 @@ marker_screen_smem_kernel(const GenomeView* __restrict__ queries, uint32_t n_que
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // Bitmap hits (true matches and ~6 % false positives) are not searched on the spot — that would leave 1-2 lanes of a
+    // warp running a 12-step search while 30 wait.  They are queued per warp and searched 32 at a time by full warps.
+    uint64_t* qv = s_qv[warp];
+    uint8_t* qt = s_qt[warp];
     for (uint32_t r = blockIdx.x; r < n_refs; r += gridDim.x) {
         const uint64_t* b = refs[r].markers;
         const uint32_t nb = refs[r].n_markers;
-        uint32_t c[SCREEN_QT];
+        uint32_t cnt[SCREEN_QT];                    // warp-uniform match counts
 #pragma unroll
-        for (int t = 0; t < SCREEN_QT; t++) c[t] = 0;
-        for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
-            const uint64_t v = __ldg(b + i);
-            const uint32_t h = (uint32_t)((v * 0x9E3779B97F4A7C15ull) >> 40);
+        for (int t = 0; t < SCREEN_QT; t++) cnt[t] = 0;
+        uint32_t qn = 0;                            // queue length (warp-uniform)
+        auto drain = [&](uint32_t take) {           // search the last `take` (<= 32) queued entries, one per lane
+            const bool act = (uint32_t)lane < take;
+            uint64_t v = 0; uint32_t tt = 0;
+            if (act) { v = qv[qn - take + lane]; tt = qt[qn - take + lane]; }
+            const uint64_t* lt = list[0]; uint32_t n = 0;
 #pragma unroll
-            for (int t = 0; t < SCREEN_QT; t++) {
-                const uint32_t sl = h & bmask[t];
-                if ((bits[t][sl >> 5] >> (sl & 31u)) & 1u) {
-                    uint32_t lo = 0, hi = nq[t];
-                    const uint64_t* lt = list[t];
-                    while (lo < hi) {
-                        const uint32_t mid = (lo + hi) >> 1;
-                        if (lt[mid] < v) lo = mid + 1; else hi = mid;
+            for (int t = 0; t < SCREEN_QT; t++) if (tt == (uint32_t)t) { lt = list[t]; n = nq[t]; }
+            uint32_t lo = 0, hi = act ? n : 0u;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (lt[mid] < v) lo = mid + 1; else hi = mid;
+            }
+            const bool found = act && lo < n && lt[lo] == v;
+#pragma unroll
+            for (int t = 0; t < SCREEN_QT; t++) cnt[t] += __popc(__ballot_sync(0xffffffffu, found && tt == (uint32_t)t));
+            qn -= take;
+        };
+        constexpr int U = 4;                        // independent 8-byte loads in flight per thread
+        for (uint32_t i0 = threadIdx.x; i0 - threadIdx.x < nb; i0 += blockDim.x * U) {   // warp-uniform trip count
+            uint64_t vv[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const uint32_t i = i0 + u * blockDim.x;
+                vv[u] = i < nb ? __ldg(b + i) : ~0ull;       // ~0 is not a 42-bit marker: it never matches
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const uint64_t v = vv[u];
+                const uint32_t h = (uint32_t)((v * 0x9E3779B97F4A7C15ull) >> 40);
+#pragma unroll
+                for (int t = 0; t < SCREEN_QT; t++) {
+                    const uint32_t sl = h & bmask[t];
+                    const bool hit = (bits[t][sl >> 5] >> (sl & 31u)) & 1u;
+                    const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                    if (m) {
+                        if (hit) { const uint32_t at = qn + __popc(m & ((1u << lane) - 1u)); qv[at] = v; qt[at] = (uint8_t)t; }
+                        qn += __popc(m);
+                        __syncwarp();
+                        if (qn >= 32) drain(32);
                     }
-                    c[t] += (lo < nq[t] && lt[lo] == v) ? 1u : 0u;
                 }
             }
         }
+        __syncwarp();
+        if (qn) drain(qn);                          // qn < 32 here
+        if (lane == 0) {
 #pragma unroll
-        for (int t = 0; t < SCREEN_QT; t++) {
-            const uint32_t w = __reduce_add_sync(0xffffffffu, c[t]);
-            if (lane == 0) s_part[warp][t] = w;
+            for (int t = 0; t < SCREEN_QT; t++) s_part[warp][t] = cnt[t];
         }
         __syncthreads();
         if (threadIdx.x < nqt) {
             uint32_t tot = 0;
-#pragma unroll
-            for (int w = 0; w < SCREEN_WARPS; w++) tot += s_part[w][threadIdx.x];
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += s_part[w][threadIdx.x];
             count[(size_t)(q0 + threadIdx.x) * n_refs + r] = tot;
         }
         __syncthreads();
@@ -177,16 +212,23 @@ void launch_marker_screen(const GenomeView* queries, uint32_t n_queries, const G
     }
     smem += 64;
     cudaFuncSetAttribute(marker_screen_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SCREEN_SMEM_BYTES + 64));
-    const uint32_t per_sm = smem > 100 * 1024 ? 1u : (smem > 48 * 1024 ? 2u : 4u);   // resident CTAs per SM at this footprint
+    // resident CTAs per SM at this footprint; fewer resident CTAs are compensated by wider CTAs (always 32 warps per SM)
+    const uint32_t per_sm = smem > 100 * 1024 ? 1u : (smem > 48 * 1024 ? 2u : 4u);
+    const uint32_t threads = per_sm == 1 ? 1024u : (per_sm == 2 ? 512u : 256u);
     const uint32_t n_groups = (n_queries + SCREEN_QT - 1) / SCREEN_QT;
     for (uint32_t g0 = 0; g0 < n_groups; g0 += 65535) {
         const uint32_t ng = n_groups - g0 < 65535 ? n_groups - g0 : 65535;
         const uint32_t qb = g0 * SCREEN_QT, nq = n_queries - qb < ng * SCREEN_QT ? n_queries - qb : ng * SCREEN_QT;
         // enough CTAs to fill the machine; each CTA walks references with stride gridDim.x
-        uint32_t gx = ((uint32_t)n_sm * per_sm + ng - 1) / ng;
-        if (gx > n_refs) gx = n_refs;
-        if (gx == 0) gx = 1;
-        marker_screen_smem_kernel<<<dim3(gx, ng), SCREEN_WARPS * 32, smem, st>>>(queries + qb, nq, refs, n_refs,
+        // split the references over gx CTAs per group: measured on B200, ~8 CTAs per resident slot balance the
+        // uneven per-pair cost best (related pairs search far more), as long as a CTA still streams >= 8 references
+        // to amortise staging its queries
+        const uint32_t slots = (uint32_t)n_sm * per_sm;
+        uint32_t gx = (8u * slots + ng - 1) / ng;
+        if (gx > n_refs / 8u) gx = n_refs / 8u;
+        if (gx < 1) gx = 1;
+        if (const char* e = getenv("SKB_SCREEN_GX")) { gx = (uint32_t)atoi(e); if (gx < 1) gx = 1; if (gx > n_refs) gx = n_refs; }
+        marker_screen_smem_kernel<<<dim3(gx, ng), threads, smem, st>>>(queries + qb, nq, refs, n_refs,
                                                                                  count + (size_t)qb * n_refs);
         g_kernel_launches++;
     }
