@@ -159,7 +159,7 @@ __device__ __forceinline__ uint32_t next_set_bit(const uint32_t* bits, uint32_t 
     return r < n ? r : n;
 }
 
-__global__ void __launch_bounds__(256) window_walk_smem_kernel(const ChainBatch b, const uint32_t F) {
+__global__ void __launch_bounds__(1024) window_walk_smem_kernel(const ChainBatch b, const uint32_t F) {
     extern __shared__ uint32_t sm[];
     const PairDesc pd = b.pairs[blockIdx.x];
     const GenomeView& Q = b.qviews[pd.q];
@@ -194,14 +194,31 @@ __global__ void __launch_bounds__(256) window_walk_smem_kernel(const ChainBatch 
         const uint32_t cs = Q.contig_seed_start[c], ce = Q.contig_seed_start[c + 1];
         uint32_t slot = pd.win_off + Q.contig_win_start[c];
         uint32_t s = cs;
+        // expected number of seeds per window of this contig
+        const uint32_t clen = Q.contig_len[c];
+        const uint32_t est = clen ? (uint32_t)(((uint64_t)F * (ce - cs)) / clen) : 0u;
         while (s < ce) {
             // first matched seed at or after s (uniform across the warp: every lane runs the same scan)
             const uint32_t i = next_set_bit(s_bits, s, ce);
             if (i >= ce) break;
             const uint32_t target = s_pos[i] + F;
+            uint32_t lo = i + 1, e = 0;
+            bool done = false;
+            // one-shot guess: seeds are roughly evenly spaced, so the answer is close to i + est; probe 32 consecutive
+            // seeds around it and accept if the bracket is inside (the seed before the probes is still below target)
+            if (est > 16) {
+                const uint32_t g0 = min(i + 1 + (est - 16), ce);
+                const uint32_t idx = g0 + (uint32_t)lane;
+                const bool ge = idx >= ce || s_pos[idx] >= target;
+                const uint32_t bal = __ballot_sync(FULL, ge);
+                const bool before_ok = g0 == i + 1 || s_pos[g0 - 1] < target;     // uniform: same address for every lane
+                if (before_ok) {
+                    if (bal) { e = g0 + (uint32_t)(__ffs(bal) - 1); done = true; }
+                    else lo = g0 + 32;                                             // every probe below target: continue behind them
+                }
+            }
             // gallop: 32 probes, 8 seeds apart, then resolve inside the 8-seed bracket
-            uint32_t lo = i + 1, e;
-            while (true) {
+            while (!done) {
                 const uint32_t idx = lo + (uint32_t)lane * 8u;
                 const bool ge = idx >= ce || s_pos[idx] >= target;
                 const uint32_t bal = __ballot_sync(FULL, ge);
@@ -212,7 +229,7 @@ __global__ void __launch_bounds__(256) window_walk_smem_kernel(const ChainBatch 
                 const uint32_t j = blo + (uint32_t)lane;
                 const bool ge2 = j >= bhi || s_pos[j] >= target;       // lanes >= 8 are past bhi: vote true
                 e = blo + (uint32_t)(__ffs(__ballot_sync(FULL, ge2)) - 1);
-                break;
+                done = true;
             }
             if (lane == 0) {
                 b.win_start[slot] = i;
@@ -486,7 +503,7 @@ void launch_window_walk(const ChainBatch& b, const ChainConsts& c, uint32_t max_
     cudaFuncSetAttribute(window_walk_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap_bytes);
     const uint32_t n = max_query_seeds < WALK_SMEM_SEEDS ? max_query_seeds : WALK_SMEM_SEEDS;
     const size_t bytes = (size_t)n * 4 + ((n + 31) / 32) * 4 + 16;
-    window_walk_smem_kernel<<<b.n_pairs, 256, bytes, st>>>(b, c.fragment_length);
+    window_walk_smem_kernel<<<b.n_pairs, 1024, bytes, st>>>(b, c.fragment_length);
     g_kernel_launches++;
     if (max_query_seeds > WALK_SMEM_SEEDS) {
         window_walk_kernel<<<b.n_pairs, 128, 0, st>>>(b, c.fragment_length, 1);

@@ -224,8 +224,11 @@ void launch_marker_screen(const GenomeView* queries, uint32_t n_queries, const G
         // uneven per-pair cost best (related pairs search far more), as long as a CTA still streams >= 8 references
         // to amortise staging its queries
         const uint32_t slots = (uint32_t)n_sm * per_sm;
-        uint32_t gx = (8u * slots + ng - 1) / ng;
-        if (gx > n_refs / 8u) gx = n_refs / 8u;
+        const uint32_t gx_target = (8u * slots + ng - 1) / ng;      // ~8 CTAs per slot
+        const uint32_t gx_fill = (slots + ng - 1) / ng;              // at least fill the machine once
+        const uint32_t gx_amort = n_refs / 8u;                       // >= 8 references per CTA
+        uint32_t gx = gx_target < (gx_amort > gx_fill ? gx_amort : gx_fill) ? gx_target : (gx_amort > gx_fill ? gx_amort : gx_fill);
+        if (gx > n_refs) gx = n_refs;
         if (gx < 1) gx = 1;
         if (const char* e = getenv("SKB_SCREEN_GX")) { gx = (uint32_t)atoi(e); if (gx < 1) gx = 1; if (gx > n_refs) gx = n_refs; }
         marker_screen_smem_kernel<<<dim3(gx, ng), threads, smem, st>>>(queries + qb, nq, refs, n_refs,
