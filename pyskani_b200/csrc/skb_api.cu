@@ -188,7 +188,7 @@ struct KeptContig { uint64_t off; uint32_t len; };
 static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_params_t& P, int seed,
                          uint32_t n_genomes, const std::vector<std::vector<uint32_t>>& contig_lens,
                          std::shared_ptr<BatchStore> store, const std::vector<uint32_t>& seed_start,
-                         const std::vector<uint32_t>& marker_start, skb_sketch_t** out);
+                         std::vector<uint32_t>& marker_start, const uint32_t* d_marker_start, skb_sketch_t** out);
 
 // A chunk of the batch whose bytes become available on the device when `ready` fires (host->device pipelining):
 // flat contigs [previous contig_end, contig_end).
@@ -373,23 +373,23 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             const size_t mark_bytes = marker_scratch_bytes(nm);
             void* mark_scratch = c.scratch(SLOT_MARK, mark_bytes);
             build_marker_sets(n_genomes, nm, t_mkeys, store->markers.as<uint64_t>(), d_gm, mark_scratch, mark_bytes, st);
-            download(c, marker_start.data(), d_gm, n_genomes + 1);
             t2.mark("enqueued index");
-            CU(cudaStreamSynchronize(st));
-            t2.mark("sync after index");
         }
         CU(cudaEventRecord(c.ev[3], st));
+        finish_batch(core, P, seed, n_genomes, contig_lens, store, seed_start, marker_start, d_gm, out);
     } else {
         CU(cudaEventRecord(c.ev[1], st)); CU(cudaEventRecord(c.ev[2], st)); CU(cudaEventRecord(c.ev[3], st));
+        finish_batch(core, P, seed, n_genomes, contig_lens, store, seed_start, marker_start, nullptr, out);
     }
-    finish_batch(core, P, seed, n_genomes, contig_lens, store, seed_start, marker_start, out);
     t2.mark("finish_batch done");
 }
 
 static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_params_t& P, int seed,
                          uint32_t n_genomes, const std::vector<std::vector<uint32_t>>& contig_lens,
                          std::shared_ptr<BatchStore> store, const std::vector<uint32_t>& seed_start,
-                         const std::vector<uint32_t>& marker_start, skb_sketch_t** out) {
+                         std::vector<uint32_t>& marker_start, const uint32_t* d_marker_start, skb_sketch_t** out) {
+    // d_marker_start (device, may be NULL): per-genome offsets into the de-duplicated marker array, produced by the
+    // marker kernels that are still in flight; they are fetched together with the end-of-batch synchronisation below
     Core& c = *core;
     cudaStream_t st = c.stream;
     // ---- per-genome tables: buckets, contig seed starts, contig lengths, window capacities
@@ -421,7 +421,7 @@ static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_par
         }
         h_cwin.push_back(wcap);
         v.win_cap = wcap; v.total_len = tot; v.n_contigs = nc;
-        v.n_seeds = ns; v.n_markers = marker_start[g + 1] - marker_start[g];
+        v.n_seeds = ns; v.n_markers = 0;      // marker fields are filled in after the final synchronisation
     }
     store->bucket = DevMem(core, 4 * bucket_total);
     store->contig_seed_start = DevMem(core, 4 * std::max<size_t>(cstart_total, 1));
@@ -437,7 +437,7 @@ static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_par
         v.contig_seed_start = store->contig_seed_start.as<uint32_t>() + cstart_off[g];
         v.contig_win_start = store->contig_win_start.as<uint32_t>() + cstart_off[g];
         v.contig_len = store->contig_len.as<uint32_t>() + clen_off[g];
-        v.markers = store->markers.as<uint64_t>() + marker_start[g];
+        v.markers = nullptr;
     }
     {
         DevMem d_views(core, sizeof(GenomeView) * n_genomes);
@@ -447,7 +447,12 @@ static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_par
         // per-genome layout of contig_win_start mirrors contig_seed_start (nc + 1 entries each)
         launch_build_buckets(d_views.as<GenomeView>(), n_genomes, max_buckets, st);
         launch_contig_starts(d_views.as<GenomeView>(), n_genomes, max_contigs, st);
-        CU(cudaStreamSynchronize(st));   // staging block is reused by the next call
+        if (d_marker_start) download(c, marker_start.data(), d_marker_start, n_genomes + 1);
+        CU(cudaStreamSynchronize(st));   // the one synchronisation of the index build
+    }
+    for (uint32_t g = 0; g < n_genomes; g++) {
+        views[g].n_markers = marker_start[g + 1] - marker_start[g];
+        views[g].markers = store->markers.as<uint64_t>() + marker_start[g];
     }
     for (uint32_t g = 0; g < n_genomes; g++) {
         auto impl = std::make_shared<SketchImpl>();
@@ -762,7 +767,7 @@ int skb_sketch_import(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t
         CU(cudaStreamSynchronize(st));
         std::vector<std::vector<uint32_t>> cl(1);
         cl[0].assign(contig_lengths, contig_lengths + n_contigs);
-        finish_batch(ctx->core, *params, has_seeds, 1, cl, store, seed_start, marker_start, out);
+        finish_batch(ctx->core, *params, has_seeds, 1, cl, store, seed_start, marker_start, nullptr, out);
         return SKB_OK;
     });
 }
