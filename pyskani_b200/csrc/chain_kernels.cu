@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(DP_WARPS * 32) chain_dp_kernel(const ChainBatc
     if (we <= ws) return;                                   // unused slot
     const PairDesc pd = b.pairs[b.win_contig[slot]];
     const uint32_t A0 = b.a_off[pd.seed_off + ws], A1 = b.a_off[pd.seed_off + we];
+    if (A1 > b.anchor_cap) return;                          // anchor arrays were sized too small: the host reruns the batch
     const uint32_t n = A1 - A0;
     const uint32_t* qp_a = b.a_qp + A0; const uint32_t* rp_a = b.a_rp + A0; const uint32_t* meta_a = b.a_meta + A0;
     int32_t* f_a = b.a_f + A0; uint32_t* root_a = b.a_root + A0; uint32_t* aux_a = b.a_aux + A0;

@@ -845,7 +845,13 @@ void run_screen(skb_db& db, const std::vector<std::shared_ptr<SketchImpl>>& quer
                          d_pass.as<uint8_t>(), st);
     if (pass_host) download(c, pass_host, d_pass.as<uint8_t>(), n);
     if (shared_host) download(c, shared_host, d_count.as<uint32_t>(), n);
-    if (out) {
+    if (out && n <= (1u << 16)) {
+        // few pairs: fetch the flags themselves and list the survivors on the host (one synchronisation, no select pass)
+        std::vector<uint8_t> flags(n);
+        download(c, flags.data(), d_pass.as<uint8_t>(), n);
+        CU(cudaStreamSynchronize(st));
+        for (uint32_t i = 0; i < (uint32_t)n; i++) if (flags[i]) out->pass_idx.push_back(i);
+    } else if (out) {
         DevMem d_idx(db.core, 4 * n + 4);
         uint32_t* d_cnt = d_idx.as<uint32_t>() + n;
         select_passing((uint32_t)n, d_pass.as<uint8_t>(), d_idx.as<uint32_t>(), d_cnt, st);
@@ -951,42 +957,53 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
                 DevMem scratch(db->core, scan_scratch_bytes((uint32_t)seeds + 1));
                 scan_match_counts(B, scratch.p, scratch.bytes, st);
             }
-            uint32_t n_anchors = 0;
-            download(c, &n_anchors, B.a_off + seeds, 1);
-            CU(cudaStreamSynchronize(st));   // also keeps `pairs` alive until its upload has finished
-            const size_t na = std::max<uint32_t>(n_anchors, 1);
-            B.anchor_cap = n_anchors;
-            DevMem d_a(db->core, na * 4 * 7), d_best(db->core, na * 8);
-            B.a_qi = d_a.as<uint32_t>(); B.a_qp = B.a_qi + na; B.a_rp = B.a_qp + na; B.a_meta = B.a_rp + na;
-            B.a_f = (int32_t*)(B.a_meta + na); B.a_root = (uint32_t*)(B.a_f + na); B.a_aux = B.a_root + na;
-            B.a_best = d_best.as<unsigned long long>();
-            CU(cudaMemsetAsync(B.a_aux, 0, 4 * na, st));
-            CU(cudaMemsetAsync(B.a_best, 0, 8 * na, st));
-            const size_t nw = std::max<uint64_t>(wins, 1);
-            DevMem d_w(db->core, nw * 4 * 3 + 4 * (size_t)np), d_rec(db->core, nw * sizeof(WindowRec));
-            B.win_start = d_w.as<uint32_t>(); B.win_end = B.win_start + nw; B.win_contig = B.win_end + nw; B.pair_nwin = B.win_contig + nw;
-            B.win_rec = d_rec.as<WindowRec>();
-            CU(cudaMemsetAsync(B.win_start, 0, 8 * nw, st));   // start == end == 0 marks an unused slot
-            DevMem d_keys(db->core, nw * 8 * 2), d_vals(db->core, nw * 4 * 2), d_res(db->core, sizeof(PairResult) * np);
-            B.sort_keys = d_keys.as<uint64_t>(); B.sort_vals = d_vals.as<uint32_t>();
-            uint64_t* keys_sorted = B.sort_keys + nw; uint32_t* vals_sorted = B.sort_vals + nw;
-            B.results = d_res.as<PairResult>();
-
-            launch_anchor_fill(B, st);
-            launch_window_walk(B, C, max_qseeds, st);
-            launch_chain_dp(B, C, st);
-            launch_window_keys(B, st);
-            {
-                int pbits = 1;
-                while ((1ull << pbits) <= (uint64_t)np) pbits++;
-                DevMem scratch(db->core, sort_pairs_scratch_bytes((uint32_t)wins));
-                sort_window_keys((uint32_t)wins, B.sort_keys, keys_sorted, B.sort_vals, vals_sorted, 32 + pbits, scratch.p,
-                                 scratch.bytes, st);
-            }
-            launch_ani_reduce(B, C, keys_sorted, vals_sorted, st);
+            // The number of anchors is only known on the device.  Size the anchor arrays from an estimate (twice the
+            // smaller seed count of every pair), run the whole batch, and read the true total back together with the
+            // results: one synchronisation per batch; a batch whose estimate was too small is simply run again.
+            uint64_t est = 1024;
+            for (const PairDesc& pd : pairs) est += 2ull * std::min(qs[pd.q]->view.n_seeds, db->items[pd.r]->view.n_seeds);
+            if (est > 0x7FFFFFFFull) est = 0x7FFFFFFFull;
+            if (const char* e = std::getenv("SKB_FORCE_ANCHOR_EST")) est = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10));   // test hook: exercises the rerun
             std::vector<PairResult> res(np);
-            download(c, res.data(), B.results, np);
-            CU(cudaStreamSynchronize(st));
+            for (int attempt = 0; attempt < 2; attempt++) {
+                const size_t na = (size_t)est;
+                B.anchor_cap = (uint32_t)est;
+                DevMem d_a(db->core, na * 4 * 7), d_best(db->core, na * 8);
+                B.a_qi = d_a.as<uint32_t>(); B.a_qp = B.a_qi + na; B.a_rp = B.a_qp + na; B.a_meta = B.a_rp + na;
+                B.a_f = (int32_t*)(B.a_meta + na); B.a_root = (uint32_t*)(B.a_f + na); B.a_aux = B.a_root + na;
+                B.a_best = d_best.as<unsigned long long>();
+                CU(cudaMemsetAsync(B.a_aux, 0, 4 * na, st));
+                CU(cudaMemsetAsync(B.a_best, 0, 8 * na, st));
+                const size_t nw = std::max<uint64_t>(wins, 1);
+                DevMem d_w(db->core, nw * 4 * 3 + 4 * (size_t)np), d_rec(db->core, nw * sizeof(WindowRec));
+                B.win_start = d_w.as<uint32_t>(); B.win_end = B.win_start + nw; B.win_contig = B.win_end + nw; B.pair_nwin = B.win_contig + nw;
+                B.win_rec = d_rec.as<WindowRec>();
+                CU(cudaMemsetAsync(B.win_start, 0, 8 * nw, st));   // start == end == 0 marks an unused slot
+                DevMem d_keys(db->core, nw * 8 * 2), d_vals(db->core, nw * 4 * 2), d_res(db->core, sizeof(PairResult) * np);
+                B.sort_keys = d_keys.as<uint64_t>(); B.sort_vals = d_vals.as<uint32_t>();
+                uint64_t* keys_sorted = B.sort_keys + nw; uint32_t* vals_sorted = B.sort_vals + nw;
+                B.results = d_res.as<PairResult>();
+
+                launch_anchor_fill(B, st);
+                launch_window_walk(B, C, max_qseeds, st);
+                launch_chain_dp(B, C, st);
+                launch_window_keys(B, st);
+                {
+                    int pbits = 1;
+                    while ((1ull << pbits) <= (uint64_t)np) pbits++;
+                    DevMem scratch(db->core, sort_pairs_scratch_bytes((uint32_t)wins));
+                    sort_window_keys((uint32_t)wins, B.sort_keys, keys_sorted, B.sort_vals, vals_sorted, 32 + pbits, scratch.p,
+                                     scratch.bytes, st);
+                }
+                launch_ani_reduce(B, C, keys_sorted, vals_sorted, st);
+                uint32_t n_anchors = 0;
+                download(c, &n_anchors, B.a_off + seeds, 1);
+                download(c, res.data(), B.results, np);
+                CU(cudaStreamSynchronize(st));   // also keeps `pairs` alive until its upload has finished
+                if (n_anchors <= B.anchor_cap) break;
+                if (attempt == 1) throw Fail{SKB_ERR_CUDA, "anchor arrays overflowed twice"};
+                est = n_anchors;
+            }
             for (uint32_t i = 0; i < np; i++) {
                 if (res[i].ani > 0.1f) {   // reference lib.rs:654
                     skb_hit_t h{};

@@ -291,3 +291,18 @@ def test_all_vs_all_driver_single_rank(ctx):
     a = be.query(imported, local)
     b = be.query(local, local)
     assert a == b
+
+
+def test_anchor_capacity_rerun(ctx, monkeypatch):
+    """The anchor arrays are sized from an estimate; a batch that overflows it is rerun with the exact size."""
+    from pyskani_b200 import capi
+    base = synth.random_genome(300_000, 41)
+    refs = [synth.mutate(base, d, 410 + i) for i, d in enumerate((0.02, 0.08))]
+    gs = ctx.sketch_batch([[r.tobytes()] for r in refs] + [[base.tobytes()]])
+    db = capi.Database(ctx)
+    for g in gs[:-1]:
+        db.add(g)
+    want = db.query([gs[-1]])
+    monkeypatch.setenv("SKB_FORCE_ANCHOR_EST", "100")
+    got = db.query([gs[-1]])
+    assert got == want and len(want[0]) == 2
