@@ -603,6 +603,7 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
         constexpr size_t STAGE = (size_t)8 << 20;
         constexpr uint64_t CHUNK = (uint64_t)16 << 20;      // granularity of copy -> seeding hand-over
         constexpr uint64_t SUB = (uint64_t)192 << 20;       // genomes are indexed in sub-batches of about this size
+        constexpr uint64_t SUB_MAX = (uint64_t)1536 << 20;  // upper bound of a sub-batch (the batch limit is 2^31 bases)
         // All copies are enqueued up front.  The batch is then processed in sub-batches (whole genomes): while the
         // index of sub-batch i is built, the copies of the later sub-batches keep the PCIe link busy, so only the
         // last sub-batch's index build is exposed after the final byte has arrived.
@@ -617,7 +618,13 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
                 used = 0;
             }
         };
-        uint64_t in_chunk = 0, in_sub = 0;
+        uint64_t kept_bytes = 0;
+        for (uint32_t i = 0; i < n_contigs; i++) if (contig_lens[i] >= SKB_MIN_LENGTH_CONTIG) kept_bytes += contig_lens[i];
+        // cut points (cumulative bytes): equal parts of about SUB bytes (measured best on B200 among head/tail splits:
+        // the index build runs ~2.5x slower while the copy engine is busy, so parts must stay small enough to keep up)
+        std::vector<uint64_t> cuts;
+        for (uint64_t cut = SUB; cut + SUB / 2 < kept_bytes; cut += SUB) cuts.push_back(cut);
+        uint64_t in_chunk = 0, in_sub = 0, done_bytes = 0;
         SubBatch cur_sub{0, 0, {}};
         auto close_chunk = [&](uint32_t contig_end) {
             flush();
@@ -641,12 +648,13 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
                     std::memcpy(stage + used, contigs[i], len);
                     used += span;
                 }
-                in_chunk += len; in_sub += len;
+                in_chunk += len; in_sub += len; done_bytes += len;
                 if (in_chunk >= CHUNK && i + 1 < genome_contig_start[g + 1]) close_chunk(i + 1);
             }
             const bool last = g + 1 == n_genomes;
-            if (in_chunk >= CHUNK || in_sub >= SUB || last) close_chunk(genome_contig_start[g + 1]);
-            if (in_sub >= SUB || last) {
+            const bool end_sub = last || (subs.size() < cuts.size() && done_bytes >= cuts[subs.size()]) || in_sub >= SUB_MAX;
+            if (in_chunk >= CHUNK || end_sub) close_chunk(genome_contig_start[g + 1]);
+            if (end_sub) {
                 cur_sub.g1 = g + 1;
                 subs.push_back(std::move(cur_sub));
                 cur_sub = SubBatch{g + 1, g + 1, {}};
