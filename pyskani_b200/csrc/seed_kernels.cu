@@ -46,7 +46,7 @@ __device__ __forceinline__ U64 mul_c(U64 x, uint32_t c) {            // x * c mo
 // issue on the FMA pipe and leave the ALU pipe to the xors and compares.
 template <int S>
 __device__ __forceinline__ uint32_t shr_hi(uint32_t hi) {
-#if SKB_XS_FMA
+#if SKB_XS_FMA >= 1
     return __umulhi(hi, 1u << (32 - S));
 #else
     return hi >> S;
@@ -54,7 +54,7 @@ __device__ __forceinline__ uint32_t shr_hi(uint32_t hi) {
 }
 template <int S>
 __device__ __forceinline__ uint32_t shr_lo(uint32_t lo, uint32_t hi) {
-#if SKB_XS_FMA
+#if SKB_XS_FMA == 1
     return hi * (1u << (32 - S)) + __umulhi(lo, 1u << (32 - S));     // disjoint bit ranges: + == |
 #else
     return __funnelshift_r(lo, hi, S);

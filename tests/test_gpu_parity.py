@@ -306,3 +306,33 @@ def test_anchor_capacity_rerun(ctx, monkeypatch):
     monkeypatch.setenv("SKB_FORCE_ANCHOR_EST", "100")
     got = db.query([gs[-1]])
     assert got == want and len(want[0]) == 2
+
+
+def test_large_genomes_take_the_global_memory_paths(ctx):
+    """Genomes beyond the shared-memory fast paths: > 49 152 seeds (window walk falls back to global memory) and
+    > ~20 000 markers (the screen falls back to the warp-per-pair kernel)."""
+    from pyskani_b200 import capi
+    base = synth.random_genome(26_000_000, 71)
+    refs = [synth.mutate(base, 0.03, 72), synth.random_genome(7_000_000, 73)]
+    contigs = [[r.tobytes()] for r in refs] + [[base.tobytes()]]
+    gs = ctx.sketch_batch(contigs)
+    os_ = [oracle.Sketch(c) for c in contigs]
+    assert gs[-1].info().n_seeds > 49152 and gs[-1].info().n_markers > 21000
+    for g, o in zip(gs, os_):
+        assert_sketch_equal(g, o)
+    db = capi.Database(ctx)
+    for g in gs[:-1]:
+        db.add(g)
+    ok, shared = db.screen([gs[-1]], 0.8, True)
+    for j in range(2):
+        want_ok, want_shared = oracle.screen(os_[-1], os_[j], 0.8, True)
+        assert shared[0, j] == want_shared and ok[0, j] == want_ok
+    hits, n_in = db.query([gs[-1]])
+    assert check_hits(hits, os_[-1], os_[:-1]) == n_in
+    assert len(hits) == 1
+    # and the other way round: small query against the large reference
+    db2 = capi.Database(ctx)
+    db2.add(gs[-1])
+    hits2, _ = db2.query([gs[0], gs[1]])
+    for qi in range(2):
+        check_hits([h for h in hits2 if h[0] == qi], os_[qi], [os_[-1]])

@@ -133,7 +133,8 @@ class TestStorageRoundTrip:
     """Not covered by the reference: what is written can be read back and gives the same answers."""
 
     @pytest.fixture(scope="class")
-    def genomes(self):
+    @classmethod
+    def genomes(cls):
         from pyskani_b200 import synth
         base = synth.random_genome(400_000, 5)
         return {"base": base.tobytes(), "m3": synth.mutate(base, 0.03, 6).tobytes(), "m9": synth.mutate(base, 0.09, 7).tobytes(),
