@@ -432,6 +432,42 @@ Sketch sketch_impl(Database& db, const std::string& name, const py::tuple& conti
     return s;
 }
 
+// Batched form of sketch_impl: items = [(name, contigs), ...]; ONE skb_sketch_batch call for all genomes.
+std::vector<Sketch> sketch_many_impl(Database& db, const py::sequence& items, bool seed) {
+    std::vector<View> views;
+    std::vector<const uint8_t*> ptrs; std::vector<uint64_t> lens; std::vector<uint32_t> gstart{0};
+    std::vector<Sketch> out;
+    for (auto item : items) {
+        py::tuple tp = py::cast<py::tuple>(item);
+        if (tp.size() != 2) throw py::value_error("expected (name, contigs) pairs");
+        Sketch s;
+        s.name = tp[0].cast<std::string>(); s.c = db.params.c;
+        py::object contigs = tp[1];
+        if (py::isinstance<py::str>(contigs) || py::isinstance<py::bytes>(contigs) || PyByteArray_Check(contigs.ptr()) || PyMemoryView_Check(contigs.ptr()))
+            contigs = py::make_tuple(contigs);      // a single contig
+        size_t i = 0;
+        for (auto cobj : contigs) {
+            views.push_back(view_of(cobj));
+            ptrs.push_back(views.back().ptr); lens.push_back(views.back().len);
+            if (views.back().len >= SKB_MIN_LENGTH_CONTIG) s.contig_names.push_back(s.name + "_" + std::to_string(i));
+            i++;
+        }
+        gstart.push_back((uint32_t)ptrs.size());
+        out.push_back(std::move(s));
+    }
+    const uint32_t n = (uint32_t)out.size();
+    std::vector<skb_sketch_t*> handles(n, nullptr);
+    skb_sketch_params_t p{(int32_t)db.params.k, (int32_t)db.params.c, (int32_t)db.params.marker_c};
+    int rc;
+    {
+        py::gil_scoped_release nogil;
+        rc = skb_sketch_batch(global_ctx(), &p, seed ? 1 : 0, n, gstart.data(), ptrs.data(), lens.data(), handles.data());
+    }
+    for (uint32_t g = 0; g < n; g++) { out[g].handle = std::make_shared<SketchHandle>(); out[g].handle->h = handles[g]; }
+    check(global_ctx(), rc);
+    return out;
+}
+
 }  // namespace
 
 PYBIND11_MODULE(_skani, m) {
@@ -540,6 +576,40 @@ PYBIND11_MODULE(_skani, m) {
              }, py::arg("name"), py::arg("seed") = true, py::arg("learned_ani") = py::none(), py::arg("median") = false,
              py::arg("robust") = false, py::arg("cutoff") = py::none(), py::arg("faster_small") = false,
              "Query the database with a genome.")
+        .def("sketch_many", [](Database& db, const py::sequence& items, bool seed) {
+                 std::vector<Sketch> sk = sketch_many_impl(db, items, seed);
+                 std::lock_guard<std::mutex> lk(db.mu);
+                 for (auto& s : sk) db.add(std::move(s), true);
+             }, py::arg("items"), py::kw_only(), py::arg("seed") = true,
+             "Add many reference genomes in one GPU batch: items = [(name, contigs), ...] (extension over pyskani).")
+        .def("query_many", [](Database& db, const py::sequence& items, bool seed, const py::object& learned_ani, bool median, bool robust,
+                              const py::object& cutoff, bool faster_small) {
+                 std::vector<Sketch> qs = sketch_many_impl(db, items, seed);
+                 skb_query_opts_t o{};
+                 o.cutoff = cutoff.is_none() ? 0.0 : cutoff.cast<double>();
+                 o.learned_ani = learned_ani.is_none() ? -1 : (learned_ani.cast<bool>() ? 1 : 0);
+                 o.median = median; o.robust = robust; o.faster_small = faster_small;
+                 std::vector<skb_sketch_t*> qh;
+                 for (auto& q : qs) qh.push_back(q.handle->h);
+                 skb_hit_t* hits = nullptr; uint64_t n = 0;
+                 int rc;
+                 {
+                     std::lock_guard<std::mutex> lk(db.mu);
+                     py::gil_scoped_release nogil;
+                     rc = skb_db_query(db.db, (uint32_t)qh.size(), qh.data(), &o, &hits, &n, nullptr);
+                 }
+                 if (rc == SKB_ERR_UNSUPPORTED) throw std::runtime_error(skb_last_error(global_ctx()));
+                 check(global_ctx(), rc);
+                 std::vector<std::vector<Hit>> out(qs.size());
+                 for (uint64_t i = 0; i < n; i++)
+                     out[hits[i].query_index].push_back(Hit{hits[i].ani, qs[hits[i].query_index].name, hits[i].af_query,
+                                                            db.items[hits[i].ref_index].name, hits[i].af_ref});
+                 skb_hits_free(hits);
+                 return out;
+             }, py::arg("items"), py::kw_only(), py::arg("seed") = true, py::arg("learned_ani") = py::none(), py::arg("median") = false,
+             py::arg("robust") = false, py::arg("cutoff") = py::none(), py::arg("faster_small") = false,
+             "Query with many genomes in one GPU batch: items = [(name, contigs), ...]; returns one list of Hit per query "
+             "(extension over pyskani).")
         .def("save", [](Database& db, const py::object& path, bool overwrite, const py::object& format) {
                  const std::string folder = fsdecode(path);
                  if (!exists(folder)) mkdirs(folder);

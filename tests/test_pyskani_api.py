@@ -194,3 +194,27 @@ class TestStorageRoundTrip:
         (folder / "markers.bin").write_bytes(b"\x01\x02\x03")
         with pytest.raises(ValueError):
             pyskani.Database.load(str(folder))
+
+
+class TestBatchedEntryPoints:
+    """batched calls give the same answers as the per-genome API."""
+
+    def test_sketch_many_and_query_many(self, pyskani):
+        from pyskani_b200 import synth
+        base = synth.random_genome(300_000, 15)
+        refs = {"r%d" % i: synth.mutate(base, d, 16 + i).tobytes() for i, d in enumerate((0.01, 0.05, 0.1))}
+        frag = [c.tobytes() for c in synth.fragment(synth.mutate(base, 0.04, 30), 31, lo=500, hi=40_000)]
+        one = pyskani.Database()
+        for name, seq in refs.items():
+            one.sketch(name, seq)
+        one.sketch("frag", *frag)
+        many = pyskani.Database()
+        many.sketch_many([(n, s) for n, s in refs.items()] + [("frag", frag)])
+        assert len(many) == len(one) == 4
+        queries = [("q0", base.tobytes()), ("q1", frag), ("q2", synth.random_genome(100_000, 99).tobytes())]
+        want = [one.query(n, *(c if isinstance(c, list) else [c]), learned_ani=False) for n, c in queries]
+        got = many.query_many(queries, learned_ani=False)
+        assert len(got) == 3 and got[2] == []
+        for w, g in zip(want, got):
+            assert [(h.reference_name, h.identity, h.query_fraction, h.reference_fraction, h.query_name) for h in w] == \
+                   [(h.reference_name, h.identity, h.query_fraction, h.reference_fraction, h.query_name) for h in g]
