@@ -117,7 +117,10 @@ class Context:
 
     def close(self):
         if self._h:
-            lib().skb_ctx_destroy(self._h)
+            try:
+                lib().skb_ctx_destroy(self._h)
+            except TypeError:      # interpreter shutdown: module globals are already gone
+                pass
             self._h = None
 
     def __del__(self):
@@ -203,7 +206,10 @@ class Sketch:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib().skb_sketch_free(self._h)
+            try:
+                lib().skb_sketch_free(self._h)
+            except TypeError:
+                pass
             self._h = None
 
     def info(self):
@@ -230,7 +236,10 @@ class Database:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib().skb_db_destroy(self._h)
+            try:
+                lib().skb_db_destroy(self._h)
+            except TypeError:
+                pass
             self._h = None
 
     def add(self, sketch):
