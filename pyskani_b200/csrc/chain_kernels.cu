@@ -61,23 +61,30 @@ __global__ void match_count_kernel(const ChainBatch b) {
     const GenomeView& Q = b.qviews[pd.q];
     const GenomeView& R = b.rviews[pd.r];
     const uint32_t nq = Q.n_seeds;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
-        const uint32_t km = __ldg(Q.kmer_p + i);
+    const int lane = threadIdx.x & 31;
+    // warp-aligned strips of 32 consecutive query seeds: the strip's "has a match" bits are one word of the bitmask
+    for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < nq; i0 += gridDim.x * blockDim.x) {
+        const uint32_t i = i0 + lane;
         uint32_t first = 0, cnt = 0;
-        if (R.n_seeds) {
+        if (i < nq && R.n_seeds) {
+            const uint32_t km = __ldg(Q.kmer_p + i);
             const uint32_t bk = km >> R.bucket_shift;
             uint32_t lo = __ldg(R.bucket + bk), hi = __ldg(R.bucket + bk + 1);
+            const uint32_t end = hi;
             while (lo < hi) {               // buckets hold ~8 seeds: a short search
                 uint32_t mid = (lo + hi) >> 1;
                 if (__ldg(R.kmer_k + mid) < km) lo = mid + 1; else hi = mid;
             }
             first = lo;
-            const uint32_t end = __ldg(R.bucket + bk + 1);
             while (lo < end && __ldg(R.kmer_k + lo) == km) lo++;
             cnt = lo - first;
         }
-        b.m_first[pd.seed_off + i] = first;
-        b.m_cnt[pd.seed_off + i] = cnt;
+        if (i < nq) {
+            b.m_first[pd.seed_off + i] = first;
+            b.m_cnt[pd.seed_off + i] = cnt;
+        }
+        const uint32_t bal = __ballot_sync(FULL, cnt != 0);
+        if (lane == 0) b.m_bits[pd.bits_off + (i0 >> 5)] = bal;
     }
 }
 
@@ -111,9 +118,9 @@ __global__ void anchor_fill_kernel(const ChainBatch b) {
 // >= the previous opening position + F.  That is a serial chain per contig (~230 links for a 5 Mbp contig), so the
 // cost is the latency of one link.  Window j of contig c lands in slot win_off + contig_win_start[c] + j.
 //
-// Fast path (window_walk_smem_kernel): one CTA per pair stages the query's seed positions and a "has a match" bitmask
-// in shared memory (4 B + 1 bit per seed; <= WALK_SMEM_SEEDS seeds), then one warp per contig follows the chain with
-// every link resolved on chip.  Fallback (window_walk_kernel): same walk with 32-ary searches in global memory.
+// Fast path (window_walk_smem_kernel): one CTA per pair stages the query's seed positions and the "has a match" bitmask
+// (written by match_count_kernel) in shared memory with TMA bulk copies (4 B + 1 bit per seed; <= WALK_SMEM_SEEDS
+// seeds), then one warp per contig follows the chain with every link resolved on chip.  Fallback (window_walk_kernel): same walk with 32-ary searches in global memory.
 constexpr uint32_t WALK_SMEM_SEEDS = 49152;     // 192 KB of positions + 6 KB of bits
 
 __global__ void window_walk_kernel(const ChainBatch b, const uint32_t F, const int only_large) {
@@ -159,36 +166,64 @@ __device__ __forceinline__ uint32_t next_set_bit(const uint32_t* bits, uint32_t 
     return r < n ? r : n;
 }
 
+// ---- TMA 1-D bulk copy (cp.async.bulk, SASS: UBLKCP) + mbarrier, used to stage a pair's arrays in shared memory
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 __global__ void __launch_bounds__(1024) window_walk_smem_kernel(const ChainBatch b, const uint32_t F) {
-    extern __shared__ uint32_t sm[];
+    extern __shared__ __align__(128) uint32_t sm[];
+    __shared__ uint64_t s_bar;
     const PairDesc pd = b.pairs[blockIdx.x];
     const GenomeView& Q = b.qviews[pd.q];
     const uint32_t n = Q.n_seeds;
     if (n > WALK_SMEM_SEEDS) return;                  // handled by the global-memory kernel
-    uint32_t* s_pos = sm;                             // [n]
-    uint32_t* s_bits = sm + n;                        // [(n + 31) / 32]
-    const uint32_t* cnt = b.m_cnt + pd.seed_off;
+    // The query's seed positions keep their 16-byte phase in shared memory, so the 16-byte aligned middle of the
+    // array can go through one TMA bulk copy per 32 KB; the (<= 3 + 3) unaligned head/tail words are copied by threads.
+    const uint32_t* src = Q.pos_p;
+    const uint32_t phase = (uint32_t)(((uintptr_t)src >> 2) & 3u);
+    uint32_t* s_pos = sm + phase;                     // [n]
+    const uint32_t head = min(n, (4u - phase) & 3u);
+    const uint32_t mid = ((n - head) >> 2) << 2;
+    const uint32_t n_bit_words = (((n + 31) >> 5) + 3u) & ~3u;                 // padded to 16 bytes (so is the source slice)
+    uint32_t* s_bits = sm + ((phase + n + 3u) & ~3u);                          // 16-byte aligned
+    const uint32_t* bits_src = b.m_bits + pd.bits_off;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    // staging: 8 independent loads in flight per lane (the loop is latency-bound otherwise)
-    constexpr int U = 4;
-    for (uint32_t i0 = warp * 32; i0 < n; i0 += nwarps * 32 * U) {
-        uint32_t p[U], cv[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t i = i0 + u * nwarps * 32 + lane;
-            p[u] = i < n ? __ldg(Q.pos_p + i) : 0u;
-            cv[u] = i < n ? __ldg(cnt + i) : 0u;
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&s_bar, mid * 4u + n_bit_words * 4u);
+        for (uint32_t off = 0; off < mid; off += 8192) {
+            const uint32_t cnt = min(8192u, mid - off);
+            bulk_g2s(s_pos + head + off, src + head + off, cnt * 4u, &s_bar);
         }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t ib = i0 + u * nwarps * 32;       // warp-uniform
-            if (ib >= n) break;
-            const uint32_t i = ib + lane;
-            if (i < n) s_pos[i] = p[u];
-            const uint32_t bal = __ballot_sync(FULL, i < n && cv[u] != 0);
-            if (lane == 0) s_bits[ib >> 5] = bal;
-        }
+        if (n_bit_words) bulk_g2s(s_bits, bits_src, n_bit_words * 4u, &s_bar);
     }
+    for (uint32_t i = threadIdx.x; i < n - mid; i += blockDim.x) {             // head and tail words
+        const uint32_t j = i < head ? i : mid + i;
+        s_pos[j] = __ldg(src + j);
+    }
+    mbar_wait(&s_bar, 0);
     __syncthreads();
     for (uint32_t c = warp; c < Q.n_contigs; c += nwarps) {
         const uint32_t cs = Q.contig_seed_start[c], ce = Q.contig_seed_start[c + 1];
@@ -500,10 +535,10 @@ void launch_anchor_fill(const ChainBatch& b, cudaStream_t st) {
 void launch_window_walk(const ChainBatch& b, const ChainConsts& c, uint32_t max_query_seeds, cudaStream_t st) {
     if (b.n_pairs == 0) return;
     // shared-memory walk for every pair whose query fits, global-memory walk for the rest
-    const size_t cap_bytes = (size_t)WALK_SMEM_SEEDS * 4 + ((WALK_SMEM_SEEDS + 31) / 32) * 4 + 16;
+    const size_t cap_bytes = ((size_t)WALK_SMEM_SEEDS + 8) * 4 + (((size_t)WALK_SMEM_SEEDS + 31) / 32 + 4) * 4 + 64;
     cudaFuncSetAttribute(window_walk_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap_bytes);
     const uint32_t n = max_query_seeds < WALK_SMEM_SEEDS ? max_query_seeds : WALK_SMEM_SEEDS;
-    const size_t bytes = (size_t)n * 4 + ((n + 31) / 32) * 4 + 16;
+    const size_t bytes = ((size_t)n + 8) * 4 + ((((size_t)n + 31) / 32 + 3) / 4 * 4) * 4 + 64;
     window_walk_smem_kernel<<<b.n_pairs, 1024, bytes, st>>>(b, c.fragment_length);
     g_kernel_launches++;
     if (max_query_seeds > WALK_SMEM_SEEDS) {

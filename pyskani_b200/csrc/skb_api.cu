@@ -937,14 +937,15 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
         size_t p0 = 0;
         while (p0 < n_pass) {
             std::vector<PairDesc> pairs;
-            uint64_t seeds = 0, wins = 0;
+            uint64_t seeds = 0, wins = 0, bit_words = 0;
             uint32_t max_qseeds = 0;
             size_t p1 = p0;
             while (p1 < n_pass) {
                 const uint32_t q = so.pass_idx[p1] / nr, r = so.pass_idx[p1] % nr;
                 const GenomeView& qv = qs[q]->view;
                 if (!pairs.empty() && (seeds + qv.n_seeds > MAX_BATCH_SEEDS || pairs.size() >= 65535)) break;
-                pairs.push_back(PairDesc{q, r, (uint32_t)seeds, (uint32_t)wins});
+                pairs.push_back(PairDesc{q, r, (uint32_t)seeds, (uint32_t)wins, (uint32_t)bit_words});
+                bit_words += ((qv.n_seeds + 31) / 32 + 3) / 4 * 4;     // 16-byte aligned slices (bulk-copy source)
                 seeds += qv.n_seeds; wins += qv.win_cap;
                 max_qseeds = std::max(max_qseeds, qv.n_seeds);
                 p1++;
@@ -958,7 +959,8 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
             CU(cudaMemcpyAsync(d_pairs.p, pairs.data(), sizeof(PairDesc) * np, cudaMemcpyHostToDevice, st));
             B.pairs = d_pairs.as<PairDesc>();
             DevMem d_first(db->core, 4 * (seeds + 1)), d_cnt(db->core, 4 * (seeds + 1)), d_aoff(db->core, 4 * (seeds + 2));
-            B.m_first = d_first.as<uint32_t>(); B.m_cnt = d_cnt.as<uint32_t>(); B.a_off = d_aoff.as<uint32_t>();
+            DevMem d_bits(db->core, 4 * (bit_words + 4));
+            B.m_first = d_first.as<uint32_t>(); B.m_cnt = d_cnt.as<uint32_t>(); B.a_off = d_aoff.as<uint32_t>(); B.m_bits = d_bits.as<uint32_t>();
             CU(cudaMemsetAsync(B.m_cnt + seeds, 0, 4, st));
             launch_match_count(B, st);
             {

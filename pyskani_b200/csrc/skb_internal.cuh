@@ -157,6 +157,7 @@ struct PairDesc {
     uint32_t q, r;             // indices into the query / reference view arrays
     uint32_t seed_off;         // offset of this pair's slice in the per-query-seed scratch arrays
     uint32_t win_off;          // offset of this pair's slice in the window arrays
+    uint32_t bits_off;         // word offset of this pair's slice in the match bitmask (ceil(n_seeds / 32) words, 16-byte aligned)
 };
 
 struct WindowRec {             // one 20 kb query window of one pair
@@ -179,6 +180,7 @@ struct ChainBatch {            // device pointers of one batch of pairs
     // per query seed of each pair
     uint32_t* m_first;         // first matching index in the reference's k-mer order
     uint32_t* m_cnt;           // number of matches
+    uint32_t* m_bits;          // bit i of a pair's slice = query seed i has at least one match
     uint32_t* a_off;           // exclusive scan of m_cnt (+1 trailing element = total)
     // anchors
     uint32_t anchor_cap;
