@@ -230,8 +230,7 @@ def main():
         sk = ctx.sketch_batch_device(d_ptr, gstart, offs, lens)
         st = ctx.stats()
         db = capi.Database(ctx)
-        for s in sk[:-1]:
-            db.add(s)
+        db.add_many(sk[:-1])
         hits, n_in = db.query([sk[-1]])
         st2 = ctx.stats()
         return len(hits), st.seed_ms, st.total_ms, st2.total_ms
@@ -242,8 +241,7 @@ def main():
         ctx.check(L.skb_sketch_batch(ctx._h, C.byref(params), 1, n_g, gs_c, host_ptrs, host_lens, out))
         sk = [capi.Sketch(ctx, out[i]) for i in range(n_g)]
         db = capi.Database(ctx)
-        for s in sk[:-1]:
-            db.add(s)
+        db.add_many(sk[:-1])
         hits, n_in = db.query([sk[-1]])
         return len(hits)
 

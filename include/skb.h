@@ -130,6 +130,8 @@ int  skb_db_create(skb_ctx_t* ctx, skb_db_t** out);
 void skb_db_destroy(skb_db_t* db);
 /* Database.sketch's two pushes (lib.rs:501-508).  The database shares ownership of the sketch. */
 int  skb_db_add(skb_db_t* db, skb_sketch_t* s, uint32_t* index_out);
+/* the same for n sketches in one call; index_out (may be NULL) receives the index of the first one */
+int  skb_db_add_many(skb_db_t* db, uint32_t n, skb_sketch_t* const* sketches, uint32_t* index_out);
 uint64_t skb_db_size(const skb_db_t* db);
 
 /* ---- query: lib.rs:616-657 for n_queries queries at once ----

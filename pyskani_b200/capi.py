@@ -48,7 +48,7 @@ SYMBOLS = [
     "skb_ctx_create", "skb_ctx_destroy", "skb_last_error", "skb_ctx_stats", "skb_ctx_sync", "skb_ctx_stream",
     "skb_host_alloc", "skb_host_free", "skb_dev_alloc", "skb_dev_free", "skb_memcpy_h2d",
     "skb_sketch_batch", "skb_sketch_batch_device", "skb_sketch_free", "skb_sketch_info", "skb_sketch_export",
-    "skb_sketch_import", "skb_db_create", "skb_db_destroy", "skb_db_add", "skb_db_size", "skb_db_query",
+    "skb_sketch_import", "skb_db_create", "skb_db_destroy", "skb_db_add", "skb_db_add_many", "skb_db_size", "skb_db_query",
     "skb_hits_free", "skb_db_screen", "skb_version",
 ]
 
@@ -93,6 +93,7 @@ def lib():
         L.skb_db_create.argtypes = [vp, C.POINTER(vp)]
         L.skb_db_destroy.argtypes = [vp]
         L.skb_db_add.argtypes = [vp, vp, C.POINTER(u32)]
+        L.skb_db_add_many.argtypes = [vp, u32, vp, C.POINTER(u32)]
         L.skb_db_size.restype = u64
         L.skb_db_size.argtypes = [vp]
         L.skb_db_query.argtypes = [vp, u32, vp, C.POINTER(QueryOpts), C.POINTER(C.POINTER(Hit)), C.POINTER(u64),
@@ -246,6 +247,14 @@ class Database:
         idx = C.c_uint32()
         self.ctx.check(lib().skb_db_add(self._h, sketch._h, C.byref(idx)))
         self._keep.append(sketch)
+        return idx.value
+
+    def add_many(self, sketches):
+        n = len(sketches)
+        hs = (C.c_void_p * max(n, 1))(*[s._h for s in sketches])
+        idx = C.c_uint32()
+        self.ctx.check(lib().skb_db_add_many(self._h, n, hs, C.byref(idx)))
+        self._keep.extend(sketches)
         return idx.value
 
     def __len__(self):

@@ -806,6 +806,22 @@ int skb_db_add(skb_db_t* db, skb_sketch_t* s, uint32_t* index_out) {
         return SKB_OK;
     });
 }
+int skb_db_add_many(skb_db_t* db, uint32_t n, skb_sketch_t* const* sketches, uint32_t* index_out) {
+    if (!db || (n && !sketches)) return SKB_ERR_ARG;
+    return guarded(db->core.get(), [&] {
+        for (uint32_t i = 0; i < n; i++) {
+            if (!sketches[i]) throw Fail{SKB_ERR_ARG, "null sketch"};
+            if (sketches[i]->impl->core != db->core) throw Fail{SKB_ERR_ARG, "sketch belongs to another context"};
+            const auto& a0 = db->items.empty() ? sketches[0]->impl->info : db->items[0]->info;
+            const auto& b0 = sketches[i]->impl->info;
+            if (a0.k != b0.k || a0.c != b0.c || a0.marker_c != b0.marker_c) throw Fail{SKB_ERR_ARG, "sketch parameters differ from the database's"};
+        }
+        if (index_out) *index_out = (uint32_t)db->items.size();
+        for (uint32_t i = 0; i < n; i++) db->items.push_back(sketches[i]->impl);
+        db->dirty = true;
+        return SKB_OK;
+    });
+}
 uint64_t skb_db_size(const skb_db_t* db) { return db ? db->items.size() : 0; }
 
 void skb_hits_free(skb_hit_t* hits) { delete[] hits; }
