@@ -6,6 +6,7 @@
 //   marker_seeds : FxHashSet<u64>                            ->  sorted unique 21-mers per genome
 // Sorting is CUB's device radix sort (library code, like cuBLAS for a GEMM); everything around it is ours.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_segmented_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
@@ -114,22 +115,53 @@ __global__ void pull_copy_kernel(uint32_t* __restrict__ dst, const uint32_t* __r
 }  // namespace
 
 size_t kmer_order_scratch_bytes(uint32_t n) {
-    size_t cub_bytes = 0;
+    size_t cub_bytes = 0, seg_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
                                     (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 64);
+    cub::DeviceSegmentedRadixSort::SortPairs(nullptr, seg_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                             (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 1 << 22,
+                                             (const uint32_t*)nullptr, (const uint32_t*)nullptr, 0, 32);
+    if (seg_bytes > cub_bytes) cub_bytes = seg_bytes;
     return align_up(cub_bytes) + 2 * align_up((size_t)n * 8) + 2 * align_up((size_t)n * 4) + 1024;
+}
+
+__global__ void iota_kernel(uint32_t* out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
+__global__ void gather_pos_meta(uint32_t n, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ pos_p,
+                                const uint32_t* __restrict__ meta_p, uint32_t* __restrict__ pos_k, uint32_t* __restrict__ meta_k) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t src = vals[i];
+    pos_k[i] = pos_p[src];
+    meta_k[i] = meta_p[src];
 }
 
 void build_kmer_order(const IndexBuildArgs& a, void* scratch, size_t scratch_bytes, cudaStream_t st) {
     const uint32_t n = a.n_seeds_total;
     if (n == 0) return;
+    const int T = 256;
     char* p = (char*)scratch;
+    if (a.max_genome_seeds <= SEGMENTED_SORT_MAX) {
+        // Seeds are already grouped by genome (position order), so the (genome, kmer) order is a SEGMENTED sort by
+        // k-mer: 32-bit keys straight from kmer_p, 2k bits, one CTA per genome working in L2.  Stable, so equal k-mers
+        // keep their (contig, pos) order.
+        uint32_t* vals_in = (uint32_t*)p; p += align_up((size_t)n * 4);
+        uint32_t* vals_out = (uint32_t*)p; p += align_up((size_t)n * 4);
+        size_t cub_bytes = scratch_bytes - (size_t)(p - (char*)scratch);
+        iota_kernel<<<(n + T - 1) / T, T, 0, st>>>(vals_in, n);
+        cub::DeviceSegmentedRadixSort::SortPairs(p, cub_bytes, a.kmer_p, a.kmer_k, vals_in, vals_out, (int)n, (int)a.n_genomes,
+                                                 a.genome_seed_start, a.genome_seed_start + 1, 0, 2 * a.k, st);
+        gather_pos_meta<<<(n + T - 1) / T, T, 0, st>>>(n, vals_out, a.pos_p, a.meta_p, a.pos_k, a.meta_k);
+        g_kernel_launches += 3;
+        return;
+    }
     uint64_t* keys_in = (uint64_t*)p; p += align_up((size_t)n * 8);
     uint64_t* keys_out = (uint64_t*)p; p += align_up((size_t)n * 8);
     uint32_t* vals_in = (uint32_t*)p; p += align_up((size_t)n * 4);
     uint32_t* vals_out = (uint32_t*)p; p += align_up((size_t)n * 4);
     size_t cub_bytes = scratch_bytes - (size_t)(p - (char*)scratch);
-    const int T = 256;
     make_seed_keys<<<(n + T - 1) / T, T, 0, st>>>(n, a.n_genomes, a.genome_seed_start, a.kmer_p, keys_in, vals_in);
     g_kernel_launches++;
     int gbits = 0;

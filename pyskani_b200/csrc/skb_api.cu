@@ -362,6 +362,7 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             void* sort_scratch = c.scratch(SLOT_SORT, sort_bytes);
             IndexBuildArgs ib{};
             ib.n_genomes = n_genomes; ib.n_seeds_total = ns; ib.genome_seed_start = d_gs;
+            for (uint32_t g = 0; g < n_genomes; g++) ib.max_genome_seeds = std::max(ib.max_genome_seeds, seed_start[g + 1] - seed_start[g]);
             ib.kmer_p = store->kmer_p.as<uint32_t>(); ib.pos_p = store->pos_p.as<uint32_t>(); ib.meta_p = store->meta_p.as<uint32_t>();
             ib.kmer_k = store->kmer_k.as<uint32_t>(); ib.pos_k = store->pos_k.as<uint32_t>(); ib.meta_k = store->meta_k.as<uint32_t>();
             ib.k = P.k;
@@ -765,7 +766,7 @@ int skb_sketch_import(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t
             CU(cudaMemcpyAsync(d_gs.p, seed_start.data(), 8, cudaMemcpyHostToDevice, st));
             DevMem scratch(ctx->core, kmer_order_scratch_bytes(n));
             IndexBuildArgs ib{};
-            ib.n_genomes = 1; ib.n_seeds_total = n; ib.genome_seed_start = d_gs.as<uint32_t>();
+            ib.n_genomes = 1; ib.n_seeds_total = n; ib.genome_seed_start = d_gs.as<uint32_t>(); ib.max_genome_seeds = n;
             ib.kmer_p = store->kmer_p.as<uint32_t>(); ib.pos_p = store->pos_p.as<uint32_t>(); ib.meta_p = store->meta_p.as<uint32_t>();
             ib.kmer_k = store->kmer_k.as<uint32_t>(); ib.pos_k = store->pos_k.as<uint32_t>(); ib.meta_k = store->meta_k.as<uint32_t>();
             ib.k = params->k;

@@ -107,11 +107,14 @@ void launch_seed_scan(const SeedScanArgs& a, int n_sm, cudaStream_t st);
 struct IndexBuildArgs {
     uint32_t n_genomes;
     uint32_t n_seeds_total, n_markers_total;
+    uint32_t max_genome_seeds;            // largest per-genome seed count of the batch (chooses the sort strategy)
     const uint32_t* genome_seed_start;    // device [n_genomes+1]
     const uint32_t* kmer_p; const uint32_t* pos_p; const uint32_t* meta_p;
     uint32_t* kmer_k; uint32_t* pos_k; uint32_t* meta_k;
     int k;
 };
+
+constexpr uint32_t SEGMENTED_SORT_MAX = 262144;   // genomes up to ~32 Mbp are sorted by one CTA each
 
 // sorts (genome,kmer) keys carrying the position-order index, then gathers the *_k arrays
 void build_kmer_order(const IndexBuildArgs& a, void* scratch, size_t scratch_bytes, cudaStream_t st);
