@@ -174,14 +174,18 @@ void build_kmer_order(const IndexBuildArgs& a, void* scratch, size_t scratch_byt
 }
 
 size_t marker_scratch_bytes(uint32_t n) {
-    size_t s1 = 0, s2 = 0;
+    size_t s1 = 0, s2 = 0, s3 = 0;
     cub::DeviceRadixSort::SortKeys(nullptr, s1, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int)n, 0, 64);
+    cub::DeviceSegmentedRadixSort::SortKeys(nullptr, s3, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int)n, 1 << 22,
+                                            (const uint32_t*)nullptr, (const uint32_t*)nullptr, 0, 64);
+    if (s3 > s1) s1 = s3;
     cub::DeviceSelect::Unique(nullptr, s2, (const uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (int)n);
     return align_up(s1 > s2 ? s1 : s2) + 2 * align_up((size_t)n * 8 + 8) + 256 + 1024;
 }
 
 void build_marker_sets(uint32_t n_genomes, uint32_t n, uint64_t* marker_keys, uint64_t* markers_out,
-                       uint32_t* genome_marker_out, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+                       uint32_t* genome_marker_out, const uint32_t* genome_marker_in, uint32_t max_genome_markers,
+                       void* scratch, size_t scratch_bytes, cudaStream_t st) {
     const int T = 256;
     char* p = (char*)scratch;
     uint64_t* sorted = (uint64_t*)p; p += align_up((size_t)n * 8 + 8);
@@ -194,8 +198,15 @@ void build_marker_sets(uint32_t n_genomes, uint32_t n, uint64_t* marker_keys, ui
     }
     int gbits = 0;
     while ((1ull << gbits) < (uint64_t)n_genomes) gbits++;
-    cub::DeviceRadixSort::SortKeys(p, cub_bytes, marker_keys, sorted, (int)n, 0, 42 + gbits, st);
-    g_kernel_launches += 1 + (42 + gbits + 7) / 8;
+    if (genome_marker_in && max_genome_markers <= SEGMENTED_SORT_MAX) {
+        // marker keys arrive grouped by genome: sort the 42 marker bits inside each genome's segment
+        cub::DeviceSegmentedRadixSort::SortKeys(p, cub_bytes, marker_keys, sorted, (int)n, (int)n_genomes, genome_marker_in,
+                                                genome_marker_in + 1, 0, 42, st);
+        g_kernel_launches += 1;
+    } else {
+        cub::DeviceRadixSort::SortKeys(p, cub_bytes, marker_keys, sorted, (int)n, 0, 42 + gbits, st);
+        g_kernel_launches += 1 + (42 + gbits + 7) / 8;
+    }
     cub::DeviceSelect::Unique(p, cub_bytes, sorted, uniq, n_unique, (int)n, st);
     g_kernel_launches += 2;
     strip_marker_keys<<<(n + T - 1) / T, T, 0, st>>>(n, n_unique, uniq, markers_out);

@@ -90,7 +90,7 @@ void* Core::scratch(int slot, size_t bytes) {
     }
     return b.p;
 }
-enum { SLOT_SEQ = 0, SLOT_KMER, SLOT_POS, SLOT_META, SLOT_MKEYS, SLOT_STATUS, SLOT_SORT, SLOT_MARK, SLOT_GS, SLOT_GM, SLOT_DESC, SLOT_MKEYS2, SLOT_RSCAN };
+enum { SLOT_SEQ = 0, SLOT_KMER, SLOT_POS, SLOT_META, SLOT_MKEYS, SLOT_STATUS, SLOT_SORT, SLOT_MARK, SLOT_GS, SLOT_GM, SLOT_DESC, SLOT_MKEYS2, SLOT_RSCAN, SLOT_GM_IN };
 
 // stream-ordered device buffer
 struct DevMem {
@@ -373,7 +373,13 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
         {
             const size_t mark_bytes = marker_scratch_bytes(nm);
             void* mark_scratch = c.scratch(SLOT_MARK, mark_bytes);
-            build_marker_sets(n_genomes, nm, t_mkeys, store->markers.as<uint64_t>(), d_gm, mark_scratch, mark_bytes, st);
+            // pre-deduplication offsets (repaired on the host like the seed starts) live in their own small buffer: d_gm is
+            // overwritten with the post-deduplication offsets
+            uint32_t* d_gm_in = (uint32_t*)c.scratch(SLOT_GM_IN, g_bytes);
+            table_upload(c, d_gm_in, marker_start.data(), g_bytes);
+            uint32_t max_gm = 0;
+            for (uint32_t g = 0; g < n_genomes; g++) max_gm = std::max(max_gm, marker_start[g + 1] - marker_start[g]);
+            build_marker_sets(n_genomes, nm, t_mkeys, store->markers.as<uint64_t>(), d_gm, d_gm_in, max_gm, mark_scratch, mark_bytes, st);
             t2.mark("enqueued index");
         }
         CU(cudaEventRecord(c.ev[3], st));

@@ -122,8 +122,10 @@ size_t kmer_order_scratch_bytes(uint32_t n_seeds_total);
 
 // sorts marker keys and removes duplicates per genome; writes marker values (42-bit) to markers_out and the
 // per-genome offsets [n_genomes+1] to genome_marker_out (device)
+// genome_marker_in (device, [n_genomes + 1], may be NULL): offsets of each genome's keys before de-duplication
 void build_marker_sets(uint32_t n_genomes, uint32_t n_markers_total, uint64_t* marker_keys, uint64_t* markers_out,
-                       uint32_t* genome_marker_out, void* scratch, size_t scratch_bytes, cudaStream_t st);
+                       uint32_t* genome_marker_out, const uint32_t* genome_marker_in, uint32_t max_genome_markers,
+                       void* scratch, size_t scratch_bytes, cudaStream_t st);
 size_t marker_scratch_bytes(uint32_t n_markers_total);
 
 // copies `bytes` (rounded up to 4) from pinned, device-mapped host memory to device memory with a kernel
