@@ -69,7 +69,7 @@ __device__ __forceinline__ U64 xorshr(U64 x) {                        // x ^ (x 
 }
 // hash(x) < thr, x given in halves.  Step 1 is ~(x * (2^21 + 1)); the complement is folded into the first
 // xor-shift:  ~a ^ (~a >> 24) == a ^ (a >> 24) ^ 0xFFFFFF00_00000000.
-__device__ __forceinline__ bool hash_below(U64 x, uint32_t thr_lo, uint32_t thr_hi) {
+__device__ __forceinline__ U64 hash_halves(U64 x) {
     U64 a = mul_c(x, (1u << 21) + 1u);
     U64 b;
     b.lo = a.lo ^ shr_lo<24>(a.lo, a.hi);
@@ -78,7 +78,10 @@ __device__ __forceinline__ bool hash_below(U64 x, uint32_t thr_lo, uint32_t thr_
     b = xorshr<14>(b);
     b = mul_c(b, 21u);
     b = xorshr<28>(b);
-    b = mul_c(b, 0x80000001u);                                        // x + (x << 31)
+    return mul_c(b, 0x80000001u);                                     // x + (x << 31)
+}
+__device__ __forceinline__ bool hash_below(U64 x, uint32_t thr_lo, uint32_t thr_hi) {
+    const U64 b = hash_halves(x);
     return (((uint64_t)b.hi << 32) | b.lo) < (((uint64_t)thr_hi << 32) | thr_lo);
 }
 
