@@ -173,6 +173,129 @@ void build_kmer_order(const IndexBuildArgs& a, void* scratch, size_t scratch_byt
     g_kernel_launches++;
 }
 
+// ------------------------------------------------------------------ k-mer order by bucket partition
+// The k-mer order of a genome is (top-B-bit bucket, then k-mer, then position).  Buckets hold ~8 seeds, so instead of a
+// 30-bit radix sort the seeds are (1) counted per bucket, (2) the counts scanned per genome — which IS the bucket table
+// the anchor lookup needs —, (3) scattered to their bucket with an atomic cursor, and (4) each bucket's handful of
+// entries is put in (k-mer, position-index) order by one thread.  The result is identical to the stable radix sort.
+namespace {
+
+__device__ __forceinline__ uint32_t genome_of(const BucketGenome* __restrict__ G, uint32_t n_genomes, uint32_t i) {
+    uint32_t lo = 0, hi = n_genomes;           // last genome whose seed_start <= i and that is not empty
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (G[mid].seed_start <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void bucket_count_kernel(uint32_t n, uint32_t n_genomes, const BucketGenome* __restrict__ G,
+                                    const uint32_t* __restrict__ kmer_p, uint32_t* __restrict__ counts) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const BucketGenome g = G[genome_of(G, n_genomes, i)];
+    atomicAdd(&counts[g.bucket_off + (__ldg(kmer_p + i) >> g.shift)], 1u);
+}
+
+// one CTA per genome: bucket[b] = number of seeds in buckets < b (b = 0..n_buckets), cursor[b] = bucket[b]
+__global__ void __launch_bounds__(1024) bucket_scan_kernel(const BucketGenome* __restrict__ G, uint32_t* __restrict__ counts_to_cursor,
+                                                           uint32_t* __restrict__ bucket) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const BucketGenome g = G[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 <= g.n_buckets; b0 += 1024) {
+        const uint32_t b = b0 + threadIdx.x;
+        const uint32_t v = b < g.n_buckets ? counts_to_cursor[g.bucket_off + b] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+            s_warp[lane] = winc - w;
+        }
+        __syncthreads();
+        const uint32_t excl = s_carry + s_warp[warp] + inc - v;
+        if (b <= g.n_buckets) { bucket[g.bucket_off + b] = excl; counts_to_cursor[g.bucket_off + b] = excl; }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+}
+
+// record of one seed inside its bucket: (k-mer, index in position order, position, meta)
+__global__ void bucket_scatter_kernel(uint32_t n, uint32_t n_genomes, const BucketGenome* __restrict__ G,
+                                      const uint32_t* __restrict__ kmer_p, const uint32_t* __restrict__ pos_p,
+                                      const uint32_t* __restrict__ meta_p, uint32_t* __restrict__ cursor, uint4* __restrict__ tmp) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const BucketGenome g = G[genome_of(G, n_genomes, i)];
+    const uint32_t km = __ldg(kmer_p + i);
+    const uint32_t slot = atomicAdd(&cursor[g.bucket_off + (km >> g.shift)], 1u);
+    tmp[g.seed_start + slot] = make_uint4(km, i - g.seed_start, __ldg(pos_p + i), __ldg(meta_p + i));
+}
+
+constexpr uint32_t BUCKET_RANK_MAX = 256;   // larger buckets (low-complexity genomes) send the batch to the radix-sort path
+
+// one thread per scattered record: its rank inside the bucket = number of bucket entries with a smaller
+// (k-mer, position index); the bucket's ~8 records sit in the same few cache lines for all of its threads
+__global__ void bucket_rank_kernel(uint32_t n, uint32_t n_genomes, const BucketGenome* __restrict__ G,
+                                   const uint32_t* __restrict__ bucket, const uint4* __restrict__ tmp,
+                                   uint32_t* __restrict__ kmer_k, uint32_t* __restrict__ pos_k, uint32_t* __restrict__ meta_k,
+                                   uint32_t* __restrict__ overflow) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const BucketGenome g = G[genome_of(G, n_genomes, t)];
+    const uint4 me = tmp[t];
+    const uint32_t b = me.x >> g.shift;
+    const uint32_t s = bucket[g.bucket_off + b], e = bucket[g.bucket_off + b + 1];
+    if (e - s > BUCKET_RANK_MAX) { *overflow = 1u; return; }
+    const uint64_t key = ((uint64_t)me.x << 32) | me.y;
+    uint32_t rank = 0;
+    const uint4* src = tmp + g.seed_start;
+    for (uint32_t j = s; j < e; j++) {
+        const uint4 o = src[j];
+        rank += ((((uint64_t)o.x << 32) | o.y) < key) ? 1u : 0u;
+    }
+    const uint32_t dst = g.seed_start + s + rank;
+    kmer_k[dst] = me.x; pos_k[dst] = me.z; meta_k[dst] = me.w;
+}
+
+}  // namespace
+
+size_t bucket_order_scratch_bytes(uint32_t n_seeds, size_t bucket_total) {
+    (void)bucket_total;
+    return align_up((size_t)n_seeds * 16) + 1024;
+}
+
+// genomes_dev: [n_genomes] table; bucket: the store's bucket array [bucket_total]; overflow: device flag (pre-zeroed)
+void build_kmer_order_buckets(uint32_t n_seeds, uint32_t n_genomes, const BucketGenome* genomes_dev, size_t bucket_total,
+                              uint32_t* counts, int counts_ready, const uint32_t* kmer_p, const uint32_t* pos_p,
+                              const uint32_t* meta_p, uint32_t* kmer_k, uint32_t* pos_k, uint32_t* meta_k, uint32_t* bucket,
+                              uint32_t* overflow, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    if (n_genomes == 0) return;
+    (void)scratch_bytes;
+    uint4* tmp = (uint4*)scratch;
+    const int T = 256;
+    if (counts_ready == 0) {
+        cudaMemsetAsync(counts, 0, bucket_total * 4, st);
+        if (n_seeds) bucket_count_kernel<<<(n_seeds + T - 1) / T, T, 0, st>>>(n_seeds, n_genomes, genomes_dev, kmer_p, counts);
+        g_kernel_launches++;
+    }
+    bucket_scan_kernel<<<n_genomes, 1024, 0, st>>>(genomes_dev, counts, bucket);       // counts become the scatter cursors
+    if (n_seeds) {
+        bucket_scatter_kernel<<<(n_seeds + T - 1) / T, T, 0, st>>>(n_seeds, n_genomes, genomes_dev, kmer_p, pos_p, meta_p, counts, tmp);
+        bucket_rank_kernel<<<(n_seeds + T - 1) / T, T, 0, st>>>(n_seeds, n_genomes, genomes_dev, bucket, tmp, kmer_k, pos_k, meta_k, overflow);
+    }
+    g_kernel_launches += 3;
+}
+
 size_t marker_scratch_bytes(uint32_t n) {
     size_t s1 = 0, s2 = 0, s3 = 0;
     cub::DeviceRadixSort::SortKeys(nullptr, s1, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int)n, 0, 64);

@@ -31,7 +31,7 @@ struct Core {
     // grow-only scratch blocks reused by every call on this context (calls are serialised by `mu`): keeps the big
     // transient buffers out of the allocator so that repeated batches never re-map device memory
     struct Block { void* p = nullptr; size_t bytes = 0; };
-    Block arena[16];
+    Block arena[20];
     void* scratch(int slot, size_t bytes);
     cudaStream_t copy_stream = nullptr;       // host->device copies of skb_sketch_batch run here, ahead of the kernels
     std::vector<cudaEvent_t> ev_pool;         // "chunk is on the device" events (timing disabled)
@@ -90,7 +90,7 @@ void* Core::scratch(int slot, size_t bytes) {
     }
     return b.p;
 }
-enum { SLOT_SEQ = 0, SLOT_KMER, SLOT_POS, SLOT_META, SLOT_MKEYS, SLOT_STATUS, SLOT_SORT, SLOT_MARK, SLOT_GS, SLOT_GM, SLOT_DESC, SLOT_MKEYS2, SLOT_RSCAN, SLOT_GM_IN };
+enum { SLOT_SEQ = 0, SLOT_KMER, SLOT_POS, SLOT_META, SLOT_MKEYS, SLOT_STATUS, SLOT_SORT, SLOT_MARK, SLOT_GS, SLOT_GM, SLOT_DESC, SLOT_MKEYS2, SLOT_RSCAN, SLOT_GM_IN, SLOT_BTAB, SLOT_BCOUNT };
 
 // stream-ordered device buffer
 struct DevMem {
@@ -183,12 +183,37 @@ static void table_upload(Core& c, void* dst, const void* src, size_t bytes) {
 // ------------------------------------------------------------------------------------------------ sketching
 struct KeptContig { uint64_t off; uint32_t len; };
 
+// Bucket table geometry of every genome of a batch: ~8 seeds per bucket, bucket id = kmer >> shift (shift <= 31).
+struct BucketPlan { std::vector<BucketGenome> genomes; size_t total = 0; uint32_t max_buckets = 1; };
+static BucketPlan plan_buckets(const skb_sketch_params_t& P, int seed, const std::vector<std::vector<uint32_t>>& contig_lens) {
+    // sized from the EXPECTED seed count (total length / c), which is known before seeding: the seeding kernel can then
+    // build the bucket histogram while it writes the seeds
+    BucketPlan bp;
+    const uint32_t n_genomes = (uint32_t)contig_lens.size();
+    bp.genomes.resize(n_genomes);
+    for (uint32_t g = 0; g < n_genomes; g++) {
+        uint64_t tot = 0;
+        for (uint32_t l : contig_lens[g]) tot += l;
+        const uint64_t ns = seed ? tot / (uint64_t)P.c : 0;
+        int B = 1;
+        while (B < 2 * P.k - 1 && B < 20 && ((uint64_t)8 << B) < ns) B++;
+        if (2 * P.k - B > 31) B = 2 * P.k - 31;
+        BucketGenome& bg = bp.genomes[g];
+        bg.seed_start = 0; bg.n_seeds = 0; bg.shift = (uint32_t)(2 * P.k - B); bg.n_buckets = 1u << B;
+        bg.bucket_off = (uint32_t)bp.total;
+        bp.total += bg.n_buckets + 1;
+        bp.max_buckets = std::max(bp.max_buckets, bg.n_buckets);
+    }
+    return bp;
+}
+
 // Finishes a batch whose seeds/markers are described by per-genome contig tables; shared by the scan path
 // (seq on device) and the import path (arrays from the host).
 static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_params_t& P, int seed,
                          uint32_t n_genomes, const std::vector<std::vector<uint32_t>>& contig_lens,
                          std::shared_ptr<BatchStore> store, const std::vector<uint32_t>& seed_start,
-                         std::vector<uint32_t>& marker_start, const uint32_t* d_marker_start, skb_sketch_t** out);
+                         std::vector<uint32_t>& marker_start, const uint32_t* d_marker_start, skb_sketch_t** out,
+                         const uint32_t* d_bucket_overflow = nullptr);
 
 // A chunk of the batch whose bytes become available on the device when `ready` fires (host->device pipelining):
 // flat contigs [previous contig_end, contig_end).
@@ -232,6 +257,7 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
         }
     }
     while (plan && plan_i < plan->size()) { chunk_desc_end.push_back((uint32_t)descs.size()); plan_i++; }
+    BucketPlan bplan = plan_buckets(P, seed, contig_lens);
     if (total_bases >= 0x7FFFFFFFull) throw Fail{SKB_ERR_ARG, "a sketch batch is limited to 2^31 bases; split the call"};
     if (n_genomes >= (1u << 22)) throw Fail{SKB_ERR_ARG, "a sketch batch is limited to 2^22 genomes"};
     const uint32_t n_tiles = (uint32_t)tile_count;
@@ -279,6 +305,7 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
         void* rscan_scratch = c.scratch(SLOT_RSCAN, rscan_bytes);
         uint32_t* d_gs = (uint32_t*)c.scratch(SLOT_GS, g_bytes);
         uint32_t* d_gm = (uint32_t*)c.scratch(SLOT_GM, g_bytes);
+        uint32_t* d_bcounts = (uint32_t*)c.scratch(SLOT_BCOUNT, 4 * bplan.total + 16);   // k-mer bucket histogram of the batch
 
         // per-tile capacities of the region storage: generous multiples of the expected hit counts; a region that
         // still overflows (low-complexity sequence) triggers one retry with the exact layout
@@ -356,17 +383,23 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
         // ---- k-mer order
         store->kmer_k = DevMem(core, 4 * (size_t)ns); store->pos_k = DevMem(core, 4 * (size_t)ns);
         store->meta_k = DevMem(core, 4 * (size_t)ns);
-        if (ns) {
-            table_upload(c, d_gs, seed_start.data(), 4 * (size_t)(n_genomes + 1));   // repaired starts
-            const size_t sort_bytes = kmer_order_scratch_bytes(ns);
-            void* sort_scratch = c.scratch(SLOT_SORT, sort_bytes);
-            IndexBuildArgs ib{};
-            ib.n_genomes = n_genomes; ib.n_seeds_total = ns; ib.genome_seed_start = d_gs;
-            for (uint32_t g = 0; g < n_genomes; g++) ib.max_genome_seeds = std::max(ib.max_genome_seeds, seed_start[g + 1] - seed_start[g]);
-            ib.kmer_p = store->kmer_p.as<uint32_t>(); ib.pos_p = store->pos_p.as<uint32_t>(); ib.meta_p = store->meta_p.as<uint32_t>();
-            ib.kmer_k = store->kmer_k.as<uint32_t>(); ib.pos_k = store->pos_k.as<uint32_t>(); ib.meta_k = store->meta_k.as<uint32_t>();
-            ib.k = P.k;
-            build_kmer_order(ib, sort_scratch, sort_bytes, st);
+        uint32_t* d_bover = nullptr;
+        {
+            // bucket partition: histogram (from the seeding kernel) -> per-genome scan (= the bucket tables) -> scatter ->
+            // rank inside the bucket
+            for (uint32_t g = 0; g < n_genomes; g++) { bplan.genomes[g].seed_start = seed_start[g]; bplan.genomes[g].n_seeds = seed_start[g + 1] - seed_start[g]; }
+            store->bucket = DevMem(core, 4 * bplan.total);
+            const size_t tab_bytes = sizeof(BucketGenome) * n_genomes;
+            char* d_tab = (char*)c.scratch(SLOT_BTAB, tab_bytes + 16);
+            table_upload(c, d_tab, bplan.genomes.data(), tab_bytes);
+            d_bover = (uint32_t*)(d_tab + (tab_bytes + 3) / 4 * 4);
+            CU(cudaMemsetAsync(d_bover, 0, 4, st));
+            const size_t bscr_bytes = bucket_order_scratch_bytes(ns, bplan.total);
+            void* bscr = c.scratch(SLOT_SORT, bscr_bytes);
+            build_kmer_order_buckets(ns, n_genomes, (const BucketGenome*)d_tab, bplan.total, d_bcounts, 0, store->kmer_p.as<uint32_t>(),
+                                     store->pos_p.as<uint32_t>(), store->meta_p.as<uint32_t>(), store->kmer_k.as<uint32_t>(),
+                                     store->pos_k.as<uint32_t>(), store->meta_k.as<uint32_t>(), store->bucket.as<uint32_t>(), d_bover,
+                                     bscr, bscr_bytes, st);
         }
         // ---- marker sets
         store->markers = DevMem(core, 8 * (size_t)std::max<uint32_t>(nm, 1));
@@ -383,7 +416,7 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             t2.mark("enqueued index");
         }
         CU(cudaEventRecord(c.ev[3], st));
-        finish_batch(core, P, seed, n_genomes, contig_lens, store, seed_start, marker_start, d_gm, out);
+        finish_batch(core, P, seed, n_genomes, contig_lens, store, seed_start, marker_start, d_gm, out, d_bover);
     } else {
         CU(cudaEventRecord(c.ev[1], st)); CU(cudaEventRecord(c.ev[2], st)); CU(cudaEventRecord(c.ev[3], st));
         finish_batch(core, P, seed, n_genomes, contig_lens, store, seed_start, marker_start, nullptr, out);
@@ -394,7 +427,10 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
 static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_params_t& P, int seed,
                          uint32_t n_genomes, const std::vector<std::vector<uint32_t>>& contig_lens,
                          std::shared_ptr<BatchStore> store, const std::vector<uint32_t>& seed_start,
-                         std::vector<uint32_t>& marker_start, const uint32_t* d_marker_start, skb_sketch_t** out) {
+                         std::vector<uint32_t>& marker_start, const uint32_t* d_marker_start, skb_sketch_t** out,
+                         const uint32_t* d_bucket_overflow) {
+    // d_bucket_overflow != NULL: the k-mer order and the bucket tables were already produced by the bucket-partition
+    // path (store->bucket is allocated and filled); the flag tells whether a bucket was too large for it
     // d_marker_start (device, may be NULL): per-genome offsets into the de-duplicated marker array, produced by the
     // marker kernels that are still in flight; they are fetched together with the end-of-batch synchronisation below
     Core& c = *core;
@@ -402,19 +438,18 @@ static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_par
     // ---- per-genome tables: buckets, contig seed starts, contig lengths, window capacities
     std::vector<GenomeView> views(n_genomes);
     std::vector<uint32_t> h_clen, h_cwin;
-    size_t bucket_total = 0, cstart_total = 0;
-    uint32_t max_buckets = 1, max_contigs = 0;
+    size_t cstart_total = 0;
+    uint32_t max_contigs = 0;
+    const BucketPlan bp = plan_buckets(P, seed, contig_lens);
+    const size_t bucket_total = bp.total;
+    const uint32_t max_buckets = bp.max_buckets;
     std::vector<size_t> bucket_off(n_genomes), cstart_off(n_genomes), clen_off(n_genomes);
     for (uint32_t g = 0; g < n_genomes; g++) {
         const uint32_t ns = seed_start[g + 1] - seed_start[g];
-        int B = 1;
-        while (B < 2 * P.k - 1 && B < 20 && ((uint64_t)8 << B) < ns) B++;   // ~8 seeds per bucket, shift <= 31
-        if (2 * P.k - B > 31) B = 2 * P.k - 31;
         GenomeView& v = views[g];
-        v.n_buckets = 1u << B;
-        v.bucket_shift = (uint32_t)(2 * P.k - B);
-        max_buckets = std::max(max_buckets, v.n_buckets);
-        bucket_off[g] = bucket_total; bucket_total += v.n_buckets + 1;
+        v.n_buckets = bp.genomes[g].n_buckets;
+        v.bucket_shift = bp.genomes[g].shift;
+        bucket_off[g] = bp.genomes[g].bucket_off;
         const uint32_t nc = (uint32_t)contig_lens[g].size();
         max_contigs = std::max(max_contigs, nc);
         cstart_off[g] = cstart_total; cstart_total += nc + 1;
@@ -430,7 +465,7 @@ static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_par
         v.win_cap = wcap; v.total_len = tot; v.n_contigs = nc;
         v.n_seeds = ns; v.n_markers = 0;      // marker fields are filled in after the final synchronisation
     }
-    store->bucket = DevMem(core, 4 * bucket_total);
+    if (!d_bucket_overflow) store->bucket = DevMem(core, 4 * bucket_total);
     store->contig_seed_start = DevMem(core, 4 * std::max<size_t>(cstart_total, 1));
     store->contig_win_start = DevMem(core, 4 * std::max<size_t>(cstart_total, 1));
     store->contig_len = DevMem(core, 4 * std::max<size_t>(h_clen.size(), 1));
@@ -452,10 +487,30 @@ static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_par
         table_upload(c, store->contig_len.p, h_clen.data(), 4 * h_clen.size());
         table_upload(c, store->contig_win_start.p, h_cwin.data(), 4 * h_cwin.size());
         // per-genome layout of contig_win_start mirrors contig_seed_start (nc + 1 entries each)
-        launch_build_buckets(d_views.as<GenomeView>(), n_genomes, max_buckets, st);
+        if (!d_bucket_overflow) launch_build_buckets(d_views.as<GenomeView>(), n_genomes, max_buckets, st);
         launch_contig_starts(d_views.as<GenomeView>(), n_genomes, max_contigs, st);
         if (d_marker_start) download(c, marker_start.data(), d_marker_start, n_genomes + 1);
+        uint32_t h_bover = 0;
+        if (d_bucket_overflow) download(c, &h_bover, d_bucket_overflow, 1);
         CU(cudaStreamSynchronize(st));   // the one synchronisation of the index build
+        if (h_bover) {
+            // a bucket was too large for the partition path (low-complexity genome): redo the k-mer order with the
+            // radix sort and rebuild the bucket tables from it
+            const uint32_t ns = seed_start[n_genomes];
+            DevMem d_gs(core, 4 * (size_t)(n_genomes + 1));
+            table_upload(c, d_gs.p, seed_start.data(), 4 * (size_t)(n_genomes + 1));
+            const size_t sort_bytes = kmer_order_scratch_bytes(ns);
+            void* sort_scratch = c.scratch(SLOT_SORT, sort_bytes);
+            IndexBuildArgs ib{};
+            ib.n_genomes = n_genomes; ib.n_seeds_total = ns; ib.genome_seed_start = d_gs.as<uint32_t>();
+            for (uint32_t g = 0; g < n_genomes; g++) ib.max_genome_seeds = std::max(ib.max_genome_seeds, seed_start[g + 1] - seed_start[g]);
+            ib.kmer_p = store->kmer_p.as<uint32_t>(); ib.pos_p = store->pos_p.as<uint32_t>(); ib.meta_p = store->meta_p.as<uint32_t>();
+            ib.kmer_k = store->kmer_k.as<uint32_t>(); ib.pos_k = store->pos_k.as<uint32_t>(); ib.meta_k = store->meta_k.as<uint32_t>();
+            ib.k = P.k;
+            build_kmer_order(ib, sort_scratch, sort_bytes, st);
+            launch_build_buckets(d_views.as<GenomeView>(), n_genomes, max_buckets, st);
+            CU(cudaStreamSynchronize(st));
+        }
     }
     for (uint32_t g = 0; g < n_genomes; g++) {
         views[g].n_markers = marker_start[g + 1] - marker_start[g];
