@@ -34,6 +34,7 @@ struct Core {
     Block arena[20];
     void* scratch(int slot, size_t bytes);
     cudaStream_t copy_stream = nullptr;       // host->device copies of skb_sketch_batch run here, ahead of the kernels
+    cudaStream_t aux_stream = nullptr;        // marker-set build of a batch, beside the k-mer order build on `stream`
     std::vector<cudaEvent_t> ev_pool;         // "chunk is on the device" events (timing disabled)
     cudaEvent_t pool_event(size_t i) {
         while (ev_pool.size() <= i) {
@@ -46,6 +47,7 @@ struct Core {
     ~Core() {
         cudaSetDevice(device);
         if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+        if (aux_stream) { cudaStreamSynchronize(aux_stream); cudaStreamDestroy(aux_stream); }
         if (stream) cudaStreamSynchronize(stream);
         for (auto& b : arena) if (b.p) cudaFree(b.p);
         for (auto& e : ev_pool) cudaEventDestroy(e);
@@ -83,7 +85,7 @@ struct Fail {
 void* Core::scratch(int slot, size_t bytes) {
     Block& b = arena[slot];
     if (b.bytes < bytes) {
-        if (b.p) { CU(cudaStreamSynchronize(stream)); CU(cudaStreamSynchronize(copy_stream)); CU(cudaFree(b.p)); b.p = nullptr; b.bytes = 0; }
+        if (b.p) { CU(cudaStreamSynchronize(stream)); CU(cudaStreamSynchronize(copy_stream)); CU(cudaStreamSynchronize(aux_stream)); CU(cudaFree(b.p)); b.p = nullptr; b.bytes = 0; }
         const size_t want = bytes + bytes / 8 + 4096;
         CU(cudaMalloc(&b.p, want));
         b.bytes = want;
@@ -380,6 +382,22 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             launch_region_gather(ga, st);
         }
         t2.mark("gather enqueued");
+        // ---- marker sets, on the auxiliary stream: a chain of small latency-bound launches that runs beside the k-mer order
+        store->markers = DevMem(core, 8 * (size_t)std::max<uint32_t>(nm, 1));
+        {
+            const size_t mark_bytes = marker_scratch_bytes(nm);
+            void* mark_scratch = c.scratch(SLOT_MARK, mark_bytes);
+            // pre-deduplication offsets (repaired on the host like the seed starts) live in their own small buffer: d_gm is
+            // overwritten with the post-deduplication offsets
+            uint32_t* d_gm_in = (uint32_t*)c.scratch(SLOT_GM_IN, g_bytes);
+            table_upload(c, d_gm_in, marker_start.data(), g_bytes);
+            uint32_t max_gm = 0;
+            for (uint32_t g = 0; g < n_genomes; g++) max_gm = std::max(max_gm, marker_start[g + 1] - marker_start[g]);
+            CU(cudaEventRecord(c.ev[6], st));
+            CU(cudaStreamWaitEvent(c.aux_stream, c.ev[6], 0));
+            build_marker_sets(n_genomes, nm, t_mkeys, store->markers.as<uint64_t>(), d_gm, d_gm_in, max_gm, mark_scratch, mark_bytes, c.aux_stream);
+            CU(cudaEventRecord(c.ev[7], c.aux_stream));
+        }
         // ---- k-mer order
         store->kmer_k = DevMem(core, 4 * (size_t)ns); store->pos_k = DevMem(core, 4 * (size_t)ns);
         store->meta_k = DevMem(core, 4 * (size_t)ns);
@@ -401,20 +419,8 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
                                      store->pos_k.as<uint32_t>(), store->meta_k.as<uint32_t>(), store->bucket.as<uint32_t>(), d_bover,
                                      bscr, bscr_bytes, st);
         }
-        // ---- marker sets
-        store->markers = DevMem(core, 8 * (size_t)std::max<uint32_t>(nm, 1));
-        {
-            const size_t mark_bytes = marker_scratch_bytes(nm);
-            void* mark_scratch = c.scratch(SLOT_MARK, mark_bytes);
-            // pre-deduplication offsets (repaired on the host like the seed starts) live in their own small buffer: d_gm is
-            // overwritten with the post-deduplication offsets
-            uint32_t* d_gm_in = (uint32_t*)c.scratch(SLOT_GM_IN, g_bytes);
-            table_upload(c, d_gm_in, marker_start.data(), g_bytes);
-            uint32_t max_gm = 0;
-            for (uint32_t g = 0; g < n_genomes; g++) max_gm = std::max(max_gm, marker_start[g + 1] - marker_start[g]);
-            build_marker_sets(n_genomes, nm, t_mkeys, store->markers.as<uint64_t>(), d_gm, d_gm_in, max_gm, mark_scratch, mark_bytes, st);
-            t2.mark("enqueued index");
-        }
+        CU(cudaStreamWaitEvent(st, c.ev[7], 0));
+        t2.mark("enqueued index");
         CU(cudaEventRecord(c.ev[3], st));
         finish_batch(core, P, seed, n_genomes, contig_lens, store, seed_start, marker_start, d_gm, out, d_bover);
     } else {
@@ -573,6 +579,7 @@ int skb_ctx_create(int device, skb_ctx_t** out) {
     core->n_sm = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&core->stream, cudaStreamNonBlocking) != cudaSuccess) return SKB_ERR_CUDA;
     if (cudaStreamCreateWithFlags(&core->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return SKB_ERR_CUDA;
+    if (cudaStreamCreateWithFlags(&core->aux_stream, cudaStreamNonBlocking) != cudaSuccess) return SKB_ERR_CUDA;
     for (auto& e : core->ev) if (cudaEventCreate(&e) != cudaSuccess) return SKB_ERR_CUDA;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
