@@ -31,6 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALG_BYTES_PER_BASE = 1.0 + 16.0 / 125.0 + 8.0 / 1000.0   # 1 B read + seeds + markers written
+NCU_SEED_TRAFFIC_BYTES = 508_747_008 + 16_123_392         # profiles/r1_seed_scan_kernel_ncu_full.txt (read + write, one launch)
 
 
 def parse():
@@ -306,6 +307,10 @@ def main():
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = ALG_BYTES_PER_BASE * total_bases / (seed_ms / 1e3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of one seed_scan_kernel launch, from the committed
+        # `ncu --set full` capture of this command (profiles/r1_seed_scan_kernel_ncu_full.txt); only valid for the
+        # default workload, which is the one that capture ran
+        traffic = NCU_SEED_TRAFFIC_BYTES if (args.genome_len, args.n_refs) == (5_000_000, 100) else None
         line = {
             "metric": "ANI pairs/s (sketch + screen + chain + ANI, 1 x 5 Mbp query vs 100 mutated refs)",
             "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -325,7 +330,8 @@ def main():
                     "pinned_h2d_copy_gbs": h2d_gbs, "per_step_wall_ms": [round(x, 3) for x in e2e_per_step]},
             "gpu_launches": int(k1 - k0),
             "roofline": {"bound": "hbm", "kernel": "seed_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read + write)",
+                         "algorithmic_bytes": ALG_BYTES_PER_BASE * total_bases, "peak_source": peak_src,
                          "note": "algorithmic bytes = 1.136 B/base x %d bases per launch; the kernel is integer-issue bound, see DESIGN.md" % total_bases},
             "clocks": clocks,
         }

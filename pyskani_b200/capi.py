@@ -31,6 +31,10 @@ class Hit(C.Structure):
                 ("n_chains", C.c_uint32), ("n_anchors", C.c_uint32)]
 
 
+HIT_DTYPE = np.dtype([('query_index', '<u4'), ('ref_index', '<u4'), ('ani', '<f4'), ('af_query', '<f4'), ('af_ref', '<f4'),
+                      ('n_windows', '<u4'), ('n_chains', '<u4'), ('n_anchors', '<u4')])
+
+
 class SketchInfo(C.Structure):
     _fields_ = [("n_seeds", C.c_uint64), ("n_markers", C.c_uint64), ("total_len", C.c_uint64),
                 ("n_contigs", C.c_uint32), ("k", C.c_int32), ("c", C.c_int32), ("marker_c", C.c_int32),
@@ -267,8 +271,10 @@ class Database:
         hits = C.POINTER(Hit)()
         nh, ns = C.c_uint64(0), C.c_uint64(0)
         self.ctx.check(lib().skb_db_query(self._h, n, qs, C.byref(o), C.byref(hits), C.byref(nh), C.byref(ns)))
-        out = [(hits[i].query_index, hits[i].ref_index, hits[i].ani, hits[i].af_query, hits[i].af_ref,
-                hits[i].n_windows, hits[i].n_chains, hits[i].n_anchors) for i in range(nh.value)]
+        out = []
+        if nh.value:
+            raw = np.ctypeslib.as_array(C.cast(hits, C.POINTER(C.c_uint8)), shape=(nh.value * C.sizeof(Hit),))
+            out = raw.view(HIT_DTYPE).tolist()       # tuples in skb_hit_t field order
         lib().skb_hits_free(hits)
         return out, ns.value
 

@@ -998,6 +998,7 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
             if (qi.k != dbi.k || qi.c != dbi.c || qi.marker_c != dbi.marker_c) throw Fail{SKB_ERR_ARG, "query sketch parameters differ from the database's"};
             qs.push_back(queries[i]->impl); hv.push_back(queries[i]->impl->view);
         }
+        Trace tq("db_query");
         CU(cudaEventRecord(c.ev[0], st));
         DevMem d_q(db->core, sizeof(GenomeView) * n_queries);
         CU(cudaMemcpyAsync(d_q.p, hv.data(), sizeof(GenomeView) * n_queries, cudaMemcpyHostToDevice, st));
@@ -1008,6 +1009,7 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
         ScreenOut so;
         run_screen(*db, qs, d_q.as<GenomeView>(), screen_val, opts->faster_small ? 0 : 1, &so, nullptr, nullptr);
         CU(cudaEventRecord(c.ev[1], st));
+        tq.mark("screen done");
         if (n_screened_in) *n_screened_in = so.pass_idx.size();
 
         // ---- chain survivors in batches (reference lib.rs:640-657)
@@ -1079,6 +1081,7 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
                 uint64_t* keys_sorted = B.sort_keys + nw; uint32_t* vals_sorted = B.sort_vals + nw;
                 B.results = d_res.as<PairResult>();
 
+                tq.mark("batch allocated");
                 launch_anchor_fill(B, st);
                 launch_window_walk(B, C, max_qseeds, st);
                 launch_chain_dp(B, C, st);
@@ -1094,7 +1097,9 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
                 uint32_t n_anchors = 0;
                 download(c, &n_anchors, B.a_off + seeds, 1);
                 download(c, res.data(), B.results, np);
+                tq.mark("batch enqueued");
                 CU(cudaStreamSynchronize(st));   // also keeps `pairs` alive until its upload has finished
+                tq.mark("batch synced");
                 if (n_anchors <= B.anchor_cap) break;
                 if (attempt == 1) throw Fail{SKB_ERR_CUDA, "anchor arrays overflowed twice"};
                 est = n_anchors;

@@ -1,0 +1,245 @@
+"""Full-size runs of BASELINE.json configs[2..4] on ONE GPU, with the genomes generated on the device.
+
+    python tools/scale_bench.py --families 100 --members 100                       # configs[4]: 10 000 x 10 000 all-vs-all
+    python tools/scale_bench.py --families 100 --members 10                        # configs[2]: 1 000 x 1 000 all-vs-all
+    python tools/scale_bench.py --families 500 --members 10 --mag-queries 500      # configs[3]: 500 fragmented MAGs vs 5 000
+
+Genomes never exist on the host: a family is a random base genome plus mutated copies (substitutions with probability
+0.9 d, indel events with probability 0.1 d, geometric lengths, as pyskani_b200.synth does on the CPU), written as ASCII into
+one device buffer that skb_sketch_batch_device reads.  torch is only the random-number generator and the allocator here.
+The run checks properties that do not need the oracle: every genome hits itself with ANI 1, every hit stays inside its
+family, ANI against the family's base genome decreases with the divergence it was generated with.
+"""
+import argparse, os, sys, time, json
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pyskani_b200 import capi
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--families", type=int, default=20)
+    ap.add_argument("--members", type=int, default=10)
+    ap.add_argument("--genome-len", type=int, default=5_000_000)
+    ap.add_argument("--max-div", type=float, default=0.15)
+    ap.add_argument("--query-chunk", type=int, default=500, help="queries per skb_db_query call")
+    ap.add_argument("--mag-queries", type=int, default=0, help="configs[3]: N fragmented queries instead of all-vs-all")
+    ap.add_argument("--screen-only", action="store_true")
+    ap.add_argument("--json", default=None)
+    return ap.parse_args()
+
+
+ACGT = None
+
+
+def mutate_dev(codes, d, gen):
+    """codes: uint8 tensor of 2-bit codes on the device -> mutated copy"""
+    n = codes.numel()
+    out = codes.clone()
+    sub = torch.rand(n, device=codes.device, generator=gen) < 0.9 * d
+    out[sub] = (out[sub] + torch.randint(1, 4, (int(sub.sum()),), device=codes.device, generator=gen, dtype=torch.uint8)) & 3
+    ev = torch.rand(n, device=codes.device, generator=gen) < 0.1 * d
+    idx = ev.nonzero().flatten()
+    if idx.numel():
+        m = idx.numel()
+        length = torch.clamp((torch.log(torch.rand(m, device=codes.device, generator=gen)) / np.log(2.0 / 3.0)).long() + 1, max=50)
+        is_ins = torch.rand(m, device=codes.device, generator=gen) < 0.5
+        # deletions: drop [p, p + l)
+        diff = torch.zeros(n + 64, dtype=torch.int32, device=codes.device)
+        dp, dl = idx[~is_ins], length[~is_ins]
+        diff.index_add_(0, dp, torch.ones_like(dp, dtype=torch.int32))
+        diff.index_add_(0, dp + dl, -torch.ones_like(dp, dtype=torch.int32))
+        keep = torch.cumsum(diff[:n], 0) <= 0
+        # insertions: l random bases in front of position p
+        counts = torch.ones(n, dtype=torch.long, device=codes.device)
+        counts[idx[is_ins]] += length[is_ins]
+        counts = counts[keep]
+        kept = out[keep]
+        rep = torch.repeat_interleave(kept, counts)
+        orig = torch.zeros(rep.numel(), dtype=torch.bool, device=codes.device)
+        orig[torch.cumsum(counts, 0) - 1] = True
+        n_new = int((~orig).sum())
+        rep[~orig] = torch.randint(0, 4, (n_new,), device=codes.device, generator=gen, dtype=torch.uint8)
+        out = rep
+    return out
+
+
+class DeviceBatch:
+    """ASCII contigs of several genomes in one device buffer, each contig at a 16-byte aligned offset"""
+
+    def __init__(self, device, cap_bytes):
+        self.buf = torch.zeros(cap_bytes, dtype=torch.uint8, device=device)
+        self.reset()
+
+    def reset(self):
+        self.cur = 64
+        self.offs, self.lens, self.gstart = [], [], [0]
+
+    def add_genome(self, contigs):
+        for c in contigs:
+            l = c.numel()
+            assert self.cur + l + 128 <= self.buf.numel(), "device batch buffer too small"
+            self.buf[self.cur:self.cur + l] = ACGT[c.long()]
+            self.offs.append(self.cur); self.lens.append(l)
+            self.cur += (l + 15) // 16 * 16 + 16
+        self.gstart.append(len(self.offs))
+
+    def sketch(self, ctx):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sk = ctx.sketch_batch_device(self.buf.data_ptr(), np.array(self.gstart, np.uint32), np.array(self.offs, np.uint64),
+                                     np.array(self.lens, np.uint64))
+        t1 = time.perf_counter()
+        st = ctx.stats()
+        bases = int(sum(self.lens))
+        self.reset()
+        return sk, t1 - t0, st.total_ms / 1e3, bases
+
+
+def fragment_dev(codes, rng, lo=1000, hi=50000):
+    """MAG-style query: log-uniform contig lengths in [lo, hi], shuffled, half reverse-complemented"""
+    n = codes.numel()
+    cuts, p = [], 0
+    while p < n:
+        l = int(np.exp(rng.uniform(np.log(lo), np.log(hi))))
+        cuts.append((p, min(n, p + l)))
+        p += l
+    out = []
+    for i in rng.permutation(len(cuts)):
+        a, b = cuts[i]
+        s = codes[a:b]
+        if rng.random() < 0.5:
+            s = 3 - torch.flip(s, [0])
+        out.append(s)
+    return out
+
+
+def main():
+    global ACGT
+    args = parse()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    ACGT = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(1234)
+    ctx = capi.Context(0)
+    F, M, L = args.families, args.members, args.genome_len
+    divs = [0.0] + [0.01 + (args.max_div - 0.01) * i / max(1, M - 2) for i in range(M - 1)]
+    batch_genomes = max(1, min(100, (600 << 20) // int(L * 1.03)))
+    batch = DeviceBatch(dev, int(batch_genomes * (L * 1.03 + 64)) + 4096)
+
+    db = capi.Database(ctx)
+    sketches, div_of = [], []
+    pending = 0
+    t_sketch_wall = t_sketch_dev = 0.0
+    total_bases = 0
+    bases_kept = {}                      # family -> base codes, only for the families MAG queries are drawn from
+    rng = np.random.default_rng(7)
+    mag_families = set(rng.choice(F, size=min(F, args.mag_queries), replace=False).tolist()) if args.mag_queries else set()
+    t_gen0 = time.perf_counter()
+
+    def flush():
+        nonlocal pending, t_sketch_wall, t_sketch_dev, total_bases
+        if not pending:
+            return
+        sk, w, d, b = batch.sketch(ctx)
+        t_sketch_wall += w; t_sketch_dev += d; total_bases += b
+        sketches.extend(sk)
+        pending = 0
+
+    for f in range(F):
+        base = torch.randint(0, 4, (L,), device=dev, generator=gen, dtype=torch.uint8)
+        if f in mag_families:
+            bases_kept[f] = base
+        for m in range(M):
+            g = base if m == 0 else mutate_dev(base, divs[m], gen)
+            batch.add_genome([g]); div_of.append(divs[m])
+            pending += 1
+            if pending == batch_genomes:
+                flush()
+    flush()
+    t_gen = time.perf_counter() - t_gen0 - t_sketch_wall
+    n = len(sketches)
+    db.add_many(sketches)
+    print("database: %d genomes, %.2f Gbp | generation %.1f s | sketching wall %.3f s (device %.3f s) = %.1f Gbp/s" % (
+        n, total_bases / 1e9, t_gen, t_sketch_wall, t_sketch_dev, total_bases / t_sketch_wall / 1e9), flush=True)
+
+    # ---- queries
+    if args.mag_queries:
+        queries, q_family, q_div = [], [], []
+        fams = sorted(bases_kept)
+        t_q = 0.0
+        qb = 0
+        for i in range(args.mag_queries):
+            f = fams[i % len(fams)]
+            d = 0.01 + 0.09 * rng.random()
+            g = mutate_dev(bases_kept[f], d, gen)
+            batch.add_genome(fragment_dev(g, rng)); q_family.append(f); q_div.append(d)
+            pending += 1
+            if pending == batch_genomes // 2 or i == args.mag_queries - 1:
+                sk, w, dd, b = batch.sketch(ctx)
+                queries.extend(sk); t_q += w; qb += b; pending = 0
+        print("queries: %d fragmented genomes (%.2f Gbp, %d contigs on average) sketched in %.3f s" % (
+            len(queries), qb / 1e9, int(np.mean([s.info().n_contigs for s in queries])), t_q), flush=True)
+    else:
+        queries, q_family, q_div = sketches, [i // M for i in range(n)], div_of
+
+    if args.screen_only:
+        t0 = time.perf_counter()
+        n_pass = 0
+        for q0 in range(0, len(queries), args.query_chunk):
+            p, _ = db.screen(queries[q0:q0 + args.query_chunk])
+            n_pass += int(np.count_nonzero(p))
+        t1 = time.perf_counter()
+        print("screen only: %d pairs in %.3f s = %.1f M pairs/s, %d pass" % (len(queries) * n, t1 - t0, len(queries) * n / (t1 - t0) / 1e6, n_pass))
+        return
+
+    t_wall = t_screen = t_chain = 0.0
+    n_in = 0
+    hits = []
+    for q0 in range(0, len(queries), args.query_chunk):
+        t0 = time.perf_counter()
+        h, k = db.query(queries[q0:q0 + args.query_chunk])
+        t1 = time.perf_counter()
+        st = ctx.stats()
+        t_wall += t1 - t0; t_screen += st.screen_ms / 1e3; t_chain += st.chain_ms / 1e3; n_in += k
+        hits.extend((q0 + a, b, c, d, e) for a, b, c, d, e in (x[:5] for x in h))
+    n_pairs = len(queries) * n
+    print("query: %d x %d = %.3g pairs in %.3f s wall = %.2f M pairs/s | screen %.3f s (%.1f M pairs/s) | %d pairs chained in %.3f s "
+          "(%.0f pairs/s) | %d hits" % (len(queries), n, n_pairs, t_wall, n_pairs / t_wall / 1e6, t_screen,
+                                        n_pairs / max(t_screen, 1e-9) / 1e6, n_in, t_chain, n_in / max(t_chain, 1e-9), len(hits)), flush=True)
+
+    # ---- properties
+    intra = all(q_family[h[0]] == h[1] // M for h in hits)
+    ok_self = True
+    if not args.mag_queries:
+        self_ani = {h[0]: h[2] for h in hits if h[0] == h[1]}
+        ok_self = len(self_ani) == n and min(self_ani.values()) > 0.9999
+    # ANI against the family's base genome (member 0) must fall as the generating divergence grows
+    to_base = {}
+    for h in hits:
+        if h[1] % M == 0:
+            to_base.setdefault(q_family[h[0]], []).append((q_div[h[0]], h[2]))
+    mono = True; worst = 0.0
+    for f, lst in to_base.items():
+        lst.sort()
+        for (d0, a0), (d1, a1) in zip(lst, lst[1:]):
+            if d1 - d0 > 0.004 and a1 > a0 + 1e-3:
+                mono = False
+        for d, a in lst:
+            if d <= 0.10:
+                worst = max(worst, abs((1 - a) - d))
+    print("properties: hits intra-family %s | self hits ANI 1 %s | ANI monotone in divergence %s | max |(1-ANI) - d| for d<=10%% = %.4f" % (
+        intra, ok_self, mono, worst))
+    if args.json:
+        json.dump({"genomes": n, "queries": len(queries), "bases": total_bases, "sketch_wall_s": t_sketch_wall, "query_wall_s": t_wall,
+                   "screen_s": t_screen, "chain_s": t_chain, "pairs": n_pairs, "chained": n_in, "hits": len(hits),
+                   "intra_family": intra, "self_hits": ok_self, "monotone": mono, "max_abs_err_vs_divergence": worst},
+                  open(args.json, "w"))
+    if not (intra and ok_self and mono):
+        raise SystemExit(1)
+
+
+if __name__ == "__main__":
+    main()
