@@ -109,6 +109,8 @@ __global__ void anchor_fill_kernel(const ChainBatch b) {
             b.a_qp[o] = qp;
             b.a_rp[o] = __ldg(R.pos_k + first + m);
             b.a_meta[o] = (rm & ~1u) | ((qm ^ rm) & 1u);    // ref contig << 1 | reverse_match
+            b.a_aux[o] = 0u;                                // component size / flags and best end, accumulated by the DP kernel
+            b.a_best[o] = 0ull;
         }
     }
 }

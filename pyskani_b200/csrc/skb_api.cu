@@ -18,8 +18,54 @@ void launch_screen_decide(const GenomeView*, uint32_t, const GenomeView*, uint32
                           uint8_t*, cudaStream_t);
 void select_passing(uint32_t n, const uint8_t* flags, uint32_t* out_idx, uint32_t* out_count, cudaStream_t st);
 
+// Storage of the sketches themselves.  Sketch arrays live as long as their handles, so they cannot sit in the grow-only
+// scratch arena; the stream-ordered pool (cudaMallocAsync) turned out to need 20-150 ms per 100 MB batch while it grows
+// (against < 1 ms for a 1 GB cudaMalloc).  So: slabs from cudaMalloc (64 MB doubling to 1 GB, or the request if larger),
+// bump allocation inside the current slab, one live-count per slab.  A slab whose count returns to zero is reused from
+// the start; freeing the most recent allocation rolls the bump pointer back, which is what the query-sketch-per-call
+// pattern of Database.query produces.  All users of the memory are ordered on the context's stream, so reuse needs no event.
+struct Slab { char* base = nullptr; size_t cap = 0, used = 0; uint32_t live = 0; };
+struct SlabPool {
+    std::mutex mu;
+    std::vector<std::unique_ptr<Slab>> slabs;
+    Slab* cur = nullptr;
+    size_t next_cap = (size_t)64 << 20;
+    void* alloc(size_t bytes, Slab** owner) {
+        bytes = (bytes + 511) & ~(size_t)511;
+        std::lock_guard<std::mutex> lock(mu);
+        if (!cur || cur->used + bytes > cur->cap) {
+            Slab* pick = nullptr;
+            for (auto& sl : slabs) if (sl->live == 0 && sl->cap >= bytes && (!pick || sl->cap < pick->cap)) pick = sl.get();
+            if (!pick) {
+                std::unique_ptr<Slab> sl(new Slab);
+                sl->cap = std::max(next_cap, bytes);
+                cudaError_t e = cudaMalloc((void**)&sl->base, sl->cap);
+                if (e != cudaSuccess && sl->cap > bytes) { cudaGetLastError(); sl->cap = bytes; e = cudaMalloc((void**)&sl->base, sl->cap); }
+                if (e != cudaSuccess) { cudaGetLastError(); return nullptr; }
+                next_cap = std::min(next_cap * 2, (size_t)1 << 30);
+                pick = sl.get();
+                slabs.push_back(std::move(sl));
+            }
+            pick->used = 0;
+            cur = pick;
+        }
+        void* p = cur->base + cur->used;
+        cur->used += bytes; cur->live++;
+        *owner = cur;
+        return p;
+    }
+    void free(Slab* sl, void* p, size_t bytes) {
+        bytes = (bytes + 511) & ~(size_t)511;
+        std::lock_guard<std::mutex> lock(mu);
+        if ((char*)p + bytes == sl->base + sl->used) sl->used -= bytes;
+        if (--sl->live == 0) sl->used = 0;
+    }
+    void destroy() { for (auto& sl : slabs) if (sl->base) cudaFree(sl->base); slabs.clear(); cur = nullptr; }
+};
+
 struct Core {
     int device = 0;
+    SlabPool slabs;
     int n_sm = 148;
     cudaStream_t stream = nullptr;
     std::mutex mu;
@@ -50,6 +96,7 @@ struct Core {
         if (aux_stream) { cudaStreamSynchronize(aux_stream); cudaStreamDestroy(aux_stream); }
         if (stream) cudaStreamSynchronize(stream);
         for (auto& b : arena) if (b.p) cudaFree(b.p);
+        slabs.destroy();
         for (auto& e : ev_pool) cudaEventDestroy(e);
         if (stream) cudaStreamSynchronize(stream);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -92,7 +139,7 @@ void* Core::scratch(int slot, size_t bytes) {
     }
     return b.p;
 }
-enum { SLOT_SEQ = 0, SLOT_KMER, SLOT_POS, SLOT_META, SLOT_MKEYS, SLOT_STATUS, SLOT_SORT, SLOT_MARK, SLOT_GS, SLOT_GM, SLOT_DESC, SLOT_MKEYS2, SLOT_RSCAN, SLOT_GM_IN, SLOT_BTAB, SLOT_BCOUNT };
+enum { SLOT_SEQ = 0, SLOT_KMER, SLOT_POS, SLOT_META, SLOT_MKEYS, SLOT_STATUS, SLOT_SORT, SLOT_MARK, SLOT_GS, SLOT_GM, SLOT_DESC, SLOT_MKEYS2, SLOT_RSCAN, SLOT_GM_IN, SLOT_BTAB, SLOT_BCOUNT, SLOT_CHAIN };
 
 // stream-ordered device buffer
 struct DevMem {
@@ -100,19 +147,32 @@ struct DevMem {
     size_t bytes = 0;
     std::shared_ptr<Core> core;
     DevMem() = default;
+    Slab* slab = nullptr;       // non-null: sketch storage from the context's slabs; null: transient, stream-ordered pool
     DevMem(const std::shared_ptr<Core>& c, size_t n) : bytes(n), core(c) {
         if (n) CU(cudaMallocAsync(&p, n, c->stream));
+    }
+    static DevMem persistent(const std::shared_ptr<Core>& c, size_t n) {
+        DevMem m;
+        m.bytes = n; m.core = c;
+        if (n) {
+            m.p = c->slabs.alloc(n, &m.slab);
+            if (!m.p) throw Fail{SKB_ERR_NOMEM, "out of device memory for sketch storage"};
+        }
+        return m;
     }
     DevMem(const DevMem&) = delete;
     DevMem& operator=(const DevMem&) = delete;
     DevMem(DevMem&& o) noexcept { *this = std::move(o); }
     DevMem& operator=(DevMem&& o) noexcept {
-        if (this != &o) { release(); p = o.p; bytes = o.bytes; core = std::move(o.core); o.p = nullptr; o.bytes = 0; }
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; slab = o.slab; core = std::move(o.core); o.p = nullptr; o.bytes = 0; o.slab = nullptr; }
         return *this;
     }
     void release() {
-        if (p && core) { cudaSetDevice(core->device); cudaFreeAsync(p, core->stream); }
-        p = nullptr; bytes = 0;
+        if (p && core) {
+            if (slab) core->slabs.free(slab, p, bytes);
+            else { cudaSetDevice(core->device); cudaFreeAsync(p, core->stream); }
+        }
+        p = nullptr; bytes = 0; slab = nullptr;
     }
     ~DevMem() { release(); }
     template <typename T> T* as() const { return (T*)p; }
@@ -370,8 +430,8 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
 
         t2.mark("host fixups");
         // ---- exact-size position-order arrays + contiguous marker keys: the gather is also the compaction copy
-        store->kmer_p = DevMem(core, 4 * (size_t)ns); store->pos_p = DevMem(core, 4 * (size_t)ns);
-        store->meta_p = DevMem(core, 4 * (size_t)ns);
+        store->kmer_p = DevMem::persistent(core, 4 * (size_t)ns); store->pos_p = DevMem::persistent(core, 4 * (size_t)ns);
+        store->meta_p = DevMem::persistent(core, 4 * (size_t)ns);
         uint64_t* t_mkeys = (uint64_t*)c.scratch(SLOT_MKEYS2, 8 * (size_t)nm + 16);
         {
             RegionGatherArgs ga{};
@@ -383,7 +443,7 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
         }
         t2.mark("gather enqueued");
         // ---- marker sets, on the auxiliary stream: a chain of small latency-bound launches that runs beside the k-mer order
-        store->markers = DevMem(core, 8 * (size_t)std::max<uint32_t>(nm, 1));
+        store->markers = DevMem::persistent(core, 8 * (size_t)std::max<uint32_t>(nm, 1));
         {
             const size_t mark_bytes = marker_scratch_bytes(nm);
             void* mark_scratch = c.scratch(SLOT_MARK, mark_bytes);
@@ -399,14 +459,14 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             CU(cudaEventRecord(c.ev[7], c.aux_stream));
         }
         // ---- k-mer order
-        store->kmer_k = DevMem(core, 4 * (size_t)ns); store->pos_k = DevMem(core, 4 * (size_t)ns);
-        store->meta_k = DevMem(core, 4 * (size_t)ns);
+        store->kmer_k = DevMem::persistent(core, 4 * (size_t)ns); store->pos_k = DevMem::persistent(core, 4 * (size_t)ns);
+        store->meta_k = DevMem::persistent(core, 4 * (size_t)ns);
         uint32_t* d_bover = nullptr;
         {
             // bucket partition: histogram (from the seeding kernel) -> per-genome scan (= the bucket tables) -> scatter ->
             // rank inside the bucket
             for (uint32_t g = 0; g < n_genomes; g++) { bplan.genomes[g].seed_start = seed_start[g]; bplan.genomes[g].n_seeds = seed_start[g + 1] - seed_start[g]; }
-            store->bucket = DevMem(core, 4 * bplan.total);
+            store->bucket = DevMem::persistent(core, 4 * bplan.total);
             const size_t tab_bytes = sizeof(BucketGenome) * n_genomes;
             char* d_tab = (char*)c.scratch(SLOT_BTAB, tab_bytes + 16);
             table_upload(c, d_tab, bplan.genomes.data(), tab_bytes);
@@ -471,10 +531,10 @@ static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_par
         v.win_cap = wcap; v.total_len = tot; v.n_contigs = nc;
         v.n_seeds = ns; v.n_markers = 0;      // marker fields are filled in after the final synchronisation
     }
-    if (!d_bucket_overflow) store->bucket = DevMem(core, 4 * bucket_total);
-    store->contig_seed_start = DevMem(core, 4 * std::max<size_t>(cstart_total, 1));
-    store->contig_win_start = DevMem(core, 4 * std::max<size_t>(cstart_total, 1));
-    store->contig_len = DevMem(core, 4 * std::max<size_t>(h_clen.size(), 1));
+    if (!d_bucket_overflow) store->bucket = DevMem::persistent(core, 4 * bucket_total);
+    store->contig_seed_start = DevMem::persistent(core, 4 * std::max<size_t>(cstart_total, 1));
+    store->contig_win_start = DevMem::persistent(core, 4 * std::max<size_t>(cstart_total, 1));
+    store->contig_len = DevMem::persistent(core, 4 * std::max<size_t>(h_clen.size(), 1));
     for (uint32_t g = 0; g < n_genomes; g++) {
         GenomeView& v = views[g];
         const size_t so = seed_start[g];
@@ -820,10 +880,10 @@ int skb_sketch_import(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t
         std::sort(hmark.begin(), hmark.end());
         hmark.erase(std::unique(hmark.begin(), hmark.end()), hmark.end());
         auto store = std::make_shared<BatchStore>();
-        store->kmer_p = DevMem(ctx->core, 4 * (size_t)n); store->pos_p = DevMem(ctx->core, 4 * (size_t)n);
-        store->meta_p = DevMem(ctx->core, 4 * (size_t)n); store->kmer_k = DevMem(ctx->core, 4 * (size_t)n);
-        store->pos_k = DevMem(ctx->core, 4 * (size_t)n); store->meta_k = DevMem(ctx->core, 4 * (size_t)n);
-        store->markers = DevMem(ctx->core, 8 * std::max<size_t>(hmark.size(), 1));
+        store->kmer_p = DevMem::persistent(ctx->core, 4 * (size_t)n); store->pos_p = DevMem::persistent(ctx->core, 4 * (size_t)n);
+        store->meta_p = DevMem::persistent(ctx->core, 4 * (size_t)n); store->kmer_k = DevMem::persistent(ctx->core, 4 * (size_t)n);
+        store->pos_k = DevMem::persistent(ctx->core, 4 * (size_t)n); store->meta_k = DevMem::persistent(ctx->core, 4 * (size_t)n);
+        store->markers = DevMem::persistent(ctx->core, 8 * std::max<size_t>(hmark.size(), 1));
         CU(cudaMemcpyAsync(store->kmer_p.p, hk.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(store->pos_p.p, hp.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(store->meta_p.p, hm.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
@@ -1039,21 +1099,6 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
             }
             if (seeds >= 0x7FFFFFFFull) throw Fail{SKB_ERR_ARG, "query sketch too large for one chaining batch"};
             const uint32_t np = (uint32_t)pairs.size();
-            ChainBatch B{};
-            B.qviews = d_q.as<GenomeView>(); B.rviews = d_r; B.n_pairs = np;
-            B.n_qseeds_total = (uint32_t)seeds; B.n_win_total = (uint32_t)wins;
-            DevMem d_pairs(db->core, sizeof(PairDesc) * np);
-            CU(cudaMemcpyAsync(d_pairs.p, pairs.data(), sizeof(PairDesc) * np, cudaMemcpyHostToDevice, st));
-            B.pairs = d_pairs.as<PairDesc>();
-            DevMem d_first(db->core, 4 * (seeds + 1)), d_cnt(db->core, 4 * (seeds + 1)), d_aoff(db->core, 4 * (seeds + 2));
-            DevMem d_bits(db->core, 4 * (bit_words + 4));
-            B.m_first = d_first.as<uint32_t>(); B.m_cnt = d_cnt.as<uint32_t>(); B.a_off = d_aoff.as<uint32_t>(); B.m_bits = d_bits.as<uint32_t>();
-            CU(cudaMemsetAsync(B.m_cnt + seeds, 0, 4, st));
-            launch_match_count(B, st);
-            {
-                DevMem scratch(db->core, scan_scratch_bytes((uint32_t)seeds + 1));
-                scan_match_counts(B, scratch.p, scratch.bytes, st);
-            }
             // The number of anchors is only known on the device.  Size the anchor arrays from an estimate (twice the
             // smaller seed count of every pair), run the whole batch, and read the true total back together with the
             // results: one synchronisation per batch; a batch whose estimate was too small is simply run again.
@@ -1062,25 +1107,40 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
             if (est > 0x7FFFFFFFull) est = 0x7FFFFFFFull;
             if (const char* e = std::getenv("SKB_FORCE_ANCHOR_EST")) est = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10));   // test hook: exercises the rerun
             std::vector<PairResult> res(np);
+            const size_t nw = std::max<uint64_t>(wins, 1);
+            const size_t scan_bytes = scan_scratch_bytes((uint32_t)seeds + 1), sort_bytes = sort_pairs_scratch_bytes((uint32_t)wins);
             for (int attempt = 0; attempt < 2; attempt++) {
                 const size_t na = (size_t)est;
+                // every transient array of the batch is carved out of ONE grow-only block of the context: a cold
+                // stream-ordered pool needed 20-150 ms to grow through the fifteen allocations this used to make
+                size_t total = 0;
+                auto plan = [&](size_t bytes) { const size_t o = total; total += (bytes + 255) & ~(size_t)255; return o; };
+                const size_t o_pairs = plan(sizeof(PairDesc) * np), o_first = plan(4 * (seeds + 1)), o_cnt = plan(4 * (seeds + 1)),
+                             o_aoff = plan(4 * (seeds + 2)), o_bits = plan(4 * (bit_words + 4)), o_scan = plan(scan_bytes),
+                             o_a = plan(na * 4 * 7), o_best = plan(na * 8), o_w = plan(nw * 4 * 3 + 4 * (size_t)np),
+                             o_rec = plan(nw * sizeof(WindowRec)), o_keys = plan(nw * 8 * 2), o_vals = plan(nw * 4 * 2),
+                             o_res = plan(sizeof(PairResult) * np), o_sort = plan(sort_bytes);
+                char* base = (char*)c.scratch(SLOT_CHAIN, total);
+                ChainBatch B{};
+                B.qviews = d_q.as<GenomeView>(); B.rviews = d_r; B.n_pairs = np;
+                B.n_qseeds_total = (uint32_t)seeds; B.n_win_total = (uint32_t)wins;
+                B.pairs = (PairDesc*)(base + o_pairs);
+                CU(cudaMemcpyAsync(base + o_pairs, pairs.data(), sizeof(PairDesc) * np, cudaMemcpyHostToDevice, st));
+                B.m_first = (uint32_t*)(base + o_first); B.m_cnt = (uint32_t*)(base + o_cnt); B.a_off = (uint32_t*)(base + o_aoff);
+                B.m_bits = (uint32_t*)(base + o_bits);
+                CU(cudaMemsetAsync(B.m_cnt + seeds, 0, 4, st));
+                launch_match_count(B, st);
+                scan_match_counts(B, base + o_scan, scan_bytes, st);
                 B.anchor_cap = (uint32_t)est;
-                DevMem d_a(db->core, na * 4 * 7), d_best(db->core, na * 8);
-                B.a_qi = d_a.as<uint32_t>(); B.a_qp = B.a_qi + na; B.a_rp = B.a_qp + na; B.a_meta = B.a_rp + na;
+                B.a_qi = (uint32_t*)(base + o_a); B.a_qp = B.a_qi + na; B.a_rp = B.a_qp + na; B.a_meta = B.a_rp + na;
                 B.a_f = (int32_t*)(B.a_meta + na); B.a_root = (uint32_t*)(B.a_f + na); B.a_aux = B.a_root + na;
-                B.a_best = d_best.as<unsigned long long>();
-                CU(cudaMemsetAsync(B.a_aux, 0, 4 * na, st));
-                CU(cudaMemsetAsync(B.a_best, 0, 8 * na, st));
-                const size_t nw = std::max<uint64_t>(wins, 1);
-                DevMem d_w(db->core, nw * 4 * 3 + 4 * (size_t)np), d_rec(db->core, nw * sizeof(WindowRec));
-                B.win_start = d_w.as<uint32_t>(); B.win_end = B.win_start + nw; B.win_contig = B.win_end + nw; B.pair_nwin = B.win_contig + nw;
-                B.win_rec = d_rec.as<WindowRec>();
+                B.a_best = (unsigned long long*)(base + o_best);
+                B.win_start = (uint32_t*)(base + o_w); B.win_end = B.win_start + nw; B.win_contig = B.win_end + nw; B.pair_nwin = B.win_contig + nw;
+                B.win_rec = (WindowRec*)(base + o_rec);
                 CU(cudaMemsetAsync(B.win_start, 0, 8 * nw, st));   // start == end == 0 marks an unused slot
-                DevMem d_keys(db->core, nw * 8 * 2), d_vals(db->core, nw * 4 * 2), d_res(db->core, sizeof(PairResult) * np);
-                B.sort_keys = d_keys.as<uint64_t>(); B.sort_vals = d_vals.as<uint32_t>();
+                B.sort_keys = (uint64_t*)(base + o_keys); B.sort_vals = (uint32_t*)(base + o_vals);
                 uint64_t* keys_sorted = B.sort_keys + nw; uint32_t* vals_sorted = B.sort_vals + nw;
-                B.results = d_res.as<PairResult>();
-
+                B.results = (PairResult*)(base + o_res);
                 tq.mark("batch allocated");
                 launch_anchor_fill(B, st);
                 launch_window_walk(B, C, max_qseeds, st);
@@ -1089,9 +1149,8 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
                 {
                     int pbits = 1;
                     while ((1ull << pbits) <= (uint64_t)np) pbits++;
-                    DevMem scratch(db->core, sort_pairs_scratch_bytes((uint32_t)wins));
-                    sort_window_keys((uint32_t)wins, B.sort_keys, keys_sorted, B.sort_vals, vals_sorted, 32 + pbits, scratch.p,
-                                     scratch.bytes, st);
+                    sort_window_keys((uint32_t)wins, B.sort_keys, keys_sorted, B.sort_vals, vals_sorted, 32 + pbits, base + o_sort,
+                                     sort_bytes, st);
                 }
                 launch_ani_reduce(B, C, keys_sorted, vals_sorted, st);
                 uint32_t n_anchors = 0;

@@ -27,6 +27,7 @@ def parse():
     ap.add_argument("--query-chunk", type=int, default=500, help="queries per skb_db_query call")
     ap.add_argument("--mag-queries", type=int, default=0, help="configs[3]: N fragmented queries instead of all-vs-all")
     ap.add_argument("--screen-only", action="store_true")
+    ap.add_argument("--repeat", type=int, default=1, help="run the query phase N times (the first pays for growing the scratch arena)")
     ap.add_argument("--json", default=None)
     return ap.parse_args()
 
@@ -44,7 +45,8 @@ def mutate_dev(codes, d, gen):
     idx = ev.nonzero().flatten()
     if idx.numel():
         m = idx.numel()
-        length = torch.clamp((torch.log(torch.rand(m, device=codes.device, generator=gen)) / np.log(2.0 / 3.0)).long() + 1, max=50)
+        u = torch.rand(m, device=codes.device, generator=gen).clamp_(min=1e-9)
+        length = torch.clamp((torch.log(u) / np.log(2.0 / 3.0)).long() + 1, min=1, max=50)
         is_ins = torch.rand(m, device=codes.device, generator=gen) < 0.5
         # deletions: drop [p, p + l)
         diff = torch.zeros(n + 64, dtype=torch.int32, device=codes.device)
@@ -195,20 +197,22 @@ def main():
         print("screen only: %d pairs in %.3f s = %.1f M pairs/s, %d pass" % (len(queries) * n, t1 - t0, len(queries) * n / (t1 - t0) / 1e6, n_pass))
         return
 
-    t_wall = t_screen = t_chain = 0.0
-    n_in = 0
-    hits = []
-    for q0 in range(0, len(queries), args.query_chunk):
-        t0 = time.perf_counter()
-        h, k = db.query(queries[q0:q0 + args.query_chunk])
-        t1 = time.perf_counter()
-        st = ctx.stats()
-        t_wall += t1 - t0; t_screen += st.screen_ms / 1e3; t_chain += st.chain_ms / 1e3; n_in += k
-        hits.extend((q0 + a, b, c, d, e) for a, b, c, d, e in (x[:5] for x in h))
-    n_pairs = len(queries) * n
-    print("query: %d x %d = %.3g pairs in %.3f s wall = %.2f M pairs/s | screen %.3f s (%.1f M pairs/s) | %d pairs chained in %.3f s "
-          "(%.0f pairs/s) | %d hits" % (len(queries), n, n_pairs, t_wall, n_pairs / t_wall / 1e6, t_screen,
-                                        n_pairs / max(t_screen, 1e-9) / 1e6, n_in, t_chain, n_in / max(t_chain, 1e-9), len(hits)), flush=True)
+    for rep in range(args.repeat):
+        t_wall = t_screen = t_chain = 0.0
+        n_in = 0
+        hits = []
+        for q0 in range(0, len(queries), args.query_chunk):
+            t0 = time.perf_counter()
+            h, k = db.query(queries[q0:q0 + args.query_chunk])
+            t1 = time.perf_counter()
+            st = ctx.stats()
+            t_wall += t1 - t0; t_screen += st.screen_ms / 1e3; t_chain += st.chain_ms / 1e3; n_in += k
+            hits.extend((q0 + x[0],) + x[1:5] for x in h)
+        n_pairs = len(queries) * n
+        print("query%s: %d x %d = %.3g pairs in %.3f s wall = %.2f M pairs/s | screen %.3f s (%.1f M pairs/s) | %d pairs chained in %.3f s "
+              "(%.0f pairs/s) | %d hits" % (" (repeat %d)" % rep if rep else "", len(queries), n, n_pairs, t_wall, n_pairs / t_wall / 1e6,
+                                            t_screen, n_pairs / max(t_screen, 1e-9) / 1e6, n_in, t_chain, n_in / max(t_chain, 1e-9),
+                                            len(hits)), flush=True)
 
     # ---- properties
     intra = all(q_family[h[0]] == h[1] // M for h in hits)
