@@ -306,56 +306,84 @@ __global__ void __launch_bounds__(DP_WARPS * 32) chain_dp_kernel(const ChainBatc
     unsigned long long* best_a = b.a_best + A0;
 
     // ---------------- DP
-    Gen g0{0, 0, 0xFFFFFFFFu, 0, 0}, g1 = g0, g2 = g0, g3 = g0;     // meta 0xFFFFFFFF never matches
+    // Lane l keeps the newest anchor with index == l (mod 32) in registers: the 32 nearest predecessors of the current
+    // anchor are always on chip.  Anchors are ordered by query position and ~20 of them fall inside the 2 500 bp band,
+    // so older predecessors (distance 33..index_band) are only needed in repeat-rich windows; they are read back from
+    // the anchor arrays (f/root of a finished strip of 32 are already stored), which keeps the common path free of any
+    // per-anchor register shuffling.  Score and distance travel through ONE warp reduction as (score + bias) << 8 |
+    // (255 - distance): maximal score first, nearest predecessor on ties.  Windows with so many anchors that the packed
+    // score could overflow (> 2^22 / anchor_score anchors) take the two-reduction path.
+    Gen g0{0, 0, 0xFFFFFFFFu, 0, 0};                                 // meta 0xFFFFFFFF never matches
+    const int32_t bias = C.max_gap + 1;                               // score of a valid link is >= anchor_score * 2 - max_gap
+    const bool wide = (uint64_t)n * (uint32_t)C.anchor_score >= (1u << 22);
     for (uint32_t sb = 0; sb < n; sb += 32) {
         const uint32_t mine = sb + lane;
         uint32_t sq = 0, sr = 0, sm = 0;
         if (mine < n) { sq = qp_a[mine]; sr = rp_a[mine]; sm = meta_a[mine]; }
         const uint32_t lim = min(32u, n - sb);
-        for (uint32_t u = 0; u < lim; u++) {
-            const uint32_t i = sb + u;                       // window-local anchor index; owner lane = u
+        int d0 = 32 - lane;                                           // distance of this lane's newest anchor from sb + u, u = 0
+        for (uint32_t u = 0; u < lim; u++, d0 = d0 == 32 ? 1 : d0 + 1) {
+            const uint32_t i = sb + u;                                // window-local anchor index; owner lane = u
             const uint32_t cq = __shfl_sync(FULL, sq, u), cr = __shfl_sync(FULL, sr, u), cm = __shfl_sync(FULL, sm, u);
             const bool rev = cm & 1u;
-            const int d0 = (int)((u - 1 - lane) & 31) + 1;  // distance of this lane's newest anchor from i
             int32_t best = C.anchor_score; int bestd = 0;
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-                const Gen& G = g == 0 ? g0 : g == 1 ? g1 : g == 2 ? g2 : g3;
-                const int d = d0 + 32 * g;
-                const bool exists = (uint32_t)d <= i;
-                const bool inband = exists && d <= C.index_band && (cq - G.qp) <= (uint32_t)C.bp_band;
+            // ---- the 32 nearest predecessors (registers)
+            const uint32_t dq0 = cq - g0.qp;
+            const bool inband0 = (uint32_t)d0 <= i && dq0 <= (uint32_t)C.bp_band;
+            {
                 int32_t sc = INT32_MIN;
-                if (inband && G.meta == cm) {
-                    const int32_t dq = (int32_t)(cq - G.qp);
-                    const int32_t dr = rev ? (int32_t)(G.rp - cr) : (int32_t)(cr - G.rp);
+                if (inband0 && g0.meta == cm) {
+                    const int32_t dq = (int32_t)dq0;
+                    const int32_t dr = rev ? (int32_t)(g0.rp - cr) : (int32_t)(cr - g0.rp);
                     const int32_t gap = abs(dr - dq);
-                    if (dq > 0 && dr > 0 && gap <= C.max_gap) sc = G.f + C.anchor_score - gap;
+                    if (dq > 0 && dr > 0 && gap <= C.max_gap) sc = g0.f + C.anchor_score - gap;
                 }
-                const int32_t m = __reduce_max_sync(FULL, sc);
-                if (m > best) {                               // strictly better than anything nearer
-                    best = m;
-                    bestd = (int)__reduce_min_sync(FULL, sc == m ? (uint32_t)d : 0x7FFFFFFFu);
+                if (!wide) {
+                    const uint32_t key = sc == INT32_MIN ? 0u : ((uint32_t)(sc + bias) << 8) | (uint32_t)(255 - d0);
+                    const uint32_t mk = __reduce_max_sync(FULL, key);
+                    const int32_t m = (int32_t)(mk >> 8) - bias;
+                    if (mk && m > best) { best = m; bestd = 255 - (int)(mk & 255u); }
+                } else {
+                    const int32_t m = __reduce_max_sync(FULL, sc);
+                    if (m > best) { best = m; bestd = (int)__reduce_min_sync(FULL, sc == m ? (uint32_t)d0 : 0x7FFFFFFFu); }
                 }
-                // the anchor at distance 32(g+1) is this generation's oldest: if it is out of band, so is the rest
-                const uint32_t ib = __ballot_sync(FULL, inband);
-                if (!((ib >> u) & 1u)) break;
+            }
+            // ---- older predecessors: only while the oldest anchor seen so far (distance 32 g, lane u) is still in band
+            if ((__ballot_sync(FULL, inband0) >> u) & 1u) {
+                for (int g = 1; g < 4; g++) {
+                    const int d = d0 + 32 * g;
+                    bool inband = (uint32_t)d <= i && d <= C.index_band;
+                    int32_t sc = INT32_MIN;
+                    if (inband) {
+                        const uint32_t j = i - (uint32_t)d;
+                        const uint32_t pq = qp_a[j];
+                        inband = (cq - pq) <= (uint32_t)C.bp_band;
+                        if (inband && meta_a[j] == cm) {
+                            const uint32_t pr = rp_a[j];
+                            const int32_t dq = (int32_t)(cq - pq);
+                            const int32_t dr = rev ? (int32_t)(pr - cr) : (int32_t)(cr - pr);
+                            const int32_t gap = abs(dr - dq);
+                            if (dq > 0 && dr > 0 && gap <= C.max_gap) sc = f_a[j] + C.anchor_score - gap;
+                        }
+                    }
+                    const int32_t m = __reduce_max_sync(FULL, sc);
+                    if (m > best) {                               // strictly better than anything nearer
+                        best = m;
+                        bestd = (int)__reduce_min_sync(FULL, sc == m ? (uint32_t)d : 0x7FFFFFFFu);
+                    }
+                    if (!((__ballot_sync(FULL, inband) >> u) & 1u)) break;
+                }
             }
             // component root of i
             uint32_t root = i;
             if (bestd) {
-                const uint32_t j = i - (uint32_t)bestd;
-                const int L = (int)(j & 31);
-                const int dL = (int)((u - 1 - L) & 31) + 1;
-                const int gsel = (bestd - dL) >> 5;
-                const uint32_t rsel = gsel == 0 ? g0.root : gsel == 1 ? g1.root : gsel == 2 ? g2.root : g3.root;
-                root = __shfl_sync(FULL, rsel, L);
+                const uint32_t r0 = __shfl_sync(FULL, g0.root, (int)((u - (uint32_t)bestd) & 31u));
+                root = bestd <= 32 ? r0 : root_a[i - (uint32_t)bestd];
             }
-            if (lane == (int)u) {
-                g3 = g2; g2 = g1; g1 = g0;
-                g0 = Gen{cq, cr, cm, best, root};
-            }
+            if (lane == (int)u) g0 = Gen{cq, cr, cm, best, root};
         }
         if (mine < n) { f_a[mine] = g0.f; root_a[mine] = g0.root; }
+        __syncwarp();                                              // the strip's f/root are read by other lanes from here on
     }
 
     // ---------------- per-component size and best end

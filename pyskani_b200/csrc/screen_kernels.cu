@@ -8,6 +8,7 @@
 // that the comparison is one IEEE multiply + compare, identical to the oracle's.
 #include <cstdlib>
 
+#include <cub/device/device_radix_sort.cuh>
 #include "skb_internal.cuh"
 
 namespace skb {
@@ -254,6 +255,122 @@ void launch_screen_decide(const GenomeView* queries, uint32_t n_queries, const G
     const int T = 256;
     screen_decide_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(queries, n_queries, refs, n_refs, count, p21,
                                                                     always, rescue_small, pass);
+    g_kernel_launches++;
+}
+
+// ---------------------------------------------------------------- screen through a marker index (many queries x many refs)
+// The pairwise kernels above stream every reference list past every query: |Q| x |R| x markers work even when the genomes
+// share nothing.  For large pair matrices the database's markers are instead kept as ONE sorted array of (marker, genome)
+// postings with a bucket table on the top bits (built once per database state).  A CTA owns one query and a tile of
+// references: its counters sit in shared memory, each query marker is looked up once, and every posting found bumps a
+// shared-memory counter.  Work = |Q| x markers lookups + the postings actually shared.  The counts are exactly the
+// intersection sizes the pairwise kernels produce (marker sets are duplicate-free), so the decision kernel is the same.
+namespace {
+
+__global__ void marker_postings_kernel(const GenomeView* __restrict__ refs, const uint32_t* __restrict__ genome_off,
+                                       uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t g = blockIdx.x;
+    const GenomeView& R = refs[g];
+    const uint32_t off = genome_off[g], n = R.n_markers;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) { keys[off + i] = R.markers[i]; vals[off + i] = g; }
+}
+
+__global__ void marker_index_buckets_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t shift, uint32_t n_buckets,
+                                            uint32_t* __restrict__ bucket) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > n_buckets) return;
+    const uint64_t target = (uint64_t)b << shift;
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (keys[mid] < target) lo = mid + 1; else hi = mid; }
+    bucket[b] = lo;
+}
+
+constexpr int JOIN_THREADS = 256;
+
+__global__ void __launch_bounds__(JOIN_THREADS) marker_join_kernel(const GenomeView* __restrict__ queries,
+                                                                    const uint64_t* __restrict__ keys,
+                                                                    const uint32_t* __restrict__ vals,
+                                                                    const uint32_t* __restrict__ bucket, uint32_t shift,
+                                                                    uint32_t n_refs, uint32_t tile, uint32_t* __restrict__ count) {
+    extern __shared__ uint32_t s_cnt[];
+    const uint32_t t0 = blockIdx.x * tile, tn = min(tile, n_refs - t0);
+    const GenomeView& Q = queries[blockIdx.y];
+    for (uint32_t i = threadIdx.x; i < tn; i += JOIN_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t nm = Q.n_markers;
+    // a warp takes 32 consecutive query markers: every lane finds its own first posting, then the warp walks the
+    // posting run of each marker that has one with coalesced loads
+    for (uint32_t base = (threadIdx.x >> 5) * 32; base < nm; base += JOIN_THREADS) {
+        const uint32_t i = base + (uint32_t)lane;
+        uint64_t m = ~0ull; uint32_t lo = 0, hi = 0;
+        if (i < nm) {
+            m = __ldg(Q.markers + i);
+            const uint32_t b = (uint32_t)(m >> shift);
+            lo = __ldg(bucket + b); hi = __ldg(bucket + b + 1);
+            const uint32_t end = hi;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(keys + mid) < m) lo = mid + 1; else hi = mid; }
+            hi = end;
+        }
+        const bool found = i < nm && lo < hi && __ldg(keys + lo) == m;
+        uint32_t todo = __ballot_sync(0xFFFFFFFFu, found);
+        while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint64_t ml = __shfl_sync(0xFFFFFFFFu, m, l);
+            const uint32_t lol = __shfl_sync(0xFFFFFFFFu, lo, l), hil = __shfl_sync(0xFFFFFFFFu, hi, l);
+            for (uint32_t j = lol;; j += 32) {
+                const uint32_t idx = j + (uint32_t)lane;
+                const bool ok = idx < hil && __ldg(keys + idx) == ml;
+                if (ok) {
+                    const uint32_t g = __ldg(vals + idx) - t0;
+                    if (g < tn) atomicAdd(&s_cnt[g], 1u);
+                }
+                if (!__all_sync(0xFFFFFFFFu, ok)) break;
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t* row = count + (size_t)blockIdx.y * n_refs + t0;
+    for (uint32_t i = threadIdx.x; i < tn; i += JOIN_THREADS) row[i] = s_cnt[i];
+}
+
+}  // namespace
+
+size_t marker_index_scratch_bytes(uint32_t n_postings) {
+    size_t sort_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)n_postings, 0, MARKER_BITS);
+    return (((size_t)n_postings * 8 + 255) & ~(size_t)255) + (((size_t)n_postings * 4 + 255) & ~(size_t)255) + sort_bytes + 256;
+}
+
+void build_marker_index(const GenomeView* refs, uint32_t n_refs, const uint32_t* genome_off, uint32_t n_postings,
+                        uint64_t* keys, uint32_t* vals, uint32_t* bucket, uint32_t shift, uint32_t n_buckets,
+                        void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    if (n_refs == 0) return;
+    char* p = (char*)scratch;
+    uint64_t* k_in = (uint64_t*)p; p += ((size_t)n_postings * 8 + 255) & ~(size_t)255;
+    uint32_t* v_in = (uint32_t*)p; p += ((size_t)n_postings * 4 + 255) & ~(size_t)255;
+    size_t sort_bytes = scratch_bytes - (size_t)(p - (char*)scratch);
+    marker_postings_kernel<<<n_refs, 256, 0, st>>>(refs, genome_off, k_in, v_in);
+    g_kernel_launches++;
+    if (n_postings) {
+        cub::DeviceRadixSort::SortPairs(p, sort_bytes, k_in, keys, v_in, vals, (int)n_postings, 0, MARKER_BITS, st);
+        g_kernel_launches += 2 * ((MARKER_BITS + 7) / 8);
+    }
+    marker_index_buckets_kernel<<<(n_buckets + 1 + 255) / 256, 256, 0, st>>>(keys, n_postings, shift, n_buckets, bucket);
+    g_kernel_launches++;
+}
+
+void launch_marker_join(const GenomeView* queries, uint32_t n_queries, uint32_t n_refs, const uint64_t* keys,
+                        const uint32_t* vals, const uint32_t* bucket, uint32_t shift, uint32_t* count, cudaStream_t st) {
+    if (n_queries == 0 || n_refs == 0) return;
+    const uint32_t tile = n_refs < 32768u ? n_refs : 32768u;
+    const size_t smem = (size_t)tile * 4;
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(marker_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4); attr_set = true; }
+    dim3 grid((n_refs + tile - 1) / tile, n_queries);
+    marker_join_kernel<<<grid, JOIN_THREADS, smem, st>>>(queries, keys, vals, bucket, shift, n_refs, tile, count);
     g_kernel_launches++;
 }
 

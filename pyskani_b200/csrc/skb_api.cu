@@ -139,7 +139,7 @@ void* Core::scratch(int slot, size_t bytes) {
     }
     return b.p;
 }
-enum { SLOT_SEQ = 0, SLOT_KMER, SLOT_POS, SLOT_META, SLOT_MKEYS, SLOT_STATUS, SLOT_SORT, SLOT_MARK, SLOT_GS, SLOT_GM, SLOT_DESC, SLOT_MKEYS2, SLOT_RSCAN, SLOT_GM_IN, SLOT_BTAB, SLOT_BCOUNT, SLOT_CHAIN };
+enum { SLOT_SEQ = 0, SLOT_KMER, SLOT_POS, SLOT_META, SLOT_MKEYS, SLOT_STATUS, SLOT_SORT, SLOT_MARK, SLOT_GS, SLOT_GM, SLOT_DESC, SLOT_MKEYS2, SLOT_RSCAN, SLOT_GM_IN, SLOT_BTAB, SLOT_BCOUNT, SLOT_CHAIN, SLOT_MIDX };
 
 // stream-ordered device buffer
 struct DevMem {
@@ -201,6 +201,10 @@ struct skb_db {
     std::vector<std::shared_ptr<skb::SketchImpl>> items;
     skb::DevMem d_views;
     bool dirty = true;
+    // marker index (postings sorted by marker), built on the first large screen after the database changed
+    skb::DevMem idx_keys, idx_vals, idx_bucket;
+    uint32_t idx_shift = 0, idx_postings = 0;
+    bool idx_dirty = true;
 };
 
 namespace skb {
@@ -931,7 +935,7 @@ int skb_db_add(skb_db_t* db, skb_sketch_t* s, uint32_t* index_out) {
         }
         if (index_out) *index_out = (uint32_t)db->items.size();
         db->items.push_back(s->impl);
-        db->dirty = true;
+        db->dirty = true; db->idx_dirty = true;
         return SKB_OK;
     });
 }
@@ -947,7 +951,7 @@ int skb_db_add_many(skb_db_t* db, uint32_t n, skb_sketch_t* const* sketches, uin
         }
         if (index_out) *index_out = (uint32_t)db->items.size();
         for (uint32_t i = 0; i < n; i++) db->items.push_back(sketches[i]->impl);
-        db->dirty = true;
+        db->dirty = true; db->idx_dirty = true;
         return SKB_OK;
     });
 }
@@ -974,6 +978,36 @@ const GenomeView* db_views(skb_db& db) {
     return db.d_views.as<GenomeView>();
 }
 
+// (Re)builds the marker index of the database if sketches were added since the last build.  Returns false if the
+// database cannot be indexed (no markers, or more than 2^31 postings).
+bool db_marker_index(skb_db& db, const GenomeView* d_r) {
+    Core& c = *db.core;
+    const uint32_t nr = (uint32_t)db.items.size();
+    if (!db.idx_dirty) return db.idx_postings != 0;
+    std::vector<uint32_t> off(nr + 1, 0);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < nr; i++) { off[i] = (uint32_t)total; total += db.items[i]->view.n_markers; }
+    db.idx_dirty = false; db.idx_postings = 0;
+    if (total == 0 || total >= 0x7FFFFFFFull) return false;
+    off[nr] = (uint32_t)total;
+    int B = 1;
+    while (B < 24 && ((uint64_t)16 << B) < total) B++;
+    const uint32_t nb = 1u << B;
+    db.idx_shift = (uint32_t)(MARKER_BITS - B);
+    db.idx_keys = DevMem::persistent(db.core, 8 * total);
+    db.idx_vals = DevMem::persistent(db.core, 4 * total);
+    db.idx_bucket = DevMem::persistent(db.core, 4 * ((size_t)nb + 1));
+    const size_t off_bytes = (4 * ((size_t)nr + 1) + 255) & ~(size_t)255;
+    const size_t scr_bytes = marker_index_scratch_bytes((uint32_t)total);
+    char* scr = (char*)c.scratch(SLOT_MIDX, off_bytes + scr_bytes);
+    CU(cudaMemcpyAsync(scr, off.data(), 4 * ((size_t)nr + 1), cudaMemcpyHostToDevice, c.stream));
+    build_marker_index(d_r, nr, (const uint32_t*)scr, (uint32_t)total, db.idx_keys.as<uint64_t>(), db.idx_vals.as<uint32_t>(),
+                       db.idx_bucket.as<uint32_t>(), db.idx_shift, nb, scr + off_bytes, scr_bytes, c.stream);
+    CU(cudaStreamSynchronize(c.stream));      // `off` is pageable host memory
+    db.idx_postings = (uint32_t)total;
+    return true;
+}
+
 struct ScreenOut {
     std::vector<uint32_t> pass_idx;   // q * n_refs + r, ascending
 };
@@ -993,7 +1027,15 @@ void run_screen(skb_db& db, const std::vector<std::shared_ptr<SketchImpl>>& quer
     DevMem d_count(db.core, 4 * n), d_pass(db.core, n);
     std::vector<uint32_t> qm(nq);
     for (uint32_t i = 0; i < nq; i++) qm[i] = queries[i]->view.n_markers;
-    launch_marker_screen(d_q, nq, d_r, nr, d_count.as<uint32_t>(), qm.data(), c.n_sm, st);
+    // large pair matrices go through the database's marker index, small ones through the pairwise kernels
+    // (SKB_SCREEN_MODE=index|pairwise forces one of them: used by the parity tests)
+    bool use_index = n >= 16384;
+    if (const char* e = std::getenv("SKB_SCREEN_MODE")) use_index = std::strcmp(e, "index") == 0;
+    if (use_index && db_marker_index(db, d_r))
+        launch_marker_join(d_q, nq, nr, db.idx_keys.as<uint64_t>(), db.idx_vals.as<uint32_t>(), db.idx_bucket.as<uint32_t>(),
+                           db.idx_shift, d_count.as<uint32_t>(), st);
+    else
+        launch_marker_screen(d_q, nq, d_r, nr, d_count.as<uint32_t>(), qm.data(), c.n_sm, st);
     launch_screen_decide(d_q, nq, d_r, nr, d_count.as<uint32_t>(), pow21(screen_val), screen_val == 0.0, rescue_small,
                          d_pass.as<uint8_t>(), st);
     if (pass_host) download(c, pass_host, d_pass.as<uint8_t>(), n);

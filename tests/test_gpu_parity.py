@@ -142,6 +142,41 @@ def test_screen_matches_oracle(ctx):
                 assert ok[i, j] == want_ok, (i, j, cutoff, rescue)
 
 
+@pytest.mark.parametrize("mode", ["index", "pairwise"])
+def test_screen_modes_match_oracle(ctx, monkeypatch, mode):
+    """Both screen implementations (pairwise list intersection; join through the database's marker index) give the
+    oracle's intersection sizes and decisions, also after the database grew behind an already built index."""
+    from pyskani_b200 import capi
+    monkeypatch.setenv("SKB_SCREEN_MODE", mode)
+    fams = []
+    for f in range(3):
+        fams += make_family(4, 300_000, 140 + f, [0.01, 0.05, 0.12, 0.22])
+    fams.append(synth.random_genome(5_000, 199))
+    fams.append(np.frombuffer(b"ACGT" * 200, np.uint8))            # passes the contig gate, almost no markers
+    contigs = [[g.tobytes()] for g in fams]
+    gs = ctx.sketch_batch(contigs)
+    os_ = [oracle.Sketch(c) for c in contigs]
+    db = capi.Database(ctx)
+    db.add_many(gs[:7])
+
+    def check(n_refs):
+        for cutoff, rescue in ((0.8, True), (0.95, False)):
+            ok, shared = db.screen(gs, cutoff, rescue)
+            assert ok.shape == (len(gs), n_refs)
+            for i, qo in enumerate(os_):
+                for j in range(n_refs):
+                    want_ok, want_shared = oracle.screen(qo, os_[j], cutoff, rescue)
+                    assert shared[i, j] == want_shared and ok[i, j] == want_ok, (mode, i, j, cutoff, rescue)
+
+    check(7)
+    db.add_many(gs[7:])
+    check(len(gs))
+    hits_a, n_a = db.query(gs)
+    monkeypatch.setenv("SKB_SCREEN_MODE", "pairwise" if mode == "index" else "index")
+    hits_b, n_b = db.query(gs)
+    assert hits_a == hits_b and n_a == n_b
+
+
 # ------------------------------------------------------------------ chain / ANI
 def check_hits(hits, oq, orefs, cutoff=0.8, rescue=True, **flags):
     idx, res, n_in = oracle.query(oq, orefs, cutoff, rescue, oracle.default_params(**flags))
