@@ -18,6 +18,8 @@
 //   5. window ANI = min(1, anchors / query seeds spanned)^(1/k); genome ANI = seed-weighted mean (or
 //                  10-90 % trimmed, or median); AF = sum of (chain span + 198) / genome length.
 // Scores are integers (20 per anchor minus integer gaps), so the int32 DP is bit-identical to skani's f64.
+#include <cstdio>
+#include <cstdlib>
 #include "skb_internal.cuh"
 
 namespace skb {
@@ -289,6 +291,113 @@ __device__ __forceinline__ void tuple_min(int32_t& sc, uint32_t& qs, uint32_t& r
     if (take) { sc = sc2; qs = qs2; rs = rs2; idx = idx2; }
 }
 
+// The chaining DP of one window, run by one warp.
+// Lane l keeps the newest anchor with index == l (mod 32) in registers: the 32 nearest predecessors of the current anchor
+// are always on chip.  Anchors are ordered by query position and ~20 of them fall inside the 2 500 bp band, so older
+// predecessors (distance 33..index_band) are only needed in repeat-rich windows; they are read back from the anchor
+// arrays (f/root of a finished strip of 32 are already stored), which keeps the common path free of any per-anchor
+// register shuffling.  Score and distance travel through ONE warp reduction as (score + bias) << 8 | (255 - distance):
+// maximal score first, nearest predecessor on ties.  WIDE: windows with so many anchors that the packed score could
+// overflow (>= 2^22 / anchor_score anchors) use one reduction for the score and one for the distance.
+// The common path is straight-line code (selects instead of branches) so that the warp stays provably converged.
+constexpr int32_t DP_ANCHOR_SCORE = 20, DP_MAX_GAP = 300;
+constexpr uint32_t DP_BP_BAND = 2500, DP_INDEX_BAND = 100;
+
+template <bool WIDE>
+__device__ __forceinline__ void dp_window(const uint32_t* __restrict__ qp_a, const uint32_t* __restrict__ rp_a,
+                                          const uint32_t* __restrict__ meta_a, int32_t* f_a, uint32_t* root_a,
+                                          const uint32_t n, const int lane) {
+    // skani's chaining constants are frozen (pyskani exposes none of them): compile-time values
+    // here, checked against the ChainConsts of the call by launch_chain_dp
+    constexpr uint32_t bp_band = DP_BP_BAND, index_band = DP_INDEX_BAND;
+    constexpr int32_t max_gap = DP_MAX_GAP, anchor_score = DP_ANCHOR_SCORE;
+    constexpr int32_t link_bias = anchor_score + max_gap + 1;      // score of a valid link + max_gap + 1 - gap  >=  1
+    uint32_t g_qp = 0, g_rp = 0, g_meta = 0xFFFFFFFFu, g_root = 0;  // meta 0xFFFFFFFF never matches
+    int32_t g_f = 0;
+    for (uint32_t sb = 0; sb < n; sb += 32) {
+        const uint32_t mine = sb + lane;
+        uint32_t sq = 0, sr = 0, sm = 0;
+        if (mine < n) { sq = qp_a[mine]; sr = rp_a[mine]; sm = meta_a[mine]; }
+        const uint32_t lim = min(32u, n - sb);
+        uint32_t kd = 255u - (uint32_t)(32 - lane);                 // 255 - distance of this lane's newest anchor from sb + u
+        for (uint32_t u = 0; u < lim; u++) {
+            const uint32_t i = sb + u;                              // window-local anchor index; owner lane = u
+            const uint32_t cq = __shfl_sync(FULL, sq, u), cr = __shfl_sync(FULL, sr, u), cm = __shfl_sync(FULL, sm, u);
+            const uint32_t revmask = 0u - (cm & 1u);
+            // ---- the 32 nearest predecessors (registers)
+            const int32_t dq = (int32_t)(cq - g_qp);
+            const int32_t dr = (int32_t)(((cr - g_rp) ^ revmask) - revmask);      // reverse strand: g.rp - cr
+            const int32_t gap = abs(dr - dq);
+            const bool near_band = (uint32_t)dq <= bp_band;
+            const bool ok = ((uint32_t)(dq - 1) < bp_band) & (g_meta == cm) & (dr > 0) & (gap <= max_gap);
+            int32_t best; uint32_t bestd;
+            if (!WIDE) {
+                // key = ok ? packed : 0, with the four conditions chained through one predicate (the compiler otherwise
+                // emits one select per condition)
+                const uint32_t packed = ((uint32_t)(g_f + link_bias - gap) << 8) | kd;
+                uint32_t key;
+                asm("{\n\t.reg .pred p;\n\t"
+                    "setp.lt.u32 p, %1, %2;\n\t"
+                    "setp.eq.and.u32 p, %3, %4, p;\n\t"
+                    "setp.gt.and.s32 p, %5, 0, p;\n\t"
+                    "setp.le.and.s32 p, %6, %7, p;\n\t"
+                    "selp.u32 %0, %8, 0, p;\n\t}"
+                    : "=r"(key)
+                    : "r"((uint32_t)(dq - 1)), "r"(bp_band), "r"(g_meta), "r"(cm), "r"(dr), "r"(gap), "r"(max_gap), "r"(packed));
+                const uint32_t mk = __reduce_max_sync(FULL, key);
+                const int32_t m = (int32_t)(mk >> 8) - (max_gap + 1);
+                const bool take = m > anchor_score;                 // mk == 0 gives m < 0
+                best = take ? m : anchor_score;
+                bestd = take ? 255u - (mk & 255u) : 0u;
+            } else {
+                const int32_t sc = ok ? g_f + anchor_score - gap : INT32_MIN;
+                const int32_t m = __reduce_max_sync(FULL, sc);
+                const uint32_t dm = __reduce_min_sync(FULL, sc == m ? 255u - kd : 0x7FFFFFFFu);
+                const bool take = m > anchor_score;
+                best = take ? m : anchor_score;
+                bestd = take ? dm : 0u;
+            }
+            // ---- older predecessors: only while the oldest anchor seen so far (distance 32 g, lane u) is still in band
+            if (i >= 32 && ((__ballot_sync(FULL, near_band) >> u) & 1u)) {
+                const uint32_t d0 = 255u - kd;
+                for (uint32_t g = 1; g < 4; g++) {
+                    const uint32_t d = d0 + 32u * g;
+                    bool inband = d <= i && d <= index_band;
+                    int32_t sc = INT32_MIN;
+                    if (inband) {
+                        const uint32_t j = i - d;
+                        const uint32_t pq = qp_a[j];
+                        inband = (cq - pq) <= bp_band;
+                        if (inband && meta_a[j] == cm) {
+                            const uint32_t pr = rp_a[j];
+                            const int32_t dq2 = (int32_t)(cq - pq);
+                            const int32_t dr2 = (int32_t)(((cr - pr) ^ revmask) - revmask);
+                            const int32_t gap2 = abs(dr2 - dq2);
+                            if (dq2 > 0 && dr2 > 0 && gap2 <= max_gap) sc = f_a[j] + anchor_score - gap2;
+                        }
+                    }
+                    const int32_t m = __reduce_max_sync(FULL, sc);
+                    if (m > best) {                               // strictly better than anything nearer
+                        best = m;
+                        bestd = __reduce_min_sync(FULL, sc == m ? d : 0x7FFFFFFFu);
+                    }
+                    if (!((__ballot_sync(FULL, inband) >> u) & 1u)) break;
+                }
+            }
+            // component root of i
+            const uint32_t r0 = __shfl_sync(FULL, g_root, (int)((u - bestd) & 31u));
+            uint32_t root = bestd ? r0 : i;
+            if (bestd > 32u) root = root_a[i - bestd];
+            const bool own = lane == (int)u;
+            g_qp = own ? cq : g_qp; g_rp = own ? cr : g_rp; g_meta = own ? cm : g_meta;
+            g_f = own ? best : g_f; g_root = own ? root : g_root;
+            kd = kd == 223u ? 254u : kd - 1u;
+        }
+        if (mine < n) { f_a[mine] = g_f; root_a[mine] = g_root; }
+        __syncwarp();                                              // the strip's f/root are read by other lanes from here on
+    }
+}
+
 constexpr int DP_WARPS = 4;
 
 __global__ void __launch_bounds__(DP_WARPS * 32) chain_dp_kernel(const ChainBatch b, const ChainConsts C) {
@@ -306,85 +415,8 @@ __global__ void __launch_bounds__(DP_WARPS * 32) chain_dp_kernel(const ChainBatc
     unsigned long long* best_a = b.a_best + A0;
 
     // ---------------- DP
-    // Lane l keeps the newest anchor with index == l (mod 32) in registers: the 32 nearest predecessors of the current
-    // anchor are always on chip.  Anchors are ordered by query position and ~20 of them fall inside the 2 500 bp band,
-    // so older predecessors (distance 33..index_band) are only needed in repeat-rich windows; they are read back from
-    // the anchor arrays (f/root of a finished strip of 32 are already stored), which keeps the common path free of any
-    // per-anchor register shuffling.  Score and distance travel through ONE warp reduction as (score + bias) << 8 |
-    // (255 - distance): maximal score first, nearest predecessor on ties.  Windows with so many anchors that the packed
-    // score could overflow (> 2^22 / anchor_score anchors) take the two-reduction path.
-    Gen g0{0, 0, 0xFFFFFFFFu, 0, 0};                                 // meta 0xFFFFFFFF never matches
-    const int32_t bias = C.max_gap + 1;                               // score of a valid link is >= anchor_score * 2 - max_gap
-    const bool wide = (uint64_t)n * (uint32_t)C.anchor_score >= (1u << 22);
-    for (uint32_t sb = 0; sb < n; sb += 32) {
-        const uint32_t mine = sb + lane;
-        uint32_t sq = 0, sr = 0, sm = 0;
-        if (mine < n) { sq = qp_a[mine]; sr = rp_a[mine]; sm = meta_a[mine]; }
-        const uint32_t lim = min(32u, n - sb);
-        int d0 = 32 - lane;                                           // distance of this lane's newest anchor from sb + u, u = 0
-        for (uint32_t u = 0; u < lim; u++, d0 = d0 == 32 ? 1 : d0 + 1) {
-            const uint32_t i = sb + u;                                // window-local anchor index; owner lane = u
-            const uint32_t cq = __shfl_sync(FULL, sq, u), cr = __shfl_sync(FULL, sr, u), cm = __shfl_sync(FULL, sm, u);
-            const bool rev = cm & 1u;
-            int32_t best = C.anchor_score; int bestd = 0;
-            // ---- the 32 nearest predecessors (registers)
-            const uint32_t dq0 = cq - g0.qp;
-            const bool inband0 = (uint32_t)d0 <= i && dq0 <= (uint32_t)C.bp_band;
-            {
-                int32_t sc = INT32_MIN;
-                if (inband0 && g0.meta == cm) {
-                    const int32_t dq = (int32_t)dq0;
-                    const int32_t dr = rev ? (int32_t)(g0.rp - cr) : (int32_t)(cr - g0.rp);
-                    const int32_t gap = abs(dr - dq);
-                    if (dq > 0 && dr > 0 && gap <= C.max_gap) sc = g0.f + C.anchor_score - gap;
-                }
-                if (!wide) {
-                    const uint32_t key = sc == INT32_MIN ? 0u : ((uint32_t)(sc + bias) << 8) | (uint32_t)(255 - d0);
-                    const uint32_t mk = __reduce_max_sync(FULL, key);
-                    const int32_t m = (int32_t)(mk >> 8) - bias;
-                    if (mk && m > best) { best = m; bestd = 255 - (int)(mk & 255u); }
-                } else {
-                    const int32_t m = __reduce_max_sync(FULL, sc);
-                    if (m > best) { best = m; bestd = (int)__reduce_min_sync(FULL, sc == m ? (uint32_t)d0 : 0x7FFFFFFFu); }
-                }
-            }
-            // ---- older predecessors: only while the oldest anchor seen so far (distance 32 g, lane u) is still in band
-            if ((__ballot_sync(FULL, inband0) >> u) & 1u) {
-                for (int g = 1; g < 4; g++) {
-                    const int d = d0 + 32 * g;
-                    bool inband = (uint32_t)d <= i && d <= C.index_band;
-                    int32_t sc = INT32_MIN;
-                    if (inband) {
-                        const uint32_t j = i - (uint32_t)d;
-                        const uint32_t pq = qp_a[j];
-                        inband = (cq - pq) <= (uint32_t)C.bp_band;
-                        if (inband && meta_a[j] == cm) {
-                            const uint32_t pr = rp_a[j];
-                            const int32_t dq = (int32_t)(cq - pq);
-                            const int32_t dr = rev ? (int32_t)(pr - cr) : (int32_t)(cr - pr);
-                            const int32_t gap = abs(dr - dq);
-                            if (dq > 0 && dr > 0 && gap <= C.max_gap) sc = f_a[j] + C.anchor_score - gap;
-                        }
-                    }
-                    const int32_t m = __reduce_max_sync(FULL, sc);
-                    if (m > best) {                               // strictly better than anything nearer
-                        best = m;
-                        bestd = (int)__reduce_min_sync(FULL, sc == m ? (uint32_t)d : 0x7FFFFFFFu);
-                    }
-                    if (!((__ballot_sync(FULL, inband) >> u) & 1u)) break;
-                }
-            }
-            // component root of i
-            uint32_t root = i;
-            if (bestd) {
-                const uint32_t r0 = __shfl_sync(FULL, g0.root, (int)((u - (uint32_t)bestd) & 31u));
-                root = bestd <= 32 ? r0 : root_a[i - (uint32_t)bestd];
-            }
-            if (lane == (int)u) g0 = Gen{cq, cr, cm, best, root};
-        }
-        if (mine < n) { f_a[mine] = g0.f; root_a[mine] = g0.root; }
-        __syncwarp();                                              // the strip's f/root are read by other lanes from here on
-    }
+    if ((uint64_t)n * (uint32_t)DP_ANCHOR_SCORE < (1u << 22)) dp_window<false>(qp_a, rp_a, meta_a, f_a, root_a, n, lane);
+    else dp_window<true>(qp_a, rp_a, meta_a, f_a, root_a, n, lane);
 
     // ---------------- per-component size and best end
     for (uint32_t i = lane; i < n; i += 32) {
@@ -578,6 +610,11 @@ void launch_window_walk(const ChainBatch& b, const ChainConsts& c, uint32_t max_
 }
 void launch_chain_dp(const ChainBatch& b, const ChainConsts& c, cudaStream_t st) {
     if (b.n_win_total == 0) return;
+    if (c.anchor_score != DP_ANCHOR_SCORE || c.max_gap != DP_MAX_GAP || c.bp_band != (int32_t)DP_BP_BAND ||
+        c.index_band != (int32_t)DP_INDEX_BAND) {
+        std::fprintf(stderr, "skb: chain_dp_kernel is compiled for skani's frozen chaining constants\n");
+        std::abort();
+    }
     chain_dp_kernel<<<(b.n_win_total + DP_WARPS - 1) / DP_WARPS, DP_WARPS * 32, 0, st>>>(b, c);
     g_kernel_launches++;
 }
