@@ -195,11 +195,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// One CTA per *walk group*: up to walk_group_max consecutive pairs of the batch that share their query.  The query's
+// seed positions are staged once, the match bitmask of every pair of the group next to them, and the (pair, contig) chains
+// of the group are spread over the warps: with many pairs per query (all-vs-all) a group keeps 8+ chains in flight per SM
+// instead of one.
 __global__ void __launch_bounds__(1024) window_walk_smem_kernel(const ChainBatch b, const uint32_t F) {
     extern __shared__ __align__(128) uint32_t sm[];
     __shared__ uint64_t s_bar;
-    const PairDesc pd = b.pairs[blockIdx.x];
-    const GenomeView& Q = b.qviews[pd.q];
+    const uint2 grp = b.walk_groups[blockIdx.x];      // first pair, number of pairs
+    const PairDesc pd0 = b.pairs[grp.x];
+    const GenomeView& Q = b.qviews[pd0.q];
     const uint32_t n = Q.n_seeds;
     if (n > WALK_SMEM_SEEDS) return;                  // handled by the global-memory kernel
     // The query's seed positions keep their 16-byte phase in shared memory, so the 16-byte aligned middle of the
@@ -210,18 +215,19 @@ __global__ void __launch_bounds__(1024) window_walk_smem_kernel(const ChainBatch
     const uint32_t head = min(n, (4u - phase) & 3u);
     const uint32_t mid = ((n - head) >> 2) << 2;
     const uint32_t n_bit_words = (((n + 31) >> 5) + 3u) & ~3u;                 // padded to 16 bytes (so is the source slice)
-    uint32_t* s_bits = sm + ((phase + n + 3u) & ~3u);                          // 16-byte aligned
-    const uint32_t* bits_src = b.m_bits + pd.bits_off;
+    uint32_t* s_bits0 = sm + ((phase + n + 3u) & ~3u);                         // 16-byte aligned; pair k at + k * n_bit_words
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     if (threadIdx.x == 0) mbar_init(&s_bar, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
-        mbar_expect_tx(&s_bar, mid * 4u + n_bit_words * 4u);
+        mbar_expect_tx(&s_bar, mid * 4u + grp.y * n_bit_words * 4u);
         for (uint32_t off = 0; off < mid; off += 8192) {
             const uint32_t cnt = min(8192u, mid - off);
             bulk_g2s(s_pos + head + off, src + head + off, cnt * 4u, &s_bar);
         }
-        if (n_bit_words) bulk_g2s(s_bits, bits_src, n_bit_words * 4u, &s_bar);
+        if (n_bit_words)
+            for (uint32_t k = 0; k < grp.y; k++)
+                bulk_g2s(s_bits0 + k * n_bit_words, b.m_bits + b.pairs[grp.x + k].bits_off, n_bit_words * 4u, &s_bar);
     }
     for (uint32_t i = threadIdx.x; i < n - mid; i += blockDim.x) {             // head and tail words
         const uint32_t j = i < head ? i : mid + i;
@@ -229,7 +235,12 @@ __global__ void __launch_bounds__(1024) window_walk_smem_kernel(const ChainBatch
     }
     mbar_wait(&s_bar, 0);
     __syncthreads();
-    for (uint32_t c = warp; c < Q.n_contigs; c += nwarps) {
+    const uint32_t n_contigs = Q.n_contigs;
+    for (uint32_t item = warp; item < grp.y * n_contigs; item += nwarps) {
+        const uint32_t k = item / n_contigs, c = item - k * n_contigs;
+        const uint32_t pair = grp.x + k;
+        const PairDesc pd = b.pairs[pair];
+        const uint32_t* s_bits = s_bits0 + k * n_bit_words;
         const uint32_t cs = Q.contig_seed_start[c], ce = Q.contig_seed_start[c + 1];
         uint32_t slot = pd.win_off + Q.contig_win_start[c];
         uint32_t s = cs;
@@ -273,7 +284,7 @@ __global__ void __launch_bounds__(1024) window_walk_smem_kernel(const ChainBatch
             if (lane == 0) {
                 b.win_start[slot] = i;
                 b.win_end[slot] = e;
-                b.win_contig[slot] = blockIdx.x;
+                b.win_contig[slot] = pair;
             }
             slot++;
             s = e;
@@ -594,14 +605,25 @@ void launch_anchor_fill(const ChainBatch& b, cudaStream_t st) {
     anchor_fill_kernel<<<grid, 256, 0, st>>>(b);
     g_kernel_launches++;
 }
+constexpr size_t WALK_SMEM_MAX = 226 * 1024;     // dynamic part; the kernel also has a few bytes of static shared memory
+size_t walk_smem_bytes(uint32_t n_seeds, uint32_t group) {
+    return ((size_t)n_seeds + 8) * 4 + (size_t)group * ((((size_t)n_seeds + 31) / 32 + 3) / 4 * 4) * 4 + 64;
+}
+// most pairs of one query that fit beside its positions in the 227 KB of one CTA (at most one chain per warp)
+uint32_t walk_group_capacity(uint32_t max_query_seeds) {
+    const uint32_t n = max_query_seeds < WALK_SMEM_SEEDS ? max_query_seeds : WALK_SMEM_SEEDS;
+    uint32_t g = 1;
+    while (g < 32 && walk_smem_bytes(n, g + 1) <= WALK_SMEM_MAX) g++;
+    return g;
+}
 void launch_window_walk(const ChainBatch& b, const ChainConsts& c, uint32_t max_query_seeds, cudaStream_t st) {
     if (b.n_pairs == 0) return;
     // shared-memory walk for every pair whose query fits, global-memory walk for the rest
-    const size_t cap_bytes = ((size_t)WALK_SMEM_SEEDS + 8) * 4 + (((size_t)WALK_SMEM_SEEDS + 31) / 32 + 4) * 4 + 64;
-    cudaFuncSetAttribute(window_walk_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap_bytes);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(window_walk_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WALK_SMEM_MAX); attr_set = true; }
     const uint32_t n = max_query_seeds < WALK_SMEM_SEEDS ? max_query_seeds : WALK_SMEM_SEEDS;
-    const size_t bytes = ((size_t)n + 8) * 4 + ((((size_t)n + 31) / 32 + 3) / 4 * 4) * 4 + 64;
-    window_walk_smem_kernel<<<b.n_pairs, 1024, bytes, st>>>(b, c.fragment_length);
+    const size_t bytes = walk_smem_bytes(n, b.walk_group_max);
+    window_walk_smem_kernel<<<b.n_walk_groups, 1024, bytes, st>>>(b, c.fragment_length);
     g_kernel_launches++;
     if (max_query_seeds > WALK_SMEM_SEEDS) {
         window_walk_kernel<<<b.n_pairs, 128, 0, st>>>(b, c.fragment_length, 1);

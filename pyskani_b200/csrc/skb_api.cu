@@ -484,6 +484,7 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
                                      bscr, bscr_bytes, st);
         }
         CU(cudaStreamWaitEvent(st, c.ev[7], 0));
+        CU(cudaGetLastError());                  // refused launches must not pass silently
         t2.mark("enqueued index");
         CU(cudaEventRecord(c.ev[3], st));
         finish_batch(core, P, seed, n_genomes, contig_lens, store, seed_start, marker_start, d_gm, out, d_bover);
@@ -1038,6 +1039,7 @@ void run_screen(skb_db& db, const std::vector<std::shared_ptr<SketchImpl>>& quer
         launch_marker_screen(d_q, nq, d_r, nr, d_count.as<uint32_t>(), qm.data(), c.n_sm, st);
     launch_screen_decide(d_q, nq, d_r, nr, d_count.as<uint32_t>(), pow21(screen_val), screen_val == 0.0, rescue_small,
                          d_pass.as<uint8_t>(), st);
+    CU(cudaGetLastError());
     if (pass_host) download(c, pass_host, d_pass.as<uint8_t>(), n);
     if (shared_host) download(c, shared_host, d_count.as<uint32_t>(), n);
     if (out && n <= (1u << 16)) {
@@ -1149,6 +1151,15 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
             if (est > 0x7FFFFFFFull) est = 0x7FFFFFFFull;
             if (const char* e = std::getenv("SKB_FORCE_ANCHOR_EST")) est = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10));   // test hook: exercises the rerun
             std::vector<PairResult> res(np);
+            // walk groups: runs of pairs with the same query, cut so that the groups about fill the SMs once
+            std::vector<uint2> groups;
+            uint32_t group_max = std::min<uint32_t>(walk_group_capacity(max_qseeds), std::max<uint32_t>(1, (np + c.n_sm - 1) / c.n_sm));
+            for (uint32_t i = 0; i < np;) {
+                uint32_t j = i + 1;
+                while (j < np && j - i < group_max && pairs[j].q == pairs[i].q) j++;
+                groups.push_back(make_uint2(i, j - i));
+                i = j;
+            }
             const size_t nw = std::max<uint64_t>(wins, 1);
             const size_t scan_bytes = scan_scratch_bytes((uint32_t)seeds + 1), sort_bytes = sort_pairs_scratch_bytes((uint32_t)wins);
             for (int attempt = 0; attempt < 2; attempt++) {
@@ -1161,7 +1172,8 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
                              o_aoff = plan(4 * (seeds + 2)), o_bits = plan(4 * (bit_words + 4)), o_scan = plan(scan_bytes),
                              o_a = plan(na * 4 * 7), o_best = plan(na * 8), o_w = plan(nw * 4 * 3 + 4 * (size_t)np),
                              o_rec = plan(nw * sizeof(WindowRec)), o_keys = plan(nw * 8 * 2), o_vals = plan(nw * 4 * 2),
-                             o_res = plan(sizeof(PairResult) * np), o_sort = plan(sort_bytes);
+                             o_res = plan(sizeof(PairResult) * np), o_sort = plan(sort_bytes),
+                             o_groups = plan(sizeof(uint2) * groups.size());
                 char* base = (char*)c.scratch(SLOT_CHAIN, total);
                 ChainBatch B{};
                 B.qviews = d_q.as<GenomeView>(); B.rviews = d_r; B.n_pairs = np;
@@ -1170,6 +1182,8 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
                 CU(cudaMemcpyAsync(base + o_pairs, pairs.data(), sizeof(PairDesc) * np, cudaMemcpyHostToDevice, st));
                 B.m_first = (uint32_t*)(base + o_first); B.m_cnt = (uint32_t*)(base + o_cnt); B.a_off = (uint32_t*)(base + o_aoff);
                 B.m_bits = (uint32_t*)(base + o_bits);
+                B.walk_groups = (const uint2*)(base + o_groups); B.n_walk_groups = (uint32_t)groups.size(); B.walk_group_max = group_max;
+                CU(cudaMemcpyAsync(base + o_groups, groups.data(), sizeof(uint2) * groups.size(), cudaMemcpyHostToDevice, st));
                 CU(cudaMemsetAsync(B.m_cnt + seeds, 0, 4, st));
                 launch_match_count(B, st);
                 scan_match_counts(B, base + o_scan, scan_bytes, st);
@@ -1195,6 +1209,7 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
                                      sort_bytes, st);
                 }
                 launch_ani_reduce(B, C, keys_sorted, vals_sorted, st);
+                CU(cudaGetLastError());          // a launch that was refused (configuration) must not pass silently
                 uint32_t n_anchors = 0;
                 download(c, &n_anchors, B.a_off + seeds, 1);
                 download(c, res.data(), B.results, np);

@@ -213,6 +213,8 @@ struct ChainBatch {            // device pointers of one batch of pairs
     uint32_t* m_first;         // first matching index in the reference's k-mer order
     uint32_t* m_cnt;           // number of matches
     uint32_t* m_bits;          // bit i of a pair's slice = query seed i has at least one match
+    const uint2* walk_groups;  // (first pair, count): consecutive pairs with the same query, walked by one CTA
+    uint32_t n_walk_groups, walk_group_max;
     uint32_t* a_off;           // exclusive scan of m_cnt (+1 trailing element = total)
     // anchors
     uint32_t anchor_cap;
@@ -231,6 +233,7 @@ struct ChainBatch {            // device pointers of one batch of pairs
 
 void launch_match_count(const ChainBatch& b, cudaStream_t st);
 void launch_anchor_fill(const ChainBatch& b, cudaStream_t st);
+uint32_t walk_group_capacity(uint32_t max_query_seeds);
 void launch_window_walk(const ChainBatch& b, const ChainConsts& c, uint32_t max_query_seeds, cudaStream_t st);
 void launch_chain_dp(const ChainBatch& b, const ChainConsts& c, cudaStream_t st);
 void launch_window_keys(const ChainBatch& b, cudaStream_t st);
