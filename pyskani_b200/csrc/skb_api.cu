@@ -1154,6 +1154,8 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
             // walk groups: runs of pairs with the same query, cut so that the groups about fill the SMs once
             std::vector<uint2> groups;
             uint32_t group_max = std::min<uint32_t>(walk_group_capacity(max_qseeds), std::max<uint32_t>(1, (np + c.n_sm - 1) / c.n_sm));
+            if (const char* e = std::getenv("SKB_WALK_GROUP"))    // test hook: group size independent of the batch size
+                group_max = std::min<uint32_t>(walk_group_capacity(max_qseeds), std::max<uint32_t>(1, (uint32_t)std::atoi(e)));
             for (uint32_t i = 0; i < np;) {
                 uint32_t j = i + 1;
                 while (j < np && j - i < group_max && pairs[j].q == pairs[i].q) j++;

@@ -285,6 +285,30 @@ def test_all_vs_all_small(ctx):
     assert all(h[0] // 4 == h[1] // 4 for h in hits)
 
 
+def test_walk_groups(ctx, monkeypatch):
+    """The window walk handles several pairs of one query per CTA once a batch holds more pairs than SMs.  Force that
+    grouping on a small all-vs-all (single-contig and fragmented queries) and compare with the ungrouped run and the oracle."""
+    from pyskani_b200 import capi
+    genomes = []
+    for f in range(3):
+        fam = make_family(4, 250_000, 170 + f, [0.01, 0.04, 0.08, 0.12])
+        genomes += [[g.tobytes()] for g in fam[:3]]
+        genomes.append([c.tobytes() for c in synth.fragment(fam[3], 180 + f, 2_000, 30_000)])
+    gs = ctx.sketch_batch(genomes)
+    db = capi.Database(ctx)
+    db.add_many(gs)
+    monkeypatch.setenv("SKB_WALK_GROUP", "1")
+    want = db.query(gs)
+    for g in ("3", "7"):
+        monkeypatch.setenv("SKB_WALK_GROUP", g)
+        assert db.query(gs) == want
+    os_ = [oracle.Sketch(c) for c in genomes]
+    total = 0
+    for qi, oq in enumerate(os_):
+        total += check_hits([h for h in want[0] if h[0] == qi], oq, os_)
+    assert total == want[1] and total >= 36
+
+
 def test_empty_and_degenerate_queries(ctx):
     from pyskani_b200 import capi
     s = rand(100_000, 77)
