@@ -112,6 +112,7 @@ marker_screen_smem_kernel(const GenomeView* __restrict__ queries, uint32_t n_que
 #pragma unroll
             for (int t = 0; t < SCREEN_QT; t++) cnt[t] += __popc(__ballot_sync(0xffffffffu, found && tt == (uint32_t)t));
             qn -= take;
+            __syncwarp();                           // the drained slots are written again by other lanes of the warp
         };
         constexpr int U = 4;                        // independent 8-byte loads in flight per thread
         for (uint32_t i0 = threadIdx.x; i0 - threadIdx.x < nb; i0 += blockDim.x * U) {   // warp-uniform trip count
