@@ -125,6 +125,19 @@ int  skb_sketch_import(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_
                        const uint8_t* canonical, uint64_t n_markers, const uint64_t* markers,
                        uint32_t n_contigs, const uint32_t* contig_lengths, skb_sketch_t** out);
 
+/* ---- device-to-device transfer of sketches (the one exchange step of a multi-GPU all-vs-all: SURVEY.md section 8e;
+ * the reference has no counterpart, its Database lives in one process, lib.rs:132-137) ----
+ * pack: the device arrays of n sketches are concatenated into a caller-provided DEVICE buffer (which a collective can
+ * then send over NVLink) plus a small HOST descriptor; unpack: rebuilds the sketches on another context from such a pair
+ * with one device-to-device copy — no host staging and no re-sorting, unlike skb_sketch_export / skb_sketch_import.
+ * The payload is position independent. */
+int  skb_sketch_pack_size(uint32_t n, skb_sketch_t* const* sketches, uint64_t* payload_bytes, uint64_t* meta_bytes);
+int  skb_sketch_pack(skb_ctx_t* ctx, uint32_t n, skb_sketch_t* const* sketches, void* payload_dev, uint64_t payload_bytes,
+                     void* meta_host, uint64_t meta_bytes);
+/* out receives *n_out handles (the count is part of the descriptor); out_cap is the capacity of out[]. */
+int  skb_sketch_unpack(skb_ctx_t* ctx, const void* meta_host, uint64_t meta_bytes, const void* payload_dev,
+                       uint64_t payload_bytes, skb_sketch_t** out, uint32_t out_cap, uint32_t* n_out);
+
 /* ---- database: the (markers, sketches) pair a Database owns (lib.rs:132-137) ---- */
 int  skb_db_create(skb_ctx_t* ctx, skb_db_t** out);
 void skb_db_destroy(skb_db_t* db);

@@ -52,7 +52,7 @@ SYMBOLS = [
     "skb_ctx_create", "skb_ctx_destroy", "skb_last_error", "skb_ctx_stats", "skb_ctx_sync", "skb_ctx_stream",
     "skb_host_alloc", "skb_host_free", "skb_dev_alloc", "skb_dev_free", "skb_memcpy_h2d",
     "skb_sketch_batch", "skb_sketch_batch_device", "skb_sketch_free", "skb_sketch_info", "skb_sketch_export",
-    "skb_sketch_import", "skb_db_create", "skb_db_destroy", "skb_db_add", "skb_db_add_many", "skb_db_size", "skb_db_query",
+    "skb_sketch_import", "skb_sketch_pack_size", "skb_sketch_pack", "skb_sketch_unpack", "skb_db_create", "skb_db_destroy", "skb_db_add", "skb_db_add_many", "skb_db_size", "skb_db_query",
     "skb_hits_free", "skb_db_screen", "skb_version",
 ]
 
@@ -94,6 +94,9 @@ def lib():
         L.skb_sketch_export.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.skb_sketch_import.argtypes = [vp, C.POINTER(SketchParams), i32, u64, vp, vp, vp, vp, u64, vp, u32, vp,
                                         C.POINTER(vp)]
+        L.skb_sketch_pack_size.argtypes = [u32, vp, C.POINTER(u64), C.POINTER(u64)]
+        L.skb_sketch_pack.argtypes = [vp, u32, vp, vp, u64, vp, u64]
+        L.skb_sketch_unpack.argtypes = [vp, vp, u64, vp, u64, vp, u32, C.POINTER(u32)]
         L.skb_db_create.argtypes = [vp, C.POINTER(vp)]
         L.skb_db_destroy.argtypes = [vp]
         L.skb_db_add.argtypes = [vp, vp, C.POINTER(u32)]
@@ -184,6 +187,34 @@ class Context:
                                            pos.ctypes.data, contig.ctypes.data, canonical.ctypes.data, len(markers),
                                            markers.ctypes.data, len(cl), cl.ctypes.data, C.byref(out)))
         return Sketch(self, out.value)
+
+    # ---- device-to-device transfer (multi-GPU exchange)
+    def pack_size(self, sketches):
+        """(payload bytes on the device, descriptor bytes on the host) that pack() needs for these sketches"""
+        n = len(sketches)
+        hs = (C.c_void_p * max(n, 1))(*[s._h for s in sketches])
+        pb, mb = C.c_uint64(), C.c_uint64()
+        self.check(lib().skb_sketch_pack_size(n, hs, C.byref(pb), C.byref(mb)))
+        return pb.value, mb.value
+
+    def pack(self, sketches, payload_dev_ptr, payload_bytes):
+        """Concatenates the sketches' device arrays into the device buffer; returns the host descriptor (uint8 array)."""
+        n = len(sketches)
+        hs = (C.c_void_p * max(n, 1))(*[s._h for s in sketches])
+        _, mb = self.pack_size(sketches)
+        meta = np.zeros(mb, np.uint8)
+        self.check(lib().skb_sketch_pack(self._h, n, hs, payload_dev_ptr, payload_bytes, meta.ctypes.data, mb))
+        return meta
+
+    def unpack(self, meta, payload_dev_ptr, payload_bytes):
+        """Rebuilds the sketches described by `meta` from a device payload (one device-to-device copy)."""
+        meta = np.ascontiguousarray(meta, np.uint8)
+        n = int(meta[4:8].view(np.uint32)[0]) if meta.size >= 8 else 0
+        out = (C.c_void_p * max(n, 1))()
+        got = C.c_uint32()
+        self.check(lib().skb_sketch_unpack(self._h, meta.ctypes.data, meta.size, payload_dev_ptr, payload_bytes, out, n,
+                                           C.byref(got)))
+        return [Sketch(self, out[i]) for i in range(got.value)]
 
     def host_alloc(self, nbytes):
         p = C.c_void_p()

@@ -371,6 +371,30 @@ void select_passing(uint32_t n, const uint8_t* flags, uint32_t* out_idx, uint32_
     g_kernel_launches += 2;
 }
 
+// ---------------------------------------------------------------- device-to-device packing of sketches (multi-GPU exchange)
+__global__ void segment_copy_kernel(const SegmentCopy* __restrict__ segs, uint32_t n_segs, char* __restrict__ dst_base) {
+    // one CTA per 64 KB piece of a segment; segments are 4-byte granular (sources are only 4-byte aligned)
+    const uint32_t s = blockIdx.y;
+    if (s >= n_segs) return;
+    const SegmentCopy sg = segs[s];
+    const uint64_t words = sg.bytes >> 2;
+    const uint32_t* src = (const uint32_t*)sg.src;
+    uint32_t* dst = (uint32_t*)(dst_base + sg.dst_off);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+void launch_segment_copy(const SegmentCopy* d_segs, uint32_t n_segs, uint64_t max_bytes, void* dst_base, cudaStream_t st) {
+    if (n_segs == 0) return;
+    unsigned gx = (unsigned)((max_bytes / 4 + 256 * 16 - 1) / (256 * 16));
+    if (gx < 1) gx = 1;
+    if (gx > 64) gx = 64;
+    for (uint32_t s0 = 0; s0 < n_segs; s0 += 65535) {
+        const uint32_t cnt = n_segs - s0 < 65535 ? n_segs - s0 : 65535;
+        segment_copy_kernel<<<dim3(gx, cnt), 256, 0, st>>>(d_segs + s0, cnt, (char*)dst_base);
+        g_kernel_launches++;
+    }
+}
+
 void launch_pull_copy(void* dst, const void* src_pinned, size_t bytes, cudaStream_t st) {
     if (bytes == 0) return;
     const size_t n = (bytes + 3) / 4;

@@ -139,7 +139,7 @@ void* Core::scratch(int slot, size_t bytes) {
     }
     return b.p;
 }
-enum { SLOT_SEQ = 0, SLOT_KMER, SLOT_POS, SLOT_META, SLOT_MKEYS, SLOT_STATUS, SLOT_SORT, SLOT_MARK, SLOT_GS, SLOT_GM, SLOT_DESC, SLOT_MKEYS2, SLOT_RSCAN, SLOT_GM_IN, SLOT_BTAB, SLOT_BCOUNT, SLOT_CHAIN, SLOT_MIDX };
+enum { SLOT_SEQ = 0, SLOT_KMER, SLOT_POS, SLOT_META, SLOT_MKEYS, SLOT_STATUS, SLOT_SORT, SLOT_MARK, SLOT_GS, SLOT_GM, SLOT_DESC, SLOT_MKEYS2, SLOT_RSCAN, SLOT_GM_IN, SLOT_BTAB, SLOT_BCOUNT, SLOT_CHAIN, SLOT_MIDX, SLOT_PACK };
 
 // stream-ordered device buffer
 struct DevMem {
@@ -180,6 +180,7 @@ struct DevMem {
 
 struct BatchStore {   // device arrays shared by the sketches that were produced together
     DevMem kmer_p, pos_p, meta_p, kmer_k, pos_k, meta_k, bucket, contig_seed_start, contig_len, contig_win_start, markers;
+    DevMem blob;      // sketches received through skb_sketch_unpack: every array is a slice of this one block
 };
 
 struct SketchImpl {
@@ -973,6 +974,145 @@ int skb_db_add_many(skb_db_t* db, uint32_t n, skb_sketch_t* const* sketches, uin
 uint64_t skb_db_size(const skb_db_t* db) { return db ? db->items.size() : 0; }
 
 void skb_hits_free(skb_hit_t* hits) { delete[] hits; }
+
+}  // extern "C"
+
+
+// ---------------------------------------------------------------- device-to-device transfer of sketches
+namespace {
+constexpr uint32_t PACK_MAGIC = 0x534B4250u;   // "SKBP"
+constexpr int PACK_ARRAYS = 11;
+struct PackHeader { uint32_t magic, n; uint64_t payload_bytes; };
+struct PackSketch {
+    uint64_t total_len;
+    uint32_t n_seeds, n_markers, n_contigs, bucket_shift, n_buckets, win_cap;
+    int32_t k, c, marker_c, has_seeds;
+    uint64_t off[PACK_ARRAYS];                 // kmer_p pos_p meta_p kmer_k pos_k meta_k bucket cstart clen cwin markers
+};
+inline uint64_t pad16(uint64_t x) { return (x + 15) & ~(uint64_t)15; }
+// byte sizes of the eleven device arrays of one sketch, in PackSketch::off order
+void pack_sizes(const GenomeView& v, uint64_t* sz) {
+    const uint64_t n = v.n_seeds, nc = v.n_contigs;
+    for (int i = 0; i < 6; i++) sz[i] = 4 * n;
+    sz[6] = v.bucket ? 4 * ((uint64_t)v.n_buckets + 1) : 0;
+    sz[7] = 4 * (nc + 1); sz[8] = 4 * nc; sz[9] = 4 * (nc + 1);
+    sz[10] = 8 * (uint64_t)v.n_markers;
+}
+}  // namespace
+
+extern "C" {
+
+int skb_sketch_pack_size(uint32_t n, skb_sketch_t* const* sketches, uint64_t* payload_bytes, uint64_t* meta_bytes) {
+    if ((n && !sketches) || !payload_bytes || !meta_bytes) return SKB_ERR_ARG;
+    uint64_t pb = 0, mb = sizeof(PackHeader) + (uint64_t)n * sizeof(PackSketch);
+    for (uint32_t i = 0; i < n; i++) {
+        if (!sketches[i]) return SKB_ERR_ARG;
+        uint64_t sz[PACK_ARRAYS];
+        pack_sizes(sketches[i]->impl->view, sz);
+        for (int a = 0; a < PACK_ARRAYS; a++) pb += pad16(sz[a]);
+        mb += 4 * (uint64_t)sketches[i]->impl->view.n_contigs;
+    }
+    *payload_bytes = pb; *meta_bytes = mb;
+    return SKB_OK;
+}
+
+int skb_sketch_pack(skb_ctx_t* ctx, uint32_t n, skb_sketch_t* const* sketches, void* payload_dev, uint64_t payload_bytes,
+                    void* meta_host, uint64_t meta_bytes) {
+    if (!ctx || (n && !sketches) || !meta_host || (payload_bytes && !payload_dev)) return SKB_ERR_ARG;
+    return guarded(ctx->core.get(), [&] {
+        Core& c = *ctx->core;
+        uint64_t need_p = 0, need_m = 0;
+        if (skb_sketch_pack_size(n, sketches, &need_p, &need_m) != SKB_OK) throw Fail{SKB_ERR_ARG, "null sketch"};
+        if (payload_bytes < need_p || meta_bytes < need_m) throw Fail{SKB_ERR_ARG, "pack buffers too small (see skb_sketch_pack_size)"};
+        char* m = (char*)meta_host;
+        PackHeader hd{PACK_MAGIC, n, need_p};
+        std::memcpy(m, &hd, sizeof(hd));
+        PackSketch* ps = (PackSketch*)(m + sizeof(PackHeader));
+        uint32_t* clens = (uint32_t*)(m + sizeof(PackHeader) + (uint64_t)n * sizeof(PackSketch));
+        std::vector<SegmentCopy> segs;
+        uint64_t off = 0, max_bytes = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            const SketchImpl& I = *sketches[i]->impl;
+            if (I.core.get() != &c) throw Fail{SKB_ERR_ARG, "sketch belongs to another context"};
+            const GenomeView& v = I.view;
+            PackSketch p{};
+            p.total_len = v.total_len; p.n_seeds = v.n_seeds; p.n_markers = v.n_markers; p.n_contigs = v.n_contigs;
+            p.bucket_shift = v.bucket_shift; p.n_buckets = v.n_buckets; p.win_cap = v.win_cap;
+            p.k = I.info.k; p.c = I.info.c; p.marker_c = I.info.marker_c; p.has_seeds = I.info.has_seeds;
+            uint64_t sz[PACK_ARRAYS];
+            pack_sizes(v, sz);
+            const void* src[PACK_ARRAYS] = {v.kmer_p, v.pos_p, v.meta_p, v.kmer_k, v.pos_k, v.meta_k, v.bucket,
+                                            v.contig_seed_start, v.contig_len, v.contig_win_start, v.markers};
+            for (int a = 0; a < PACK_ARRAYS; a++) {
+                p.off[a] = off;
+                if (sz[a]) { segs.push_back(SegmentCopy{src[a], off, sz[a]}); max_bytes = std::max(max_bytes, sz[a]); }
+                off += pad16(sz[a]);
+            }
+            std::memcpy(&ps[i], &p, sizeof(p));
+            if (v.n_contigs) std::memcpy(clens, I.contig_len_host.data(), 4 * (size_t)v.n_contigs);
+            clens += v.n_contigs;
+        }
+        if (!segs.empty()) {
+            const size_t tb = sizeof(SegmentCopy) * segs.size();
+            void* d_segs = c.scratch(SLOT_PACK, tb);
+            table_upload(c, d_segs, segs.data(), tb);
+            launch_segment_copy((const SegmentCopy*)d_segs, (uint32_t)segs.size(), max_bytes, payload_dev, c.stream);
+            CU(cudaGetLastError());
+        }
+        CU(cudaStreamSynchronize(c.stream));      // the payload is complete (and `segs` no longer needed) on return
+        return SKB_OK;
+    });
+}
+
+int skb_sketch_unpack(skb_ctx_t* ctx, const void* meta_host, uint64_t meta_bytes, const void* payload_dev, uint64_t payload_bytes,
+                      skb_sketch_t** out, uint32_t out_cap, uint32_t* n_out) {
+    if (!ctx || !meta_host || meta_bytes < sizeof(PackHeader) || !n_out) return SKB_ERR_ARG;
+    return guarded(ctx->core.get(), [&] {
+        Core& c = *ctx->core;
+        const char* m = (const char*)meta_host;
+        PackHeader hd;
+        std::memcpy(&hd, m, sizeof(hd));
+        if (hd.magic != PACK_MAGIC) throw Fail{SKB_ERR_ARG, "not a sketch pack descriptor"};
+        if (meta_bytes < sizeof(PackHeader) + (uint64_t)hd.n * sizeof(PackSketch)) throw Fail{SKB_ERR_ARG, "truncated pack descriptor"};
+        if (payload_bytes < hd.payload_bytes || (hd.payload_bytes && !payload_dev)) throw Fail{SKB_ERR_ARG, "truncated pack payload"};
+        *n_out = hd.n;
+        if (hd.n == 0) return SKB_OK;
+        if (!out || out_cap < hd.n) throw Fail{SKB_ERR_ARG, "output array too small for the packed sketches"};
+        const PackSketch* ps = (const PackSketch*)(m + sizeof(PackHeader));
+        const uint32_t* clens = (const uint32_t*)(m + sizeof(PackHeader) + (uint64_t)hd.n * sizeof(PackSketch));
+        uint64_t nc_total = 0;
+        for (uint32_t i = 0; i < hd.n; i++) { PackSketch p; std::memcpy(&p, &ps[i], sizeof(p)); nc_total += p.n_contigs; }
+        if (meta_bytes < sizeof(PackHeader) + (uint64_t)hd.n * sizeof(PackSketch) + 4 * nc_total) throw Fail{SKB_ERR_ARG, "truncated pack descriptor"};
+        auto store = std::make_shared<BatchStore>();
+        store->blob = DevMem::persistent(ctx->core, std::max<uint64_t>(hd.payload_bytes, 16));
+        if (hd.payload_bytes)
+            CU(cudaMemcpyAsync(store->blob.p, payload_dev, hd.payload_bytes, cudaMemcpyDeviceToDevice, c.stream));
+        const char* base = (const char*)store->blob.p;
+        for (uint32_t i = 0; i < hd.n; i++) {
+            PackSketch p;
+            std::memcpy(&p, &ps[i], sizeof(p));
+            GenomeView v{};
+            v.kmer_p = (const uint32_t*)(base + p.off[0]); v.pos_p = (const uint32_t*)(base + p.off[1]);
+            v.meta_p = (const uint32_t*)(base + p.off[2]); v.kmer_k = (const uint32_t*)(base + p.off[3]);
+            v.pos_k = (const uint32_t*)(base + p.off[4]); v.meta_k = (const uint32_t*)(base + p.off[5]);
+            v.bucket = (const uint32_t*)(base + p.off[6]); v.contig_seed_start = (const uint32_t*)(base + p.off[7]);
+            v.contig_len = (const uint32_t*)(base + p.off[8]); v.contig_win_start = (const uint32_t*)(base + p.off[9]);
+            v.markers = (const uint64_t*)(base + p.off[10]);
+            v.total_len = p.total_len; v.n_seeds = p.n_seeds; v.n_markers = p.n_markers; v.n_contigs = p.n_contigs;
+            v.bucket_shift = p.bucket_shift; v.n_buckets = p.n_buckets; v.win_cap = p.win_cap;
+            auto impl = std::make_shared<SketchImpl>();
+            impl->core = ctx->core; impl->store = store; impl->view = v;
+            impl->contig_len_host.assign(clens, clens + p.n_contigs);
+            clens += p.n_contigs;
+            impl->info.n_seeds = p.n_seeds; impl->info.n_markers = p.n_markers; impl->info.total_len = p.total_len;
+            impl->info.n_contigs = p.n_contigs; impl->info.k = p.k; impl->info.c = p.c; impl->info.marker_c = p.marker_c;
+            impl->info.has_seeds = p.has_seeds;
+            out[i] = new skb_sketch{impl};
+        }
+        CU(cudaStreamSynchronize(c.stream));      // the caller may reuse the payload buffer on return
+        return SKB_OK;
+    });
+}
 
 }  // extern "C"
 

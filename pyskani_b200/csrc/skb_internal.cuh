@@ -146,6 +146,8 @@ void build_marker_sets(uint32_t n_genomes, uint32_t n_markers_total, uint64_t* m
 size_t marker_scratch_bytes(uint32_t n_markers_total);
 
 // copies `bytes` (rounded up to 4) from pinned, device-mapped host memory to device memory with a kernel
+struct SegmentCopy { const void* src; uint64_t dst_off; uint64_t bytes; };   // bytes: multiple of 4
+void launch_segment_copy(const SegmentCopy* d_segs, uint32_t n_segs, uint64_t max_bytes, void* dst_base, cudaStream_t st);
 void launch_pull_copy(void* dst, const void* src_pinned, size_t bytes, cudaStream_t st);
 
 // bucket offsets + per-contig seed starts for a set of genomes described by views

@@ -5,8 +5,12 @@ query, so the only exchange step is the sketch database:
 
   1. genomes are split across ranks, balanced by total bases        (partition_by_size)
   2. every rank sketches its share on its own GPU                    (backend.sketch)
-  3. sketches are exchanged ONCE: an all-gather of the exported SoA  (exchange_sketches)
-  4. every rank imports the others' sketches, builds the full database and queries ITS genomes against it
+  3. sketches are exchanged ONCE.  On GPUs: every rank packs the device arrays of its sketches into one device
+     buffer (skb_sketch_pack), NCCL all-gathers those buffers over NVLink, every rank rebuilds the others' sketches
+     with one device-to-device copy each (skb_sketch_unpack) - nothing goes through the host and nothing is sorted
+     again                                                           (exchange_sketches_device)
+     Fallback / CPU tests: an all-gather of the exported host SoA    (exchange_sketches)
+  4. every rank builds the full database and queries ITS genomes against it
   5. hits are gathered on rank 0                                     (gather_hits)
 
 There is no collective inside screen / chain / ANI.  `backend` is the object that talks to the device:
@@ -85,6 +89,29 @@ def exchange_sketches(local_exports, dist, device="cpu"):
     return [unpack_sketches(h, p) for h, p in zip(headers, payloads)]
 
 
+def exchange_sketches_device(backend, local_sketches, dist, device):
+    """Device-resident version of exchange_sketches for backends that can pack/unpack (CudaBackend): returns a list
+    over ranks of lists of sketch handles living on this rank's GPU (this rank's entry is `local_sketches` itself)."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    payload, meta = backend.pack(local_sketches, device)              # torch.uint8 cuda tensor, numpy uint8
+    metas = _all_gather_var(meta, dist, device)
+    n = torch.tensor([payload.numel()], dtype=torch.int64, device=device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(x.item()) for x in sizes]
+    m = max(sizes + [16])
+    if payload.numel() < m:
+        payload = torch.cat([payload, torch.zeros(m - payload.numel(), dtype=torch.uint8, device=device)])
+    bufs = torch.empty(world * m, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(bufs, payload)
+    torch.cuda.synchronize(device)
+    out = []
+    for r in range(world):
+        out.append(local_sketches if r == rank else backend.unpack(metas[r], bufs[r * m:r * m + sizes[r]]))
+    return out
+
+
 def gather_hits(local_hits, dist, device="cpu"):
     """hits: (n, 5) float64 rows [query_global, ref_global, ani, af_query, af_ref]; returned on rank 0 sorted by (query, ref)."""
     flat = np.asarray(local_hits, np.float64).reshape(-1)
@@ -111,10 +138,20 @@ class CudaBackend:
     def import_(self, e, **params):
         return self.ctx.import_sketch(e["kmer"], e["pos"], e["contig"], e["canonical"], e["markers"], e["contig_lengths"], **params)
 
+    def pack(self, sketches, device):
+        import torch
+        pb, _ = self.ctx.pack_size(sketches)
+        payload = torch.empty(max(pb, 16), dtype=torch.uint8, device=device)
+        torch.cuda.synchronize(device)
+        meta = self.ctx.pack(sketches, payload.data_ptr(), payload.numel())
+        return payload[:max(pb, 0)] if pb else payload[:0], meta
+
+    def unpack(self, meta, payload):
+        return self.ctx.unpack(meta, payload.data_ptr() if payload.numel() else None, payload.numel())
+
     def query(self, db_sketches, query_sketches, **opts):
         db = self.capi.Database(self.ctx)
-        for s in db_sketches:
-            db.add(s)
+        db.add_many(list(db_sketches))
         hits, _ = db.query(query_sketches, **opts)
         return [(h[0], h[1], h[2], h[3], h[4]) for h in hits]
 
@@ -130,15 +167,19 @@ def all_vs_all(genomes, backend, dist=None, device="cpu", sketch_params=None, qu
     plan = partition_by_size(sizes, world)
     mine = plan[rank]
     local = backend.sketch([genomes[i] for i in mine], **sketch_params)
-    if world > 1:
-        gathered = exchange_sketches([backend.export(s) for s in local], dist, device)
-    else:
-        gathered = None
-    # the full database in global genome order; this rank's own sketches are reused, the others are imported
+    # the full database in global genome order; this rank's own sketches are reused, the others arrive over the fabric
     full = [None] * len(genomes)
-    for r, idxs in enumerate(plan):
-        for j, gi in enumerate(idxs):
-            full[gi] = local[j] if r == rank else backend.import_(gathered[r][j], **sketch_params)
+    on_gpu = world > 1 and hasattr(backend, "pack") and str(device).startswith("cuda")
+    if on_gpu:
+        per_rank = exchange_sketches_device(backend, local, dist, device)
+        for r, idxs in enumerate(plan):
+            for j, gi in enumerate(idxs):
+                full[gi] = per_rank[r][j]
+    else:
+        gathered = exchange_sketches([backend.export(s) for s in local], dist, device) if world > 1 else None
+        for r, idxs in enumerate(plan):
+            for j, gi in enumerate(idxs):
+                full[gi] = local[j] if r == rank else backend.import_(gathered[r][j], **sketch_params)
     hits = backend.query(full, local, **query_opts)
     rows = [(mine[q], r, ani, afq, afr) for (q, r, ani, afq, afr) in hits]
     if world == 1:

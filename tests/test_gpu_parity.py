@@ -309,6 +309,42 @@ def test_walk_groups(ctx, monkeypatch):
     assert total == want[1] and total >= 36
 
 
+def test_pack_unpack_device_roundtrip(ctx):
+    """skb_sketch_pack / skb_sketch_unpack (the multi-GPU exchange path): sketches rebuilt from a packed device payload on
+    ANOTHER context are identical to the originals and answer queries identically."""
+    from pyskani_b200 import capi
+    fam = make_family(3, 200_000, 210, [0.02, 0.06, 0.1])
+    genomes = [[g.tobytes()] for g in fam]
+    genomes.append([c.tobytes() for c in synth.fragment(fam[1], 211, 2_000, 20_000)])
+    genomes.append([b"ACGT" * 50])                                   # below the contig gate: an empty sketch travels too
+    gs = ctx.sketch_batch(genomes)
+    pb, mb = ctx.pack_size(gs)
+    assert pb % 16 == 0 and mb > 0
+    other = capi.Context(0)
+    buf = ctx.dev_alloc(pb)
+    try:
+        meta = ctx.pack(gs, buf, pb)
+        got = other.unpack(meta, buf, pb)
+        with pytest.raises(capi.SkbError):
+            other.unpack(meta[:10], buf, pb)
+        with pytest.raises(capi.SkbError):
+            other.unpack(meta, buf, pb - 16)
+    finally:
+        ctx.dev_free(buf)
+    assert len(got) == len(gs)
+    for a, b in zip(gs, got):
+        ia, ib = a.info(), b.info()
+        assert (ia.n_seeds, ia.n_markers, ia.n_contigs, ia.total_len, ia.k, ia.c, ia.marker_c, ia.has_seeds) == \
+               (ib.n_seeds, ib.n_markers, ib.n_contigs, ib.total_len, ib.k, ib.c, ib.marker_c, ib.has_seeds)
+        ea, eb = a.export(), b.export()
+        for key in ea:
+            assert np.array_equal(ea[key], eb[key]), key
+    db_a, db_b = capi.Database(ctx), capi.Database(other)
+    db_a.add_many(gs); db_b.add_many(got)
+    assert db_a.query(gs) == db_b.query(got)
+    assert len(other.unpack(ctx.pack([], None, 0), None, 0)) == 0
+
+
 def test_empty_and_degenerate_queries(ctx):
     from pyskani_b200 import capi
     s = rand(100_000, 77)
