@@ -39,7 +39,11 @@ struct SlabPool {
             if (!pick) {
                 std::unique_ptr<Slab> sl(new Slab);
                 sl->cap = std::max(next_cap, bytes);
+                const auto t0 = std::chrono::steady_clock::now();
                 cudaError_t e = cudaMalloc((void**)&sl->base, sl->cap);
+                if (std::getenv("SKB_TRACE"))
+                    std::fprintf(stderr, "[skb] slab: cudaMalloc of %zu MB took %.3f ms\n", sl->cap >> 20,
+                                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
                 if (e != cudaSuccess && sl->cap > bytes) { cudaGetLastError(); sl->cap = bytes; e = cudaMalloc((void**)&sl->base, sl->cap); }
                 if (e != cudaSuccess) { cudaGetLastError(); return nullptr; }
                 next_cap = std::min(next_cap * 2, (size_t)1 << 30);

@@ -69,4 +69,13 @@ with open(os.path.join(P, "r1_scale_configs.txt"), "w") as f:
                       ("scale_cfg4", "--families 100 --members 100")):
         f.write("\n$ python tools/scale_bench.py %s\n" % cmd)
         f.write(open(os.path.join(G, name + ".log")).read())
+    if os.path.exists(os.path.join(G, "scale_cfg4_2gpu.log")):
+        f.write("\n# Two GPUs (gpurun --gpus 2, tools/profile_round_2gpu.sh): families dealt to the ranks, sketches exchanged once on the device\n")
+        for name, cmd in (("scale_cfg2_2gpu", "--families 100 --members 10"), ("scale_cfg4_2gpu", "--families 100 --members 100")):
+            f.write("\n$ torchrun --nproc-per-node 2 tools/scale_bench.py %s\n" % cmd)
+            f.write(open(os.path.join(G, name + ".log")).read())
+        f.write("\n$ torchrun --nproc-per-node 2 tools/allvsall_multi.py 40 1000000   (host genomes, pyskani_b200.parallel.all_vs_all)\n")
+        f.write(open(os.path.join(G, "allvsall_multi_2gpu.log")).read())
+if os.path.exists(os.path.join(G, "bench_r1_2gpu.json")):
+    open(os.path.join(P, "r1_bench_line_2gpu.json"), "w").write(open(os.path.join(G, "bench_r1_2gpu.json")).read().strip().splitlines()[-1] + "\n")
 print(open(os.path.join(P, "r1_device_step_kernel_shares.txt")).read())

@@ -3,6 +3,9 @@
     python tools/scale_bench.py --families 100 --members 100                       # configs[4]: 10 000 x 10 000 all-vs-all
     python tools/scale_bench.py --families 100 --members 10                        # configs[2]: 1 000 x 1 000 all-vs-all
     python tools/scale_bench.py --families 500 --members 10 --mag-queries 500      # configs[3]: 500 fragmented MAGs vs 5 000
+    torchrun --nproc-per-node N tools/scale_bench.py --families 100 --members 100  # all-vs-all over N GPUs: families are dealt
+        # to the ranks, every rank sketches its share, the sketches are exchanged once on the device (skb_sketch_pack +
+        # NCCL all-gather + skb_sketch_unpack), every rank queries its genomes against the full database
 
 Genomes never exist on the host: a family is a random base genome plus mutated copies (substitutions with probability
 0.9 d, indel events with probability 0.1 d, geometric lengths, as pyskani_b200.synth does on the CPU), written as ASCII into
@@ -121,23 +124,49 @@ def fragment_dev(codes, rng, lo=1000, hi=50000):
 def main():
     global ACGT
     args = parse()
-    dev = torch.device("cuda", 0)
+    rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        if args.mag_queries:
+            raise SystemExit("the MAG configuration is single-GPU in this tool")
+    say = print if rank == 0 else (lambda *a, **k: None)
+
+    def tmax(x):          # a per-rank time -> max over ranks
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def tsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     ACGT = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
-    gen = torch.Generator(device=dev); gen.manual_seed(1234)
-    ctx = capi.Context(0)
+    gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+    ctx = capi.Context(local)
     F, M, L = args.families, args.members, args.genome_len
     divs = [0.0] + [0.01 + (args.max_div - 0.01) * i / max(1, M - 2) for i in range(M - 1)]
     batch_genomes = max(1, min(100, (600 << 20) // int(L * 1.03)))
     batch = DeviceBatch(dev, int(batch_genomes * (L * 1.03 + 64)) + 4096)
 
-    # context warm-up (module load, first arena blocks): one small genome, timed separately
+    # context warm-up, timed separately: one full batch through sketch + query grows the context's scratch arena and its
+    # first storage slabs (the first few cudaMalloc calls of a process cost 20-100 ms each; later ones ~1 ms)
     t0 = time.perf_counter()
-    batch.add_genome([torch.randint(0, 4, (200_000,), device=dev, generator=gen, dtype=torch.uint8)])
+    wbase = torch.randint(0, 4, (L,), device=dev, generator=gen, dtype=torch.uint8)
+    for i in range(batch_genomes):
+        batch.add_genome([wbase if i % 2 == 0 else torch.roll(wbase, 1000 * i)])
     warm = batch.sketch(ctx)[0]
-    wdb = capi.Database(ctx); wdb.add_many(warm); wdb.query(warm)
-    del wdb, warm
-    print("context warm-up %.3f s" % (time.perf_counter() - t0), flush=True)
+    wdb = capi.Database(ctx); wdb.add_many(warm); wdb.query(warm[:8])
+    del wdb, warm, wbase
+    say("context warm-up %.3f s" % (time.perf_counter() - t0), flush=True)
 
     db = capi.Database(ctx)
     sketches, div_of = [], []
@@ -148,6 +177,7 @@ def main():
     rng = np.random.default_rng(7)
     mag_families = set(rng.choice(F, size=min(F, args.mag_queries), replace=False).tolist()) if args.mag_queries else set()
     t_gen0 = time.perf_counter()
+    batch_walls = []
 
     def flush():
         nonlocal pending, t_sketch_wall, t_sketch_dev, total_bases
@@ -155,10 +185,12 @@ def main():
             return
         sk, w, d, b = batch.sketch(ctx)
         t_sketch_wall += w; t_sketch_dev += d; total_bases += b
+        batch_walls.append(w)
         sketches.extend(sk)
         pending = 0
 
-    for f in range(F):
+    my_fams = list(range(rank, F, world))          # families are dealt round-robin; genome id = family * M + member
+    for f in my_fams:
         base = torch.randint(0, 4, (L,), device=dev, generator=gen, dtype=torch.uint8)
         if f in mag_families:
             bases_kept[f] = base
@@ -170,10 +202,34 @@ def main():
                 flush()
     flush()
     t_gen = time.perf_counter() - t_gen0 - t_sketch_wall
-    n = len(sketches)
-    db.add_many(sketches)
-    print("database: %d genomes, %.2f Gbp | generation %.1f s | sketching wall %.3f s (device %.3f s) = %.1f Gbp/s" % (
-        n, total_bases / 1e9, t_gen, t_sketch_wall, t_sketch_dev, total_bases / t_sketch_wall / 1e9), flush=True)
+    gid = [f * M + m for f in my_fams for m in range(M)]          # global ids of this rank's sketches
+    t_exchange = 0.0
+    if world > 1:
+        # the one exchange step: packed device buffers, NCCL all-gather over NVLink, device-to-device unpack
+        from pyskani_b200 import parallel
+        be = parallel.CudaBackend.__new__(parallel.CudaBackend); be.capi = capi; be.ctx = ctx
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        per_rank = parallel.exchange_sketches_device(be, sketches, dist, dev)
+        torch.cuda.synchronize()
+        t_exchange = tmax(time.perf_counter() - t0)
+        full = [None] * (F * M)
+        for r in range(world):
+            ids = [f * M + m for f in range(r, F, world) for m in range(M)]
+            for j, g in enumerate(ids):
+                full[g] = per_rank[r][j]
+    else:
+        full = sketches
+    n = len(full)
+    db.add_many(full)
+    if batch_walls:
+        bw = sorted(batch_walls)
+        say("sketch calls: %d, median %.2f ms, slowest %s ms (fresh device memory for the growing database)" % (
+            len(bw), 1e3 * bw[len(bw) // 2], ", ".join("%.1f" % (1e3 * x) for x in bw[-4:][::-1])), flush=True)
+    total_bases = int(tsum(total_bases)); t_sketch_wall = tmax(t_sketch_wall); t_sketch_dev = tmax(t_sketch_dev)
+    say("database: %d genomes on %d GPU(s), %.2f Gbp | generation %.1f s | sketching wall %.3f s (device %.3f s) = %.1f Gbp/s%s" % (
+        n, world, total_bases / 1e9, t_gen, t_sketch_wall, t_sketch_dev, total_bases / t_sketch_wall / 1e9,
+        " | sketch exchange (pack + NCCL all-gather + unpack) %.3f s" % t_exchange if world > 1 else ""), flush=True)
 
     # ---- queries
     if args.mag_queries:
@@ -193,7 +249,7 @@ def main():
         print("queries: %d fragmented genomes (%.2f Gbp, %d contigs on average) sketched in %.3f s" % (
             len(queries), qb / 1e9, int(np.mean([s.info().n_contigs for s in queries])), t_q), flush=True)
     else:
-        queries, q_family, q_div = sketches, [i // M for i in range(n)], div_of
+        queries, q_family, q_div = sketches, [g // M for g in gid], div_of
 
     if args.screen_only:
         t0 = time.perf_counter()
@@ -206,6 +262,8 @@ def main():
         return
 
     for rep in range(args.repeat):
+        if world > 1:
+            dist.barrier()
         t_wall = t_screen = t_chain = 0.0
         n_in = 0
         hits = []
@@ -216,18 +274,19 @@ def main():
             st = ctx.stats()
             t_wall += t1 - t0; t_screen += st.screen_ms / 1e3; t_chain += st.chain_ms / 1e3; n_in += k
             hits.extend((q0 + x[0],) + x[1:5] for x in h)
-        n_pairs = len(queries) * n
-        print("query%s: %d x %d = %.3g pairs in %.3f s wall = %.2f M pairs/s | screen %.3f s (%.1f M pairs/s) | %d pairs chained in %.3f s "
-              "(%.0f pairs/s) | %d hits" % (" (repeat %d)" % rep if rep else "", len(queries), n, n_pairs, t_wall, n_pairs / t_wall / 1e6,
-                                            t_screen, n_pairs / max(t_screen, 1e-9) / 1e6, n_in, t_chain, n_in / max(t_chain, 1e-9),
-                                            len(hits)), flush=True)
+        n_pairs = int(tsum(len(queries))) * n
+        t_wall, t_screen, t_chain, n_in_all, n_hits_all = tmax(t_wall), tmax(t_screen), tmax(t_chain), int(tsum(n_in)), int(tsum(len(hits)))
+        say("query%s: %d x %d = %.3g pairs in %.3f s wall = %.2f M pairs/s | screen %.3f s (%.1f M pairs/s) | %d pairs chained in %.3f s "
+              "(%.0f pairs/s) | %d hits" % (" (repeat %d)" % rep if rep else "", n_pairs // n, n, n_pairs, t_wall, n_pairs / t_wall / 1e6,
+                                            t_screen, n_pairs / max(t_screen, 1e-9) / 1e6, n_in_all, t_chain, n_in_all / max(t_chain, 1e-9),
+                                            n_hits_all), flush=True)
 
     # ---- properties
     intra = all(q_family[h[0]] == h[1] // M for h in hits)
     ok_self = True
     if not args.mag_queries:
-        self_ani = {h[0]: h[2] for h in hits if h[0] == h[1]}
-        ok_self = len(self_ani) == n and min(self_ani.values()) > 0.9999
+        self_ani = {h[0]: h[2] for h in hits if gid[h[0]] == h[1]}
+        ok_self = len(self_ani) == len(queries) and min(self_ani.values()) > 0.9999
     # ANI against the family's base genome (member 0) must fall as the generating divergence grows
     to_base = {}
     for h in hits:
@@ -242,14 +301,18 @@ def main():
         for d, a in lst:
             if d <= 0.10:
                 worst = max(worst, abs((1 - a) - d))
-    print("properties: hits intra-family %s | self hits ANI 1 %s | ANI monotone in divergence %s | max |(1-ANI) - d| for d<=10%% = %.4f" % (
-        intra, ok_self, mono, worst))
-    if args.json:
-        json.dump({"genomes": n, "queries": len(queries), "bases": total_bases, "sketch_wall_s": t_sketch_wall, "query_wall_s": t_wall,
-                   "screen_s": t_screen, "chain_s": t_chain, "pairs": n_pairs, "chained": n_in, "hits": len(hits),
-                   "intra_family": intra, "self_hits": ok_self, "monotone": mono, "max_abs_err_vs_divergence": worst},
+    all_ok = tsum(0.0 if (intra and ok_self and mono) else 1.0) == 0.0
+    worst = tmax(worst)
+    say("properties%s: hits intra-family %s | self hits ANI 1 %s | ANI monotone in divergence %s | max |(1-ANI) - d| for d<=10%% = %.4f" % (
+        " (all ranks)" if world > 1 else "", intra and all_ok, ok_self and all_ok, mono and all_ok, worst))
+    if args.json and rank == 0:
+        json.dump({"gpus": world, "genomes": n, "queries": n_pairs // n, "bases": total_bases, "sketch_wall_s": t_sketch_wall,
+                   "exchange_s": t_exchange, "query_wall_s": t_wall, "screen_s": t_screen, "chain_s": t_chain, "pairs": n_pairs,
+                   "chained": n_in_all, "hits": n_hits_all, "properties_ok": all_ok, "max_abs_err_vs_divergence": worst},
                   open(args.json, "w"))
-    if not (intra and ok_self and mono):
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+    if not all_ok:
         raise SystemExit(1)
 
 
