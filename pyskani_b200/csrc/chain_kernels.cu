@@ -306,10 +306,14 @@ __device__ __forceinline__ void tuple_min(int32_t& sc, uint32_t& qs, uint32_t& r
 // Lane l keeps the newest anchor with index == l (mod 32) in registers: the 32 nearest predecessors of the current anchor
 // are always on chip.  Anchors are ordered by query position and ~20 of them fall inside the 2 500 bp band, so older
 // predecessors (distance 33..index_band) are only needed in repeat-rich windows; they are read back from the anchor
-// arrays (f/root of a finished strip of 32 are already stored), which keeps the common path free of any per-anchor
-// register shuffling.  Score and distance travel through ONE warp reduction as (score + bias) << 8 | (255 - distance):
-// maximal score first, nearest predecessor on ties.  WIDE: windows with so many anchors that the packed score could
-// overflow (>= 2^22 / anchor_score anchors) use one reduction for the score and one for the distance.
+// arrays (f of a finished strip of 32 is already stored).  Which anchors of a strip need that is known when the strip
+// is loaded (anchor i needs it iff anchor i - 32 is still within the band), so it costs one ballot per strip.
+// The strip itself sits in shared memory as (qp, rp, meta) records: one broadcast LDS.128 per anchor.
+// Score and distance travel through ONE warp reduction as (score + bias) << 8 | (255 - distance): maximal score first,
+// nearest predecessor on ties.  WIDE: windows with so many anchors that the packed score could overflow (>= 2^22 /
+// anchor_score anchors) use one reduction for the score and one for the distance.
+// The loop only records each anchor's predecessor; the component roots follow afterwards by pointer jumping
+// (~log2(chain length) rounds over the window instead of a dependent lookup per anchor).
 // The common path is straight-line code (selects instead of branches) so that the warp stays provably converged.
 constexpr int32_t DP_ANCHOR_SCORE = 20, DP_MAX_GAP = 300;
 constexpr uint32_t DP_BP_BAND = 2500, DP_INDEX_BAND = 100;
@@ -317,30 +321,33 @@ constexpr uint32_t DP_BP_BAND = 2500, DP_INDEX_BAND = 100;
 template <bool WIDE>
 __device__ __forceinline__ void dp_window(const uint32_t* __restrict__ qp_a, const uint32_t* __restrict__ rp_a,
                                           const uint32_t* __restrict__ meta_a, int32_t* f_a, uint32_t* root_a,
-                                          const uint32_t n, const int lane) {
+                                          const uint32_t n, const int lane, uint4* s_strip) {
     // skani's chaining constants are frozen (pyskani exposes none of them): compile-time values
     // here, checked against the ChainConsts of the call by launch_chain_dp
     constexpr uint32_t bp_band = DP_BP_BAND, index_band = DP_INDEX_BAND;
     constexpr int32_t max_gap = DP_MAX_GAP, anchor_score = DP_ANCHOR_SCORE;
     constexpr int32_t link_bias = anchor_score + max_gap + 1;      // score of a valid link + max_gap + 1 - gap  >=  1
-    uint32_t g_qp = 0, g_rp = 0, g_meta = 0xFFFFFFFFu, g_root = 0;  // meta 0xFFFFFFFF never matches
+    uint32_t g_qp = 0, g_rp = 0, g_meta = 0xFFFFFFFFu, g_par = 0;   // meta 0xFFFFFFFF never matches
     int32_t g_f = 0;
     for (uint32_t sb = 0; sb < n; sb += 32) {
         const uint32_t mine = sb + lane;
         uint32_t sq = 0, sr = 0, sm = 0;
         if (mine < n) { sq = qp_a[mine]; sr = rp_a[mine]; sm = meta_a[mine]; }
+        s_strip[lane] = make_uint4(sq, sr, sm, 0u);
+        // g_* still holds anchor mine - 32 here: bit u of need_old = anchor sb + u must also look at distances > 32
+        const uint32_t need_old = __ballot_sync(FULL, mine < n && mine >= 32u && (sq - g_qp) <= bp_band);
+        __syncwarp();
         const uint32_t lim = min(32u, n - sb);
         uint32_t kd = 255u - (uint32_t)(32 - lane);                 // 255 - distance of this lane's newest anchor from sb + u
         for (uint32_t u = 0; u < lim; u++) {
             const uint32_t i = sb + u;                              // window-local anchor index; owner lane = u
-            const uint32_t cq = __shfl_sync(FULL, sq, u), cr = __shfl_sync(FULL, sr, u), cm = __shfl_sync(FULL, sm, u);
+            const uint4 cur = s_strip[u];
+            const uint32_t cq = cur.x, cr = cur.y, cm = cur.z;
             const uint32_t revmask = 0u - (cm & 1u);
             // ---- the 32 nearest predecessors (registers)
             const int32_t dq = (int32_t)(cq - g_qp);
             const int32_t dr = (int32_t)(((cr - g_rp) ^ revmask) - revmask);      // reverse strand: g.rp - cr
             const int32_t gap = abs(dr - dq);
-            const bool near_band = (uint32_t)dq <= bp_band;
-            const bool ok = ((uint32_t)(dq - 1) < bp_band) & (g_meta == cm) & (dr > 0) & (gap <= max_gap);
             int32_t best; uint32_t bestd;
             if (!WIDE) {
                 // key = ok ? packed : 0, with the four conditions chained through one predicate (the compiler otherwise
@@ -361,6 +368,7 @@ __device__ __forceinline__ void dp_window(const uint32_t* __restrict__ qp_a, con
                 best = take ? m : anchor_score;
                 bestd = take ? 255u - (mk & 255u) : 0u;
             } else {
+                const bool ok = ((uint32_t)(dq - 1) < bp_band) & (g_meta == cm) & (dr > 0) & (gap <= max_gap);
                 const int32_t sc = ok ? g_f + anchor_score - gap : INT32_MIN;
                 const int32_t m = __reduce_max_sync(FULL, sc);
                 const uint32_t dm = __reduce_min_sync(FULL, sc == m ? 255u - kd : 0x7FFFFFFFu);
@@ -368,8 +376,8 @@ __device__ __forceinline__ void dp_window(const uint32_t* __restrict__ qp_a, con
                 best = take ? m : anchor_score;
                 bestd = take ? dm : 0u;
             }
-            // ---- older predecessors: only while the oldest anchor seen so far (distance 32 g, lane u) is still in band
-            if (i >= 32 && ((__ballot_sync(FULL, near_band) >> u) & 1u)) {
+            // ---- older predecessors: only if the anchor 32 back is still in band (then 64 back, 96 back)
+            if ((need_old >> u) & 1u) {
                 const uint32_t d0 = 255u - kd;
                 for (uint32_t g = 1; g < 4; g++) {
                     const uint32_t d = d0 + 32u * g;
@@ -395,23 +403,38 @@ __device__ __forceinline__ void dp_window(const uint32_t* __restrict__ qp_a, con
                     if (!((__ballot_sync(FULL, inband) >> u) & 1u)) break;
                 }
             }
-            // component root of i
-            const uint32_t r0 = __shfl_sync(FULL, g_root, (int)((u - bestd) & 31u));
-            uint32_t root = bestd ? r0 : i;
-            if (bestd > 32u) root = root_a[i - bestd];
             const bool own = lane == (int)u;
             g_qp = own ? cq : g_qp; g_rp = own ? cr : g_rp; g_meta = own ? cm : g_meta;
-            g_f = own ? best : g_f; g_root = own ? root : g_root;
+            g_f = own ? best : g_f; g_par = own ? bestd : g_par;
             kd = kd == 223u ? 254u : kd - 1u;
         }
-        if (mine < n) { f_a[mine] = g_f; root_a[mine] = g_root; }
-        __syncwarp();                                              // the strip's f/root are read by other lanes from here on
+        if (mine < n) { f_a[mine] = g_f; root_a[mine] = mine - g_par; }      // predecessor (itself if none)
+        __syncwarp();                              // the strip's f is read by other lanes from here on; s_strip is rewritten
+    }
+    // ---- component roots: pointer jumping over the predecessor links until nothing moves
+    for (;;) {
+        bool moved = false;
+        for (uint32_t sb = 0; sb < n; sb += 32) {
+            const uint32_t i = sb + lane;
+            if (i < n) {
+                const uint32_t p = *(volatile const uint32_t*)(root_a + i);      // generic: shared or global
+                const uint32_t pp = *(volatile const uint32_t*)(root_a + p);
+                if (pp != p) { root_a[i] = pp; moved = true; }
+            }
+        }
+        __syncwarp();
+        if (!__any_sync(FULL, moved)) break;
     }
 }
 
 constexpr int DP_WARPS = 4;
+constexpr uint32_t DP_SMEM_ANCHORS = 256;
+__device__ __forceinline__ uint32_t ldv(const uint32_t* p) { return *(volatile const uint32_t*)p; }
+__device__ __forceinline__ unsigned long long ldv(const unsigned long long* p) { return *(volatile const unsigned long long*)p; }
 
 __global__ void __launch_bounds__(DP_WARPS * 32) chain_dp_kernel(const ChainBatch b, const ChainConsts C) {
+    __shared__ uint4 s_strip[DP_WARPS][32];          // the strip of 32 anchors a warp is working on; later its candidate list
+    __shared__ __align__(16) uint32_t s_work[DP_WARPS][4 * DP_SMEM_ANCHORS];   // root | size+flags | best end (64 bit)
     const int lane = threadIdx.x & 31;
     const uint32_t slot = blockIdx.x * DP_WARPS + (threadIdx.x >> 5);
     if (slot >= b.n_win_total) return;
@@ -422,12 +445,25 @@ __global__ void __launch_bounds__(DP_WARPS * 32) chain_dp_kernel(const ChainBatc
     if (A1 > b.anchor_cap) return;                          // anchor arrays were sized too small: the host reruns the batch
     const uint32_t n = A1 - A0;
     const uint32_t* qp_a = b.a_qp + A0; const uint32_t* rp_a = b.a_rp + A0; const uint32_t* meta_a = b.a_meta + A0;
-    int32_t* f_a = b.a_f + A0; uint32_t* root_a = b.a_root + A0; uint32_t* aux_a = b.a_aux + A0;
-    unsigned long long* best_a = b.a_best + A0;
+    int32_t* f_a = b.a_f + A0;
+    // Per-anchor working state of the chain phases (component root, size | flags, best end).  Windows of up to
+    // DP_SMEM_ANCHORS anchors - nearly all of them - keep it in shared memory: the phases after the DP are chains of
+    // dependent scattered accesses, which cost ~30 cycles there against an L2 round trip each in the global arrays.
+    const int warp = threadIdx.x >> 5;
+    const bool small = n <= DP_SMEM_ANCHORS;
+    uint32_t* root_a = small ? s_work[warp] : b.a_root + A0;
+    uint32_t* aux_a = small ? s_work[warp] + DP_SMEM_ANCHORS : b.a_aux + A0;
+    unsigned long long* best_a = small ? (unsigned long long*)(s_work[warp] + 2 * DP_SMEM_ANCHORS) : b.a_best + A0;
+    if (small) {
+        for (uint32_t i = lane; i < n; i += 32) { aux_a[i] = 0u; best_a[i] = 0ull; }      // the global arrays come zeroed
+        __syncwarp();
+    }
+    // candidate list: at most n / min_anchors entries
+    int32_t* cand_a = (small && n <= 128u * (uint32_t)max(C.min_anchors, 1)) ? (int32_t*)s_strip[warp] : f_a;
 
     // ---------------- DP
-    if ((uint64_t)n * (uint32_t)DP_ANCHOR_SCORE < (1u << 22)) dp_window<false>(qp_a, rp_a, meta_a, f_a, root_a, n, lane);
-    else dp_window<true>(qp_a, rp_a, meta_a, f_a, root_a, n, lane);
+    if ((uint64_t)n * (uint32_t)DP_ANCHOR_SCORE < (1u << 22)) dp_window<false>(qp_a, rp_a, meta_a, f_a, root_a, n, lane, s_strip[warp]);
+    else dp_window<true>(qp_a, rp_a, meta_a, f_a, root_a, n, lane, s_strip[warp]);
 
     // ---------------- per-component size and best end
     for (uint32_t i = lane; i < n; i += 32) {
@@ -435,24 +471,24 @@ __global__ void __launch_bounds__(DP_WARPS * 32) chain_dp_kernel(const ChainBatc
         atomicAdd(&aux_a[r], 1u);
         atomicMax(&best_a[r], ((unsigned long long)(uint32_t)f_a[i] << 32) | (0xFFFFFFFFu - i));
     }
-    __threadfence();
+    __threadfence_block();
     __syncwarp();
 
-    // ---------------- candidate chains -> compact list of roots in f_a[0..ncand)
+    // ---------------- candidate chains -> compact list of roots in cand_a[0..ncand)
     uint32_t ncand = 0;
     for (uint32_t sb = 0; sb < n; sb += 32) {
         const uint32_t i = sb + lane;
         bool cand = false;
         if (i < n && root_a[i] == i) {
-            const uint32_t size = __ldcg(&aux_a[i]) & AUX_SIZE;
-            const int32_t score = (int32_t)(__ldcg(&best_a[i]) >> 32);
+            const uint32_t size = ldv(&aux_a[i]) & AUX_SIZE;
+            const int32_t score = (int32_t)(ldv(&best_a[i]) >> 32);
             cand = size >= (uint32_t)C.min_anchors && score >= C.min_score;
         }
         const uint32_t bal = __ballot_sync(FULL, cand);
-        // f_a[0..ncand) is overwritten only at indices < i's strip start or by earlier lanes of the strip,
-        // whose f values are no longer needed (f lives on in best_a)
+        // when the list shares f_a: f_a[0..ncand) is overwritten only at indices < i's strip start or by earlier lanes of
+        // the strip, whose f values are no longer needed (f lives on in best_a)
         __syncwarp();
-        if (cand) f_a[ncand + __popc(bal & ((1u << lane) - 1u))] = (int32_t)i;
+        if (cand) cand_a[ncand + __popc(bal & ((1u << lane) - 1u))] = (int32_t)i;
         ncand += __popc(bal);
         __syncwarp();
     }
@@ -462,9 +498,9 @@ __global__ void __launch_bounds__(DP_WARPS * 32) chain_dp_kernel(const ChainBatc
     for (uint32_t round = 0; round < ncand; round++) {
         int32_t sc = INT32_MIN; uint32_t qs = 0xFFFFFFFFu, rs = 0xFFFFFFFFu, idx = 0xFFFFFFFFu;
         for (uint32_t t = lane; t < ncand; t += 32) {
-            const uint32_t r = (uint32_t)f_a[t];
-            if (__ldcg(&aux_a[r]) & AUX_PROCESSED) continue;
-            const unsigned long long bb = __ldcg(&best_a[r]);
+            const uint32_t r = (uint32_t)cand_a[t];
+            if (ldv(&aux_a[r]) & AUX_PROCESSED) continue;
+            const unsigned long long bb = ldv(&best_a[r]);
             const uint32_t bi = 0xFFFFFFFFu - (uint32_t)bb;
             const bool rv = meta_a[r] & 1u;
             const uint32_t rs2 = rv ? rp_a[bi] : rp_a[r];
@@ -477,19 +513,19 @@ __global__ void __launch_bounds__(DP_WARPS * 32) chain_dp_kernel(const ChainBatc
             tuple_min(sc, qs, rs, idx, sc2, qs2, rs2, idx2);
         }
         const uint32_t r = idx;                                 // uniform: the best unprocessed candidate
-        const unsigned long long bb = __ldcg(&best_a[r]);
+        const unsigned long long bb = ldv(&best_a[r]);
         const uint32_t bi = 0xFFFFFFFFu - (uint32_t)bb;
         const uint32_t cqs = qp_a[r], cqe = qp_a[bi];
         bool ov = false;
         for (uint32_t t = lane; t < ncand; t += 32) {
-            const uint32_t r2 = (uint32_t)f_a[t];
-            if (!(__ldcg(&aux_a[r2]) & AUX_ACCEPTED)) continue;
-            const uint32_t bi2 = 0xFFFFFFFFu - (uint32_t)__ldcg(&best_a[r2]);
+            const uint32_t r2 = (uint32_t)cand_a[t];
+            if (!(ldv(&aux_a[r2]) & AUX_ACCEPTED)) continue;
+            const uint32_t bi2 = 0xFFFFFFFFu - (uint32_t)ldv(&best_a[r2]);
             const uint32_t lo = max(cqs, qp_a[r2]), hi = min(cqe, qp_a[bi2]);
             ov |= hi >= lo;
         }
         ov = __any_sync(FULL, ov);
-        const uint32_t size = __ldcg(&aux_a[r]) & AUX_SIZE;
+        const uint32_t size = ldv(&aux_a[r]) & AUX_SIZE;
         if (lane == 0) aux_a[r] = size | AUX_PROCESSED | (ov ? 0u : AUX_ACCEPTED);
         __threadfence_block();
         __syncwarp();
