@@ -76,6 +76,12 @@ with open(os.path.join(P, "r1_scale_configs.txt"), "w") as f:
             f.write(open(os.path.join(G, name + ".log")).read())
         f.write("\n$ torchrun --nproc-per-node 2 tools/allvsall_multi.py 40 1000000   (host genomes, pyskani_b200.parallel.all_vs_all)\n")
         f.write(open(os.path.join(G, "allvsall_multi_2gpu.log")).read())
+    if os.path.exists(os.path.join(G, "scale_cfg4_8gpu.log")):
+        f.write("\n# Eight GPUs (gpurun --gpus 8 -- bash tools/profile_round_ngpu.sh 8): BASELINE.json's target configuration on one 8 x B200 box\n")
+        f.write("\n$ torchrun --nproc-per-node 8 tools/scale_bench.py --families 100 --members 100\n")
+        f.write(open(os.path.join(G, "scale_cfg4_8gpu.log")).read())
+if os.path.exists(os.path.join(G, "bench_r1_8gpu.json")):
+    open(os.path.join(P, "r1_bench_line_8gpu.json"), "w").write(open(os.path.join(G, "bench_r1_8gpu.json")).read().strip().splitlines()[-1] + "\n")
 if os.path.exists(os.path.join(G, "bench_r1_2gpu.json")):
     open(os.path.join(P, "r1_bench_line_2gpu.json"), "w").write(open(os.path.join(G, "bench_r1_2gpu.json")).read().strip().splitlines()[-1] + "\n")
 print(open(os.path.join(P, "r1_device_step_kernel_shares.txt")).read())
