@@ -10,8 +10,9 @@
 //   3. DP        : inside a window, f[i] = max(20, max_j f[j] + 20 - |dr - dq|) over the <= 100 previous
 //                  anchors within 2500 bp on the query, same reference contig and strand, dq > 0, dr > 0,
 //                  |dr - dq| <= 300; ties go to the nearest predecessor.  One warp per window: lane l keeps
-//                  the last four anchors whose index is congruent to l (mod 32) in registers, so the 128
-//                  most recent anchors are scored against the current one without touching memory.
+//                  the newest anchor whose index is congruent to l (mod 32) in registers, so the 32 most recent
+//                  anchors are scored against the current one on chip; older ones (rarely in band) are read back
+//                  from the anchor arrays (dp_window below).
 //   4. chains    = components of the back-pointer forest; score = best f in the component, extent = root ..
 //                  best anchor, weight = component size; keep size >= 3 and score >= 45; greedy by score
 //                  without query overlap inside the window.
@@ -293,7 +294,6 @@ __global__ void __launch_bounds__(1024) window_walk_smem_kernel(const ChainBatch
 }
 
 // ------------------------------------------------------------------ 3+4. DP, chains, per-window record
-struct Gen { uint32_t qp, rp, meta; int32_t f; uint32_t root; };
 
 __device__ __forceinline__ void tuple_min(int32_t& sc, uint32_t& qs, uint32_t& rs, uint32_t& idx,
                                           int32_t sc2, uint32_t qs2, uint32_t rs2, uint32_t idx2) {

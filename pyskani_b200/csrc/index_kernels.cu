@@ -4,7 +4,9 @@
 //   kmer_seeds_k : FxHashMap<kmer, SmallVec<SeedPosition>>  ->  seeds sorted by (genome, kmer, contig, pos)
 //                                                                + a bucket table over the k-mer's top bits
 //   marker_seeds : FxHashSet<u64>                            ->  sorted unique 21-mers per genome
-// Sorting is CUB's device radix sort (library code, like cuBLAS for a GEMM); everything around it is ours.
+// The k-mer order is built by a bucket partition (histogram -> per-genome scan, whose output is the bucket table ->
+// scatter -> rank inside the <= 256-entry bucket); CUB's radix sort (library code, like cuBLAS for a GEMM) remains as
+// the fallback for genomes whose buckets overflow, and sorts the marker sets (one segment per genome).
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_segmented_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>

@@ -1,11 +1,15 @@
 // screen_kernels.cu — marker-containment screen.
 //
-// Replaces skani::screen::check_markers_quickly (reference lib.rs:623-628), which probes the smaller
-// marker FxHashSet element by element into the larger one, with a warp-cooperative sorted-set
-// intersection: one warp per (query, reference) pair, lanes stride over the smaller sorted list and
-// binary-search the larger one.  The kernel produces the exact intersection size; the pass/fail
-// decision (count > screen_val^21 * |smaller|, or the small-genome rescue) is a second tiny kernel so
-// that the comparison is one IEEE multiply + compare, identical to the oracle's.
+// Replaces skani::screen::check_markers_quickly (reference lib.rs:623-628), which probes the smaller marker FxHashSet
+// element by element into the larger one.  Three ways to the same exact intersection sizes:
+//   * marker_screen_smem_kernel — small pair matrices: up to four queries per CTA staged in shared memory (sorted list +
+//     hashed bitmap), every reference list streams past them once;
+//   * marker_screen_kernel      — fallback for marker sets too large for shared memory: a warp per pair, lanes stride over
+//     the smaller sorted list and binary-search the larger one;
+//   * marker_join_kernel        — large pair matrices: the database's markers as one sorted array of (marker, genome)
+//     postings; a CTA looks a query's markers up once and counts per reference in shared memory.
+// The pass/fail decision (count > screen_val^21 * |smaller|, or the small-genome rescue) is a second tiny kernel so that
+// the comparison is one IEEE multiply + compare, identical to the oracle's.
 #include <cstdlib>
 
 #include <cub/device/device_radix_sort.cuh>

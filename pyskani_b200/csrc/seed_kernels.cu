@@ -2,7 +2,8 @@
 //
 // Replaces skani::seeding::fmh_seeds (one call per contig at reference lib.rs:165-171) for a whole batch
 // of genomes in ONE launch.  Work unit: a tile of TILE_BASES (2 048) consecutive bases of one contig, owned by
-// one WARP; every warp owns a contiguous run of tiles and a private, ordered output region.
+// one WARP; warps claim regions of CHUNK_TILES consecutive tiles from one atomic counter and own a private, ordered
+// output region for each.
 //   * each lane loads 4 x 16 ASCII bytes with 128-bit read-only loads (warp-contiguous 512 B each) and packs
 //     them to 2-bit words in the warp's slice of shared memory
 //   * k-mers are cut out of three consecutive words with funnel shifts (no rolling dependency chain)
@@ -10,7 +11,8 @@
 //     multiplies go to the FMA pipe (IMAD.WIDE / IMAD), xor-shifts and compares to the ALU pipe
 //   * popcounts are scanned over the warp with shuffles; hit positions are re-extracted and written to their
 //     exact slot of the warp's region, so a region is ordered by (genome, contig, position)
-//   * there is no block barrier, no atomic and no inter-warp dependency anywhere: warps never wait on each other.
+//   * apart from the claim counter there is no block barrier, no atomic on data and no inter-warp dependency: warps
+//     never wait on each other.
 // A one-CTA scan over the region counts and a gather (which doubles as the copy into exact-size arrays) stitch
 // the regions together in tile order, so seeds come out ordered without a sort and without a second pass over
 // the sequence.
