@@ -315,15 +315,13 @@ __device__ __forceinline__ void tuple_min(int32_t& sc, uint32_t& qs, uint32_t& r
 // The loop only records each anchor's predecessor; the component roots follow afterwards by pointer jumping
 // (~log2(chain length) rounds over the window instead of a dependent lookup per anchor).
 // The common path is straight-line code (selects instead of branches) so that the warp stays provably converged.
-constexpr int32_t DP_ANCHOR_SCORE = 20, DP_MAX_GAP = 300;
-constexpr uint32_t DP_BP_BAND = 2500, DP_INDEX_BAND = 100;
 
 template <bool WIDE>
 __device__ __forceinline__ void dp_window(const uint32_t* __restrict__ qp_a, const uint32_t* __restrict__ rp_a,
                                           const uint32_t* __restrict__ meta_a, int32_t* f_a, uint32_t* root_a,
                                           const uint32_t n, const int lane, uint4* s_strip) {
     // skani's chaining constants are frozen (pyskani exposes none of them): compile-time values
-    // here, checked against the ChainConsts of the call by launch_chain_dp
+    // here, shared with the host through skb_internal.cuh (ChainConsts is filled from the same constants)
     constexpr uint32_t bp_band = DP_BP_BAND, index_band = DP_INDEX_BAND;
     constexpr int32_t max_gap = DP_MAX_GAP, anchor_score = DP_ANCHOR_SCORE;
     constexpr int32_t link_bias = anchor_score + max_gap + 1;      // score of a valid link + max_gap + 1 - gap  >=  1
@@ -668,11 +666,6 @@ void launch_window_walk(const ChainBatch& b, const ChainConsts& c, uint32_t max_
 }
 void launch_chain_dp(const ChainBatch& b, const ChainConsts& c, cudaStream_t st) {
     if (b.n_win_total == 0) return;
-    if (c.anchor_score != DP_ANCHOR_SCORE || c.max_gap != DP_MAX_GAP || c.bp_band != (int32_t)DP_BP_BAND ||
-        c.index_band != (int32_t)DP_INDEX_BAND) {
-        std::fprintf(stderr, "skb: chain_dp_kernel is compiled for skani's frozen chaining constants\n");
-        std::abort();
-    }
     chain_dp_kernel<<<(b.n_win_total + DP_WARPS - 1) / DP_WARPS, DP_WARPS * 32, 0, st>>>(b, c);
     g_kernel_launches++;
 }

@@ -1276,8 +1276,8 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
 
         // ---- chain survivors in batches (reference lib.rs:640-657)
         ChainConsts C{};
-        C.fragment_length = FRAGMENT_LENGTH; C.anchor_score = 20; C.min_anchors = 3; C.min_score = 45; C.max_gap = 300;
-        C.index_band = 100; C.bp_band = 2500; C.af_ext = 198; C.frac_cover_cutoff = 0.15;   // D_FRAC_COVER_CUTOFF / 100 (lib.rs:589)
+        C.fragment_length = FRAGMENT_LENGTH; C.anchor_score = DP_ANCHOR_SCORE; C.min_anchors = 3; C.min_score = 45; C.max_gap = DP_MAX_GAP;
+        C.index_band = (int32_t)DP_INDEX_BAND; C.bp_band = (int32_t)DP_BP_BAND; C.af_ext = 198; C.frac_cover_cutoff = 0.15;   // D_FRAC_COVER_CUTOFF / 100 (lib.rs:589)
         C.robust = opts->robust; C.median = opts->median; C.k = dbi.k;
 
         std::vector<skb_hit_t> all_hits;

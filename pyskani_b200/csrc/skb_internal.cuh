@@ -173,6 +173,11 @@ void launch_marker_join(const GenomeView* queries, uint32_t n_queries, uint32_t 
                         const uint32_t* vals, const uint32_t* bucket, uint32_t shift, uint32_t* count, cudaStream_t st);
 
 // ---------------------------------------------------------------- chain
+// skani's chaining constants (frozen: pyskani exposes none of them).  The DP kernel uses them as compile-time values;
+// skb_db_query fills ChainConsts from the same definitions.
+constexpr int32_t DP_ANCHOR_SCORE = 20, DP_MAX_GAP = 300;
+constexpr uint32_t DP_BP_BAND = 2500, DP_INDEX_BAND = 100;
+
 struct ChainConsts {           // skani::chain::map_params_from_sketch (reference lib.rs:646-651), frozen per DESIGN.md
     uint32_t fragment_length;  // 20000
     int32_t anchor_score;      // 20

@@ -72,6 +72,24 @@ def test_sketch_ragged_batch(ctx):
     assert gs[0].info().n_seeds == 0 and gs[1].info().n_contigs == 0
 
 
+def test_sketch_tile_and_region_boundaries(ctx):
+    """Contig lengths around the kernel's work units (16-base words, 2 048-base tiles, 16 384-base regions) with every
+    position a seed (c = 1), so that a k-mer dropped or duplicated at any boundary changes the sketch; host pointers at
+    odd addresses."""
+    lens = [500, 511, 512, 513, 2047, 2048, 2049, 2048 + 14, 2048 + 20, 4096, 16383, 16384, 16385, 16384 + 20, 32768 + 7,
+            3 * 16384 - 1]
+    big = np.frombuffer(rand(sum(lens) + 3 * len(lens) + 8, 41), np.uint8)
+    contigs, off = [], 1
+    for l in lens:
+        contigs.append(big[off:off + l])          # views at odd offsets of one buffer
+        off += l + 3
+    for c, mc in ((1, 1), (7, 3)):
+        gs = ctx.sketch_batch([contigs, contigs[::-1], [contigs[5]], [contigs[11], contigs[12]]], c=c, marker_c=mc)
+        want = [contigs, contigs[::-1], [contigs[5]], [contigs[11], contigs[12]]]
+        for g, w in zip(gs, want):
+            assert_sketch_equal(g, oracle.Sketch([x.tobytes() for x in w], c=c, marker_c=mc))
+
+
 def test_sketch_junk_and_lowercase(ctx):
     rng = np.random.default_rng(3)
     alpha = np.frombuffer(b"ACGTacgtNnRYKM-*", np.uint8)
