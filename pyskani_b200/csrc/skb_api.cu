@@ -511,6 +511,7 @@ static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_par
     // marker kernels that are still in flight; they are fetched together with the end-of-batch synchronisation below
     Core& c = *core;
     cudaStream_t st = c.stream;
+    Trace tf("finish_batch");
     // ---- per-genome tables: buckets, contig seed starts, contig lengths, window capacities
     std::vector<GenomeView> views(n_genomes);
     std::vector<uint32_t> h_clen, h_cwin;
@@ -568,7 +569,9 @@ static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_par
         if (d_marker_start) download(c, marker_start.data(), d_marker_start, n_genomes + 1);
         uint32_t h_bover = 0;
         if (d_bucket_overflow) download(c, &h_bover, d_bucket_overflow, 1);
+        tf.mark("tables + downloads enqueued");
         CU(cudaStreamSynchronize(st));   // the one synchronisation of the index build
+        tf.mark("synchronised");
         if (h_bover) {
             // a bucket was too large for the partition path (low-complexity genome): redo the k-mer order with the
             // radix sort and rebuild the bucket tables from it
@@ -601,6 +604,7 @@ static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_par
         impl->info.k = P.k; impl->info.c = P.c; impl->info.marker_c = P.marker_c; impl->info.has_seeds = seed ? 1 : 0;
         out[g] = new skb_sketch{impl};
     }
+    tf.mark("handles built");
 }
 
 }  // namespace skb
