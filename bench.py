@@ -34,6 +34,34 @@ ALG_BYTES_PER_BASE = 1.0 + 16.0 / 125.0 + 8.0 / 1000.0   # 1 B r
 NCU_SEED_TRAFFIC_BYTES = 508_747_008 + 16_123_392         # profiles/r1_seed_scan_kernel_ncu_full.txt (read + write, one launch)
 
 
+def bind_to_gpu_cpus(index, uuid=None):
+    """One process per GPU: run on the CPUs NVML reports as local to this GPU, so that the pinned input buffers (first
+    touched below) sit on the GPU's own NUMA node and the host->device copies of eight ranks do not cross the socket link.
+    Returns a short description for the JSON line; a no-op when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        if uuid is not None:
+            u = str(uuid)
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID((u if u.startswith("GPU-") else "GPU-" + u).encode())
+            except Exception:
+                h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1 and 64 * w + b < n_cpu]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return "unchanged (no NVML-local CPU in this process's cpuset)"
+        os.sched_setaffinity(0, allowed)
+        return "cpus %d-%d (%d) local to the GPU" % (allowed[0], allowed[-1], len(allowed))
+    except Exception as e:       # noqa: BLE001 - purely an optimisation
+        return "unchanged (%s)" % type(e).__name__
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -193,6 +221,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: pyskani_b200 has no CPU fallback (use --impl reference for the CPU port)")
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_cpus(local_rank, getattr(torch.cuda.get_device_properties(local_rank), "uuid", None))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -319,7 +349,7 @@ def main():
             "config": {"workload": "configs[1]: 1 synthetic %d bp genome vs %d mutated copies (1-15%% divergence, indels) per GPU"
                                    % (args.genome_len, args.n_refs),
                        "k": 15, "c": 125, "marker_c": 1000, "l2": "inputs (%.0f MB ASCII per step) exceed the 126 MB L2" % (total_bases / 1e6),
-                       "parallelism": "independent family per GPU, no collective"},
+                       "parallelism": "independent family per GPU, no collective", "cpu_affinity": numa},
             "hits_per_query": n_hits,
             "sketch_gbps": world * total_bases / (sketch_ms / 1e3) / 1e9,
             "seed_kernel_gbps": world * total_bases / (seed_ms / 1e3) / 1e9,
@@ -338,6 +368,7 @@ def main():
         if not args.skip_cpu_baseline:
             import oracle
             oracle.lib()
+            os.sched_setaffinity(0, all_cpus)      # the CPU baseline may use every core the process was given
             threads = args.cpu_threads or (os.cpu_count() or 1)
             cpu_step(base, refs, threads)
             a, b, nh = cpu_step(base, refs, threads)
