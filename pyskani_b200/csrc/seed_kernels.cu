@@ -128,15 +128,15 @@ __global__ void __launch_bounds__(SEED_THREADS, SKB_SEED_MINBLOCKS) seed_scan_ke
     uint32_t* pk = s_pk[warp];
     uint32_t* masks = s_masks[warp];
 
-    // Regions are claimed dynamically (one atomic per CHUNK_TILES tiles) so that no warp idles while another still
+    // Regions are claimed dynamically (one atomic per chunk_tiles <= CHUNK_TILES tiles) so that no warp idles while another still
     // has a long static range in front of it; a region's place in the output depends only on its id.
     while (true) {
     uint32_t chunk = 0;
     if (lane == 0) chunk = atomicAdd(a.chunk_counter, 1u);
     chunk = __shfl_sync(0xffffffffu, chunk, 0);
     if (chunk >= a.n_chunks) break;
-    const uint32_t t0 = chunk * CHUNK_TILES;
-    const uint32_t t1 = min(t0 + CHUNK_TILES, a.n_tiles);
+    const uint32_t t0 = chunk * a.chunk_tiles;
+    const uint32_t t1 = min(t0 + a.chunk_tiles, a.n_tiles);
     const uint32_t region = a.region_base + chunk;
     uint32_t seed_off, seed_cap, marker_off, marker_cap;
     if (a.region_off) {       // exact layout (retry): exclusive scan of the packed counts

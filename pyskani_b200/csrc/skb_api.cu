@@ -341,7 +341,7 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
         table_upload(c, d_descs, descs.data(), sizeof(ContigDesc) * descs.size());
         t2.mark("descs uploaded");
         // ---- launch plan: one launch per copy chunk (or one for everything); every warp of a launch owns a region
-        struct Launch { uint32_t d0, d1, tile_base, n_tiles, n_warps, n_chunks, region_base; cudaEvent_t ready; };
+        struct Launch { uint32_t d0, d1, tile_base, n_tiles, n_warps, n_chunks, chunk_tiles, region_base; cudaEvent_t ready; };
         std::vector<Launch> launches;
         uint32_t n_regions = 0;
         auto add_launch = [&](uint32_t d0, uint32_t d1, cudaEvent_t ready) {
@@ -349,7 +349,11 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             Launch L{};
             L.d0 = d0; L.d1 = d1; L.tile_base = descs[d0].tile_start;
             L.n_tiles = (d1 < descs.size() ? descs[d1].tile_start : n_tiles) - L.tile_base;
-            L.n_chunks = (L.n_tiles + CHUNK_TILES - 1) / CHUNK_TILES;
+            // small calls (one genome: the query of Database.query) use smaller regions so that every warp of the GPU
+            // gets work: 8-tile regions would leave a 5 Mbp genome to 305 of 4 736 warps
+            const uint32_t all_warps = (uint32_t)c.n_sm * 4u * SEED_WARPS;
+            L.chunk_tiles = std::max<uint32_t>(1, std::min<uint32_t>(CHUNK_TILES, n_tiles / (2 * all_warps)));   // by the size of the whole call
+            L.n_chunks = (L.n_tiles + L.chunk_tiles - 1) / L.chunk_tiles;
             uint32_t grid = std::min<uint32_t>((uint32_t)c.n_sm * 4u, (L.n_chunks + SEED_WARPS - 1) / SEED_WARPS);
             L.n_warps = grid * SEED_WARPS; L.region_base = n_regions; L.ready = ready;
             n_regions += L.n_chunks;
@@ -411,7 +415,7 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
                 const Launch& L = launches[li];
                 if (L.ready) CU(cudaStreamWaitEvent(st, L.ready, 0));
                 SeedScanArgs b2 = a;
-                b2.n_chunks = L.n_chunks; b2.chunk_counter = d_claim + li;
+                b2.n_chunks = L.n_chunks; b2.chunk_tiles = L.chunk_tiles; b2.chunk_counter = d_claim + li;
                 b2.contigs = d_descs + L.d0; b2.n_contigs = L.d1 - L.d0;
                 b2.tile_base = L.tile_base; b2.n_tiles = L.n_tiles; b2.n_warps = L.n_warps; b2.region_base = L.region_base;
                 launch_seed_scan(b2, c.n_sm, st);
@@ -1134,8 +1138,9 @@ const GenomeView* db_views(skb_db& db) {
         db.d_views = DevMem(db.core, sizeof(GenomeView) * std::max<size_t>(n, 1));
         std::vector<GenomeView> h(n);
         for (size_t i = 0; i < n; i++) h[i] = db.items[i]->view;
+        // pageable source: the call returns once the bytes are staged, so `h` may go out of scope; consumers are
+        // ordered behind the copy on the same stream
         CU(cudaMemcpyAsync(db.d_views.p, h.data(), sizeof(GenomeView) * n, cudaMemcpyHostToDevice, c.stream));
-        CU(cudaStreamSynchronize(c.stream));
         db.dirty = false;
     }
     return db.d_views.as<GenomeView>();

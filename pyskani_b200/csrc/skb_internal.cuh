@@ -45,7 +45,7 @@ constexpr int SEED_WARPS = SEED_THREADS / 32;
 constexpr int WORDS_PER_LANE = 4;                                     // 16-base words each lane evaluates per tile
 constexpr int TILE_WORDS = 32 * WORDS_PER_LANE;                       // 128 words per warp tile
 constexpr int TILE_BASES = TILE_WORDS * 16;                           // 2048 bases per warp tile
-constexpr int CHUNK_TILES = 8;                                        // tiles per dynamically claimed region (16 kbp)
+constexpr int CHUNK_TILES = 8;                                        // most tiles per dynamically claimed region (16 kbp)
 
 // One kept contig of the batch.  Tiles are numbered contig after contig; tile t of a contig covers its bases
 // [t * TILE_BASES, min(len, (t + 1) * TILE_BASES)).
@@ -66,7 +66,8 @@ struct SeedScanArgs {
     uint32_t n_tiles;            // tiles of this launch
     uint32_t tile_base;          // batch-wide id of this launch's first tile
     uint32_t region_base;        // id of this launch's first region
-    uint32_t n_chunks;           // regions of this launch = ceil(n_tiles / CHUNK_TILES)
+    uint32_t n_chunks;           // regions of this launch = ceil(n_tiles / chunk_tiles)
+    uint32_t chunk_tiles;        // tiles per region: CHUNK_TILES for large launches, fewer when that would leave warps idle
     uint32_t* chunk_counter;     // zero-initialised claim counter of this launch
     uint32_t n_warps;            // warps of this launch (grid * SEED_WARPS)
     uint32_t kmask, kshift;
