@@ -363,6 +363,32 @@ def test_pack_unpack_device_roundtrip(ctx):
     assert len(other.unpack(ctx.pack([], None, 0), None, 0)) == 0
 
 
+def test_repeat_rich_window_takes_the_wide_dp_path(ctx):
+    """A tandem repeat with every position a seed (c = 1) puts millions of anchors into one 20 kb window: the DP then
+    runs its wide-score variant (packed score would overflow), keeps its per-anchor state in global memory (> 256
+    anchors) and needs predecessors beyond the 32 held in registers for most anchors."""
+    from pyskani_b200 import capi
+    rng = np.random.default_rng(97)
+    unit = synth.random_genome(20, 98)
+    core = np.tile(unit, 450)
+    q = np.concatenate([synth.random_genome(4000, 99), core, synth.random_genome(4000, 100)])
+    r = np.concatenate([synth.random_genome(3000, 101), core, synth.random_genome(5000, 102)])
+    r[rng.integers(0, len(r), 40)] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 40)]
+    genomes = [[q.tobytes()], [r.tobytes()]]
+    gs = ctx.sketch_batch(genomes, c=1, marker_c=50)
+    os_ = [oracle.Sketch(g, c=1, marker_c=50) for g in genomes]
+    for g, o in zip(gs, os_):
+        assert_sketch_equal(g, o)
+    db = capi.Database(ctx)
+    db.add_many(gs)
+    hits, n_in = db.query(gs)
+    total = 0
+    for qi, oq in enumerate(os_):
+        total += check_hits([h for h in hits if h[0] == qi], oq, os_)
+    assert total == n_in and n_in >= 2
+    assert max(h[7] for h in hits) * 20 >= (1 << 22)           # anchors of a pair: the wide path was needed
+
+
 def test_empty_and_degenerate_queries(ctx):
     from pyskani_b200 import capi
     s = rand(100_000, 77)
