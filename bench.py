@@ -363,8 +363,15 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read + write)",
                          "algorithmic_bytes": ALG_BYTES_PER_BASE * total_bases, "peak_source": peak_src,
                          "note": "algorithmic bytes = 1.136 B/base x %d bases per launch; the kernel is integer-issue bound, see DESIGN.md" % total_bases},
+            # the bound that actually holds for this kernel: two exact 64-bit hashes per base cost
+            # ~54 ALU-pipe instructions per position (SASS count); the ALU pipe issues one warp instruction per 2 cycles
+            # per SM sub-partition.  ncu: sm__pipe_alu_cycles_active 81 % (profiles/r1_seed_scan_kernel_ncu_full.txt)
+            "issue_roofline": {"bound": "integer ALU pipe", "unit": "Gbp/s", "alu_inst_per_base": 54,
+                               "peak": 148 * 4 * 32 / (54 * 2) * (clocks.get("sm_mhz") or 1965.0) / 1e3,
+                               "achieved": total_bases / (seed_ms / 1e3) / 1e9},
             "clocks": clocks,
         }
+        line["issue_roofline"]["frac"] = line["issue_roofline"]["achieved"] / line["issue_roofline"]["peak"]
         if not args.skip_cpu_baseline:
             import oracle
             oracle.lib()
