@@ -653,8 +653,8 @@ uint32_t walk_group_capacity(uint32_t max_query_seeds) {
 void launch_window_walk(const ChainBatch& b, const ChainConsts& c, uint32_t max_query_seeds, cudaStream_t st) {
     if (b.n_pairs == 0) return;
     // shared-memory walk for every pair whose query fits, global-memory walk for the rest
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(window_walk_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WALK_SMEM_MAX); attr_set = true; }
+    // per launch, not once per process: the attribute belongs to the current device
+    cudaFuncSetAttribute(window_walk_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WALK_SMEM_MAX);
     const uint32_t n = max_query_seeds < WALK_SMEM_SEEDS ? max_query_seeds : WALK_SMEM_SEEDS;
     const size_t bytes = walk_smem_bytes(n, b.walk_group_max);
     window_walk_smem_kernel<<<b.n_walk_groups, 1024, bytes, st>>>(b, c.fragment_length);

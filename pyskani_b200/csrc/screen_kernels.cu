@@ -372,8 +372,7 @@ void launch_marker_join(const GenomeView* queries, uint32_t n_queries, uint32_t 
     if (n_queries == 0 || n_refs == 0) return;
     const uint32_t tile = n_refs < 32768u ? n_refs : 32768u;
     const size_t smem = (size_t)tile * 4;
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(marker_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4); attr_set = true; }
+    cudaFuncSetAttribute(marker_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4);   // per launch: the attribute belongs to the current device
     dim3 grid((n_refs + tile - 1) / tile, n_queries);
     marker_join_kernel<<<grid, JOIN_THREADS, smem, st>>>(queries, keys, vals, bucket, shift, n_refs, tile, count);
     g_kernel_launches++;

@@ -1238,7 +1238,11 @@ int skb_db_screen(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries
     return guarded(db->core.get(), [&] {
         std::vector<std::shared_ptr<SketchImpl>> qs;
         std::vector<GenomeView> hv;
-        for (uint32_t i = 0; i < n_queries; i++) { qs.push_back(queries[i]->impl); hv.push_back(queries[i]->impl->view); }
+        for (uint32_t i = 0; i < n_queries; i++) {
+            if (!queries[i]) throw Fail{SKB_ERR_ARG, "null query sketch"};
+            if (queries[i]->impl->core != db->core) throw Fail{SKB_ERR_ARG, "query sketch belongs to another context"};
+            qs.push_back(queries[i]->impl); hv.push_back(queries[i]->impl->view);
+        }
         DevMem d_q(db->core, sizeof(GenomeView) * std::max<uint32_t>(n_queries, 1));
         CU(cudaMemcpyAsync(d_q.p, hv.data(), sizeof(GenomeView) * n_queries, cudaMemcpyHostToDevice, db->core->stream));
         run_screen(*db, qs, d_q.as<GenomeView>(), cutoff, rescue_small, nullptr, pass, shared);
@@ -1265,6 +1269,7 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
         std::vector<GenomeView> hv;
         for (uint32_t i = 0; i < n_queries; i++) {
             if (!queries[i]) throw Fail{SKB_ERR_ARG, "null query sketch"};
+            if (queries[i]->impl->core != db->core) throw Fail{SKB_ERR_ARG, "query sketch belongs to another context"};
             const auto& qi = queries[i]->impl->info;
             if (qi.k != dbi.k || qi.c != dbi.c || qi.marker_c != dbi.marker_c) throw Fail{SKB_ERR_ARG, "query sketch parameters differ from the database's"};
             qs.push_back(queries[i]->impl); hv.push_back(queries[i]->impl->view);

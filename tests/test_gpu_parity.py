@@ -361,6 +361,11 @@ def test_pack_unpack_device_roundtrip(ctx):
     db_a.add_many(gs); db_b.add_many(got)
     assert db_a.query(gs) == db_b.query(got)
     assert len(other.unpack(ctx.pack([], None, 0), None, 0)) == 0
+    # sketches are bound to their context: the other context's handles are refused, not dereferenced
+    with pytest.raises(capi.SkbError):
+        db_a.query(got[:1])
+    with pytest.raises(capi.SkbError):
+        db_a.screen(got[:1])
 
 
 def test_repeat_rich_window_takes_the_wide_dp_path(ctx):
