@@ -298,14 +298,94 @@ void build_kmer_order_buckets(uint32_t n_seeds, uint32_t n_genomes, const Bucket
     g_kernel_launches += 3;
 }
 
-size_t marker_scratch_bytes(uint32_t n) {
+// ---- marker sets of a batch whose genomes have at most MARKER_SMEM_MAX markers each (16 Mbp at c = 1000): one CTA sorts a
+// genome's markers in shared memory (bitonic), drops duplicates and leaves the result at the genome's pre-deduplication
+// offset; a one-CTA scan turns the per-genome counts into the final offsets and a copy kernel closes the gaps.  Three
+// launches instead of the dozen of the segmented radix sort + select path, which remains for larger genomes.
+constexpr uint32_t MARKER_SMEM_MAX = 16384;
+
+__global__ void __launch_bounds__(1024) marker_sort_smem_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ off_in,
+                                                                uint64_t* __restrict__ sorted_unique, uint32_t* __restrict__ n_unique) {
+    extern __shared__ uint64_t s_key[];
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_base;
+    const uint32_t g = blockIdx.x, o = off_in[g], n = off_in[g + 1] - o;
+    if (n == 0) { if (threadIdx.x == 0) n_unique[g] = 0; return; }
+    uint32_t P = 2;
+    while (P < n) P <<= 1;
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) s_key[i] = i < n ? (keys_in[o + i] & ((1ull << 42) - 1)) : ~0ull;
+    __syncthreads();
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                const uint32_t i = 2 * t - (t & (j - 1)), l = i + j;        // i has bit j clear
+                const uint64_t a = s_key[i], b = s_key[l];
+                const bool up = (i & k) == 0;
+                if ((a > b) == up) { s_key[i] = b; s_key[l] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {
+        const uint32_t i = i0 + threadIdx.x;
+        const bool keep = i < n && (i == 0 || s_key[i] != s_key[i - 1]);
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { const uint32_t c = s_warp[w]; if (w < warp) before += c; total += c; }
+        const uint32_t base = s_base;
+        if (keep) sorted_unique[o + base + before + __popc(bal & ((1u << lane) - 1u))] = s_key[i];
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = base + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) n_unique[g] = s_base;
+}
+
+// out[g] = sum of counts[0..g) for g = 0..n (one CTA; n is the number of genomes of a batch)
+__global__ void __launch_bounds__(1024) exclusive_offsets_kernel(const uint32_t* __restrict__ counts, uint32_t n, uint32_t* __restrict__ out) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < n; i0 += 1024) {
+        const uint32_t i = i0 + threadIdx.x;
+        const uint32_t v = i < n ? counts[i] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (int w = 0; w < 32; w++) { const uint32_t c = s_warp[w]; if (w < warp) before += c; total += c; }
+        const uint32_t carry = s_carry;
+        if (i < n) out[i] = carry + before + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = s_carry;
+}
+
+__global__ void marker_compact_kernel(const uint64_t* __restrict__ sorted_unique, const uint32_t* __restrict__ off_in,
+                                      const uint32_t* __restrict__ off_out, uint64_t* __restrict__ markers_out) {
+    const uint32_t g = blockIdx.x, src = off_in[g], dst = off_out[g], n = off_out[g + 1] - dst;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) markers_out[dst + i] = sorted_unique[src + i];
+}
+
+size_t marker_scratch_bytes(uint32_t n, uint32_t n_genomes) {
     size_t s1 = 0, s2 = 0, s3 = 0;
     cub::DeviceRadixSort::SortKeys(nullptr, s1, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int)n, 0, 64);
     cub::DeviceSegmentedRadixSort::SortKeys(nullptr, s3, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int)n, 1 << 22,
                                             (const uint32_t*)nullptr, (const uint32_t*)nullptr, 0, 64);
     if (s3 > s1) s1 = s3;
     cub::DeviceSelect::Unique(nullptr, s2, (const uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (int)n);
-    return align_up(s1 > s2 ? s1 : s2) + 2 * align_up((size_t)n * 8 + 8) + 256 + 1024;
+    return align_up(s1 > s2 ? s1 : s2) + 2 * align_up((size_t)n * 8 + 8) + 256 + 1024 + align_up(4 * ((size_t)n_genomes + 1));
 }
 
 void build_marker_sets(uint32_t n_genomes, uint32_t n, uint64_t* marker_keys, uint64_t* markers_out,
@@ -319,6 +399,18 @@ void build_marker_sets(uint32_t n_genomes, uint32_t n, uint64_t* marker_keys, ui
     size_t cub_bytes = scratch_bytes - (size_t)(p - (char*)scratch);
     if (n == 0) {
         cudaMemsetAsync(genome_marker_out, 0, sizeof(uint32_t) * (n_genomes + 1), st);
+        return;
+    }
+    if (genome_marker_in && max_genome_markers <= MARKER_SMEM_MAX && n_genomes <= 65535u * 16u) {
+        uint32_t* per_genome = (uint32_t*)((char*)scratch + scratch_bytes - align_up(4 * ((size_t)n_genomes + 1)));
+        uint32_t P = 2;
+        while (P < max_genome_markers) P <<= 1;
+        static_assert(MARKER_SMEM_MAX * 8 <= 200 * 1024, "marker sort tile must fit the opted-in shared memory");
+        cudaFuncSetAttribute(marker_sort_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MARKER_SMEM_MAX * 8));
+        marker_sort_smem_kernel<<<n_genomes, P >= 2048 ? 1024 : 256, (size_t)P * 8, st>>>(marker_keys, genome_marker_in, sorted, per_genome);
+        exclusive_offsets_kernel<<<1, 1024, 0, st>>>(per_genome, n_genomes, genome_marker_out);
+        marker_compact_kernel<<<n_genomes, 256, 0, st>>>(sorted, genome_marker_in, genome_marker_out, markers_out);
+        g_kernel_launches += 3;
         return;
     }
     int gbits = 0;

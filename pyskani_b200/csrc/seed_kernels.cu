@@ -311,6 +311,16 @@ __global__ void genome_starts_kernel(uint32_t n_regions, const uint64_t* __restr
     genome_marker_start[g] = (uint32_t)(st >> 32) + genome_marker_local[g];
 }
 
+// last genome whose seed_start <= i (empty genomes share their successor's start and are skipped by the search order)
+__device__ __forceinline__ uint32_t gather_genome_of(const BucketGenome* __restrict__ G, uint32_t n_genomes, uint32_t i) {
+    uint32_t lo = 0, hi = n_genomes;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&G[mid].seed_start) <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 __global__ void __launch_bounds__(256) region_gather_kernel(const RegionGatherArgs a) {
     const int lane = threadIdx.x & 31;
     const uint32_t r = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -318,8 +328,16 @@ __global__ void __launch_bounds__(256) region_gather_kernel(const RegionGatherAr
     const uint64_t st0 = a.region_start[r], st1 = a.region_start[r + 1];
     {
         const uint32_t dst = (uint32_t)st0, n = (uint32_t)st1 - dst, src = a.seed_src[r];
+        // genome of the region's first and last seed (uniform); regions that straddle genomes look every seed up
+        uint32_t g_first = 0, g_last = 0;
+        if (a.bucket_counts && n) { g_first = gather_genome_of(a.genomes, a.n_genomes, dst); g_last = gather_genome_of(a.genomes, a.n_genomes, dst + n - 1); }
         for (uint32_t i = lane; i < n; i += 32) {
-            a.kmer_p[dst + i] = a.kmer_r[src + i]; a.pos_p[dst + i] = a.pos_r[src + i]; a.meta_p[dst + i] = a.meta_r[src + i];
+            const uint32_t km = a.kmer_r[src + i];
+            a.kmer_p[dst + i] = km; a.pos_p[dst + i] = a.pos_r[src + i]; a.meta_p[dst + i] = a.meta_r[src + i];
+            if (a.bucket_counts) {
+                const uint32_t g = g_first == g_last ? g_first : gather_genome_of(a.genomes, a.n_genomes, dst + i);
+                atomicAdd(&a.bucket_counts[__ldg(&a.genomes[g].bucket_off) + (km >> __ldg(&a.genomes[g].shift))], 1u);
+            }
         }
     }
     {

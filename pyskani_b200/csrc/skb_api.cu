@@ -446,19 +446,30 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
         store->kmer_p = DevMem::persistent(core, 4 * (size_t)ns); store->pos_p = DevMem::persistent(core, 4 * (size_t)ns);
         store->meta_p = DevMem::persistent(core, 4 * (size_t)ns);
         uint64_t* t_mkeys = (uint64_t*)c.scratch(SLOT_MKEYS2, 8 * (size_t)nm + 16);
+        char* d_tab = nullptr;
+        uint32_t* d_bover = nullptr;
         {
             RegionGatherArgs ga{};
             ga.n_regions = n_regions; ga.seed_src = r_ssrc; ga.marker_src = r_msrc; ga.region_start = r_start;
             ga.kmer_r = t_kmer; ga.pos_r = t_pos; ga.meta_r = t_meta; ga.marker_r = t_mreg;
             ga.kmer_p = store->kmer_p.as<uint32_t>(); ga.pos_p = store->pos_p.as<uint32_t>(); ga.meta_p = store->meta_p.as<uint32_t>();
             ga.marker_keys = t_mkeys;
+            // the gather also builds the per-genome k-mer bucket histogram of the index build (saves a pass over kmer_p)
+            for (uint32_t g = 0; g < n_genomes; g++) { bplan.genomes[g].seed_start = seed_start[g]; bplan.genomes[g].n_seeds = seed_start[g + 1] - seed_start[g]; }
+            const size_t tab_bytes = sizeof(BucketGenome) * n_genomes;
+            d_tab = (char*)c.scratch(SLOT_BTAB, tab_bytes + 16);
+            table_upload(c, d_tab, bplan.genomes.data(), tab_bytes);
+            d_bover = (uint32_t*)(d_tab + (tab_bytes + 3) / 4 * 4);
+            CU(cudaMemsetAsync(d_bover, 0, 4, st));
+            CU(cudaMemsetAsync(d_bcounts, 0, 4 * bplan.total, st));
+            ga.genomes = (const BucketGenome*)d_tab; ga.n_genomes = n_genomes; ga.bucket_counts = d_bcounts;
             launch_region_gather(ga, st);
         }
         t2.mark("gather enqueued");
         // ---- marker sets, on the auxiliary stream: a chain of small latency-bound launches that runs beside the k-mer order
         store->markers = DevMem::persistent(core, 8 * (size_t)std::max<uint32_t>(nm, 1));
         {
-            const size_t mark_bytes = marker_scratch_bytes(nm);
+            const size_t mark_bytes = marker_scratch_bytes(nm, n_genomes);
             void* mark_scratch = c.scratch(SLOT_MARK, mark_bytes);
             // pre-deduplication offsets (repaired on the host like the seed starts) live in their own small buffer: d_gm is
             // overwritten with the post-deduplication offsets
@@ -474,20 +485,13 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
         // ---- k-mer order
         store->kmer_k = DevMem::persistent(core, 4 * (size_t)ns); store->pos_k = DevMem::persistent(core, 4 * (size_t)ns);
         store->meta_k = DevMem::persistent(core, 4 * (size_t)ns);
-        uint32_t* d_bover = nullptr;
         {
-            // bucket partition: histogram (from the seeding kernel) -> per-genome scan (= the bucket tables) -> scatter ->
-            // rank inside the bucket
-            for (uint32_t g = 0; g < n_genomes; g++) { bplan.genomes[g].seed_start = seed_start[g]; bplan.genomes[g].n_seeds = seed_start[g + 1] - seed_start[g]; }
+            // bucket partition: histogram (built by the gather) -> per-genome scan (= the bucket tables) -> scatter -> rank
+            // inside the bucket
             store->bucket = DevMem::persistent(core, 4 * bplan.total);
-            const size_t tab_bytes = sizeof(BucketGenome) * n_genomes;
-            char* d_tab = (char*)c.scratch(SLOT_BTAB, tab_bytes + 16);
-            table_upload(c, d_tab, bplan.genomes.data(), tab_bytes);
-            d_bover = (uint32_t*)(d_tab + (tab_bytes + 3) / 4 * 4);
-            CU(cudaMemsetAsync(d_bover, 0, 4, st));
             const size_t bscr_bytes = bucket_order_scratch_bytes(ns, bplan.total);
             void* bscr = c.scratch(SLOT_SORT, bscr_bytes);
-            build_kmer_order_buckets(ns, n_genomes, (const BucketGenome*)d_tab, bplan.total, d_bcounts, 0, store->kmer_p.as<uint32_t>(),
+            build_kmer_order_buckets(ns, n_genomes, (const BucketGenome*)d_tab, bplan.total, d_bcounts, 1, store->kmer_p.as<uint32_t>(),
                                      store->pos_p.as<uint32_t>(), store->meta_p.as<uint32_t>(), store->kmer_k.as<uint32_t>(),
                                      store->pos_k.as<uint32_t>(), store->meta_k.as<uint32_t>(), store->bucket.as<uint32_t>(), d_bover,
                                      bscr, bscr_bytes, st);

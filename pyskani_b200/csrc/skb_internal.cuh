@@ -93,12 +93,21 @@ void launch_genome_starts(uint32_t n_regions, const uint64_t* region_start, uint
                           const uint32_t* genome_seed_local, const uint32_t* genome_marker_local, uint32_t* genome_seed_start,
                           uint32_t* genome_marker_start, cudaStream_t st);
 // copies every region's records to their final, contiguous place (warp per region)
+struct BucketGenome {
+    uint32_t seed_start;   // first seed of the genome in the batch arrays
+    uint32_t n_seeds;
+    uint32_t shift;        // bucket id = kmer >> shift
+    uint32_t n_buckets;
+    uint32_t bucket_off;   // offset of the genome's (n_buckets + 1) entries in the batch's bucket array
+};
 struct RegionGatherArgs {
     uint32_t n_regions;
     const uint32_t* seed_src; const uint32_t* marker_src;       // [n_regions] region storage offsets
     const uint64_t* region_start;                               // [n_regions + 1] destinations (seeds | markers << 32)
     const uint32_t* kmer_r; const uint32_t* pos_r; const uint32_t* meta_r; const uint64_t* marker_r;
     uint32_t* kmer_p; uint32_t* pos_p; uint32_t* meta_p; uint64_t* marker_keys;
+    // optional: while the seeds pass through, count them per (genome, k-mer bucket) for the index build
+    const BucketGenome* genomes; uint32_t n_genomes; uint32_t* bucket_counts;     // bucket_counts == NULL: no histogram
 };
 void launch_region_gather(const RegionGatherArgs& a, cudaStream_t st);
 
@@ -122,13 +131,6 @@ void build_kmer_order(const IndexBuildArgs& a, void* scratch, size_t scratch_byt
 size_t kmer_order_scratch_bytes(uint32_t n_seeds_total);
 
 // k-mer order through bucket partition (fast path of the index build); see index_kernels.cu
-struct BucketGenome {
-    uint32_t seed_start;   // first seed of the genome in the batch arrays
-    uint32_t n_seeds;
-    uint32_t shift;        // bucket id = kmer >> shift
-    uint32_t n_buckets;
-    uint32_t bucket_off;   // offset of the genome's (n_buckets + 1) entries in the batch's bucket array
-};
 size_t bucket_order_scratch_bytes(uint32_t n_seeds, size_t bucket_total);
 // counts (device, [bucket_total]): bucket histogram scratch; counts_ready != 0 means the caller already filled it,
 // otherwise it is built here (measured: a separate histogram pass, 33 us per 4 M seeds, beats atomics inside the
@@ -144,7 +146,7 @@ void build_kmer_order_buckets(uint32_t n_seeds, uint32_t n_genomes, const Bucket
 void build_marker_sets(uint32_t n_genomes, uint32_t n_markers_total, uint64_t* marker_keys, uint64_t* markers_out,
                        uint32_t* genome_marker_out, const uint32_t* genome_marker_in, uint32_t max_genome_markers,
                        void* scratch, size_t scratch_bytes, cudaStream_t st);
-size_t marker_scratch_bytes(uint32_t n_markers_total);
+size_t marker_scratch_bytes(uint32_t n_markers_total, uint32_t n_genomes);
 
 // copies `bytes` (rounded up to 4) from pinned, device-mapped host memory to device memory with a kernel
 struct SegmentCopy { const void* src; uint64_t dst_off; uint64_t bytes; };   // bytes: multiple of 4
