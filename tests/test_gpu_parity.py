@@ -90,6 +90,24 @@ def test_sketch_tile_and_region_boundaries(ctx):
             assert_sketch_equal(g, oracle.Sketch([x.tobytes() for x in w], c=c, marker_c=mc))
 
 
+def test_marker_sets_all_three_sort_paths(ctx):
+    """Marker sets are sorted per genome in shared memory (tiles of up to 16 384 markers), by CUB's segmented sort above
+    that; one batch with a tiny, a mid-size (P = 16 384 tile) and an over-size genome, plus duplicated contigs so that
+    the de-duplication has work to do."""
+    small = rand(30_000, 301)
+    mid = rand(9_500_000, 302)
+    genomes = [[small, small], [mid], [rand(600, 303)]]
+    gs = ctx.sketch_batch(genomes)
+    assert 8192 < gs[1].info().n_markers <= 16384
+    for g, contigs in zip(gs, genomes):
+        assert_sketch_equal(g, oracle.Sketch(contigs))
+    big = rand(17_500_000, 304)                     # > 16 384 markers: the whole batch takes the segmented-sort path
+    gs2 = ctx.sketch_batch([[small, small], [big]])
+    assert gs2[1].info().n_markers > 16384
+    for g, contigs in zip(gs2, [[small, small], [big]]):
+        assert_sketch_equal(g, oracle.Sketch(contigs))
+
+
 def test_sketch_junk_and_lowercase(ctx):
     rng = np.random.default_rng(3)
     alpha = np.frombuffer(b"ACGTacgtNnRYKM-*", np.uint8)
