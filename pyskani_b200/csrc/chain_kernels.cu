@@ -579,42 +579,65 @@ __global__ void ani_reduce_kernel(const ChainBatch b, const ChainConsts C, const
     const PairDesc pd = b.pairs[p];
     const GenomeView& Q = b.qviews[pd.q];
     const GenomeView& R = b.rviews[pd.r];
-    // segment of this pair in the sorted key array
-    uint32_t lo = 0, hi = b.n_win_total;
-    {
-        uint32_t l = 0, h = b.n_win_total;
-        const uint64_t t0 = (uint64_t)p << 32, t1 = (uint64_t)(p + 1) << 32;
-        while (l < h) { uint32_t m = (l + h) >> 1; if (keys[m] < t0) l = m + 1; else h = m; }
-        lo = l; h = b.n_win_total;
-        while (l < h) { uint32_t m = (l + h) >> 1; if (keys[m] < t1) l = m + 1; else h = m; }
-        hi = l;
-    }
-    const uint32_t n = hi - lo;
-    PairResult res{-1.f, 0.f, 0.f, n, 0, b.a_off[pd.seed_off + Q.n_seeds] - b.a_off[pd.seed_off]};
-    if (n) {
-        uint32_t s_lo = 0, s_hi = n;
-        if (C.robust) { s_lo = n / 10; s_hi = n * 9 / 10; if (s_hi <= s_lo) { s_lo = 0; s_hi = n; } }
-        const double inv_k = 1.0 / (double)C.k;
-        double wsum = 0, ssum = 0, covq = 0, covr = 0, chains = 0;
-        for (uint32_t t = lane; t < n; t += 32) {
-            const WindowRec rec = b.win_rec[vals[lo + t]];
+    PairResult res{-1.f, 0.f, 0.f, 0, 0, b.a_off[pd.seed_off + Q.n_seeds] - b.a_off[pd.seed_off]};
+    const double inv_k = 1.0 / (double)C.k;
+    double wsum = 0, ssum = 0, covq = 0, covr = 0, chains = 0;
+    uint32_t n = 0;
+    double median_ani = 0;
+    if (keys == nullptr) {
+        // seed-weighted mean (the default): the order of the windows does not matter, so the pair's window slots are read
+        // in place and the key sort is skipped
+        const uint32_t w0 = pd.win_off, w1 = pd.win_off + Q.win_cap;
+        for (uint32_t t = w0 + lane; t < w1; t += 32) {
+            if (b.win_end[t] <= b.win_start[t]) continue;
+            const WindowRec rec = b.win_rec[t];
+            if (!rec.n_chains || !rec.seeds) continue;
+            n++;
             covq += rec.cov_q; covr += rec.cov_r; chains += rec.n_chains;
-            if (t >= s_lo && t < s_hi) {
-                double ratio = (double)rec.anchors / (double)rec.seeds;
-                if (ratio > 1.0) ratio = 1.0;
-                wsum += pow(ratio, inv_k) * (double)rec.seeds;
-                ssum += (double)rec.seeds;
-            }
-        }
-        wsum = warp_sum_f64(wsum); ssum = warp_sum_f64(ssum);
-        covq = warp_sum_f64(covq); covr = warp_sum_f64(covr); chains = warp_sum_f64(chains);
-        double ani = wsum / ssum;
-        if (C.median) {
-            const WindowRec rec = b.win_rec[vals[lo + n / 2]];
             double ratio = (double)rec.anchors / (double)rec.seeds;
             if (ratio > 1.0) ratio = 1.0;
-            ani = pow(ratio, inv_k);
+            wsum += pow(ratio, inv_k) * (double)rec.seeds;
+            ssum += (double)rec.seeds;
         }
+        n = __reduce_add_sync(FULL, n);
+    } else {
+        // robust / median: windows in ascending order of anchors / seeds; segment of this pair in the sorted key array
+        uint32_t lo = 0, hi = b.n_win_total;
+        {
+            uint32_t l = 0, h = b.n_win_total;
+            const uint64_t t0 = (uint64_t)p << 32, t1 = (uint64_t)(p + 1) << 32;
+            while (l < h) { uint32_t m = (l + h) >> 1; if (keys[m] < t0) l = m + 1; else h = m; }
+            lo = l; h = b.n_win_total;
+            while (l < h) { uint32_t m = (l + h) >> 1; if (keys[m] < t1) l = m + 1; else h = m; }
+            hi = l;
+        }
+        n = hi - lo;
+        if (n) {
+            uint32_t s_lo = 0, s_hi = n;
+            if (C.robust) { s_lo = n / 10; s_hi = n * 9 / 10; if (s_hi <= s_lo) { s_lo = 0; s_hi = n; } }
+            for (uint32_t t = lane; t < n; t += 32) {
+                const WindowRec rec = b.win_rec[vals[lo + t]];
+                covq += rec.cov_q; covr += rec.cov_r; chains += rec.n_chains;
+                if (t >= s_lo && t < s_hi) {
+                    double ratio = (double)rec.anchors / (double)rec.seeds;
+                    if (ratio > 1.0) ratio = 1.0;
+                    wsum += pow(ratio, inv_k) * (double)rec.seeds;
+                    ssum += (double)rec.seeds;
+                }
+            }
+            if (C.median) {
+                const WindowRec rec = b.win_rec[vals[lo + n / 2]];
+                double ratio = (double)rec.anchors / (double)rec.seeds;
+                if (ratio > 1.0) ratio = 1.0;
+                median_ani = pow(ratio, inv_k);
+            }
+        }
+    }
+    res.n_windows = n;
+    if (n) {
+        wsum = warp_sum_f64(wsum); ssum = warp_sum_f64(ssum);
+        covq = warp_sum_f64(covq); covr = warp_sum_f64(covr); chains = warp_sum_f64(chains);
+        double ani = C.median ? median_ani : wsum / ssum;
         double afq = covq / (double)Q.total_len, afr = covr / (double)R.total_len;
         if (afq > 1.0) afq = 1.0;
         if (afr > 1.0) afr = 1.0;

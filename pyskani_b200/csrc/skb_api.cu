@@ -1379,14 +1379,17 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
                 launch_anchor_fill(B, st);
                 launch_window_walk(B, C, max_qseeds, st);
                 launch_chain_dp(B, C, st);
-                launch_window_keys(B, st);
-                {
+                if (C.robust || C.median) {
+                    // only the trimmed mean and the median need the windows ordered by their anchors / seeds ratio
+                    launch_window_keys(B, st);
                     int pbits = 1;
                     while ((1ull << pbits) <= (uint64_t)np) pbits++;
                     sort_window_keys((uint32_t)wins, B.sort_keys, keys_sorted, B.sort_vals, vals_sorted, 32 + pbits, base + o_sort,
                                      sort_bytes, st);
+                    launch_ani_reduce(B, C, keys_sorted, vals_sorted, st);
+                } else {
+                    launch_ani_reduce(B, C, nullptr, nullptr, st);
                 }
-                launch_ani_reduce(B, C, keys_sorted, vals_sorted, st);
                 CU(cudaGetLastError());          // a launch that was refused (configuration) must not pass silently
                 uint32_t n_anchors = 0;
                 download(c, &n_anchors, B.a_off + seeds, 1);

@@ -13,7 +13,8 @@ def capture(fn, *a):
     return buf.getvalue()
 
 KERNELS = ["seed_scan_kernel", "chain_dp_kernel", "window_walk_smem_kernel", "marker_screen_smem_kernel", "marker_join_kernel",
-           "bucket_scatter_kernel", "bucket_rank_kernel", "region_gather_kernel", "match_count_kernel", "anchor_fill_kernel"]
+           "bucket_scatter_kernel", "bucket_rank_kernel", "region_gather_kernel", "match_count_kernel", "anchor_fill_kernel",
+           "marker_sort_smem_kernel"]
 for k in KERNELS:
     rep = os.path.join(G, "r1e_%s.ncu-rep" % k)
     if not os.path.exists(rep):
@@ -41,7 +42,7 @@ L = [(r[kn], float(r[mv].replace(',', '')) / 1e3) for r in rows[hi + 1:] if len(
 idx = [i for i, (n, t) in enumerate(L) if 'seed_scan_kernel' in n]
 step = L[idx[1]:idx[2]]
 def short(n):
-    m = re.search(r'skb::<unnamed>::(\w+)', n)
+    m = re.search(r'skb::(?:<unnamed>::)?(\w+)\(', n)
     if m: return m.group(1)
     if 'RadixSort' in n: return 'CUB segmented/device radix sort (markers, window keys)'
     if 'Scan' in n: return 'CUB scan'
