@@ -14,7 +14,7 @@ def capture(fn, *a):
 
 KERNELS = ["seed_scan_kernel", "chain_dp_kernel", "window_walk_smem_kernel", "marker_screen_smem_kernel", "marker_join_kernel",
            "bucket_scatter_kernel", "bucket_rank_kernel", "region_gather_kernel", "match_count_kernel", "anchor_fill_kernel",
-           "marker_sort_smem_kernel"]
+           "marker_sort_smem_kernel", "ani_reduce_kernel"]
 for k in KERNELS:
     rep = os.path.join(G, "r1e_%s.ncu-rep" % k)
     if not os.path.exists(rep):
