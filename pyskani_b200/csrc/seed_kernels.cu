@@ -311,6 +311,14 @@ __global__ void genome_starts_kernel(uint32_t n_regions, const uint64_t* __restr
     genome_marker_start[g] = (uint32_t)(st >> 32) + genome_marker_local[g];
 }
 
+// [seed_start[n] | marker_start[n] | overflow] -> pinned host memory (seed_start == NULL: only the flag)
+__global__ void counters_to_host_kernel(const uint32_t* __restrict__ seed_start, const uint32_t* __restrict__ marker_start, uint32_t n,
+                                        const uint32_t* __restrict__ overflow, uint32_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seed_start && i < n) { out[i] = seed_start[i]; out[n + i] = marker_start[i]; }
+    if (i == 0) out[2 * (size_t)n] = *overflow;
+}
+
 // last genome whose seed_start <= i (empty genomes share their successor's start and are skipped by the search order)
 __device__ __forceinline__ uint32_t gather_genome_of(const BucketGenome* __restrict__ G, uint32_t n_genomes, uint32_t i) {
     uint32_t lo = 0, hi = n_genomes;
@@ -360,6 +368,12 @@ void launch_genome_starts(uint32_t n_regions, const uint64_t* region_start, uint
     genome_starts_kernel<<<(n_genomes + 1 + 255) / 256, 256, 0, st>>>(n_regions, region_start, n_genomes, genome_region,
                                                                        genome_seed_local, genome_marker_local, genome_seed_start,
                                                                        genome_marker_start);
+    g_kernel_launches++;
+}
+
+void launch_counters_to_host(const uint32_t* seed_start, const uint32_t* marker_start, uint32_t n, const uint32_t* overflow,
+                             uint32_t* host_out, cudaStream_t st) {
+    counters_to_host_kernel<<<seed_start ? (n + 255) / 256 : 1, 256, 0, st>>>(seed_start, marker_start, n, overflow, host_out);
     g_kernel_launches++;
 }
 

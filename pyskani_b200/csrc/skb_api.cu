@@ -78,6 +78,9 @@ struct Core {
     cudaEvent_t ev[8]{};
     void* pinned = nullptr;        // staging for small contigs / tables
     size_t pinned_bytes = 0;
+    uint32_t* pinned_cnt = nullptr; // small results written by kernels straight into host memory
+    size_t pinned_cnt_words = 0;
+    uint32_t* pinned_counts(size_t words);
     // grow-only scratch blocks reused by every call on this context (calls are serialised by `mu`): keeps the big
     // transient buffers out of the allocator so that repeated batches never re-map device memory
     struct Block { void* p = nullptr; size_t bytes = 0; };
@@ -105,6 +108,7 @@ struct Core {
         if (stream) cudaStreamSynchronize(stream);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (pinned) cudaFreeHost(pinned);
+        if (pinned_cnt) cudaFreeHost(pinned_cnt);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -132,6 +136,16 @@ struct Fail {
             throw Fail{_e == cudaErrorMemoryAllocation ? SKB_ERR_NOMEM : SKB_ERR_CUDA,              \
                        std::string(#expr) + ": " + cudaGetErrorString(_e)};                        \
     } while (0)
+
+uint32_t* Core::pinned_counts(size_t words) {
+    if (pinned_cnt_words < words) {
+        if (pinned_cnt) { CU(cudaStreamSynchronize(stream)); cudaFreeHost(pinned_cnt); pinned_cnt = nullptr; pinned_cnt_words = 0; }
+        const size_t want = std::max<size_t>(words + words / 2, 4096);
+        CU(cudaHostAlloc((void**)&pinned_cnt, 4 * want, cudaHostAllocDefault));
+        pinned_cnt_words = want;
+    }
+    return pinned_cnt;
+}
 
 void* Core::scratch(int slot, size_t bytes) {
     Block& b = arena[slot];
@@ -425,13 +439,19 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
                 // the retry reads its layout from r_sstart / r_mstart, so the scan must not run again after it
                 scan_region_counts(n_regions, r_cnt, r_start, rscan_scratch, rscan_bytes, st);
                 launch_genome_starts(n_regions, r_start, n_genomes, g_region, g_slocal, g_mlocal, d_gs, d_gm, st);
-                download(c, seed_start.data(), d_gs, n_genomes + 1);
-                download(c, marker_start.data(), d_gm, n_genomes + 1);
             }
-            download(c, &h_over, d_overflow, 1);
+            // per-genome starts and the overflow flag reach the host through one small kernel that writes into pinned
+            // host memory (three device->host copies would each cost a copy-engine round trip)
+            uint32_t* h_counts = c.pinned_counts(2 * ((size_t)n_genomes + 1) + 1);
+            launch_counters_to_host(attempt == 0 ? d_gs : nullptr, attempt == 0 ? d_gm : nullptr, n_genomes + 1, d_overflow, h_counts, st);
             t2.mark("enqueued seed+scan");
             CU(cudaStreamSynchronize(st));
             t2.mark("sync after seed");
+            if (attempt == 0) {
+                std::memcpy(seed_start.data(), h_counts, 4 * ((size_t)n_genomes + 1));
+                std::memcpy(marker_start.data(), h_counts + n_genomes + 1, 4 * ((size_t)n_genomes + 1));
+            }
+            h_over = h_counts[2 * ((size_t)n_genomes + 1)];
             if (!h_over) break;
             if (attempt == 1) throw Fail{SKB_ERR_CUDA, "seed regions overflowed twice"};
         }
@@ -448,6 +468,7 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
         uint64_t* t_mkeys = (uint64_t*)c.scratch(SLOT_MKEYS2, 8 * (size_t)nm + 16);
         char* d_tab = nullptr;
         uint32_t* d_bover = nullptr;
+        uint32_t* d_gm_in = nullptr;          // pre-deduplication marker offsets (d_gm is overwritten with the final ones)
         {
             RegionGatherArgs ga{};
             ga.n_regions = n_regions; ga.seed_src = r_ssrc; ga.marker_src = r_msrc; ga.region_start = r_start;
@@ -456,11 +477,16 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             ga.marker_keys = t_mkeys;
             // the gather also builds the per-genome k-mer bucket histogram of the index build (saves a pass over kmer_p)
             for (uint32_t g = 0; g < n_genomes; g++) { bplan.genomes[g].seed_start = seed_start[g]; bplan.genomes[g].n_seeds = seed_start[g + 1] - seed_start[g]; }
+            // one upload: [bucket plan per genome | bucket-overflow flag = 0 | pre-deduplication marker offsets]
             const size_t tab_bytes = sizeof(BucketGenome) * n_genomes;
-            d_tab = (char*)c.scratch(SLOT_BTAB, tab_bytes + 16);
-            table_upload(c, d_tab, bplan.genomes.data(), tab_bytes);
-            d_bover = (uint32_t*)(d_tab + (tab_bytes + 3) / 4 * 4);
-            CU(cudaMemsetAsync(d_bover, 0, 4, st));
+            const size_t over_off = (tab_bytes + 15) & ~(size_t)15, gm_off = over_off + 16;
+            std::vector<char> blob(gm_off + g_bytes, 0);
+            std::memcpy(blob.data(), bplan.genomes.data(), tab_bytes);
+            std::memcpy(blob.data() + gm_off, marker_start.data(), g_bytes);
+            d_tab = (char*)c.scratch(SLOT_BTAB, blob.size());
+            table_upload(c, d_tab, blob.data(), blob.size());
+            d_bover = (uint32_t*)(d_tab + over_off);
+            d_gm_in = (uint32_t*)(d_tab + gm_off);
             CU(cudaMemsetAsync(d_bcounts, 0, 4 * bplan.total, st));
             ga.genomes = (const BucketGenome*)d_tab; ga.n_genomes = n_genomes; ga.bucket_counts = d_bcounts;
             launch_region_gather(ga, st);
@@ -471,10 +497,6 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
         {
             const size_t mark_bytes = marker_scratch_bytes(nm, n_genomes);
             void* mark_scratch = c.scratch(SLOT_MARK, mark_bytes);
-            // pre-deduplication offsets (repaired on the host like the seed starts) live in their own small buffer: d_gm is
-            // overwritten with the post-deduplication offsets
-            uint32_t* d_gm_in = (uint32_t*)c.scratch(SLOT_GM_IN, g_bytes);
-            table_upload(c, d_gm_in, marker_start.data(), g_bytes);
             uint32_t max_gm = 0;
             for (uint32_t g = 0; g < n_genomes; g++) max_gm = std::max(max_gm, marker_start[g + 1] - marker_start[g]);
             CU(cudaEventRecord(c.ev[6], st));
@@ -552,8 +574,10 @@ static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_par
     }
     if (!d_bucket_overflow) store->bucket = DevMem::persistent(core, 4 * bucket_total);
     store->contig_seed_start = DevMem::persistent(core, 4 * std::max<size_t>(cstart_total, 1));
-    store->contig_win_start = DevMem::persistent(core, 4 * std::max<size_t>(cstart_total, 1));
-    store->contig_len = DevMem::persistent(core, 4 * std::max<size_t>(h_clen.size(), 1));
+    // contig lengths and window starts share one block (one upload): [lengths | window starts]
+    const size_t clen_words = (h_clen.size() + 3) & ~(size_t)3;
+    store->contig_len = DevMem::persistent(core, 4 * (clen_words + std::max<size_t>(cstart_total, 1)));
+    uint32_t* cwin_base = store->contig_len.as<uint32_t>() + clen_words;
     for (uint32_t g = 0; g < n_genomes; g++) {
         GenomeView& v = views[g];
         const size_t so = seed_start[g];
@@ -562,15 +586,19 @@ static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_par
         v.pos_k = store->pos_k.as<uint32_t>() + so; v.meta_k = store->meta_k.as<uint32_t>() + so;
         v.bucket = store->bucket.as<uint32_t>() + bucket_off[g];
         v.contig_seed_start = store->contig_seed_start.as<uint32_t>() + cstart_off[g];
-        v.contig_win_start = store->contig_win_start.as<uint32_t>() + cstart_off[g];
+        v.contig_win_start = cwin_base + cstart_off[g];
         v.contig_len = store->contig_len.as<uint32_t>() + clen_off[g];
         v.markers = nullptr;
     }
     {
         DevMem d_views(core, sizeof(GenomeView) * n_genomes);
         table_upload(c, d_views.p, views.data(), sizeof(GenomeView) * n_genomes);
-        table_upload(c, store->contig_len.p, h_clen.data(), 4 * h_clen.size());
-        table_upload(c, store->contig_win_start.p, h_cwin.data(), 4 * h_cwin.size());
+        {
+            std::vector<uint32_t> both(clen_words + h_cwin.size(), 0u);
+            std::copy(h_clen.begin(), h_clen.end(), both.begin());
+            std::copy(h_cwin.begin(), h_cwin.end(), both.begin() + clen_words);
+            table_upload(c, store->contig_len.p, both.data(), 4 * both.size());
+        }
         // per-genome layout of contig_win_start mirrors contig_seed_start (nc + 1 entries each)
         if (!d_bucket_overflow) launch_build_buckets(d_views.as<GenomeView>(), n_genomes, max_buckets, st);
         launch_contig_starts(d_views.as<GenomeView>(), n_genomes, max_contigs, st);

@@ -110,6 +110,8 @@ struct RegionGatherArgs {
     const BucketGenome* genomes; uint32_t n_genomes; uint32_t* bucket_counts;     // bucket_counts == NULL: no histogram
 };
 void launch_region_gather(const RegionGatherArgs& a, cudaStream_t st);
+void launch_counters_to_host(const uint32_t* seed_start, const uint32_t* marker_start, uint32_t n, const uint32_t* overflow,
+                             uint32_t* host_out, cudaStream_t st);
 
 void launch_seed_scan(const SeedScanArgs& a, int n_sm, cudaStream_t st);
 
