@@ -11,6 +11,7 @@
 #include <cstring>
 
 #include "skb_internal.cuh"
+#include "slab_pool.h"
 
 namespace skb {
 
@@ -18,54 +19,21 @@ void launch_screen_decide(const GenomeView*, uint32_t, const GenomeView*, uint32
                           uint8_t*, cudaStream_t);
 void select_passing(uint32_t n, const uint8_t* flags, uint32_t* out_idx, uint32_t* out_count, cudaStream_t st);
 
-// Storage of the sketches themselves.  Sketch arrays live as long as their handles, so they cannot sit in the grow-only
-// scratch arena; the stream-ordered pool (cudaMallocAsync) turned out to need 20-150 ms per 100 MB batch while it grows
-// (against < 1 ms for a 1 GB cudaMalloc).  So: slabs from cudaMalloc (64 MB doubling to 1 GB, or the request if larger),
-// bump allocation inside the current slab, one live-count per slab.  A slab whose count returns to zero is reused from
-// the start; freeing the most recent allocation rolls the bump pointer back, which is what the query-sketch-per-call
-// pattern of Database.query produces.  All users of the memory are ordered on the context's stream, so reuse needs no event.
-struct Slab { char* base = nullptr; size_t cap = 0, used = 0; uint32_t live = 0; };
-struct SlabPool {
-    std::mutex mu;
-    std::vector<std::unique_ptr<Slab>> slabs;
-    Slab* cur = nullptr;
-    size_t next_cap = (size_t)64 << 20;
-    void* alloc(size_t bytes, Slab** owner) {
-        bytes = (bytes + 511) & ~(size_t)511;
-        std::lock_guard<std::mutex> lock(mu);
-        if (!cur || cur->used + bytes > cur->cap) {
-            Slab* pick = nullptr;
-            for (auto& sl : slabs) if (sl->live == 0 && sl->cap >= bytes && (!pick || sl->cap < pick->cap)) pick = sl.get();
-            if (!pick) {
-                std::unique_ptr<Slab> sl(new Slab);
-                sl->cap = std::max(next_cap, bytes);
-                const auto t0 = std::chrono::steady_clock::now();
-                cudaError_t e = cudaMalloc((void**)&sl->base, sl->cap);
-                if (std::getenv("SKB_TRACE"))
-                    std::fprintf(stderr, "[skb] slab: cudaMalloc of %zu MB took %.3f ms\n", sl->cap >> 20,
-                                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
-                if (e != cudaSuccess && sl->cap > bytes) { cudaGetLastError(); sl->cap = bytes; e = cudaMalloc((void**)&sl->base, sl->cap); }
-                if (e != cudaSuccess) { cudaGetLastError(); return nullptr; }
-                next_cap = std::min(next_cap * 2, (size_t)1 << 30);
-                pick = sl.get();
-                slabs.push_back(std::move(sl));
-            }
-            pick->used = 0;
-            cur = pick;
-        }
-        void* p = cur->base + cur->used;
-        cur->used += bytes; cur->live++;
-        *owner = cur;
+// Storage of the sketches themselves: slabs from cudaMalloc with bump allocation (slab_pool.h)
+struct CudaRawAlloc {
+    void* operator()(size_t bytes) const {
+        void* p = nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
+        const cudaError_t e = cudaMalloc(&p, bytes);
+        if (std::getenv("SKB_TRACE"))
+            std::fprintf(stderr, "[skb] slab: cudaMalloc of %zu MB took %.3f ms\n", bytes >> 20,
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        if (e != cudaSuccess) { cudaGetLastError(); return nullptr; }
         return p;
     }
-    void free(Slab* sl, void* p, size_t bytes) {
-        bytes = (bytes + 511) & ~(size_t)511;
-        std::lock_guard<std::mutex> lock(mu);
-        if ((char*)p + bytes == sl->base + sl->used) sl->used -= bytes;
-        if (--sl->live == 0) sl->used = 0;
-    }
-    void destroy() { for (auto& sl : slabs) if (sl->base) cudaFree(sl->base); slabs.clear(); cur = nullptr; }
 };
+struct CudaRawFree { void operator()(void* p) const { cudaFree(p); } };
+using SlabPool = SlabPoolT<CudaRawAlloc, CudaRawFree>;
 
 struct Core {
     int device = 0;
