@@ -108,6 +108,29 @@ def test_marker_sets_all_three_sort_paths(ctx):
         assert_sketch_equal(g, oracle.Sketch(contigs))
 
 
+def test_host_copies_merged_or_separate_give_the_same_sketch(ctx, monkeypatch):
+    """Contigs laid out back to back in one host buffer (16-byte aligned, the device layout's spacing) are transferred as
+    merged copies; the same contigs as separate objects, or with merging switched off, must give identical sketches."""
+    lens = [300_000, 262_144, 1_000_003, 700, 400_000, 262_145, 1_500_000, 263_000]
+    seqs = [np.frombuffer(rand(l, 500 + i), np.uint8) for i, l in enumerate(lens)]
+    big = np.zeros(sum((l + 15) // 16 * 16 + 16 for l in lens) + 64, np.uint8)
+    views, off = [], 16
+    for s_ in seqs:
+        big[off:off + len(s_)] = s_
+        views.append(big[off:off + len(s_)])
+        off += (len(s_) + 15) // 16 * 16 + 16
+    split = [(0, 3), (3, 5), (5, 8)]
+    merged = ctx.sketch_batch([views[a:b] for a, b in split])
+    separate = ctx.sketch_batch([[x.tobytes() for x in seqs[a:b]] for a, b in split])
+    monkeypatch.setenv("SKB_NO_COPY_MERGE", "1")
+    unmerged = ctx.sketch_batch([views[a:b] for a, b in split])
+    for x, y, z in zip(merged, separate, unmerged):
+        ex, ey, ez = x.export(), y.export(), z.export()
+        for key in ex:
+            assert np.array_equal(ex[key], ey[key]) and np.array_equal(ex[key], ez[key]), key
+    assert_sketch_equal(merged[0], oracle.Sketch([x.tobytes() for x in seqs[0:3]]))
+
+
 def test_sketch_junk_and_lowercase(ctx):
     rng = np.random.default_rng(3)
     alpha = np.frombuffer(b"ACGTacgtNnRYKM-*", np.uint8)
