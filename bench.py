@@ -1,20 +1,28 @@
 #!/usr/bin/env python
-"""bench.py — BASELINE.json's metric on its single-GPU configuration (configs[1]):
+"""bench.py — BASELINE.json's metric on the configuration it is quoted on (configs[2]):
 
-    one synthetic 5 Mbp genome queried against 100 mutated copies (1-15 % divergence, 10 % of the events
-    indels), per GPU.  One step = the whole hot path once: sketch the 100 references and the query
-    (FracMinHash seeding + index build), marker screen, anchor lookup + chaining, ANI/AF.
+    all-vs-all ANI of 1 000 synthetic 5 Mbp genomes (100 families x 10: a random root + 9 mutants at 1-15 % divergence,
+    10 % of the events indels) at 1 / 2 / 4 / 8 B200.
+
+One step = the whole job once, through the product's multi-GPU path (pyskani_b200.parallel):
+    every rank sketches its share of the genomes (FracMinHash seeding + index build)            [skb_sketch_batch*]
+    -> the sketch database is exchanged ONCE over NVLink, device to device                      [skb_exchange_* + NCCL]
+    -> every rank screens its genomes against all 1 000, chains the survivors, computes ANI/AF  [skb_db_query]
+    -> the hit table is gathered on rank 0 (host memory).
+`--gpus N` is STRONG scaling: the same 10^6 ordered pairs are split over N ranks by query.
 
 Reported (one JSON line, rank 0):
-    value        ANI pairs/s with the ASCII sequences already resident in HBM (device-timed, max over ranks)
-    e2e          the same through the host-buffer C-ABI calls: pinned host ASCII -> H2D -> ... -> hits on the host
-    sketch_gbps  sketching throughput alone (Gbp/s, device-resident input)
+    value        ANI pairs/s (all 10^6 ordered pairs / step time) with the ASCII genomes resident in HBM
+    e2e          the same with the genomes in pinned HOST memory: H2D copies inside the timed region, hits on the host
+    sketch_gbps, screen_pairs_per_s, chained_pairs_per_s, phase_ms, exchange {ms, bytes, busbw}
     roofline     the seeding kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
-    cpu_baseline the CPU oracle (a port of skani's algorithm; the Rust reference cannot be built here) on
-                 the same workload, all host threads
-`--impl reference` times that CPU port alone (the reference arm of this tier).
-Multi-GPU (`torchrun ... bench.py --gpus N`): each rank owns an independent 1-vs-100 family (weak scaling,
-no data-path collective — SURVEY.md §8e; the sketch-DB all-gather only exists for all-vs-all workloads).
+    parity       after the timed region, a fixed sample is compared with the CPU oracle (sketches bit-exact, every
+                 screen decision of 10 queries, >= 200 chained pairs: ANI <= 1e-4, AF <= 1e-3; at N > 1 the multi-GPU
+                 hit table must equal a single-GPU run).  A mismatch exits non-zero.
+    cpu_baseline the CPU port of skani's algorithm (oracle/; the Rust reference cannot be built here) on a bounded
+                 sample of the same workload, all host threads (N = 1 only)
+    configs1     secondary block: configs[1], 1 genome vs 100 mutated copies on one GPU (the round-1 headline)
+`--impl reference` times that CPU port alone, on the same workload definition (the reference arm of this tier).
 """
 import argparse
 import ctypes as C
@@ -31,7 +39,31 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALG_BYTES_PER_BASE = 1.0 + 16.0 / 125.0 + 8.0 / 1000.0   # 1 B read + seeds + markers written
-NCU_SEED_TRAFFIC_BYTES = 508_747_008 + 16_123_392         # profiles/r1_seed_scan_kernel_ncu_full.txt (read + write, one launch)
+METRIC = "ANI pairs/s, all-vs-all (sketch + exchange + screen + chain + ANI)"
+
+
+def workload_string(a):
+    return ("configs[2]: all-vs-all of %d synthetic %d bp genomes (%d families x %d: root + mutants at 1-15%% divergence, indels)"
+            % (a.families * a.members, a.genome_len, a.families, a.members))
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--genome-len", type=int, default=5_000_000)
+    ap.add_argument("--families", type=int, default=100)
+    ap.add_argument("--members", type=int, default=10)
+    ap.add_argument("--sketch-batch", type=int, default=250, help="genomes per skb_sketch_batch call")
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries of the CPU sample (default: about 96, a multiple of the threads)")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-parity", action="store_true")
+    ap.add_argument("--skip-configs1", action="store_true")
+    ap.add_argument("--n-refs", type=int, default=100, help="configs[1] block: mutated copies")
+    return ap.parse_args()
 
 
 def bind_to_gpu_cpus(index, uuid=None):
@@ -60,31 +92,6 @@ def bind_to_gpu_cpus(index, uuid=None):
         return "cpus %d-%d (%d) local to the GPU" % (allowed[0], allowed[-1], len(allowed))
     except Exception as e:       # noqa: BLE001 - purely an optimisation
         return "unchanged (%s)" % type(e).__name__
-
-
-def parse():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--genome-len", type=int, default=5_000_000)
-    ap.add_argument("--n-refs", type=int, default=100)
-    ap.add_argument("--cpu-threads", type=int, default=0)
-    ap.add_argument("--skip-cpu-baseline", action="store_true")
-    return ap.parse_args()
-
-
-def make_family(genome_len, n_refs, rank):
-    """base seed 0x5EED0000 (+ rank family), mutant j at d_j = 1 % + 14 % * j / (n-1)."""
-    from concurrent.futures import ThreadPoolExecutor
-    from pyskani_b200 import synth
-    seed0 = 0x5EED0000 + 100_000 * rank
-    base = synth.random_genome(genome_len, seed0)
-    divs = [0.01 + 0.14 * j / max(1, n_refs - 1) for j in range(n_refs)]
-    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
-        refs = list(ex.map(lambda j: synth.mutate(base, divs[j], seed0 + 1 + j), range(n_refs)))
-    return base, refs, divs
 
 
 class ClockSampler:
@@ -162,50 +169,196 @@ class ClockSampler:
         return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
 
 
-def cpu_step(base, refs, threads):
-    """The same step on the CPU oracle: sketch all genomes, then pyskani's query loop."""
-    import oracle
+# ------------------------------------------------------------------------------------------------ workload
+class HostGenomes:
+    """The genomes `ids` as ASCII in consecutive 16-aligned slots of one uint8 buffer (ordinary or pinned memory)."""
+
+    def __init__(self, ids, genome_len, members, buf=None, threads=None):
+        import workload
+        self.ids = list(ids)
+        self.slot = workload.slot_bytes(genome_len)
+        self.lead = 64                                             # guard in front of the first contig (device layout)
+        nbytes = self.lead + self.slot * len(self.ids) + 64
+        self.buf = buf if buf is not None else np.zeros(nbytes, np.uint8)
+        assert self.buf.size >= nbytes
+        self.nbytes = nbytes
+        self.lens = workload.fill_families(self.buf[self.lead:], self.slot, genome_len, self.ids, members=members,
+                                           divergences=workload.FAMILY_DIVERGENCES[:members] if members <= len(workload.FAMILY_DIVERGENCES)
+                                           else tuple(0.15 * m / (members - 1) for m in range(members)), threads=threads)
+        self.offs = np.array([self.lead + j * self.slot for j in range(len(self.ids))], np.uint64)
+
+    def view(self, j):
+        o = int(self.offs[j])
+        return self.buf[o:o + int(self.lens[j])]
+
+
+def cpu_sample_size(threads, want=0):
+    if want:
+        return want
+    return threads * max(1, round(96 / threads))
+
+
+def cpu_sample_step(oracle, host, sample, db_sketches, threads):
+    """A bounded sample of the all-vs-all job on the CPU port: sketch the sample's genomes, query them against the full
+    database (whose sketches exist already).  Returns (sketch s, query s, hits, screened-in)."""
     t0 = time.perf_counter()
-    sk = oracle.sketch_batch([[r] for r in refs] + [[base]], threads=threads)
+    sk = oracle.sketch_batch([[host.view(j)] for j in sample], threads=threads)
     t1 = time.perf_counter()
-    idx, res, n_in = oracle.query(sk[-1], sk[:-1], 0.8, True, threads=threads)
+    hq, hr, res, n_in = oracle.query_many(sk, db_sketches, 0.8, True, threads=threads)
     t2 = time.perf_counter()
-    return t1 - t0, t2 - t1, len(idx)
+    return t1 - t0, t2 - t1, len(hq), n_in
 
 
 def run_reference(args, rank, world):
-    """Reference arm: the CPU port of the path (oracle/), all host threads, rank 0 only."""
+    """Reference arm: the CPU port of the path (oracle/), all host threads, rank 0 only.  Imports nothing of the product."""
     if rank != 0:
         return
     import oracle
     oracle.lib()
     threads = args.cpu_threads or (os.cpu_count() or 1)
-    base, refs, _ = make_family(args.genome_len, args.n_refs, 0)
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_step(base, refs, threads)
-    times = []
+    n_total = args.families * args.members
+    host = HostGenomes(range(n_total), args.genome_len, args.members)
+    db = oracle.sketch_batch([[host.view(j)] for j in range(n_total)], threads=threads)      # the database side, not timed
+    n_s = min(n_total, cpu_sample_size(threads, args.cpu_sample))
+    sample = list(range(n_s))
+    for _ in range(args.warmup):
+        cpu_sample_step(oracle, host, sample, db, threads)
+    times, sk_t, q_t = [], [], []
     for _ in range(args.steps):
-        a, b, nh = cpu_step(base, refs, threads)
-        times.append(a + b)
+        a, b, nh, n_in = cpu_sample_step(oracle, host, sample, db, threads)
+        times.append(a + b); sk_t.append(a); q_t.append(b)
     ms = 1e3 * float(np.mean(times))
-    val = args.n_refs / (ms / 1e3)
+    pairs = n_s * n_total
+    val = pairs / (ms / 1e3)
+    sample_txt = ("per step: sketch %d of the %d genomes and query them against all %d (= %d of the %d ordered pairs, same %.1f %% "
+                  "of them screened in), CPU port of skani's algorithm (oracle/) with OpenMP over genomes and pairs; the Rust "
+                  "reference itself cannot be built in this image" % (n_s, n_total, n_total, pairs, n_total * n_total,
+                                                                      100.0 * n_in / max(pairs, 1)))
     line = {
-        "impl": "reference", "metric": "ANI pairs/s (sketch + screen + chain + ANI, 1 x 5 Mbp query vs 100 mutated refs)",
-        "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-        "data": "synthetic",
-        "config": {"workload": "configs[1]: 1 synthetic %d bp genome vs %d mutated copies (1-15%% divergence, indels)"
-                               % (args.genome_len, args.n_refs), "cpu_only": True},
-        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "port",
-                         "sample": "the full step (sketch %d genomes + 1 x %d query), CPU port of skani's algorithm "
-                                   "(oracle/); the Rust reference itself cannot be built in this image"
-                                   % (args.n_refs + 1, args.n_refs)},
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_string(args), "k": 15, "c": 125, "marker_c": 1000, "cpu_only": True},
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample_txt,
+                         "sketch_gbps": float(sum(int(host.lens[j]) for j in sample) / np.mean(sk_t) / 1e9),
+                         "chained_pairs_per_s": float(n_in / np.mean(q_t)), "hits_per_step": nh},
         "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ parity gate
+def parity_gate(args, capi, ctx, host_all, table, world, threads, oracle_db):
+    """Rank 0, after the timed region: a fixed sample of the job against the CPU oracle.  Raises on any mismatch."""
+    import oracle
+    from pyskani_b200 import parallel
+    n_total = len(host_all.ids)
+    members = args.members
+    out = {}
+    # (a) sketches: bit-exact seeds (k-mer, position, contig, strand) and marker sets for 8 genomes
+    sample_sk = sorted(set([0, 1, members - 1, n_total // 3, n_total // 2, n_total // 2 + 3, n_total - 2, n_total - 1]))
+    gs = ctx.sketch_batch([[host_all.view(j)] for j in sample_sk])
+    for j, g in zip(sample_sk, gs):
+        e = g.export()
+        ok, op, oc, ocan = oracle_db[j].seeds()
+        if not (np.array_equal(e["kmer"], ok) and np.array_equal(e["pos"], op) and np.array_equal(e["contig"], oc)
+                and np.array_equal(e["canonical"], ocan) and np.array_equal(e["markers"], oracle_db[j].markers())):
+            raise SystemExit("PARITY FAILURE: sketch of genome %d differs from the oracle" % j)
+    out["sketches_bit_exact"] = len(sample_sk)
+    del gs
+    # a single-GPU database of everything on rank 0 (not timed): screen sample + reference table for N > 1
+    be = parallel.CudaBackend(0, ctx=ctx)
+    full = []
+    for b0 in range(0, n_total, args.sketch_batch):
+        full += ctx.sketch_batch([[host_all.view(j)] for j in range(b0, min(n_total, b0 + args.sketch_batch))])
+    db = capi.Database(ctx)
+    db.add_many(full)
+    # (b) every screen decision of 10 queries (and the marker intersection sizes)
+    q_screen = [int(x) for x in np.linspace(0, n_total - 1, 10)]
+    ok_gpu, shared_gpu = db.screen([full[q] for q in q_screen])
+    for i, q in enumerate(q_screen):
+        for r in range(n_total):
+            ok, sh = oracle.screen(oracle_db[q], oracle_db[r])
+            if ok != bool(ok_gpu[i, r]) or sh != int(shared_gpu[i, r]):
+                raise SystemExit("PARITY FAILURE: screen of (%d, %d): GPU %s/%d, oracle %s/%d" % (q, r, ok_gpu[i, r], shared_gpu[i, r], ok, sh))
+    out["screen_decisions"] = len(q_screen) * n_total
+    # (c) chained pairs of the TIMED run's hit table: sample queries = whole families
+    n_q = min(n_total, max(2 * members, 20))
+    q_chain = list(range(n_q // 2)) + list(range(n_total - (n_q - n_q // 2), n_total))
+    hq, hr, res, n_in = oracle.query_many([oracle_db[q] for q in q_chain], oracle_db, 0.8, True, threads=threads)
+    want = {(q_chain[int(a)], int(b)): r for a, b, r in zip(hq, hr, res)}
+    sel = np.isin(table[:, 0].astype(np.int64), q_chain)
+    got = {(int(r[0]), int(r[1])): r for r in table[sel]}
+    if set(got) != set(want):
+        raise SystemExit("PARITY FAILURE: hit set of the sample queries differs from the oracle: only GPU %s, only oracle %s"
+                         % (sorted(set(got) - set(want))[:5], sorted(set(want) - set(got))[:5]))
+    worst_ani = worst_af = 0.0
+    for key, r in want.items():
+        g = got[key]
+        worst_ani = max(worst_ani, abs(g[2] - r.ani)); worst_af = max(worst_af, abs(g[3] - r.af_query), abs(g[4] - r.af_ref))
+    if worst_ani > 1e-4 or worst_af > 1e-3:
+        raise SystemExit("PARITY FAILURE: ANI/AF of the sample differ from the oracle by %.2e / %.2e" % (worst_ani, worst_af))
+    out.update({"chained_pairs": int(n_in), "hits_compared": len(want), "max_abs_ani_err": worst_ani, "max_abs_af_err": worst_af,
+                "tolerance": {"ani": 1e-4, "af": 1e-3}})
+    # (d) N > 1: the gathered table of the multi-GPU path against a single-GPU run of the same job
+    if world > 1:
+        single = be.query(full, full)
+        single = single[np.lexsort((single[:, 1], single[:, 0]))]
+        if single.shape != table.shape or not np.array_equal(single, table):
+            raise SystemExit("PARITY FAILURE: the %d-GPU hit table differs from the single-GPU table (%s vs %s rows)"
+                             % (world, table.shape, single.shape))
+        out["multi_gpu_table_equals_single_gpu"] = True
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ configs[1] block
+def configs1_block(args, capi, ctx, torch, stream):
+    """BASELINE.json configs[1]: one 5 Mbp genome against 100 mutated copies (1-15 %), device-resident, one GPU."""
+    import workload
+    n_refs = args.n_refs
+    slot = workload.slot_bytes(args.genome_len)
+    buf = np.zeros(64 + slot * (n_refs + 1) + 64, np.uint8)
+    base = workload.random_genome(args.genome_len, workload.SEED0 + 999_983)
+    lens = []
+    from concurrent.futures import ThreadPoolExecutor
+    def make(j):
+        d = 0.01 + 0.14 * j / max(1, n_refs - 1)
+        return workload.mutate_into(base.ctypes.data, len(base), d, workload.SEED0 + 999_984 + j, buf.ctypes.data + 64 + j * slot, slot - 16)
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+        lens = list(ex.map(make, range(n_refs)))
+    buf[64 + n_refs * slot:64 + n_refs * slot + len(base)] = base
+    lens.append(len(base))
+    offs = np.array([64 + j * slot for j in range(n_refs + 1)], np.uint64)
+    lens = np.array(lens, np.uint64)
+    d_ptr = ctx.dev_alloc(buf.size)
+    ctx.memcpy_h2d(d_ptr, buf.ctypes.data, buf.size)
+    gstart = np.arange(n_refs + 2, dtype=np.uint32)
+
+    def step():
+        sk = ctx.sketch_batch_device(d_ptr, gstart, offs, lens)
+        db = capi.Database(ctx)
+        db.add_many(sk[:-1])
+        hits, n_in = db.query_array([sk[-1]])
+        return len(hits)
+    for _ in range(max(3, args.warmup)):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.sync()
+    steps = max(5, args.steps)
+    e0.record(stream)
+    for _ in range(steps):
+        nh = step()
+    e1.record(stream)
+    ctx.sync(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ctx.dev_free(d_ptr)
+    return {"workload": "configs[1]: 1 synthetic %d bp genome vs %d mutated copies (1-15%% divergence, indels), device-resident, 1 GPU"
+                        % (args.genome_len, n_refs),
+            "value": n_refs / (ms / 1e3), "unit": "pairs/s", "ms_per_step": ms, "steps": steps, "hits_per_query": nh}
+
+
+# ------------------------------------------------------------------------------------------------ the B200 arm
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -216,65 +369,72 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from pyskani_b200 import capi
+    from pyskani_b200 import capi, parallel
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: pyskani_b200 has no CPU fallback (use --impl reference for the CPU port)")
     torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
     all_cpus = os.sched_getaffinity(0)
     numa = bind_to_gpu_cpus(local_rank, getattr(torch.cuda.get_device_properties(local_rank), "uuid", None))
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=device)
+    dgroup = dist if world > 1 else None
 
     ctx = capi.Context(local_rank)
     L = capi.lib()
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    backend = parallel.CudaBackend(local_rank, ctx=ctx)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=device)
 
-    # ---------------- synthetic inputs (not timed)
-    base, refs, divs = make_family(args.genome_len, args.n_refs, rank)
-    genomes = refs + [base]
-    n_g = len(genomes)
-    lens = np.array([len(g) for g in genomes], np.uint64)
-    total_bases = int(lens.sum())
-    # host side: one pinned buffer, contigs at 16-aligned offsets (what a caller holding FASTA records would pass)
-    offs = np.zeros(n_g, np.uint64)
-    cur = 64
-    for i, l in enumerate(lens):
-        offs[i] = cur
-        cur += (int(l) + 15) // 16 * 16 + 16
-    buf_bytes = cur + 64
-    h_ptr = ctx.host_alloc(buf_bytes)
-    h_arr = np.ctypeslib.as_array(C.cast(h_ptr, C.POINTER(C.c_uint8)), shape=(buf_bytes,))
-    for g, o in zip(genomes, offs):
-        h_arr[int(o):int(o) + len(g)] = g
-    d_ptr = ctx.dev_alloc(buf_bytes)
-    ctx.memcpy_h2d(d_ptr, h_ptr, buf_bytes)
-    gstart = np.arange(n_g + 1, dtype=np.uint32)
-
-    host_ptrs = (C.c_void_p * n_g)(*[h_ptr + int(o) for o in offs])
-    host_lens = (C.c_uint64 * n_g)(*[int(l) for l in lens])
-    gs_c = (C.c_uint32 * (n_g + 1))(*range(n_g + 1))
+    # ---------------- synthetic inputs (not timed): this rank's share, ASCII, in pinned host memory and in HBM
+    n_total = args.families * args.members
+    plan = parallel.partition_by_size([args.genome_len] * n_total, world)
+    mine = plan[rank]
+    import workload
+    slot = workload.slot_bytes(args.genome_len)
+    my_bytes = 64 + slot * len(mine) + 64
+    h_ptr = ctx.host_alloc(my_bytes)
+    h_arr = np.ctypeslib.as_array(C.cast(h_ptr, C.POINTER(C.c_uint8)), shape=(my_bytes,))
+    h_arr[:64] = 0; h_arr[-64:] = 0
+    host = HostGenomes(mine, args.genome_len, args.members, buf=h_arr)
+    my_bases = int(host.lens.sum())
+    d_ptr = ctx.dev_alloc(my_bytes)
+    ctx.memcpy_h2d(d_ptr, h_ptr, my_bytes)
+    n_mine = len(mine)
+    batches = [(b0, min(n_mine, b0 + args.sketch_batch)) for b0 in range(0, n_mine, args.sketch_batch)]
     params = capi.SketchParams(15, 125, 1000)
+    host_ptr_arrays = []
+    for b0, b1 in batches:
+        n = b1 - b0
+        host_ptr_arrays.append(((C.c_void_p * n)(*[h_ptr + int(host.offs[j]) for j in range(b0, b1)]),
+                                (C.c_uint64 * n)(*[int(host.lens[j]) for j in range(b0, b1)]),
+                                (C.c_uint32 * (n + 1))(*range(n + 1))))
 
-    def step_device():
-        """inputs resident in HBM"""
-        sk = ctx.sketch_batch_device(d_ptr, gstart, offs, lens)
-        st = ctx.stats()
-        db = capi.Database(ctx)
-        db.add_many(sk[:-1])
-        hits, n_in = db.query([sk[-1]])
-        st2 = ctx.stats()
-        return len(hits), st.seed_ms, st.total_ms, st2.total_ms
+    def sketch_device(tm):
+        sk, seed_ms, tot_ms = [], 0.0, 0.0
+        for b0, b1 in batches:
+            sk += ctx.sketch_batch_device(d_ptr, np.arange(b1 - b0 + 1, dtype=np.uint32), host.offs[b0:b1], host.lens[b0:b1])
+            st = ctx.stats()
+            seed_ms += st.seed_ms; tot_ms += st.total_ms
+        tm["seed_kernel_ms"] = seed_ms; tm["sketch_device_ms"] = tot_ms
+        return sk
 
-    def step_host():
-        """inputs in (pinned) host memory: H2D inside the call, hits come back to host memory"""
-        out = (C.c_void_p * n_g)()
-        ctx.check(L.skb_sketch_batch(ctx._h, C.byref(params), 1, n_g, gs_c, host_ptrs, host_lens, out))
-        sk = [capi.Sketch(ctx, out[i]) for i in range(n_g)]
-        db = capi.Database(ctx)
-        db.add_many(sk[:-1])
-        hits, n_in = db.query([sk[-1]])
-        return len(hits)
+    def sketch_host(tm):
+        sk = []
+        for (b0, b1), (ptrs, lens, gs) in zip(batches, host_ptr_arrays):
+            out = (C.c_void_p * (b1 - b0))()
+            ctx.check(L.skb_sketch_batch(ctx._h, C.byref(params), 1, b1 - b0, gs, ptrs, lens, out))
+            sk += [capi.Sketch(ctx, out[i]) for i in range(b1 - b0)]
+        return sk
+
+    def step(sketch_fn):
+        tm = {}
+        t0 = time.perf_counter()
+        sk = sketch_fn(tm)
+        tm["sketch_ms"] = 1e3 * (time.perf_counter() - t0)
+        table = parallel.query_and_gather(backend, sk, mine, plan, dgroup, device, None, tm)
+        tm["step_wall_ms"] = 1e3 * (time.perf_counter() - t0)
+        return table, tm
 
     def barrier():
         if world > 1:
@@ -282,107 +442,150 @@ def main():
         torch.cuda.synchronize()
         ctx.sync()
 
-    def timed(fn, steps):
+    def timed(sketch_fn, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         t0 = time.perf_counter()
         e0.record(stream)
-        outs, per_step = [], []
+        tms, table = [], None
         for _ in range(steps):
-            ts = time.perf_counter()
-            outs.append(fn())
-            per_step.append(1e3 * (time.perf_counter() - ts))
-        timed.last_per_step = per_step
+            table, tm = step(sketch_fn)
+            tms.append(tm)
         e1.record(stream)
         barrier()
         wall_ms = 1e3 * (time.perf_counter() - t0)
-        dev_ms = e0.elapsed_time(e1)
-        ms = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+        ms = torch.tensor([e0.elapsed_time(e1), wall_ms], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms[0]), float(ms[1]), outs
+        return max(float(ms[0]), float(ms[1])) / steps, tms, table
+
+    def phase_stats(tms, keys):
+        """mean over steps, then max (times) or sum (counts) over ranks"""
+        out = {}
+        for k, how in keys:
+            v = float(np.mean([t.get(k, 0.0) for t in tms]))
+            if world > 1:
+                x = torch.tensor([v], dtype=torch.float64, device=device)
+                dist.all_reduce(x, op=dist.ReduceOp.MAX if how == "max" else dist.ReduceOp.SUM)
+                v = float(x[0])
+            out[k] = v
+        return out
 
     sampler = ClockSampler(local_rank, uuid=getattr(torch.cuda.get_device_properties(local_rank), 'uuid', None))
     sampler.start()
     for _ in range(args.warmup):
-        step_device()
+        step(sketch_device)
     k0 = ctx.stats().kernels_launched
-    dev_ms, wall_ms, outs = timed(step_device, args.steps)
+    ms_per_step, tms, table = timed(sketch_device, args.steps)
     k1 = ctx.stats().kernels_launched
-    n_hits = outs[-1][0]
-    seed_ms = float(np.mean([o[1] for o in outs]))
-    sketch_ms = float(np.mean([o[2] for o in outs]))
-    query_ms = float(np.mean([o[3] for o in outs]))
+    keys = [("seed_kernel_ms", "max"), ("sketch_device_ms", "max"), ("sketch_ms", "max"), ("exchange_ms", "max"), ("exchange_sizes_ms", "max"),
+            ("exchange_pack_enqueue_ms", "max"), ("exchange_allgather_ms", "max"), ("exchange_wait_adopt_ms", "max"), ("query_ms", "max"),
+            ("screen_ms", "max"), ("chain_ms", "max"), ("gather_ms", "max"), ("screened_in", "sum"), ("local_hits", "sum"),
+            ("exchange_bytes_in", "max"), ("exchange_bytes_total", "max")]
+    ph = phase_stats(tms, keys)
 
     for _ in range(max(1, args.warmup // 2)):
-        step_host()
-    e2e_dev_ms, e2e_wall_ms, outs_h = timed(step_host, args.steps)
-    e2e_per_step = list(timed.last_per_step)
+        step(sketch_host)
+    e2e_ms, tms_h, table_h = timed(sketch_host, args.steps)
+    ph_h = phase_stats(tms_h, [("sketch_ms", "max"), ("exchange_ms", "max"), ("query_ms", "max"), ("gather_ms", "max")])
     clocks = sampler.stop()      # sampled from the first warm-up step to the end of the e2e region
-    # plain pinned-host -> device copy of the same bytes, for context (the e2e floor on this box)
+    # the floor of the host->device leg: all ranks copy their pinned bytes at the same time
+    barrier()
     t0 = time.perf_counter()
-    ctx.memcpy_h2d(d_ptr, h_ptr, buf_bytes)
-    h2d_gbs = buf_bytes / (time.perf_counter() - t0) / 1e9
+    ctx.memcpy_h2d(d_ptr, h_ptr, my_bytes)
+    h2d_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    launches = torch.tensor([float(k1 - k0)], dtype=torch.float64, device=device)
+    bases_t = torch.tensor([float(my_bases)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(h2d_s, op=dist.ReduceOp.MAX)
+        dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+        dist.all_reduce(bases_t, op=dist.ReduceOp.SUM)
+    h2d_floor_ms = 1e3 * float(h2d_s[0])
+    total_bases = int(bases_t[0])
 
-    pairs_total = args.n_refs * world
-    ms_per_step = dev_ms / args.steps
+    pairs_total = n_total * n_total
     value = pairs_total / (ms_per_step / 1e3)
-    e2e_ms = max(e2e_dev_ms, e2e_wall_ms) / args.steps
     e2e_value = pairs_total / (e2e_ms / 1e3)
 
     if rank == 0:
+        if table_h.shape != table.shape or not np.array_equal(table_h, table):
+            raise SystemExit("host-buffer path and device-resident path returned different hit tables")
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        achieved = ALG_BYTES_PER_BASE * total_bases / (seed_ms / 1e3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of one seed_scan_kernel launch, from the committed
-        # `ncu --set full` capture of this command (profiles/r1_seed_scan_kernel_ncu_full.txt); only valid for the
-        # default workload, which is the one that capture ran
-        traffic = NCU_SEED_TRAFFIC_BYTES if (args.genome_len, args.n_refs) == (5_000_000, 100) else None
+        # roofline of the dominant kernel (seed_scan_kernel), this rank's launches: algorithmic bytes / time between CUDA
+        # events recorded around the seeding launches on the library's own stream
+        seed_ms = float(np.mean([t["seed_kernel_ms"] for t in tms]))
+        achieved = ALG_BYTES_PER_BASE * my_bases / (seed_ms / 1e3) / 1e9
+        traffic, traffic_note = None, "no ncu capture committed for this launch shape"
+        tpath = os.path.join(ROOT, "profiles", "r2_seed_scan_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if int(tj.get("bases_per_launch", -1)) == int(host.lens[batches[0][0]:batches[0][1]].sum()):
+                traffic, traffic_note = tj["dram_bytes_per_launch"], tj.get("source", tpath)
+        ex_ms = ph.get("exchange_allgather_ms", 0.0)
         line = {
-            "metric": "ANI pairs/s (sketch + screen + chain + ANI, 1 x 5 Mbp query vs 100 mutated refs)",
-            "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "configs[1]: 1 synthetic %d bp genome vs %d mutated copies (1-15%% divergence, indels) per GPU"
-                                   % (args.genome_len, args.n_refs),
-                       "k": 15, "c": 125, "marker_c": 1000, "l2": "inputs (%.0f MB ASCII per step) exceed the 126 MB L2" % (total_bases / 1e6),
-                       "parallelism": "independent family per GPU, no collective", "cpu_affinity": numa},
-            "hits_per_query": n_hits,
-            "sketch_gbps": world * total_bases / (sketch_ms / 1e3) / 1e9,
-            "seed_kernel_gbps": world * total_bases / (seed_ms / 1e3) / 1e9,
-            "query_pairs_per_s": pairs_total / (query_ms / 1e3),
-            "phase_ms": {"seed_kernel": seed_ms, "sketch_total": sketch_ms, "query_total": query_ms, "wall_per_step": wall_ms / args.steps},
+            "config": {"workload": workload_string(args), "k": 15, "c": 125, "marker_c": 1000,
+                       "l2": "inputs (%.0f MB of ASCII per rank and step) exceed the 126 MB L2" % (my_bases / 1e6),
+                       "parallelism": "queries split over %d rank(s); sketch database exchanged once per step%s" % (
+                           world, " (" + tms[-1].get("exchange_collective", "") + ")" if world > 1 else " (single GPU: no exchange)"),
+                       "sketch_batch": args.sketch_batch, "cpu_affinity": numa},
+            "pairs_per_step": pairs_total, "hits_per_step": int(len(table)),
+            "sketch_gbps": total_bases / (ph["sketch_ms"] / 1e3) / 1e9,
+            "seed_kernel_gbps": total_bases / (ph["seed_kernel_ms"] / 1e3) / 1e9,
+            "screen_pairs_per_s": pairs_total / (max(ph["screen_ms"], 1e-6) / 1e3),
+            "chained_pairs_per_step": int(ph["screened_in"]),
+            "chained_pairs_per_s": ph["screened_in"] / (max(ph["chain_ms"], 1e-6) / 1e3),
+            "phase_ms": {k: round(v, 4) for k, v in ph.items() if k.endswith("_ms")},
+            "exchange": None if world == 1 else {
+                "ms": ph["exchange_ms"], "allgather_ms": ex_ms, "bytes_total": int(ph["exchange_bytes_total"]),
+                "bytes_in_per_gpu": int(ph["exchange_bytes_in"]), "collective": tms[-1].get("exchange_collective"),
+                "busbw_gbs": ph["exchange_bytes_in"] / (max(ex_ms, 1e-6) / 1e3) / 1e9,
+                "note": "busbw = bytes received per GPU / all-gather time (NCCL's definition for all-gather)"},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": total_bases,
-                    "d2h_bytes_per_step": int(n_hits) * C.sizeof(capi.Hit), "ms_per_step": e2e_ms,
-                    "pinned_h2d_copy_gbs": h2d_gbs, "per_step_wall_ms": [round(x, 3) for x in e2e_per_step]},
-            "gpu_launches": int(k1 - k0),
+                    "d2h_bytes_per_step": int(len(table)) * C.sizeof(capi.Hit), "ms_per_step": e2e_ms,
+                    "phase_ms": {k: round(v, 4) for k, v in ph_h.items()},
+                    "h2d_floor_ms": h2d_floor_ms, "h2d_floor_gbs_per_gpu": my_bytes / (h2d_floor_ms / 1e3) / 1e9,
+                    "e2e_over_floor": e2e_ms / h2d_floor_ms,
+                    "note": "floor = all ranks copying their pinned input bytes to the device at the same time, nothing else running"},
+            "gpu_launches": int(launches[0]),
             "roofline": {"bound": "hbm", "kernel": "seed_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read + write)",
-                         "algorithmic_bytes": ALG_BYTES_PER_BASE * total_bases, "peak_source": peak_src,
-                         "note": "algorithmic bytes = 1.136 B/base x %d bases per launch; the kernel is integer-issue bound, see DESIGN.md" % total_bases},
-            # the bound that actually holds for this kernel: two exact 64-bit hashes per base cost
-            # ~54 ALU-pipe instructions per position (SASS count); the ALU pipe issues one warp instruction per 2 cycles
-            # per SM sub-partition.  ncu: sm__pipe_alu_cycles_active 81 % (profiles/r1_seed_scan_kernel_ncu_full.txt)
-            "issue_roofline": {"bound": "integer ALU pipe", "unit": "Gbp/s", "alu_inst_per_base": 54,
-                               "peak": 148 * 4 * 32 / (54 * 2) * (clocks.get("sm_mhz") or 1965.0) / 1e3,
-                               "achieved": total_bases / (seed_ms / 1e3) / 1e9},
+                         "traffic_source": traffic_note, "launches_per_step_per_rank": len(batches),
+                         "algorithmic_bytes_per_launch": ALG_BYTES_PER_BASE * my_bases / max(1, len(batches)), "peak_source": peak_src,
+                         "note": "algorithmic bytes = 1.136 B/base x bases per launch; the kernel is integer-issue bound (two exact "
+                                 "64-bit hashes per base), see DESIGN.md section 4"},
             "clocks": clocks,
         }
-        line["issue_roofline"]["frac"] = line["issue_roofline"]["achieved"] / line["issue_roofline"]["peak"]
-        if not args.skip_cpu_baseline:
+        threads = args.cpu_threads or (os.cpu_count() or 1)
+        if not (args.skip_parity and (args.skip_cpu_baseline or world > 1)):
             import oracle
             oracle.lib()
-            os.sched_setaffinity(0, all_cpus)      # the CPU baseline may use every core the process was given
-            threads = args.cpu_threads or (os.cpu_count() or 1)
-            cpu_step(base, refs, threads)
-            a, b, nh = cpu_step(base, refs, threads)
-            line["cpu_baseline"] = {"value": args.n_refs / (a + b), "unit": "pairs/s", "cores": threads, "kind": "port",
-                                    "sketch_gbps": total_bases / a / 1e9, "query_pairs_per_s": args.n_refs / b,
-                                    "sample": "one full step (sketch %d genomes + 1 x %d query) on the CPU port of skani's "
-                                              "algorithm (oracle/), OpenMP over genomes and pairs" % (n_g, args.n_refs)}
+            os.sched_setaffinity(0, all_cpus)      # the CPU legs may use every core the process was given
+            host_all = host if world == 1 else HostGenomes(range(n_total), args.genome_len, args.members)
+            odb = oracle.sketch_batch([[host_all.view(j)] for j in range(n_total)], threads=threads)
+            if not args.skip_parity:
+                line["parity"] = parity_gate(args, capi, ctx, host_all, table, world, threads, odb)
+                line["parity_checked"] = True
+            if world == 1 and not args.skip_cpu_baseline:
+                n_s = min(n_total, cpu_sample_size(threads, args.cpu_sample))
+                sample = list(range(n_s))
+                cpu_sample_step(oracle, host_all, sample, odb, threads)
+                a, b, nh, n_in = cpu_sample_step(oracle, host_all, sample, odb, threads)
+                line["cpu_baseline"] = {
+                    "value": n_s * n_total / (a + b), "unit": "pairs/s", "cores": threads, "kind": "port",
+                    "sketch_gbps": float(sum(int(host_all.lens[j]) for j in sample)) / a / 1e9, "chained_pairs_per_s": n_in / b,
+                    "sample": "sketch %d of the %d genomes and query them against all %d (%d ordered pairs, %d chained) on the CPU "
+                              "port of skani's algorithm (oracle/), OpenMP over genomes and pairs; database sketches prepared "
+                              "outside the timed sample" % (n_s, n_total, n_total, n_s * n_total, n_in)}
+            del odb
+        if not args.skip_configs1:
+            line["configs1"] = configs1_block(args, capi, ctx, torch, stream)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

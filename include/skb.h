@@ -138,6 +138,25 @@ int  skb_sketch_pack(skb_ctx_t* ctx, uint32_t n, skb_sketch_t* const* sketches, 
 int  skb_sketch_unpack(skb_ctx_t* ctx, const void* meta_host, uint64_t meta_bytes, const void* payload_dev,
                        uint64_t payload_bytes, skb_sketch_t** out, uint32_t out_cap, uint32_t* n_out);
 
+/* ---- zero-copy exchange region (multi-GPU all-vs-all) ----
+ * One block of sketch storage that holds one SEGMENT per rank: [descriptor | device arrays of that rank's sketches].
+ * Every rank packs its own segment in place, ONE collective (all-gather with per-rank sizes, straight into this block)
+ * fills the others, and the peers' sketches are then adopted as views into the block: no staging buffer, no padding to
+ * the largest rank, no second device-to-device copy.  The block lives until the last adopted sketch is freed. */
+typedef struct skb_exchange skb_exchange_t;
+/* bytes of the segment these sketches need (a multiple of 256) and of the descriptor at its start */
+int  skb_exchange_segment_size(uint32_t n, skb_sketch_t* const* sketches, uint64_t* segment_bytes, uint64_t* meta_bytes);
+int  skb_exchange_create(skb_ctx_t* ctx, uint64_t bytes, skb_exchange_t** out);
+void* skb_exchange_ptr(skb_exchange_t* ex);                    /* device address of the block */
+/* writes the segment of these sketches at `offset` (a multiple of 256); asynchronous on the context's stream */
+int  skb_exchange_pack(skb_exchange_t* ex, uint64_t offset, uint32_t n, skb_sketch_t* const* sketches);
+/* adopts the sketches of n_segments segments (offsets[i], descriptor sizes meta_bytes[i]) once their bytes have arrived
+ * (the caller orders the collective before this call on the context's stream).  Handles are appended to out[] segment
+ * after segment; counts[i] receives the number of sketches of segment i. */
+int  skb_exchange_adopt(skb_exchange_t* ex, uint32_t n_segments, const uint64_t* offsets, const uint64_t* meta_bytes,
+                        skb_sketch_t** out, uint32_t out_cap, uint32_t* counts);
+void skb_exchange_free(skb_exchange_t* ex);                    /* drops the caller's reference to the block */
+
 /* ---- database: the (markers, sketches) pair a Database owns (lib.rs:132-137) ---- */
 int  skb_db_create(skb_ctx_t* ctx, skb_db_t** out);
 void skb_db_destroy(skb_db_t* db);
@@ -145,6 +164,9 @@ void skb_db_destroy(skb_db_t* db);
 int  skb_db_add(skb_db_t* db, skb_sketch_t* s, uint32_t* index_out);
 /* the same for n sketches in one call; index_out (may be NULL) receives the index of the first one */
 int  skb_db_add_many(skb_db_t* db, uint32_t n, skb_sketch_t* const* sketches, uint32_t* index_out);
+/* Puts `s` in the place of the sketch at `index`: what a second Database.sketch() under an existing name amounts to
+ * in the reference, whose sketch store is a HashMap keyed by name (insert replaces, lib.rs:45,64) */
+int  skb_db_replace(skb_db_t* db, uint32_t index, skb_sketch_t* s);
 uint64_t skb_db_size(const skb_db_t* db);
 
 /* ---- query: lib.rs:616-657 for n_queries queries at once ----

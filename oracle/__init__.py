@@ -69,6 +69,9 @@ def lib():
         L.orc_query.restype = C.c_int64
         L.orc_query.argtypes = [vp, C.POINTER(vp), u64, C.c_double, i32, C.POINTER(ChainParams), i32,
                                 vp, vp, C.POINTER(u64)]
+        L.orc_query_many.restype = C.c_int64
+        L.orc_query_many.argtypes = [C.POINTER(vp), u64, C.POINTER(vp), u64, C.c_double, i32, C.POINTER(ChainParams), i32,
+                                     vp, vp, vp, u64, C.POINTER(u64)]
         _LIB = L
     return _LIB
 
@@ -174,6 +177,25 @@ def query(q, refs, screen_val=0.8, rescue_small=True, params=None, threads=1):
     nh = lib().orc_query(q._h, hs, n, screen_val, int(rescue_small), C.byref(p), threads,
                          idx.ctypes.data, C.addressof(res), C.byref(ns))
     return idx[:nh].copy(), [res[i] for i in range(nh)], ns.value
+
+
+def query_many(queries, refs, screen_val=0.8, rescue_small=True, params=None, threads=0):
+    """pyskani's query loop for many queries, parallel over (query, ref) pairs.
+    Returns (hit_q, hit_r, results, n screened-in), hits ordered by (query, ref)."""
+    p = params if params is not None else default_params()
+    nq, nr = len(queries), len(refs)
+    qh = (C.c_void_p * max(nq, 1))(*[q._h for q in queries])
+    rh = (C.c_void_p * max(nr, 1))(*[r._h for r in refs])
+    cap = max(1024, 16 * nq)
+    while True:
+        hq = np.empty(cap, np.uint32); hr = np.empty(cap, np.uint32)
+        res = (Result * cap)()
+        ns = C.c_uint64(0)
+        nh = lib().orc_query_many(qh, nq, rh, nr, screen_val, int(rescue_small), C.byref(p), threads,
+                                  hq.ctypes.data, hr.ctypes.data, C.addressof(res), cap, C.byref(ns))
+        if nh <= cap:
+            return hq[:nh].copy(), hr[:nh].copy(), [res[i] for i in range(nh)], ns.value
+        cap = nh
 
 
 def mm_hash64(x):

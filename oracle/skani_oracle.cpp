@@ -568,4 +568,34 @@ int64_t orc_query(const orc_sketch_t* query, const orc_sketch_t* const* refs, ui
     return nh;
 }
 
+// pyskani's query loop for MANY queries against one database (the all-vs-all benchmark): every (query, ref) pair is
+// screened (lib.rs:617-637), survivors are chained (lib.rs:640-657).  Both phases are parallel over pairs — the axis
+// skani's own rayon drivers use for `skani search` / `skani triangle`.  Hits come back ordered by (query, ref).
+int64_t orc_query_many(const orc_sketch_t* const* queries, uint64_t n_queries, const orc_sketch_t* const* refs, uint64_t n_refs,
+                       double screen_val, int32_t rescue_small, const orc_chain_params_t* p, int32_t threads,
+                       uint32_t* hit_q, uint32_t* hit_r, orc_result_t* out, uint64_t cap, uint64_t* n_screened_in) {
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
+    const int64_t n_pairs = (int64_t)(n_queries * n_refs);
+    std::vector<uint8_t> pass((size_t)n_pairs, 0);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n_pairs; i++)
+        pass[i] = (uint8_t)orc_screen(queries[i / (int64_t)n_refs], refs[i % (int64_t)n_refs], screen_val, rescue_small, nullptr);
+    std::vector<int64_t> in;
+    for (int64_t i = 0; i < n_pairs; i++) if (pass[i]) in.push_back(i);
+    std::vector<orc_result_t> res(in.size());
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t j = 0; j < (int64_t)in.size(); j++)
+        chain_impl(refs[in[j] % (int64_t)n_refs], queries[in[j] / (int64_t)n_refs], *p, &res[j]);
+    int64_t nh = 0;
+    for (size_t j = 0; j < in.size(); j++) {
+        if (!(res[j].ani > 0.1f)) continue;                       // reference lib.rs:654
+        if ((uint64_t)nh < cap) { hit_q[nh] = (uint32_t)(in[j] / (int64_t)n_refs); hit_r[nh] = (uint32_t)(in[j] % (int64_t)n_refs); out[nh] = res[j]; }
+        nh++;
+    }
+    if (n_screened_in) *n_screened_in = in.size();
+    return nh;
+}
+
 }  // extern "C"

@@ -119,6 +119,13 @@ int64_t  orc_query(const orc_sketch_t* query, const orc_sketch_t* const* refs, u
                    double screen_val, int32_t rescue_small, const orc_chain_params_t* p,
                    int32_t threads, uint32_t* hit_idx, orc_result_t* out, uint64_t* n_screened_in);
 
+/* The same loop for n_queries queries at once, parallel over (query, ref) pairs (CPU-baseline and parity-gate use).
+ * hit_q/hit_r/out have room for `cap` entries; returns the number of hits (which may exceed cap: call again). */
+int64_t  orc_query_many(const orc_sketch_t* const* queries, uint64_t n_queries, const orc_sketch_t* const* refs,
+                        uint64_t n_refs, double screen_val, int32_t rescue_small, const orc_chain_params_t* p,
+                        int32_t threads, uint32_t* hit_q, uint32_t* hit_r, orc_result_t* out, uint64_t cap,
+                        uint64_t* n_screened_in);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,7 +52,9 @@ SYMBOLS = [
     "skb_ctx_create", "skb_ctx_destroy", "skb_last_error", "skb_ctx_stats", "skb_ctx_sync", "skb_ctx_stream",
     "skb_host_alloc", "skb_host_free", "skb_dev_alloc", "skb_dev_free", "skb_memcpy_h2d",
     "skb_sketch_batch", "skb_sketch_batch_device", "skb_sketch_free", "skb_sketch_info", "skb_sketch_export",
-    "skb_sketch_import", "skb_sketch_pack_size", "skb_sketch_pack", "skb_sketch_unpack", "skb_db_create", "skb_db_destroy", "skb_db_add", "skb_db_add_many", "skb_db_size", "skb_db_query",
+    "skb_sketch_import", "skb_sketch_pack_size", "skb_sketch_pack", "skb_sketch_unpack",
+    "skb_exchange_segment_size", "skb_exchange_create", "skb_exchange_ptr", "skb_exchange_pack", "skb_exchange_adopt",
+    "skb_exchange_free", "skb_db_create", "skb_db_destroy", "skb_db_add", "skb_db_add_many", "skb_db_replace", "skb_db_size", "skb_db_query",
     "skb_hits_free", "skb_db_screen", "skb_version",
 ]
 
@@ -97,10 +99,18 @@ def lib():
         L.skb_sketch_pack_size.argtypes = [u32, vp, C.POINTER(u64), C.POINTER(u64)]
         L.skb_sketch_pack.argtypes = [vp, u32, vp, vp, u64, vp, u64]
         L.skb_sketch_unpack.argtypes = [vp, vp, u64, vp, u64, vp, u32, C.POINTER(u32)]
+        L.skb_exchange_segment_size.argtypes = [u32, vp, C.POINTER(u64), C.POINTER(u64)]
+        L.skb_exchange_create.argtypes = [vp, u64, C.POINTER(vp)]
+        L.skb_exchange_ptr.restype = vp
+        L.skb_exchange_ptr.argtypes = [vp]
+        L.skb_exchange_pack.argtypes = [vp, u64, u32, vp]
+        L.skb_exchange_adopt.argtypes = [vp, u32, vp, vp, vp, u32, vp]
+        L.skb_exchange_free.argtypes = [vp]
         L.skb_db_create.argtypes = [vp, C.POINTER(vp)]
         L.skb_db_destroy.argtypes = [vp]
         L.skb_db_add.argtypes = [vp, vp, C.POINTER(u32)]
         L.skb_db_add_many.argtypes = [vp, u32, vp, C.POINTER(u32)]
+        L.skb_db_replace.argtypes = [vp, u32, vp]
         L.skb_db_size.restype = u64
         L.skb_db_size.argtypes = [vp]
         L.skb_db_query.argtypes = [vp, u32, vp, C.POINTER(QueryOpts), C.POINTER(C.POINTER(Hit)), C.POINTER(u64),
@@ -216,6 +226,17 @@ class Context:
                                            C.byref(got)))
         return [Sketch(self, out[i]) for i in range(got.value)]
 
+    def segment_size(self, sketches):
+        """(segment bytes, descriptor bytes) of these sketches inside an exchange block"""
+        n = len(sketches)
+        hs = (C.c_void_p * max(n, 1))(*[s._h for s in sketches])
+        sb, mb = C.c_uint64(), C.c_uint64()
+        self.check(lib().skb_exchange_segment_size(n, hs, C.byref(sb), C.byref(mb)))
+        return sb.value, mb.value
+
+    def exchange(self, nbytes):
+        return Exchange(self, nbytes)
+
     def host_alloc(self, nbytes):
         p = C.c_void_p()
         self.check(lib().skb_host_alloc(self._h, nbytes, C.byref(p)))
@@ -234,6 +255,48 @@ class Context:
 
     def memcpy_h2d(self, dst, src, nbytes):
         self.check(lib().skb_memcpy_h2d(self._h, dst, src, nbytes))
+
+
+class Exchange:
+    """One block of sketch storage holding a segment per rank (include/skb.h, "zero-copy exchange region")."""
+
+    def __init__(self, ctx, nbytes):
+        self.ctx, self.nbytes = ctx, int(nbytes)
+        self._h = C.c_void_p()
+        ctx.check(lib().skb_exchange_create(ctx._h, self.nbytes, C.byref(self._h)))
+
+    @property
+    def ptr(self):
+        return lib().skb_exchange_ptr(self._h)
+
+    def pack(self, offset, sketches):
+        n = len(sketches)
+        hs = (C.c_void_p * max(n, 1))(*[s._h for s in sketches])
+        self.ctx.check(lib().skb_exchange_pack(self._h, int(offset), n, hs))
+
+    def adopt(self, offsets, meta_bytes, max_sketches):
+        """-> list (one per segment) of lists of Sketch whose arrays are views into this block"""
+        ns = len(offsets)
+        offs = (C.c_uint64 * max(ns, 1))(*[int(o) for o in offsets])
+        mbs = (C.c_uint64 * max(ns, 1))(*[int(m) for m in meta_bytes])
+        out = (C.c_void_p * max(max_sketches, 1))()
+        counts = (C.c_uint32 * max(ns, 1))()
+        self.ctx.check(lib().skb_exchange_adopt(self._h, ns, offs, mbs, out, max_sketches, counts))
+        res, k = [], 0
+        for i in range(ns):
+            res.append([Sketch(self.ctx, out[k + j]) for j in range(counts[i])])
+            k += counts[i]
+        return res
+
+    def close(self):
+        if getattr(self, "_h", None):
+            try:
+                lib().skb_exchange_free(self._h)
+            except TypeError:
+                pass
+            self._h = None
+
+    __del__ = close
 
 
 class Sketch:
@@ -294,6 +357,21 @@ class Database:
 
     def __len__(self):
         return lib().skb_db_size(self._h)
+
+    def query_array(self, queries, cutoff=0.0, learned_ani=0, median=False, robust=False, faster_small=False):
+        """skb_db_query; hits as a numpy structured array (HIT_DTYPE) plus the number of screened-in pairs"""
+        n = len(queries)
+        qs = (C.c_void_p * max(n, 1))(*[q._h for q in queries])
+        o = QueryOpts(cutoff, learned_ani, int(median), int(robust), int(faster_small))
+        hits = C.POINTER(Hit)()
+        nh, ns = C.c_uint64(0), C.c_uint64(0)
+        self.ctx.check(lib().skb_db_query(self._h, n, qs, C.byref(o), C.byref(hits), C.byref(nh), C.byref(ns)))
+        out = np.zeros(0, HIT_DTYPE)
+        if nh.value:
+            raw = np.ctypeslib.as_array(C.cast(hits, C.POINTER(C.c_uint8)), shape=(nh.value * C.sizeof(Hit),))
+            out = raw.view(HIT_DTYPE).copy()
+        lib().skb_hits_free(hits)
+        return out, ns.value
 
     def query(self, queries, cutoff=0.0, learned_ani=0, median=False, robust=False, faster_small=False):
         n = len(queries)

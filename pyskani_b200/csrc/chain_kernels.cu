@@ -65,6 +65,7 @@ __global__ void match_count_kernel(const ChainBatch b) {
     const GenomeView& R = b.rviews[pd.r];
     const uint32_t nq = Q.n_seeds;
     const int lane = threadIdx.x & 31;
+    unsigned long long total = 0;       // 64-bit anchor count of this thread's seeds (a_off is a 32-bit scan and may wrap)
     // warp-aligned strips of 32 consecutive query seeds: the strip's "has a match" bits are one word of the bitmask
     for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < nq; i0 += gridDim.x * blockDim.x) {
         const uint32_t i = i0 + lane;
@@ -86,9 +87,12 @@ __global__ void match_count_kernel(const ChainBatch b) {
             b.m_first[pd.seed_off + i] = first;
             b.m_cnt[pd.seed_off + i] = cnt;
         }
+        total += cnt;
         const uint32_t bal = __ballot_sync(FULL, cnt != 0);
         if (lane == 0) b.m_bits[pd.bits_off + (i0 >> 5)] = bal;
     }
+    for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
+    if (lane == 0 && total) atomicAdd(b.a_total64, total);
 }
 
 // ------------------------------------------------------------------ 1b. anchors

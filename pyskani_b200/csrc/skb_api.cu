@@ -704,7 +704,8 @@ int skb_memcpy_h2d(skb_ctx_t* ctx, void* dst, const void* src, size_t bytes) {
 int skb_sketch_batch_device(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t seed, uint32_t n_genomes,
                             const uint32_t* genome_contig_start, const uint8_t* seq, const uint64_t* contig_offsets,
                             const uint64_t* contig_lens, skb_sketch_t** out) {
-    if (!ctx || !params || !out || (n_genomes && (!genome_contig_start || !contig_lens || !contig_offsets))) return SKB_ERR_ARG;
+    if (!ctx || !params || !out || (n_genomes && !genome_contig_start)) return SKB_ERR_ARG;
+    if (n_genomes && genome_contig_start[n_genomes] && (!contig_lens || !contig_offsets)) return SKB_ERR_ARG;
     return guarded(ctx->core.get(), [&] {
         Core& c = *ctx->core;
         CU(cudaEventRecord(c.ev[0], c.stream));
@@ -720,7 +721,9 @@ int skb_sketch_batch_device(skb_ctx_t* ctx, const skb_sketch_params_t* params, i
 int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t seed, uint32_t n_genomes,
                      const uint32_t* genome_contig_start, const uint8_t* const* contigs, const uint64_t* contig_lens,
                      skb_sketch_t** out) {
-    if (!ctx || !params || !out || (n_genomes && (!genome_contig_start || !contig_lens || !contigs))) return SKB_ERR_ARG;
+    if (!ctx || !params || !out || (n_genomes && !genome_contig_start)) return SKB_ERR_ARG;
+    // a genome without any contig is legal (the reference returns an empty sketch, lib.rs:155): the arrays may then be NULL
+    if (n_genomes && genome_contig_start[n_genomes] && (!contig_lens || !contigs)) return SKB_ERR_ARG;
     return guarded(ctx->core.get(), [&] {
         Core& c = *ctx->core;
         cudaStream_t st = c.stream;
@@ -879,9 +882,13 @@ int skb_sketch_export(const skb_sketch_t* s, uint64_t* kmer, uint32_t* pos, uint
     SketchImpl& I = *s->impl;
     return guarded(I.core.get(), [&] {
         Core& c = *I.core;
-        const uint32_t n = I.view.n_seeds;
-        std::vector<uint32_t> k32(n), p32(n), m32(n);
-        download(c, k32.data(), I.view.kmer_k, n); download(c, p32.data(), I.view.pos_k, n); download(c, m32.data(), I.view.meta_k, n);
+        // markers-only exports (Database.flush / save_markers) must not pull the seed arrays off the device
+        const bool want_seeds = kmer || pos || contig || canonical;
+        const uint32_t n = want_seeds ? I.view.n_seeds : 0;
+        std::vector<uint32_t> k32(kmer ? n : 0), p32(pos ? n : 0), m32(contig || canonical ? n : 0);
+        if (kmer) download(c, k32.data(), I.view.kmer_k, n);
+        if (pos) download(c, p32.data(), I.view.pos_k, n);
+        if (contig || canonical) download(c, m32.data(), I.view.meta_k, n);
         if (markers) download(c, markers, I.view.markers, I.view.n_markers);
         CU(cudaStreamSynchronize(c.stream));
         for (uint32_t i = 0; i < n; i++) {
@@ -999,6 +1006,19 @@ int skb_db_add_many(skb_db_t* db, uint32_t n, skb_sketch_t* const* sketches, uin
         return SKB_OK;
     });
 }
+int skb_db_replace(skb_db_t* db, uint32_t index, skb_sketch_t* s) {
+    if (!db || !s) return SKB_ERR_ARG;
+    return guarded(db->core.get(), [&] {
+        if (index >= db->items.size()) throw Fail{SKB_ERR_KEY, "no sketch at this index"};
+        if (s->impl->core != db->core) throw Fail{SKB_ERR_ARG, "sketch belongs to another context"};
+        const auto& a = db->items[0]->info; const auto& b = s->impl->info;
+        if (db->items.size() > 1 && (a.k != b.k || a.c != b.c || a.marker_c != b.marker_c)) throw Fail{SKB_ERR_ARG, "sketch parameters differ from the database's"};
+        CU(cudaStreamSynchronize(db->core->stream));     // nothing in flight may still read the old sketch's arrays
+        db->items[index] = s->impl;
+        db->dirty = true; db->idx_dirty = true;
+        return SKB_OK;
+    });
+}
 uint64_t skb_db_size(const skb_db_t* db) { return db ? db->items.size() : 0; }
 
 void skb_hits_free(skb_hit_t* hits) { delete[] hits; }
@@ -1044,6 +1064,83 @@ int skb_sketch_pack_size(uint32_t n, skb_sketch_t* const* sketches, uint64_t* pa
     return SKB_OK;
 }
 
+}  // extern "C"
+
+namespace {
+
+// Fills the host descriptor of n sketches and lists the device arrays to gather (destination offsets are relative to
+// the start of the payload).  Shared by skb_sketch_pack and skb_exchange_pack.
+void build_pack_meta(Core& c, uint32_t n, skb_sketch_t* const* sketches, uint64_t payload_bytes, char* m,
+                     std::vector<SegmentCopy>& segs, uint64_t& max_bytes) {
+    PackHeader hd{PACK_MAGIC, n, payload_bytes};
+    std::memcpy(m, &hd, sizeof(hd));
+    PackSketch* ps = (PackSketch*)(m + sizeof(PackHeader));
+    uint32_t* clens = (uint32_t*)(m + sizeof(PackHeader) + (uint64_t)n * sizeof(PackSketch));
+    uint64_t off = 0;
+    max_bytes = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const SketchImpl& I = *sketches[i]->impl;
+        if (I.core.get() != &c) throw Fail{SKB_ERR_ARG, "sketch belongs to another context"};
+        const GenomeView& v = I.view;
+        PackSketch p{};
+        p.total_len = v.total_len; p.n_seeds = v.n_seeds; p.n_markers = v.n_markers; p.n_contigs = v.n_contigs;
+        p.bucket_shift = v.bucket_shift; p.n_buckets = v.n_buckets; p.win_cap = v.win_cap;
+        p.k = I.info.k; p.c = I.info.c; p.marker_c = I.info.marker_c; p.has_seeds = I.info.has_seeds;
+        uint64_t sz[PACK_ARRAYS];
+        pack_sizes(v, sz);
+        const void* src[PACK_ARRAYS] = {v.kmer_p, v.pos_p, v.meta_p, v.kmer_k, v.pos_k, v.meta_k, v.bucket,
+                                        v.contig_seed_start, v.contig_len, v.contig_win_start, v.markers};
+        for (int a = 0; a < PACK_ARRAYS; a++) {
+            p.off[a] = off;
+            if (sz[a]) { segs.push_back(SegmentCopy{src[a], off, sz[a]}); max_bytes = std::max(max_bytes, sz[a]); }
+            off += pad16(sz[a]);
+        }
+        std::memcpy(&ps[i], &p, sizeof(p));
+        if (v.n_contigs) std::memcpy(clens, I.contig_len_host.data(), 4 * (size_t)v.n_contigs);
+        clens += v.n_contigs;
+    }
+}
+
+// Sketch handles whose arrays are views into `base` (the payload the descriptor `m` describes); `store` keeps the
+// memory alive.  Returns the number of sketches.
+uint32_t views_from_meta(const std::shared_ptr<Core>& core, const std::shared_ptr<BatchStore>& store, const char* m,
+                         uint64_t meta_bytes, const char* base, skb_sketch_t** out) {
+    PackHeader hd;
+    std::memcpy(&hd, m, sizeof(hd));
+    if (meta_bytes < sizeof(PackHeader) + (uint64_t)hd.n * sizeof(PackSketch)) throw Fail{SKB_ERR_ARG, "truncated pack descriptor"};
+    const PackSketch* ps = (const PackSketch*)(m + sizeof(PackHeader));
+    const uint32_t* clens = (const uint32_t*)(m + sizeof(PackHeader) + (uint64_t)hd.n * sizeof(PackSketch));
+    uint64_t nc_total = 0;
+    for (uint32_t i = 0; i < hd.n; i++) { PackSketch p; std::memcpy(&p, &ps[i], sizeof(p)); nc_total += p.n_contigs; }
+    if (meta_bytes < sizeof(PackHeader) + (uint64_t)hd.n * sizeof(PackSketch) + 4 * nc_total) throw Fail{SKB_ERR_ARG, "truncated pack descriptor"};
+    for (uint32_t i = 0; i < hd.n; i++) {
+        PackSketch p;
+        std::memcpy(&p, &ps[i], sizeof(p));
+        GenomeView v{};
+        v.kmer_p = (const uint32_t*)(base + p.off[0]); v.pos_p = (const uint32_t*)(base + p.off[1]);
+        v.meta_p = (const uint32_t*)(base + p.off[2]); v.kmer_k = (const uint32_t*)(base + p.off[3]);
+        v.pos_k = (const uint32_t*)(base + p.off[4]); v.meta_k = (const uint32_t*)(base + p.off[5]);
+        v.bucket = (const uint32_t*)(base + p.off[6]); v.contig_seed_start = (const uint32_t*)(base + p.off[7]);
+        v.contig_len = (const uint32_t*)(base + p.off[8]); v.contig_win_start = (const uint32_t*)(base + p.off[9]);
+        v.markers = (const uint64_t*)(base + p.off[10]);
+        v.total_len = p.total_len; v.n_seeds = p.n_seeds; v.n_markers = p.n_markers; v.n_contigs = p.n_contigs;
+        v.bucket_shift = p.bucket_shift; v.n_buckets = p.n_buckets; v.win_cap = p.win_cap;
+        auto impl = std::make_shared<SketchImpl>();
+        impl->core = core; impl->store = store; impl->view = v;
+        impl->contig_len_host.assign(clens, clens + p.n_contigs);
+        clens += p.n_contigs;
+        impl->info.n_seeds = p.n_seeds; impl->info.n_markers = p.n_markers; impl->info.total_len = p.total_len;
+        impl->info.n_contigs = p.n_contigs; impl->info.k = p.k; impl->info.c = p.c; impl->info.marker_c = p.marker_c;
+        impl->info.has_seeds = p.has_seeds;
+        out[i] = new skb_sketch{impl};
+    }
+    return hd.n;
+}
+
+}  // namespace
+
+extern "C" {
+
 int skb_sketch_pack(skb_ctx_t* ctx, uint32_t n, skb_sketch_t* const* sketches, void* payload_dev, uint64_t payload_bytes,
                     void* meta_host, uint64_t meta_bytes) {
     if (!ctx || (n && !sketches) || !meta_host || (payload_bytes && !payload_dev)) return SKB_ERR_ARG;
@@ -1052,34 +1149,9 @@ int skb_sketch_pack(skb_ctx_t* ctx, uint32_t n, skb_sketch_t* const* sketches, v
         uint64_t need_p = 0, need_m = 0;
         if (skb_sketch_pack_size(n, sketches, &need_p, &need_m) != SKB_OK) throw Fail{SKB_ERR_ARG, "null sketch"};
         if (payload_bytes < need_p || meta_bytes < need_m) throw Fail{SKB_ERR_ARG, "pack buffers too small (see skb_sketch_pack_size)"};
-        char* m = (char*)meta_host;
-        PackHeader hd{PACK_MAGIC, n, need_p};
-        std::memcpy(m, &hd, sizeof(hd));
-        PackSketch* ps = (PackSketch*)(m + sizeof(PackHeader));
-        uint32_t* clens = (uint32_t*)(m + sizeof(PackHeader) + (uint64_t)n * sizeof(PackSketch));
         std::vector<SegmentCopy> segs;
-        uint64_t off = 0, max_bytes = 0;
-        for (uint32_t i = 0; i < n; i++) {
-            const SketchImpl& I = *sketches[i]->impl;
-            if (I.core.get() != &c) throw Fail{SKB_ERR_ARG, "sketch belongs to another context"};
-            const GenomeView& v = I.view;
-            PackSketch p{};
-            p.total_len = v.total_len; p.n_seeds = v.n_seeds; p.n_markers = v.n_markers; p.n_contigs = v.n_contigs;
-            p.bucket_shift = v.bucket_shift; p.n_buckets = v.n_buckets; p.win_cap = v.win_cap;
-            p.k = I.info.k; p.c = I.info.c; p.marker_c = I.info.marker_c; p.has_seeds = I.info.has_seeds;
-            uint64_t sz[PACK_ARRAYS];
-            pack_sizes(v, sz);
-            const void* src[PACK_ARRAYS] = {v.kmer_p, v.pos_p, v.meta_p, v.kmer_k, v.pos_k, v.meta_k, v.bucket,
-                                            v.contig_seed_start, v.contig_len, v.contig_win_start, v.markers};
-            for (int a = 0; a < PACK_ARRAYS; a++) {
-                p.off[a] = off;
-                if (sz[a]) { segs.push_back(SegmentCopy{src[a], off, sz[a]}); max_bytes = std::max(max_bytes, sz[a]); }
-                off += pad16(sz[a]);
-            }
-            std::memcpy(&ps[i], &p, sizeof(p));
-            if (v.n_contigs) std::memcpy(clens, I.contig_len_host.data(), 4 * (size_t)v.n_contigs);
-            clens += v.n_contigs;
-        }
+        uint64_t max_bytes = 0;
+        build_pack_meta(c, n, sketches, need_p, (char*)meta_host, segs, max_bytes);
         if (!segs.empty()) {
             const size_t tb = sizeof(SegmentCopy) * segs.size();
             void* d_segs = c.scratch(SLOT_PACK, tb);
@@ -1097,47 +1169,139 @@ int skb_sketch_unpack(skb_ctx_t* ctx, const void* meta_host, uint64_t meta_bytes
     if (!ctx || !meta_host || meta_bytes < sizeof(PackHeader) || !n_out) return SKB_ERR_ARG;
     return guarded(ctx->core.get(), [&] {
         Core& c = *ctx->core;
-        const char* m = (const char*)meta_host;
         PackHeader hd;
-        std::memcpy(&hd, m, sizeof(hd));
+        std::memcpy(&hd, meta_host, sizeof(hd));
         if (hd.magic != PACK_MAGIC) throw Fail{SKB_ERR_ARG, "not a sketch pack descriptor"};
-        if (meta_bytes < sizeof(PackHeader) + (uint64_t)hd.n * sizeof(PackSketch)) throw Fail{SKB_ERR_ARG, "truncated pack descriptor"};
         if (payload_bytes < hd.payload_bytes || (hd.payload_bytes && !payload_dev)) throw Fail{SKB_ERR_ARG, "truncated pack payload"};
         *n_out = hd.n;
         if (hd.n == 0) return SKB_OK;
         if (!out || out_cap < hd.n) throw Fail{SKB_ERR_ARG, "output array too small for the packed sketches"};
-        const PackSketch* ps = (const PackSketch*)(m + sizeof(PackHeader));
-        const uint32_t* clens = (const uint32_t*)(m + sizeof(PackHeader) + (uint64_t)hd.n * sizeof(PackSketch));
-        uint64_t nc_total = 0;
-        for (uint32_t i = 0; i < hd.n; i++) { PackSketch p; std::memcpy(&p, &ps[i], sizeof(p)); nc_total += p.n_contigs; }
-        if (meta_bytes < sizeof(PackHeader) + (uint64_t)hd.n * sizeof(PackSketch) + 4 * nc_total) throw Fail{SKB_ERR_ARG, "truncated pack descriptor"};
         auto store = std::make_shared<BatchStore>();
         store->blob = DevMem::persistent(ctx->core, std::max<uint64_t>(hd.payload_bytes, 16));
         if (hd.payload_bytes)
             CU(cudaMemcpyAsync(store->blob.p, payload_dev, hd.payload_bytes, cudaMemcpyDeviceToDevice, c.stream));
-        const char* base = (const char*)store->blob.p;
-        for (uint32_t i = 0; i < hd.n; i++) {
-            PackSketch p;
-            std::memcpy(&p, &ps[i], sizeof(p));
-            GenomeView v{};
-            v.kmer_p = (const uint32_t*)(base + p.off[0]); v.pos_p = (const uint32_t*)(base + p.off[1]);
-            v.meta_p = (const uint32_t*)(base + p.off[2]); v.kmer_k = (const uint32_t*)(base + p.off[3]);
-            v.pos_k = (const uint32_t*)(base + p.off[4]); v.meta_k = (const uint32_t*)(base + p.off[5]);
-            v.bucket = (const uint32_t*)(base + p.off[6]); v.contig_seed_start = (const uint32_t*)(base + p.off[7]);
-            v.contig_len = (const uint32_t*)(base + p.off[8]); v.contig_win_start = (const uint32_t*)(base + p.off[9]);
-            v.markers = (const uint64_t*)(base + p.off[10]);
-            v.total_len = p.total_len; v.n_seeds = p.n_seeds; v.n_markers = p.n_markers; v.n_contigs = p.n_contigs;
-            v.bucket_shift = p.bucket_shift; v.n_buckets = p.n_buckets; v.win_cap = p.win_cap;
-            auto impl = std::make_shared<SketchImpl>();
-            impl->core = ctx->core; impl->store = store; impl->view = v;
-            impl->contig_len_host.assign(clens, clens + p.n_contigs);
-            clens += p.n_contigs;
-            impl->info.n_seeds = p.n_seeds; impl->info.n_markers = p.n_markers; impl->info.total_len = p.total_len;
-            impl->info.n_contigs = p.n_contigs; impl->info.k = p.k; impl->info.c = p.c; impl->info.marker_c = p.marker_c;
-            impl->info.has_seeds = p.has_seeds;
-            out[i] = new skb_sketch{impl};
-        }
+        views_from_meta(ctx->core, store, (const char*)meta_host, meta_bytes, (const char*)store->blob.p, out);
         CU(cudaStreamSynchronize(c.stream));      // the caller may reuse the payload buffer on return
+        return SKB_OK;
+    });
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- zero-copy exchange region
+struct skb_exchange {
+    std::shared_ptr<skb::Core> core;
+    std::shared_ptr<skb::BatchStore> store;     // store->blob is the block; adopted sketches share it
+    uint64_t bytes = 0;
+};
+
+namespace {
+inline uint64_t pad256(uint64_t x) { return (x + 255) & ~(uint64_t)255; }
+}
+
+extern "C" {
+
+int skb_exchange_segment_size(uint32_t n, skb_sketch_t* const* sketches, uint64_t* segment_bytes, uint64_t* meta_bytes) {
+    if (!segment_bytes || !meta_bytes) return SKB_ERR_ARG;
+    uint64_t pb = 0, mb = 0;
+    const int rc = skb_sketch_pack_size(n, sketches, &pb, &mb);
+    if (rc != SKB_OK) return rc;
+    *meta_bytes = mb;
+    *segment_bytes = pad256(mb) + pad256(pb);
+    return SKB_OK;
+}
+
+int skb_exchange_create(skb_ctx_t* ctx, uint64_t bytes, skb_exchange_t** out) {
+    if (!ctx || !out) return SKB_ERR_ARG;
+    *out = nullptr;
+    return guarded(ctx->core.get(), [&] {
+        auto ex = std::make_unique<skb_exchange>();
+        ex->core = ctx->core;
+        ex->store = std::make_shared<BatchStore>();
+        ex->store->blob = DevMem::persistent(ctx->core, std::max<uint64_t>(bytes, 256));
+        ex->bytes = bytes;
+        *out = ex.release();
+        return SKB_OK;
+    });
+}
+
+void* skb_exchange_ptr(skb_exchange_t* ex) { return ex ? ex->store->blob.p : nullptr; }
+
+void skb_exchange_free(skb_exchange_t* ex) {
+    if (!ex) return;
+    auto core = ex->core;
+    std::lock_guard<std::mutex> lk(core->mu);
+    cudaSetDevice(core->device);
+    delete ex;
+}
+
+int skb_exchange_pack(skb_exchange_t* ex, uint64_t offset, uint32_t n, skb_sketch_t* const* sketches) {
+    if (!ex || (n && !sketches) || (offset & 255)) return SKB_ERR_ARG;
+    return guarded(ex->core.get(), [&] {
+        Core& c = *ex->core;
+        uint64_t need_p = 0, need_m = 0;
+        if (skb_sketch_pack_size(n, sketches, &need_p, &need_m) != SKB_OK) throw Fail{SKB_ERR_ARG, "null sketch"};
+        const uint64_t seg = pad256(need_m) + pad256(need_p);
+        if (offset + seg > ex->bytes) throw Fail{SKB_ERR_ARG, "segment does not fit into the exchange block"};
+        // descriptor: built in pinned memory, copied to the head of the segment; arrays: one gather kernel
+        std::vector<char> meta(need_m);
+        std::vector<SegmentCopy> segs;
+        uint64_t max_bytes = 0;
+        build_pack_meta(c, n, sketches, need_p, meta.data(), segs, max_bytes);
+        char* seg_base = (char*)ex->store->blob.p + offset;
+        const size_t tb = sizeof(SegmentCopy) * segs.size();
+        char* h = (char*)ensure_pinned(c, pad256(need_m) + tb + 64);
+        std::memcpy(h, meta.data(), need_m);
+        if (tb) std::memcpy(h + pad256(need_m), segs.data(), tb);
+        CU(cudaMemcpyAsync(seg_base, h, need_m, cudaMemcpyHostToDevice, c.stream));
+        if (!segs.empty()) {
+            void* d_segs = c.scratch(SLOT_PACK, tb);
+            CU(cudaMemcpyAsync(d_segs, h + pad256(need_m), tb, cudaMemcpyHostToDevice, c.stream));
+            launch_segment_copy((const SegmentCopy*)d_segs, (uint32_t)segs.size(), max_bytes, seg_base + pad256(need_m), c.stream);
+            CU(cudaGetLastError());
+        }
+        // the pinned staging block is shared by later calls: wait for the two small uploads (the gather kernel may
+        // still be running; callers order their collective behind it on this stream or through skb_ctx_sync)
+        CU(cudaEventRecord(c.ev[5], c.stream));
+        CU(cudaEventSynchronize(c.ev[5]));
+        return SKB_OK;
+    });
+}
+
+int skb_exchange_adopt(skb_exchange_t* ex, uint32_t n_segments, const uint64_t* offsets, const uint64_t* meta_bytes,
+                       skb_sketch_t** out, uint32_t out_cap, uint32_t* counts) {
+    if (!ex || (n_segments && (!offsets || !meta_bytes || !counts))) return SKB_ERR_ARG;
+    return guarded(ex->core.get(), [&] {
+        Core& c = *ex->core;
+        uint64_t total_meta = 0;
+        for (uint32_t i = 0; i < n_segments; i++) {
+            if ((offsets[i] & 255) || meta_bytes[i] < sizeof(PackHeader) || offsets[i] + meta_bytes[i] > ex->bytes)
+                throw Fail{SKB_ERR_ARG, "bad exchange segment"};
+            total_meta += pad256(meta_bytes[i]);
+        }
+        // all descriptors come to the host with one synchronisation
+        char* h = (char*)ensure_pinned(c, total_meta + 64);
+        const char* blk = (const char*)ex->store->blob.p;
+        uint64_t ho = 0;
+        for (uint32_t i = 0; i < n_segments; i++) {
+            CU(cudaMemcpyAsync(h + ho, blk + offsets[i], meta_bytes[i], cudaMemcpyDeviceToHost, c.stream));
+            ho += pad256(meta_bytes[i]);
+        }
+        CU(cudaStreamSynchronize(c.stream));
+        uint32_t n_total = 0;
+        ho = 0;
+        for (uint32_t i = 0; i < n_segments; i++) {
+            PackHeader hd;
+            std::memcpy(&hd, h + ho, sizeof(hd));
+            if (hd.magic != PACK_MAGIC) throw Fail{SKB_ERR_ARG, "exchange segment does not start with a sketch descriptor (collective not finished?)"};
+            const uint64_t payload_off = offsets[i] + pad256(meta_bytes[i]);
+            if (payload_off + hd.payload_bytes > ex->bytes) throw Fail{SKB_ERR_ARG, "exchange segment exceeds the block"};
+            if (n_total + hd.n > out_cap || (hd.n && !out)) throw Fail{SKB_ERR_ARG, "output array too small for the adopted sketches"};
+            views_from_meta(ex->core, ex->store, h + ho, meta_bytes[i], blk + payload_off, out + n_total);
+            counts[i] = hd.n;
+            n_total += hd.n;
+            ho += pad256(meta_bytes[i]);
+        }
         return SKB_OK;
     });
 }
@@ -1363,7 +1527,7 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
                              o_a = plan(na * 4 * 7), o_best = plan(na * 8), o_w = plan(nw * 4 * 3 + 4 * (size_t)np),
                              o_rec = plan(nw * sizeof(WindowRec)), o_keys = plan(nw * 8 * 2), o_vals = plan(nw * 4 * 2),
                              o_res = plan(sizeof(PairResult) * np), o_sort = plan(sort_bytes),
-                             o_groups = plan(sizeof(uint2) * groups.size());
+                             o_groups = plan(sizeof(uint2) * groups.size()), o_total = plan(8);
                 char* base = (char*)c.scratch(SLOT_CHAIN, total);
                 ChainBatch B{};
                 B.qviews = d_q.as<GenomeView>(); B.rviews = d_r; B.n_pairs = np;
@@ -1375,6 +1539,8 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
                 B.walk_groups = (const uint2*)(base + o_groups); B.n_walk_groups = (uint32_t)groups.size(); B.walk_group_max = group_max;
                 CU(cudaMemcpyAsync(base + o_groups, groups.data(), sizeof(uint2) * groups.size(), cudaMemcpyHostToDevice, st));
                 CU(cudaMemsetAsync(B.m_cnt + seeds, 0, 4, st));
+                B.a_total64 = (unsigned long long*)(base + o_total);
+                CU(cudaMemsetAsync(B.a_total64, 0, 8, st));
                 launch_match_count(B, st);
                 scan_match_counts(B, base + o_scan, scan_bytes, st);
                 B.anchor_cap = (uint32_t)est;
@@ -1404,11 +1570,17 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
                 }
                 CU(cudaGetLastError());          // a launch that was refused (configuration) must not pass silently
                 uint32_t n_anchors = 0;
+                unsigned long long n_anchors64 = 0;
                 download(c, &n_anchors, B.a_off + seeds, 1);
+                download(c, &n_anchors64, B.a_total64, 1);
                 download(c, res.data(), B.results, np);
                 tq.mark("batch enqueued");
                 CU(cudaStreamSynchronize(st));   // also keeps `pairs` alive until its upload has finished
                 tq.mark("batch synced");
+                // the anchor offsets are a 32-bit scan: repeat-rich genome pairs (multi-copy k-mers on both sides multiply)
+                // could wrap it, after which the capacity check below would pass on garbage
+                if (n_anchors64 >= 0x7FFFFFFFull)
+                    throw Fail{SKB_ERR_ARG, "more than 2^31 k-mer matches in one chaining batch (highly repetitive sketches); query fewer genomes per call"};
                 if (n_anchors <= B.anchor_cap) break;
                 if (attempt == 1) throw Fail{SKB_ERR_CUDA, "anchor arrays overflowed twice"};
                 est = n_anchors;

@@ -228,6 +228,7 @@ struct ChainBatch {            // device pointers of one batch of pairs
     const uint2* walk_groups;  // (first pair, count): consecutive pairs with the same query, walked by one CTA
     uint32_t n_walk_groups, walk_group_max;
     uint32_t* a_off;           // exclusive scan of m_cnt (+1 trailing element = total)
+    unsigned long long* a_total64;   // the same total accumulated in 64 bits (guards the 32-bit scan against wrap-around)
     // anchors
     uint32_t anchor_cap;
     uint32_t* a_qi; uint32_t* a_qp; uint32_t* a_rp; uint32_t* a_meta;   // meta = ref contig << 1 | reverse

@@ -20,6 +20,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <stdexcept>
 #include <string>
 #include <sys/stat.h>
@@ -261,15 +262,20 @@ struct Sketch {
     bool amino_acid = false;
 };
 
-HostSketch export_sketch(const Sketch& s, const Params& params) {
+HostSketch export_sketch(const Sketch& s, const Params& params, bool markers_only = false) {
     skb_sketch_info_t info;
     check(global_ctx(), skb_sketch_info(s.handle->h, &info));
     HostSketch o;
     o.file_name = s.name; o.has_seeds = info.has_seeds != 0; o.params = params;
-    o.kmer.resize(info.n_seeds); o.pos.resize(info.n_seeds); o.contig.resize(info.n_seeds); o.canonical.resize(info.n_seeds);
     o.markers.resize(info.n_markers); o.contig_lengths.resize(info.n_contigs);
-    check(global_ctx(), skb_sketch_export(s.handle->h, o.kmer.data(), o.pos.data(), o.contig.data(), o.canonical.data(),
-                                          o.markers.data(), o.contig_lengths.data()));
+    if (markers_only) {
+        // markers.bin holds no seeds (get_markers_only, lib.rs:495): leave the seed arrays on the device
+        check(global_ctx(), skb_sketch_export(s.handle->h, nullptr, nullptr, nullptr, nullptr, o.markers.data(), o.contig_lengths.data()));
+    } else {
+        o.kmer.resize(info.n_seeds); o.pos.resize(info.n_seeds); o.contig.resize(info.n_seeds); o.canonical.resize(info.n_seeds);
+        check(global_ctx(), skb_sketch_export(s.handle->h, o.kmer.data(), o.pos.data(), o.contig.data(), o.canonical.data(),
+                                              o.markers.data(), o.contig_lengths.data()));
+    }
     o.contigs = s.contig_names; o.total_len = info.total_len;
     return o;
 }
@@ -298,7 +304,9 @@ struct Database {
     std::unordered_map<std::string, size_t> by_name;    // Memory keys / Consolidated index keys
     std::vector<IndexEntry> index;                      // Consolidated: entries in append order (= offset order)
     skb_db_t* db = nullptr;
-    std::mutex mu;
+    // Readers (query) share, writers (sketch, flush) exclude: the reference's RwLocks (lib.rs:135-136).  NEVER taken while
+    // the GIL is held: a thread that blocks on `mu` with the GIL would stop the holder from ever re-acquiring the GIL.
+    std::shared_mutex mu;
 
     Database() { check(global_ctx(), skb_db_create(global_ctx(), &db)); }
     ~Database() { if (db) skb_db_destroy(db); }
@@ -313,8 +321,7 @@ struct Database {
         if (storage == Storage::Folder) {
             write_file(join(folder, s.name + ".sketch"), w.buf, "wb");
         } else {
-            for (auto& e : index)
-                if (e.file_name == s.name) throw py::value_error("duplicate name in sketches: \"" + s.name + "\"");
+            if (by_name.count(s.name)) throw py::value_error("duplicate name in sketches: \"" + s.name + "\"");   // lib.rs:67-72
             const std::string path = join(folder, "sketches.db");
             IndexEntry e{s.name, file_size(path), (uint64_t)w.buf.size()};
             write_file(path, w.buf, "ab");
@@ -324,6 +331,14 @@ struct Database {
 
     void add(Sketch s, bool persist) {
         if (persist) store(s);
+        auto it = by_name.find(s.name);
+        if (it != by_name.end()) {
+            // same name again (Memory / Folder storage): the reference's sketch store is a map keyed by name, so the new
+            // sketch takes the place of the old one and a query reports the name once (lib.rs:45,64,617-640)
+            check(global_ctx(), skb_db_replace(db, (uint32_t)it->second, s.handle->h));
+            items[it->second] = std::move(s);
+            return;
+        }
         uint32_t idx = 0;
         check(global_ctx(), skb_db_add(db, s.handle->h, &idx));
         by_name[s.name] = items.size();
@@ -335,7 +350,7 @@ struct Database {
         Writer w;
         write_params(w, params);
         w.u64(items.size());
-        for (auto& s : items) write_sketch(w, export_sketch(s, params), true);
+        for (auto& s : items) write_sketch(w, export_sketch(s, params, true), true);
         write_file(path, w.buf, "wb");
     }
     // Database::_save_index (lib.rs:203-215)
@@ -347,8 +362,8 @@ struct Database {
         write_file(path, w.buf, "wb");
     }
     // Database::_flush (lib.rs:217-227)
-    void flush() {
-        std::lock_guard<std::mutex> lk(mu);
+    void flush() {          // callers hold no GIL
+        std::unique_lock<std::shared_mutex> lk(mu);
         if (storage == Storage::Memory) return;
         save_markers(join(folder, "markers.bin"));
         if (storage == Storage::Consolidated) save_index(join(folder, "index.db"), index);
@@ -468,6 +483,16 @@ std::vector<Sketch> sketch_many_impl(Database& db, const py::sequence& items, bo
     return out;
 }
 
+void raise_query_error(int rc, const std::string& err) {
+    switch (rc) {
+        case SKB_OK: return;
+        case SKB_ERR_ARG: throw py::value_error(err);
+        case SKB_ERR_KEY: throw py::key_error(err);
+        case SKB_ERR_NOMEM: throw std::bad_alloc();
+        default: throw std::runtime_error(err);
+    }
+}
+
 }  // namespace
 
 PYBIND11_MODULE(_skani, m) {
@@ -538,7 +563,10 @@ PYBIND11_MODULE(_skani, m) {
         .def_static("open", [](const py::object& path) { return open_impl(path, false); }, py::arg("path"),
                     "Open a database from a folder containing sketches; new sketches are appended to it.")
         .def("__enter__", [](py::object self) { return self; })
-        .def("__exit__", [](Database& db, const py::object&, const py::object&, const py::object&) { db.flush(); return false; })
+        .def("__exit__", [](Database& db, const py::object&, const py::object&, const py::object&) {
+            { py::gil_scoped_release nogil; db.flush(); }
+            return false;
+        })
         .def_property_readonly("path", [](const Database& db) -> py::object {
             if (db.storage == Storage::Memory) return py::none();
             return py::module_::import("pathlib").attr("Path")(db.folder);
@@ -548,7 +576,8 @@ PYBIND11_MODULE(_skani, m) {
         .def("__len__", [](const Database& db) { return db.items.size(); })
         .def("sketch", [](Database& db, const std::string& name, const py::args& contigs, bool seed) {
                  Sketch s = sketch_impl(db, name, contigs, seed);
-                 std::lock_guard<std::mutex> lk(db.mu);
+                 py::gil_scoped_release nogil;                       // before the lock, never the other way round
+                 std::unique_lock<std::shared_mutex> lk(db.mu);
                  db.add(std::move(s), true);
              }, py::arg("name"), py::arg("seed") = true, "Add a reference genome to the database.")
         .def("query", [](Database& db, const std::string& name, const py::args& contigs, bool seed, const py::object& learned_ani,
@@ -560,25 +589,29 @@ PYBIND11_MODULE(_skani, m) {
                  o.median = median; o.robust = robust; o.faster_small = faster_small;
                  skb_hit_t* hits = nullptr; uint64_t n = 0;
                  int rc;
+                 std::string err;
+                 std::vector<Hit> out;
                  {
-                     std::lock_guard<std::mutex> lk(db.mu);
+                     // GIL first, lock second (lib.rs:569 allow_threads, then RwLock::read at lib.rs:617-621): concurrent
+                     // query() calls on one Database share the lock; the GPU work itself is serialised inside libskb
                      py::gil_scoped_release nogil;
+                     std::shared_lock<std::shared_mutex> lk(db.mu);
                      skb_sketch_t* qh = q.handle->h;
                      rc = skb_db_query(db.db, 1, &qh, &o, &hits, &n, nullptr);
+                     if (rc != SKB_OK) err = skb_last_error(global_ctx());
+                     else for (uint64_t i = 0; i < n; i++)
+                         out.push_back(Hit{hits[i].ani, name, hits[i].af_query, db.items[hits[i].ref_index].name, hits[i].af_ref});
+                     skb_hits_free(hits);
                  }
-                 if (rc == SKB_ERR_UNSUPPORTED) throw std::runtime_error(skb_last_error(global_ctx()));
-                 check(global_ctx(), rc);
-                 std::vector<Hit> out;
-                 for (uint64_t i = 0; i < n; i++)
-                     out.push_back(Hit{hits[i].ani, name, hits[i].af_query, db.items[hits[i].ref_index].name, hits[i].af_ref});
-                 skb_hits_free(hits);
+                 raise_query_error(rc, err);
                  return out;
              }, py::arg("name"), py::arg("seed") = true, py::arg("learned_ani") = py::none(), py::arg("median") = false,
              py::arg("robust") = false, py::arg("cutoff") = py::none(), py::arg("faster_small") = false,
              "Query the database with a genome.")
         .def("sketch_many", [](Database& db, const py::sequence& items, bool seed) {
                  std::vector<Sketch> sk = sketch_many_impl(db, items, seed);
-                 std::lock_guard<std::mutex> lk(db.mu);
+                 py::gil_scoped_release nogil;
+                 std::unique_lock<std::shared_mutex> lk(db.mu);
                  for (auto& s : sk) db.add(std::move(s), true);
              }, py::arg("items"), py::kw_only(), py::arg("seed") = true,
              "Add many reference genomes in one GPU batch: items = [(name, contigs), ...] (extension over pyskani).")
@@ -593,43 +626,51 @@ PYBIND11_MODULE(_skani, m) {
                  for (auto& q : qs) qh.push_back(q.handle->h);
                  skb_hit_t* hits = nullptr; uint64_t n = 0;
                  int rc;
-                 {
-                     std::lock_guard<std::mutex> lk(db.mu);
-                     py::gil_scoped_release nogil;
-                     rc = skb_db_query(db.db, (uint32_t)qh.size(), qh.data(), &o, &hits, &n, nullptr);
-                 }
-                 if (rc == SKB_ERR_UNSUPPORTED) throw std::runtime_error(skb_last_error(global_ctx()));
-                 check(global_ctx(), rc);
+                 std::string err;
                  std::vector<std::vector<Hit>> out(qs.size());
-                 for (uint64_t i = 0; i < n; i++)
-                     out[hits[i].query_index].push_back(Hit{hits[i].ani, qs[hits[i].query_index].name, hits[i].af_query,
-                                                            db.items[hits[i].ref_index].name, hits[i].af_ref});
-                 skb_hits_free(hits);
+                 {
+                     py::gil_scoped_release nogil;
+                     std::shared_lock<std::shared_mutex> lk(db.mu);
+                     rc = skb_db_query(db.db, (uint32_t)qh.size(), qh.data(), &o, &hits, &n, nullptr);
+                     if (rc != SKB_OK) err = skb_last_error(global_ctx());
+                     else for (uint64_t i = 0; i < n; i++)
+                         out[hits[i].query_index].push_back(Hit{hits[i].ani, qs[hits[i].query_index].name, hits[i].af_query,
+                                                                db.items[hits[i].ref_index].name, hits[i].af_ref});
+                     skb_hits_free(hits);
+                 }
+                 raise_query_error(rc, err);
                  return out;
              }, py::arg("items"), py::kw_only(), py::arg("seed") = true, py::arg("learned_ani") = py::none(), py::arg("median") = false,
              py::arg("robust") = false, py::arg("cutoff") = py::none(), py::arg("faster_small") = false,
              "Query with many genomes in one GPU batch: items = [(name, contigs), ...]; returns one list of Hit per query "
              "(extension over pyskani).")
-        .def("save", [](Database& db, const py::object& path, bool overwrite, const py::object& format) {
+        .def("save", [](Database& db, const py::object& path, bool overwrite, const py::object& format, bool strict_format) {
                  const std::string folder = fsdecode(path);
                  if (!exists(folder)) mkdirs(folder);
                  const std::string markers = join(folder, "markers.bin");
                  if (!overwrite && exists(markers)) throw_os(EEXIST, markers);
-                 // NOTE: the reference maps the formats the wrong way round here (lib.rs:696-699); this
-                 // implementation writes the format it is asked for.
-                 const Storage st = parse_format(format);
-                 std::lock_guard<std::mutex> lk(db.mu);
+                 // The reference maps the two format names the other way round in save() (lib.rs:696-699): None and
+                 // "consolidated" write one `<name>.sketch` per genome, "separated" writes sketches.db + index.db.  That is
+                 // what existing pyskani callers get on disk, so it is the default here too; strict_format=True writes the
+                 // layout the name says.  Database.load / Database.open read either layout.
+                 Storage st = parse_format(format);
+                 if (!strict_format) st = st == Storage::Consolidated ? Storage::Folder : Storage::Consolidated;
+                 py::gil_scoped_release nogil;
+                 std::shared_lock<std::shared_mutex> lk(db.mu);
                  db.save_markers(markers);
                  std::vector<IndexEntry> idx;
-                 if (st == Storage::Consolidated) write_file(join(folder, "sketches.db"), "", "wb");
                  for (auto& s : db.items) {
                      Writer w;
                      write_params(w, db.params);
                      write_sketch(w, export_sketch(s, db.params), false);
-                     if (st == Storage::Folder) write_file(join(folder, basename(s.name) + ".sketch"), w.buf, "wb");
+                     // DatabaseStorage::store (lib.rs:56-62 / 64-88): file named after Sketch.file_name; sketches.db is opened
+                     // for appending, so an existing one grows
+                     if (st == Storage::Folder) write_file(join(folder, s.name + ".sketch"), w.buf, "wb");
                      else { idx.push_back(IndexEntry{s.name, file_size(join(folder, "sketches.db")), (uint64_t)w.buf.size()}); write_file(join(folder, "sketches.db"), w.buf, "ab"); }
                  }
                  if (st == Storage::Consolidated) Database::save_index(join(folder, "index.db"), idx);
-             }, py::arg("path"), py::arg("overwrite") = false, py::arg("format") = py::none(), "Save the database to the given path.")
-        .def("flush", [](Database& db) { db.flush(); }, "Flush the database buffers to disk.");
+             }, py::arg("path"), py::arg("overwrite") = false, py::arg("format") = py::none(), py::kw_only(), py::arg("strict_format") = false,
+             "Save the database to the given path (format names mapped as the reference maps them; strict_format=True "
+             "writes the layout the name says).")
+        .def("flush", [](Database& db) { py::gil_scoped_release nogil; db.flush(); }, "Flush the database buffers to disk.");
 }

@@ -99,6 +99,23 @@ def test_partition_is_balanced_and_deterministic():
     assert parallel.partition_by_size([4], 4) == [[0], [], [], []]
 
 
+def test_segment_layout():
+    """exchange block layout: a uniform stride (one in-place all-gather) when the segments are nearly equal, exact
+    back-to-back segments (grouped broadcasts) when padding to the largest would waste more than 10 %"""
+    from pyskani_b200 import parallel
+    offs, total, stride = parallel.segment_layout([2560, 2816, 2560, 2816])
+    assert stride == 2816 and offs == [0, 2816, 5632, 8448] and total == 11264
+    offs, total, stride = parallel.segment_layout([256, 4096, 256])
+    assert stride == 0 and offs == [0, 256, 4352] and total == 4608
+    offs, total, stride = parallel.segment_layout([0, 0])
+    assert total >= 256 and len(offs) == 2
+    for segs in ([512] * 8, [768, 256, 1024], [256]):
+        offs, total, stride = parallel.segment_layout(segs)
+        for r, (o, s) in enumerate(zip(offs, segs)):
+            assert o % 256 == 0 and o + s <= total
+            assert all(o + s <= offs[j] for j in range(r + 1, len(segs)))      # segments never overlap
+
+
 def test_pack_roundtrip():
     from pyskani_b200 import parallel
     rng = np.random.default_rng(0)

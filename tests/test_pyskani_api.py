@@ -50,6 +50,49 @@ class TestAniEC590:
         assert self.close(hits[0].query_fraction, 0.9189)
         assert self.close(hits[0].identity, 0.9995)
 
+    def test_concurrent_queries(self, ec590_db, ecoli):
+        """reference lib.rs:569 (allow_threads) + RwLock read (lib.rs:617-621): query() may run from many threads on one
+        Database.  Eight threads x 20 calls, results equal to the serial answer; a lock-order bug shows up as a timeout."""
+        from concurrent.futures import ThreadPoolExecutor, wait
+        sub = ecoli[1][:600_000]
+        want = [(h.reference_name, h.identity, h.query_fraction, h.reference_fraction) for h in ec590_db.query("K12", sub, learned_ani=False)]
+        assert len(want) == 1
+
+        def work(i):
+            out = []
+            for j in range(20):
+                if i == 0 and j % 5 == 0:
+                    ec590_db.flush()                      # a writer-side call in between (no-op for a memory database)
+                out.append([(h.reference_name, h.identity, h.query_fraction, h.reference_fraction)
+                            for h in ec590_db.query("K12", sub, learned_ani=False)])
+            return out
+        with ThreadPoolExecutor(max_workers=8) as ex:
+            futs = [ex.submit(work, i) for i in range(8)]
+            done, pending = wait(futs, timeout=120)
+            assert not pending, "concurrent Database.query() calls did not finish: lock-order inversion between the GIL and the database lock"
+        for f in futs:
+            assert all(r == want for r in f.result())
+
+    def test_concurrent_sketch_and_query(self, pyskani, ecoli):
+        from concurrent.futures import ThreadPoolExecutor, wait
+        db = pyskani.Database()
+        db.sketch("EC590", ecoli[0][:500_000])
+        q = ecoli[1][:500_000]
+
+        def sketcher():
+            for i in range(10):
+                db.sketch("extra%d" % i, ecoli[0][100_000 * i:100_000 * i + 200_000])
+
+        def querier():
+            return [len(db.query("K12", q, learned_ani=False)) for _ in range(10)]
+        with ThreadPoolExecutor(max_workers=4) as ex:
+            futs = [ex.submit(sketcher)] + [ex.submit(querier) for _ in range(3)]
+            done, pending = wait(futs, timeout=120)
+            assert not pending
+        for f in futs:
+            f.result()
+        assert len(db) == 11
+
     def test_basic_returns_uncorrected_estimate(self, ec590_db, ecoli):
         # The reference's default applies skani's learned regression (0.9939, test_ani.py:28-33).  Its weights are
         # embedded in the skani crate and unavailable here: the default returns the uncorrected estimate (DESIGN.md §0 a9).
@@ -122,6 +165,29 @@ class TestDatabase:
         db = pyskani.Database(compression=30, marker_compression=200)
         assert (db.compression, db.marker_compression) == (30, 200)
 
+    def test_duplicate_name_in_memory_replaces(self, pyskani):
+        """reference lib.rs:51-54: the Memory store is a HashMap keyed by name, the shortlist a HashSet of names
+        (lib.rs:617-640): sketching a name twice leaves ONE sketch under that name - the newer one."""
+        from pyskani_b200 import synth
+        a, b = synth.random_genome(200_000, 41), synth.random_genome(200_000, 42)
+        db = pyskani.Database()
+        db.sketch("g", a.tobytes())
+        db.sketch("g", b.tobytes())
+        assert len(db) == 1
+        assert db.query("qa", a.tobytes(), learned_ani=False) == []
+        hits = db.query("qb", b.tobytes(), learned_ani=False)
+        assert [h.reference_name for h in hits] == ["g"] and hits[0].identity > 0.9999
+
+    def test_no_contigs(self, pyskani):
+        """reference lib.rs:155: a genome without (kept) contigs is an empty sketch, a query with it finds nothing"""
+        db = pyskani.Database()
+        db.sketch("empty")
+        db.sketch("short", b"ACGT" * 10)
+        db.sketch("real", b"ATGC" * 200)
+        assert len(db) == 3
+        assert db.query("nothing") == []
+        assert db.query("tiny", b"ACGT" * 10) == []
+
     def test_duplicate_name_in_consolidated(self, pyskani, tmp_path):
         db = pyskani.Database(str(tmp_path), format="consolidated")
         db.sketch("dup", b"ATGC" * 100)
@@ -160,19 +226,23 @@ class TestStorageRoundTrip:
         assert pyskani.Database.load(folder).path is None
         assert pyskani.Database.open(folder).path == pathlib.Path(folder)
 
+    @pytest.mark.parametrize("strict", [False, True])
     @pytest.mark.parametrize("fmt", [None, "consolidated", "separated"])
-    def test_save(self, pyskani, genomes, tmp_path, fmt):
+    def test_save(self, pyskani, genomes, tmp_path, fmt, strict):
         db, want = self.expected(pyskani, genomes)
         folder = str(tmp_path / "saved")
-        db.save(folder, format=fmt)
+        db.save(folder, format=fmt, strict_format=strict)
         with pytest.raises(FileExistsError):
-            db.save(folder, format=fmt)
-        db.save(folder, overwrite=True, format=fmt)
+            db.save(folder, format=fmt, strict_format=strict)
         files = set(os.listdir(folder))
-        if fmt == "separated":
-            assert {"markers.bin", "m3.sketch", "m9.sketch", "frag.sketch"} <= files
+        # reference lib.rs:696-699: save() maps None / "consolidated" to per-genome files and "separated" to
+        # sketches.db + index.db; strict_format=True un-swaps the names
+        separate_files = (fmt == "separated") == strict
+        if separate_files:
+            assert {"markers.bin", "m3.sketch", "m9.sketch", "frag.sketch"} <= files and "sketches.db" not in files
+            db.save(folder, overwrite=True, format=fmt, strict_format=strict)
         else:
-            assert {"markers.bin", "sketches.db", "index.db"} <= files
+            assert {"markers.bin", "sketches.db", "index.db"} <= files and "m3.sketch" not in files
         got = {h.reference_name: (h.identity, h.query_fraction, h.reference_fraction)
                for h in pyskani.Database.load(folder).query("base", genomes["base"])}
         assert got == want
