@@ -284,7 +284,7 @@ def parity_gate(args, capi, ctx, host_all, table, world, threads, oracle_db):
                 raise SystemExit("PARITY FAILURE: screen of (%d, %d): GPU %s/%d, oracle %s/%d" % (q, r, ok_gpu[i, r], shared_gpu[i, r], ok, sh))
     out["screen_decisions"] = len(q_screen) * n_total
     # (c) chained pairs of the TIMED run's hit table: sample queries = whole families
-    n_q = min(n_total, max(2 * members, 20))
+    n_q = min(n_total, max(4 * members, 40))
     q_chain = list(range(n_q // 2)) + list(range(n_total - (n_q - n_q // 2), n_total))
     hq, hr, res, n_in = oracle.query_many([oracle_db[q] for q in q_chain], oracle_db, 0.8, True, threads=threads)
     want = {(q_chain[int(a)], int(b)): r for a, b, r in zip(hq, hr, res)}

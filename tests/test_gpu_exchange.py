@@ -34,7 +34,7 @@ def test_exchange_block_pack_and_adopt():
     parts = [gs[:7], gs[7:]]
     sizes = [ctx.segment_size(p) for p in parts]
     assert all(s % 256 == 0 and m > 0 for s, m in sizes)
-    for uniform_slack in (0.10, -1.0):                     # uniform stride, then exact back-to-back segments
+    for uniform_slack in (10.0, -1.0):                     # uniform stride forced, then exact back-to-back segments
         offs, total, stride = parallel.segment_layout([s for s, _ in sizes], uniform_slack)
         assert (stride != 0) == (uniform_slack > 0)
         ex = ctx.exchange(total)
