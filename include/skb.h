@@ -169,6 +169,21 @@ int  skb_db_add_many(skb_db_t* db, uint32_t n, skb_sketch_t* const* sketches, ui
 int  skb_db_replace(skb_db_t* db, uint32_t index, skb_sketch_t* s);
 uint64_t skb_db_size(const skb_db_t* db);
 
+/* ---- learned-ANI model: skani::regression::get_model / use_learned_ani (lib.rs:611-614) ----
+ * skani embeds gradient-boosted regression ensembles (crate gbdt 0.1.3) as serde_json text; their weights are not part
+ * of pyskani's sources, so the model is loaded from text in the same format that the caller supplies.  A database with
+ * a model corrects the default (mean) ANI estimate on the device exactly when the reference would:
+ *   learned_ani == 1, or learned_ani == -1 (None) with c >= 70 and median == 0          (lib.rs:611-613);
+ * robust / median estimates are returned uncorrected.  learned_ani == 1 without a model is SKB_ERR_UNSUPPORTED. */
+typedef struct skb_model skb_model_t;
+int  skb_model_load_json(skb_ctx_t* ctx, const char* json, size_t len, skb_model_t** out);
+void skb_model_free(skb_model_t* m);
+int  skb_model_info(const skb_model_t* m, uint32_t* n_trees, uint32_t* n_nodes, uint32_t* n_features);
+/* evaluates the ensemble on the device for n_rows feature rows of n_features f32 each (parity / diagnostics entry) */
+int  skb_model_predict(skb_model_t* m, const float* rows, uint32_t n_rows, uint32_t n_features, float* out);
+/* attaches a model to the database (shared ownership); NULL detaches */
+int  skb_db_set_model(skb_db_t* db, skb_model_t* m);
+
 /* ---- query: lib.rs:616-657 for n_queries queries at once ----
  * For every (query, reference) pair: check_markers_quickly (lib.rs:623-628); for survivors
  * map_params_from_sketch + chain_seeds (lib.rs:646-653); keep results with ani > 0.1 (lib.rs:654).

@@ -32,7 +32,7 @@ class Result(C.Structure):
         ("ani", C.c_float), ("af_query", C.c_float), ("af_ref", C.c_float),
         ("ani_f64", C.c_double), ("af_query_f64", C.c_double), ("af_ref_f64", C.c_double),
         ("n_anchors", C.c_int64), ("n_windows", C.c_int64), ("n_chains", C.c_int64),
-        ("switched", C.c_int32),
+        ("switched", C.c_int32), ("features", C.c_float * 10),
     ]
 
 
@@ -196,6 +196,62 @@ def query_many(queries, refs, screen_val=0.8, rescue_small=True, params=None, th
         if nh <= cap:
             return hq[:nh].copy(), hr[:nh].copy(), [res[i] for i in range(nh)], ns.value
         cap = nh
+
+
+class Gbdt:
+    """CPU evaluator of a gbdt-rs regression ensemble (crate gbdt 0.1.3, Cargo.lock:541-542), restated from its
+    published algorithm: prediction = bias + sum over the first `iterations` trees of shrinkage * tree(x), every product and
+    sum rounded to f32 (gbdt-rs' ValueType) in tree order; a tree descends left when x[feature] < feature_value, follows
+    `missing` when the feature is f32::MIN, and returns `pred` at a leaf.  Reads the serde_json text itself (python json),
+    independently of the product's C++ parser."""
+    UNKNOWN = np.float32(-3.40282347e+38)
+
+    def __init__(self, text):
+        import json
+        d = json.loads(text)
+        conf = d["conf"]
+        self.n_features = int(conf["feature_size"])
+        self.shrinkage = np.float32(conf["shrinkage"])
+        self.bias = np.float32(d.get("bias", 0.0))
+        self.trees = []
+        for t in d["trees"][:int(conf.get("iterations", len(d["trees"])))]:
+            self.trees.append([(int(n["value"]["feature_index"]), np.float32(n["value"]["feature_value"]), np.float32(n["value"]["pred"]),
+                                int(n["value"].get("missing", 0)), bool(n["value"]["is_leaf"]), int(n["left"]), int(n["right"]))
+                               for n in t["tree"]["tree"]])
+
+    def tree(self, nodes, x):
+        i = 0
+        while True:
+            f, thr, pred, miss, leaf, l, r = nodes[i]
+            if leaf:
+                return pred
+            v = np.float32(x[f])
+            if v == self.UNKNOWN:
+                if miss == 0:
+                    return pred
+                nxt = l if miss < 0 else r
+            else:
+                nxt = l if v < thr else r
+            if nxt == 0:
+                return pred
+            i = nxt
+
+    def predict(self, x):
+        p = self.bias
+        for nodes in self.trees:
+            p = np.float32(p + np.float32(self.shrinkage * self.tree(nodes, x)))
+        return p
+
+
+LEARNED_MIN_COV = 150000.0
+
+
+def learned_ani(result, model, robust=False, median=False):
+    """ANI of an orc_chain result after the learned correction, as f32 (what Hit.identity carries)."""
+    if robust or median or not (result.ani > 0) or result.features[9] < LEARNED_MIN_COV:
+        return np.float32(result.ani)
+    a = float(model.predict([result.features[i] for i in range(10)])) / 100.0
+    return np.float32(min(1.0, max(0.0, a)))
 
 
 def mm_hash64(x):

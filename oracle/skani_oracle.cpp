@@ -413,6 +413,25 @@ void chain_impl(const orc_sketch* R0, const orc_sketch* Q0, const orc_chain_para
         else ani = std::pow(std::min(1.0, sa / ss), 1.0 / (double)k);
     }
     if (af_q < P.frac_cover_cutoff && af_r < P.frac_cover_cutoff) ani = -1.0;
+    // ---- feature vector of the learned-ANI regression (skani::regression; order documented in DESIGN.md) ----
+    {
+        double su = 0;
+        for (const Est& e : ests) su += e.ani;
+        const double mean_u = su / (double)n;
+        double dev = 0;
+        for (const Est& e : ests) dev += (e.ani - mean_u) * (e.ani - mean_u);
+        auto quant = [](const std::vector<uint32_t>& lens, int q) -> float {
+            if (lens.empty()) return 0.f;
+            std::vector<uint32_t> v(lens);
+            std::sort(v.begin(), v.end());
+            return (float)v[(v.size() - 1) * (size_t)q / 100];
+        };
+        float* x = out->features;
+        x[0] = (float)(ani * 100.0); x[1] = (float)(std::sqrt(dev / (double)n) * 100.0);
+        x[2] = quant(R->contig_lengths, 90); x[3] = quant(R->contig_lengths, 50); x[4] = quant(R->contig_lengths, 10);
+        x[5] = quant(Q->contig_lengths, 90); x[6] = quant(Q->contig_lengths, 50); x[7] = quant(Q->contig_lengths, 10);
+        x[8] = (float)(cov_q / (double)kept.size()); x[9] = (float)cov_q;
+    }
     if (sw) std::swap(af_q, af_r);
     out->ani_f64 = ani; out->af_query_f64 = af_q; out->af_ref_f64 = af_r;
     out->ani = (float)ani; out->af_query = (float)af_q; out->af_ref = (float)af_r;

@@ -75,6 +75,10 @@ typedef struct {
     int64_t n_windows;         /* windows that contributed an ANI value                    */
     int64_t n_chains;          /* kept chains                                              */
     int32_t switched;
+    /* inputs of the learned-ANI regression (skani::regression, reference lib.rs:611-614), f32 like gbdt-rs' ValueType:
+     * ANI %, std of window ANIs %, ref contig-length quantiles 90/50/10, query ones, mean aligned bases per chain,
+     * aligned query bases */
+    float   features[10];
 } orc_result_t;
 
 void orc_chain_params_default(orc_chain_params_t* p);

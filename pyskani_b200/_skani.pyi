@@ -30,14 +30,22 @@ class Database:
     """
 
     def __init__(self, path: PathLike | None = None, *, compression: int = 125, marker_compression: int = 1000,
-                 k: int = 15, format: StorageFormat | None = None) -> None: ...
+                 k: int = 15, format: StorageFormat | None = None, model: PathLike | None = None) -> None:
+        """``model`` (extension over pyskani): a gbdt-rs JSON dump of skani's learned-ANI regression; defaults to
+        ``$PYSKANI_B200_MODEL``.  See ``query``."""
 
     # -- construction from disk (lib.rs:423-470): both load every sketch into device memory; ``open`` keeps the folder
     #    attached so that later ``sketch()`` calls append to it
     @classmethod
-    def open(cls, path: PathLike) -> Database: ...
+    def open(cls, path: PathLike, *, model: PathLike | None = None) -> Database: ...
     @classmethod
-    def load(cls, path: PathLike) -> Database: ...
+    def load(cls, path: PathLike, *, model: PathLike | None = None) -> Database: ...
+    def set_model(self, path: PathLike | None) -> None:
+        """Load (or, with None, drop) the learned-ANI regression: the serde_json dump of a gbdt-rs ``GBDT`` as skani embeds
+        it (lib.rs:611-614; features: ANI %, std of window ANIs %, reference contig-length quantiles 90/50/10, query
+        ones, aligned bases per chain, aligned bases).  It is evaluated on the device."""
+    @property
+    def has_model(self) -> bool: ...
 
     # -- the hot path
     def sketch(self, name: str, *contigs: Contig, seed: bool = True) -> None:
@@ -46,7 +54,14 @@ class Database:
               median: bool = False, robust: bool = False, cutoff: float | None = None,
               faster_small: bool = False) -> list[Hit]:
         """Sketch the query, screen it against every reference, chain the survivors, return hits with ANI > 0.1
-        (lib.rs:549-660).  ``learned_ani=True`` raises: the regression model is not available (README.md)."""
+        (lib.rs:549-660).
+
+        ``learned_ani``: the reference resolves ``None`` to ``compression >= 70 and not median`` and then corrects the
+        mean estimate with the regression model embedded in the skani crate (lib.rs:611-614).  Those weights are not
+        part of pyskani's sources.  With a model loaded (``model=`` / ``set_model`` / ``$PYSKANI_B200_MODEL``) the
+        correction runs on the device under the same rule; without one, ``None`` returns the UNCORRECTED estimate and
+        emits a ``RuntimeWarning`` once per process (the reference's E. coli golden 0.9939 becomes 0.9946), and
+        ``learned_ani=True`` raises ``RuntimeError``.  ``robust`` / ``median`` estimates are never corrected."""
     def sketch_many(self, items: _Seq[NamedGenome], *, seed: bool = True) -> None:
         """``sketch`` for many genomes in one device batch (no counterpart in the reference)."""
     def query_many(self, items: _Seq[NamedGenome], *, seed: bool = True, learned_ani: bool | None = None,
@@ -55,7 +70,12 @@ class Database:
         """``query`` for many genomes at once; one hit list per item, in order."""
 
     # -- persistence (lib.rs:662-744)
-    def save(self, path: PathLike, overwrite: bool = False, format: StorageFormat | None = None) -> None: ...
+    def save(self, path: PathLike, overwrite: bool = False, format: StorageFormat | None = None, *,
+             strict_format: bool = False) -> None:
+        """Writes ``markers.bin`` plus the sketches.  As in the reference (lib.rs:696-699) the two format names are
+        swapped in this method: ``None`` / ``"consolidated"`` write one ``<name>.sketch`` per genome and ``"separated"``
+        writes ``sketches.db`` + ``index.db``.  ``strict_format=True`` (extension) writes the layout the name says.
+        ``Database.load`` / ``Database.open`` read either layout."""
     def flush(self) -> None: ...
 
     # -- introspection

@@ -54,7 +54,8 @@ SYMBOLS = [
     "skb_sketch_batch", "skb_sketch_batch_device", "skb_sketch_free", "skb_sketch_info", "skb_sketch_export",
     "skb_sketch_import", "skb_sketch_pack_size", "skb_sketch_pack", "skb_sketch_unpack",
     "skb_exchange_segment_size", "skb_exchange_create", "skb_exchange_ptr", "skb_exchange_pack", "skb_exchange_adopt",
-    "skb_exchange_free", "skb_db_create", "skb_db_destroy", "skb_db_add", "skb_db_add_many", "skb_db_replace", "skb_db_size", "skb_db_query",
+    "skb_exchange_free",
+    "skb_model_load_json", "skb_model_free", "skb_model_info", "skb_model_predict", "skb_db_set_model", "skb_db_create", "skb_db_destroy", "skb_db_add", "skb_db_add_many", "skb_db_replace", "skb_db_size", "skb_db_query",
     "skb_hits_free", "skb_db_screen", "skb_version",
 ]
 
@@ -106,6 +107,11 @@ def lib():
         L.skb_exchange_pack.argtypes = [vp, u64, u32, vp]
         L.skb_exchange_adopt.argtypes = [vp, u32, vp, vp, vp, u32, vp]
         L.skb_exchange_free.argtypes = [vp]
+        L.skb_model_load_json.argtypes = [vp, C.c_char_p, C.c_size_t, C.POINTER(vp)]
+        L.skb_model_free.argtypes = [vp]
+        L.skb_model_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
+        L.skb_model_predict.argtypes = [vp, vp, u32, u32, vp]
+        L.skb_db_set_model.argtypes = [vp, vp]
         L.skb_db_create.argtypes = [vp, C.POINTER(vp)]
         L.skb_db_destroy.argtypes = [vp]
         L.skb_db_add.argtypes = [vp, vp, C.POINTER(u32)]
@@ -257,6 +263,37 @@ class Context:
         self.check(lib().skb_memcpy_h2d(self._h, dst, src, nbytes))
 
 
+class Model:
+    """A gbdt-rs regression ensemble on the device (skani's learned-ANI model, include/skb.h)."""
+
+    def __init__(self, ctx, json_text):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        raw = json_text.encode() if isinstance(json_text, str) else bytes(json_text)
+        ctx.check(lib().skb_model_load_json(ctx._h, raw, len(raw), C.byref(self._h)))
+
+    def info(self):
+        a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self.ctx.check(lib().skb_model_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"n_trees": a.value, "n_nodes": b.value, "n_features": c.value}
+
+    def predict(self, rows):
+        rows = np.ascontiguousarray(rows, np.float32)
+        if rows.ndim == 1:
+            rows = rows[None, :]
+        out = np.empty(rows.shape[0], np.float32)
+        self.ctx.check(lib().skb_model_predict(self._h, rows.ctypes.data, rows.shape[0], rows.shape[1], out.ctypes.data))
+        return out
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            try:
+                lib().skb_model_free(self._h)
+            except TypeError:
+                pass
+            self._h = None
+
+
 class Exchange:
     """One block of sketch storage holding a segment per rank (include/skb.h, "zero-copy exchange region")."""
 
@@ -354,6 +391,10 @@ class Database:
         self.ctx.check(lib().skb_db_add_many(self._h, n, hs, C.byref(idx)))
         self._keep.extend(sketches)
         return idx.value
+
+    def set_model(self, model):
+        self.ctx.check(lib().skb_db_set_model(self._h, model._h if model is not None else None))
+        self._model = model
 
     def __len__(self):
         return lib().skb_db_size(self._h)

@@ -585,7 +585,7 @@ __global__ void ani_reduce_kernel(const ChainBatch b, const ChainConsts C, const
     const GenomeView& R = b.rviews[pd.r];
     PairResult res{-1.f, 0.f, 0.f, 0, 0, b.a_off[pd.seed_off + Q.n_seeds] - b.a_off[pd.seed_off]};
     const double inv_k = 1.0 / (double)C.k;
-    double wsum = 0, ssum = 0, covq = 0, covr = 0, chains = 0;
+    double wsum = 0, ssum = 0, covq = 0, covr = 0, chains = 0, usum = 0;
     uint32_t n = 0;
     double median_ani = 0;
     if (keys == nullptr) {
@@ -600,8 +600,10 @@ __global__ void ani_reduce_kernel(const ChainBatch b, const ChainConsts C, const
             covq += rec.cov_q; covr += rec.cov_r; chains += rec.n_chains;
             double ratio = (double)rec.anchors / (double)rec.seeds;
             if (ratio > 1.0) ratio = 1.0;
-            wsum += pow(ratio, inv_k) * (double)rec.seeds;
+            const double a = pow(ratio, inv_k);
+            wsum += a * (double)rec.seeds;
             ssum += (double)rec.seeds;
+            usum += a;
         }
         n = __reduce_add_sync(FULL, n);
     } else {
@@ -646,13 +648,62 @@ __global__ void ani_reduce_kernel(const ChainBatch b, const ChainConsts C, const
         if (afq > 1.0) afq = 1.0;
         if (afr > 1.0) afr = 1.0;
         if (afq < C.frac_cover_cutoff && afr < C.frac_cover_cutoff) ani = -1.0;
+        if (C.use_model && keys == nullptr && ani > 0.0 && covq >= C.learned_min_cov) {
+            // learned-ANI correction: features of the pair -> gradient-boosted trees -> ANI in percent.
+            // Feature order (DESIGN.md "learned ANI"): ANI %, standard deviation of the window ANIs %, reference contig-length
+            // quantiles 90/50/10, query contig-length quantiles 90/50/10, mean aligned length per chain, aligned bases.
+            const double mean_u = warp_sum_f64(usum) / (double)n;
+            double dev = 0;
+            for (uint32_t t = pd.win_off + lane; t < pd.win_off + Q.win_cap; t += 32) {
+                if (b.win_end[t] <= b.win_start[t]) continue;
+                const WindowRec rec = b.win_rec[t];
+                if (!rec.n_chains || !rec.seeds) continue;
+                double ratio = (double)rec.anchors / (double)rec.seeds;
+                if (ratio > 1.0) ratio = 1.0;
+                const double d = pow(ratio, inv_k) - mean_u;
+                dev += d * d;
+            }
+            dev = warp_sum_f64(dev);
+            float x[GBDT_FEATURES];
+            x[0] = (float)(ani * 100.0); x[1] = (float)(sqrt(dev / (double)n) * 100.0);
+            x[2] = (float)R.ctg_q90; x[3] = (float)R.ctg_q50; x[4] = (float)R.ctg_q10;
+            x[5] = (float)Q.ctg_q90; x[6] = (float)Q.ctg_q50; x[7] = (float)Q.ctg_q10;
+            x[8] = (float)(covq / chains); x[9] = (float)covq;
+            // trees are evaluated 32 at a time (one per lane) and added in order, one f32 rounding per product and per sum,
+            // exactly as gbdt-rs accumulates them
+            float pred = C.model.bias;
+            for (uint32_t t0 = 0; t0 < C.model.n_trees; t0 += 32) {
+                const float v = t0 + lane < C.model.n_trees ? gbdt_tree(C.model, t0 + lane, x) : 0.f;
+                const uint32_t cnt = min(32u, C.model.n_trees - t0);
+                for (uint32_t j = 0; j < cnt; j++)
+                    pred = __fadd_rn(pred, __fmul_rn(C.model.shrinkage, __shfl_sync(FULL, v, j)));
+            }
+            ani = (double)pred / 100.0;
+            if (ani > 1.0) ani = 1.0;
+            if (ani < 0.0) ani = 0.0;
+        }
         res.ani = (float)ani; res.af_q = (float)afq; res.af_r = (float)afr;
         res.n_chains = (uint32_t)chains;
     }
     if (lane == 0) b.results[p] = res;
 }
 
+// rows of n_features f32 -> ensemble prediction, one thread per row (the same gbdt_tree / rounding as ani_reduce_kernel)
+__global__ void gbdt_predict_kernel(const GbdtView m, const float* __restrict__ rows, uint32_t n_rows, uint32_t stride, float* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    float x[GBDT_FEATURES];
+    for (uint32_t f = 0; f < GBDT_FEATURES; f++) x[f] = f < stride ? rows[(size_t)i * stride + f] : 0.f;
+    out[i] = gbdt_predict(m, x);
+}
+
 }  // namespace
+
+void launch_gbdt_predict(const GbdtView& m, const float* rows, uint32_t n_rows, uint32_t stride, float* out, cudaStream_t st) {
+    if (n_rows == 0) return;
+    gbdt_predict_kernel<<<(n_rows + 127) / 128, 128, 0, st>>>(m, rows, n_rows, stride, out);
+    g_kernel_launches++;
+}
 
 void launch_match_count(const ChainBatch& b, cudaStream_t st) {
     if (b.n_pairs == 0) return;

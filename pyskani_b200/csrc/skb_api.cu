@@ -181,7 +181,30 @@ constexpr uint32_t FRAGMENT_LENGTH = 20000;   // skani::params::CHUNK_SIZE_DNA
 
 }  // namespace skb
 
+namespace skb {
+struct ModelImpl {
+    std::shared_ptr<Core> core;
+    GbdtHost host;
+    DevMem nodes, tree_off;
+    GbdtView dev_view() const {
+        GbdtView v = host.view();
+        v.nodes = nodes.as<GbdtNode>(); v.tree_off = tree_off.as<uint32_t>();
+        return v;
+    }
+};
+// contig-length quantiles of a sketch (features of the learned-ANI model): element (n - 1) * q / 100 of the sorted lengths
+inline void contig_quantiles(const std::vector<uint32_t>& lens, GenomeView& v) {
+    v.ctg_q90 = v.ctg_q50 = v.ctg_q10 = 0;
+    if (lens.empty()) return;
+    std::vector<uint32_t> s(lens);
+    std::sort(s.begin(), s.end());
+    const size_t n = s.size();
+    v.ctg_q90 = s[(n - 1) * 90 / 100]; v.ctg_q50 = s[(n - 1) * 50 / 100]; v.ctg_q10 = s[(n - 1) * 10 / 100];
+}
+}  // namespace skb
+
 struct skb_ctx { std::shared_ptr<skb::Core> core; };
+struct skb_model { std::shared_ptr<skb::ModelImpl> impl; };
 struct skb_sketch { std::shared_ptr<skb::SketchImpl> impl; };
 struct skb_db {
     std::shared_ptr<skb::Core> core;
@@ -192,6 +215,7 @@ struct skb_db {
     skb::DevMem idx_keys, idx_vals, idx_bucket;
     uint32_t idx_shift = 0, idx_postings = 0;
     bool idx_dirty = true;
+    std::shared_ptr<skb::ModelImpl> model;      // learned-ANI ensemble, optional
 };
 
 namespace skb {
@@ -539,6 +563,7 @@ static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_par
         h_cwin.push_back(wcap);
         v.win_cap = wcap; v.total_len = tot; v.n_contigs = nc;
         v.n_seeds = ns; v.n_markers = 0;      // marker fields are filled in after the final synchronisation
+        contig_quantiles(contig_lens[g], v);
     }
     if (!d_bucket_overflow) store->bucket = DevMem::persistent(core, 4 * bucket_total);
     store->contig_seed_start = DevMem::persistent(core, 4 * std::max<size_t>(cstart_total, 1));
@@ -1021,6 +1046,62 @@ int skb_db_replace(skb_db_t* db, uint32_t index, skb_sketch_t* s) {
 }
 uint64_t skb_db_size(const skb_db_t* db) { return db ? db->items.size() : 0; }
 
+int skb_model_load_json(skb_ctx_t* ctx, const char* json, size_t len, skb_model_t** out) {
+    if (!ctx || !json || !out) return SKB_ERR_ARG;
+    *out = nullptr;
+    return guarded(ctx->core.get(), [&] {
+        auto m = std::make_shared<ModelImpl>();
+        m->core = ctx->core;
+        try { m->host = gbdt_parse(json, len); }
+        catch (const std::runtime_error& e) { throw Fail{SKB_ERR_ARG, e.what()}; }
+        Core& c = *ctx->core;
+        m->nodes = DevMem::persistent(ctx->core, sizeof(GbdtNode) * std::max<size_t>(m->host.nodes.size(), 1));
+        m->tree_off = DevMem::persistent(ctx->core, 4 * m->host.tree_off.size());
+        CU(cudaMemcpyAsync(m->nodes.p, m->host.nodes.data(), sizeof(GbdtNode) * m->host.nodes.size(), cudaMemcpyHostToDevice, c.stream));
+        CU(cudaMemcpyAsync(m->tree_off.p, m->host.tree_off.data(), 4 * m->host.tree_off.size(), cudaMemcpyHostToDevice, c.stream));
+        CU(cudaStreamSynchronize(c.stream));
+        *out = new skb_model{m};
+        return SKB_OK;
+    });
+}
+void skb_model_free(skb_model_t* m) {
+    if (!m) return;
+    std::shared_ptr<Core> core = m->impl ? m->impl->core : nullptr;
+    if (core) { std::lock_guard<std::mutex> lk(core->mu); cudaSetDevice(core->device); delete m; }
+    else delete m;
+}
+int skb_model_info(const skb_model_t* m, uint32_t* n_trees, uint32_t* n_nodes, uint32_t* n_features) {
+    if (!m) return SKB_ERR_ARG;
+    if (n_trees) *n_trees = (uint32_t)m->impl->host.tree_off.size() - 1;
+    if (n_nodes) *n_nodes = (uint32_t)m->impl->host.nodes.size();
+    if (n_features) *n_features = m->impl->host.n_features;
+    return SKB_OK;
+}
+int skb_model_predict(skb_model_t* m, const float* rows, uint32_t n_rows, uint32_t n_features, float* out) {
+    if (!m || (n_rows && (!rows || !out))) return SKB_ERR_ARG;
+    return guarded(m->impl->core.get(), [&] {
+        if (n_features < m->impl->host.n_features || n_features > GBDT_FEATURES) throw Fail{SKB_ERR_ARG, "feature rows are narrower than the model's feature_size (or wider than 10)"};
+        if (n_rows == 0) return SKB_OK;
+        Core& c = *m->impl->core;
+        DevMem d_rows(m->impl->core, 4 * (size_t)n_rows * n_features), d_out(m->impl->core, 4 * (size_t)n_rows);
+        CU(cudaMemcpyAsync(d_rows.p, rows, 4 * (size_t)n_rows * n_features, cudaMemcpyHostToDevice, c.stream));
+        launch_gbdt_predict(m->impl->dev_view(), d_rows.as<float>(), n_rows, n_features, d_out.as<float>(), c.stream);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out, d_out.p, 4 * (size_t)n_rows, cudaMemcpyDeviceToHost, c.stream));
+        CU(cudaStreamSynchronize(c.stream));
+        return SKB_OK;
+    });
+}
+int skb_db_set_model(skb_db_t* db, skb_model_t* m) {
+    if (!db) return SKB_ERR_ARG;
+    return guarded(db->core.get(), [&] {
+        if (m && m->impl->core != db->core) throw Fail{SKB_ERR_ARG, "model belongs to another context"};
+        CU(cudaStreamSynchronize(db->core->stream));
+        db->model = m ? m->impl : nullptr;
+        return SKB_OK;
+    });
+}
+
 void skb_hits_free(skb_hit_t* hits) { delete[] hits; }
 
 }  // extern "C"
@@ -1128,6 +1209,7 @@ uint32_t views_from_meta(const std::shared_ptr<Core>& core, const std::shared_pt
         auto impl = std::make_shared<SketchImpl>();
         impl->core = core; impl->store = store; impl->view = v;
         impl->contig_len_host.assign(clens, clens + p.n_contigs);
+        contig_quantiles(impl->contig_len_host, impl->view);
         clens += p.n_contigs;
         impl->info.n_seeds = p.n_seeds; impl->info.n_markers = p.n_markers; impl->info.total_len = p.total_len;
         impl->info.n_contigs = p.n_contigs; impl->info.k = p.k; impl->info.c = p.c; impl->info.marker_c = p.marker_c;
@@ -1438,10 +1520,10 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
     return guarded(db->core.get(), [&] {
         Core& c = *db->core;
         cudaStream_t st = c.stream;
-        if (opts->learned_ani == 1)
+        if (opts->learned_ani == 1 && !db->model)
             throw Fail{SKB_ERR_UNSUPPORTED,
-                       "learned_ani=True needs skani's embedded GBDT model, whose weights are not part of pyskani's "
-                       "sources; pass learned_ani=False (or None) for the uncorrected estimate"};
+                       "learned_ani=True needs skani's GBDT model, whose weights are not part of pyskani's sources: attach "
+                       "one with skb_db_set_model (Database.set_model / PYSKANI_B200_MODEL), or pass learned_ani=False"};
         const uint32_t nr = (uint32_t)db->items.size();
         if (nr == 0 || n_queries == 0) return SKB_OK;
         const skb_sketch_info_t& dbi = db->items[0]->info;
@@ -1473,6 +1555,12 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
         C.fragment_length = FRAGMENT_LENGTH; C.anchor_score = DP_ANCHOR_SCORE; C.min_anchors = 3; C.min_score = 45; C.max_gap = DP_MAX_GAP;
         C.index_band = (int32_t)DP_INDEX_BAND; C.bp_band = (int32_t)DP_BP_BAND; C.af_ext = 198; C.frac_cover_cutoff = 0.15;   // D_FRAC_COVER_CUTOFF / 100 (lib.rs:589)
         C.robust = opts->robust; C.median = opts->median; C.k = dbi.k;
+        // lib.rs:611-614: learned = learned_ani.unwrap_or_else(|| use_learned_ani(c, false, false, median)); the model is
+        // only consulted for the default (mean) estimate
+        const bool learned = opts->learned_ani == 1 || (opts->learned_ani < 0 && dbi.c >= 70 && !opts->median);
+        C.use_model = learned && db->model && !opts->robust && !opts->median ? 1 : 0;
+        C.learned_min_cov = 150000.0;
+        if (C.use_model) C.model = db->model->dev_view();
 
         std::vector<skb_hit_t> all_hits;
         const size_t n_pass = so.pass_idx.size();

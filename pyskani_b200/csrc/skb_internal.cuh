@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/skb.h"
+#include "gbdt_model.h"
 
 namespace skb {
 
@@ -37,6 +38,7 @@ struct GenomeView {
     uint32_t bucket_shift;         // bucket id = kmer >> bucket_shift
     uint32_t n_buckets;
     uint32_t win_cap;              // upper bound on 20 kb windows when this genome is the query
+    uint32_t ctg_q90, ctg_q50, ctg_q10;   // contig-length quantiles (features of the learned-ANI model)
 };
 
 // ---------------------------------------------------------------- seeding
@@ -195,6 +197,11 @@ struct ChainConsts {           // skani::chain::map_params_from_sketch (referenc
     double frac_cover_cutoff;  // 0.15
     int32_t robust, median;
     int32_t k;
+    // learned-ANI correction (skani::regression, reference lib.rs:611-614): applied to the default (mean) estimate of pairs
+    // with at least learned_min_cov aligned query bases when use_model != 0
+    int32_t use_model;
+    double learned_min_cov;    // 150000
+    GbdtView model;            // device pointers
 };
 
 struct PairDesc {
@@ -252,6 +259,7 @@ void launch_chain_dp(const ChainBatch& b, const ChainConsts& c, cudaStream_t st)
 void launch_window_keys(const ChainBatch& b, cudaStream_t st);
 void launch_ani_reduce(const ChainBatch& b, const ChainConsts& c, const uint64_t* sorted_keys,
                        const uint32_t* sorted_vals, cudaStream_t st);
+void launch_gbdt_predict(const GbdtView& m, const float* rows, uint32_t n_rows, uint32_t stride, float* out, cudaStream_t st);
 // exclusive scan of m_cnt into a_off (n+1 outputs); sort of window keys
 void scan_match_counts(const ChainBatch& b, void* scratch, size_t scratch_bytes, cudaStream_t st);
 size_t scan_scratch_bytes(uint32_t n);

@@ -291,6 +291,21 @@ Sketch import_sketch(const HostSketch& hs) {
     return s;
 }
 
+// ------------------------------------------------------------------------------------------- learned-ANI model
+// skani::regression::get_model (lib.rs:614) deserialises a gbdt-rs ensemble embedded in the skani crate.  Those weights are
+// not part of pyskani's sources; here the same JSON comes from a file: Database(model=...), Database.set_model(...) or
+// $PYSKANI_B200_MODEL.
+struct ModelHandle {
+    skb_model_t* h = nullptr;
+    ~ModelHandle() { if (h) skb_model_free(h); }
+};
+std::shared_ptr<ModelHandle> load_model_file(const std::string& path) {
+    const std::string text = read_file(path);
+    auto m = std::make_shared<ModelHandle>();
+    check(global_ctx(), skb_model_load_json(global_ctx(), text.data(), text.size(), &m->h));
+    return m;
+}
+
 // ------------------------------------------------------------------------------------------- Database (lib.rs:132-741)
 enum class Storage { Memory, Folder, Consolidated };
 
@@ -304,6 +319,15 @@ struct Database {
     std::unordered_map<std::string, size_t> by_name;    // Memory keys / Consolidated index keys
     std::vector<IndexEntry> index;                      // Consolidated: entries in append order (= offset order)
     skb_db_t* db = nullptr;
+    std::shared_ptr<ModelHandle> model;
+    void set_model(std::shared_ptr<ModelHandle> m) {
+        check(global_ctx(), skb_db_set_model(db, m ? m->h : nullptr));
+        model = std::move(m);
+    }
+    void model_from(const py::object& arg) {      // explicit argument, else the environment
+        if (!arg.is_none()) { set_model(load_model_file(fsdecode(arg))); return; }
+        if (const char* e = std::getenv("PYSKANI_B200_MODEL")) if (*e) set_model(load_model_file(e));
+    }
     // Readers (query) share, writers (sketch, flush) exclude: the reference's RwLocks (lib.rs:135-136).  NEVER taken while
     // the GIL is held: a thread that blocks on `mu` with the GIL would stop the holder from ever re-acquiring the GIL.
     std::shared_mutex mu;
@@ -381,9 +405,10 @@ Storage parse_format(const py::object& format) {
 // Database.open / Database.load (lib.rs:251-337).  Both put every sketch into HBM: the reference's lazy
 // per-query disk reads (lib.rs:99-119) make no sense next to 180 GB of device memory; `open` keeps the storage
 // mode of the folder so that later sketch() calls append to it, `load` detaches into a Memory database.
-std::unique_ptr<Database> open_impl(const py::object& path, bool detach) {
+std::unique_ptr<Database> open_impl(const py::object& path, bool detach, const py::object& model) {
     const std::string folder = fsdecode(path);
     auto db = std::make_unique<Database>();
+    db->model_from(model);
     std::string raw = read_file(join(folder, "markers.bin"));
     Reader r{(const uint8_t*)raw.data(), raw.size()};
     db->params = read_params(r);
@@ -483,6 +508,21 @@ std::vector<Sketch> sketch_many_impl(Database& db, const py::sequence& items, bo
     return out;
 }
 
+// The reference resolves learned_ani=None to use_learned_ani(c, false, false, median) = (c >= 70 && !median) and then
+// corrects the estimate with the model embedded in skani (lib.rs:611-614).  Without a model file this implementation
+// returns the uncorrected estimate; it must not do so silently.
+void warn_if_uncorrected(const Database& db, const py::object& learned_ani, bool median, bool robust) {
+    static bool warned = false;
+    if (warned || db.model || !learned_ani.is_none() || median || robust || db.params.c < 70) return;
+    warned = true;
+    if (PyErr_WarnEx(PyExc_RuntimeWarning,
+                     "pyskani applies skani's learned ANI regression by default here (compression >= 70, no median); its model is "
+                     "embedded in the skani crate and not available to pyskani_b200, so the UNCORRECTED estimate is returned. Load a "
+                     "gbdt-rs JSON model (Database(model=...), Database.set_model(), $PYSKANI_B200_MODEL) or pass learned_ani=False.",
+                     1) < 0)
+        throw py::error_already_set();
+}
+
 void raise_query_error(int rc, const std::string& err) {
     switch (rc) {
         case SKB_OK: return;
@@ -517,6 +557,41 @@ PYBIND11_MODULE(_skani, m) {
         }
     });
 
+    // Test hooks of the on-disk layout (no device needed): the very writer / reader Database.save, flush, load and open
+    // use, applied to host arrays.  tests/test_bincode_layout.py pins them byte for byte against an independent encoder.
+    m.def("_encode_sketch", [](const std::string& name, uint64_t c, uint64_t k, uint64_t marker_c, bool has_seeds,
+                               const std::vector<uint64_t>& kmer, const std::vector<uint32_t>& pos, const std::vector<uint32_t>& contig,
+                               const std::vector<uint8_t>& canonical, const std::vector<std::string>& contigs, uint64_t total_len,
+                               const std::vector<uint32_t>& contig_lengths, const std::vector<uint64_t>& markers, bool markers_only,
+                               bool with_params) {
+        HostSketch s;
+        s.file_name = name; s.has_seeds = has_seeds; s.kmer = kmer; s.pos = pos; s.contig = contig; s.canonical = canonical;
+        s.contigs = contigs; s.total_len = total_len; s.contig_lengths = contig_lengths; s.markers = markers;
+        s.params = Params{c, k, marker_c};
+        Writer w;
+        if (with_params) write_params(w, s.params);
+        write_sketch(w, s, markers_only);
+        return py::bytes(w.buf);
+    });
+    m.def("_decode_sketch", [](const py::bytes& raw, bool with_params) {
+        const std::string buf = raw;
+        Reader r{(const uint8_t*)buf.data(), buf.size()};
+        py::dict d;
+        if (with_params) { Params p = read_params(r); d["params"] = py::make_tuple(p.c, p.k, p.marker_c); }
+        HostSketch s = read_sketch(r);
+        d["file_name"] = s.file_name; d["has_seeds"] = s.has_seeds; d["kmer"] = s.kmer; d["pos"] = s.pos; d["contig"] = s.contig;
+        d["canonical"] = s.canonical; d["contigs"] = s.contigs; d["total_len"] = s.total_len; d["contig_lengths"] = s.contig_lengths;
+        d["markers"] = s.markers; d["sketch_params"] = py::make_tuple(s.params.c, s.params.k, s.params.marker_c);
+        d["consumed"] = r.off;
+        return d;
+    });
+    m.def("_encode_index", [](const std::vector<std::tuple<std::string, uint64_t, uint64_t>>& entries) {
+        Writer w;
+        w.u64(entries.size());
+        for (auto& e : entries) { w.str(std::get<0>(e)); w.u64(std::get<1>(e)); w.u64(std::get<2>(e)); }
+        return py::bytes(w.buf);
+    });
+
     py::class_<Hit>(m, "Hit", "A single hit found when querying a `~pyskani.Database` with a genome.")
         .def(py::init([](float identity, const std::string& query_name, float query_fraction, const std::string& reference_name,
                          float reference_fraction) {
@@ -543,8 +618,10 @@ PYBIND11_MODULE(_skani, m) {
         .def_property_readonly("amino_acid", [](const Sketch& s) { return s.amino_acid; });
 
     py::class_<Database>(m, "Database", "A database storing sketched genomes.")
-        .def(py::init([](const py::object& path, uint64_t compression, uint64_t marker_compression, uint64_t k, const py::object& format) {
+        .def(py::init([](const py::object& path, uint64_t compression, uint64_t marker_compression, uint64_t k, const py::object& format,
+                         const py::object& model) {
                  auto db = std::make_unique<Database>();
+                 db->model_from(model);
                  if (k < 1 || k > 16) throw py::value_error("Value of k > 16 for DNA; not allowed.");
                  if (compression < 1 || marker_compression < 1) throw py::value_error("compression factors must be positive");
                  db->params = Params{compression, k, marker_compression};
@@ -557,11 +634,21 @@ PYBIND11_MODULE(_skani, m) {
                  return db;
              }),
              py::arg("path") = py::none(), py::kw_only(), py::arg("compression") = 125, py::arg("marker_compression") = 1000,
-             py::arg("k") = 15, py::arg("format") = py::none())
-        .def_static("load", [](const py::object& path) { return open_impl(path, true); }, py::arg("path"),
+             py::arg("k") = 15, py::arg("format") = py::none(), py::arg("model") = py::none())
+        .def_static("load", [](const py::object& path, const py::object& model) { return open_impl(path, true, model); }, py::arg("path"),
+                    py::kw_only(), py::arg("model") = py::none(),
                     "Load a database from a folder containing sketches (detached from the folder).")
-        .def_static("open", [](const py::object& path) { return open_impl(path, false); }, py::arg("path"),
+        .def_static("open", [](const py::object& path, const py::object& model) { return open_impl(path, false, model); }, py::arg("path"),
+                    py::kw_only(), py::arg("model") = py::none(),
                     "Open a database from a folder containing sketches; new sketches are appended to it.")
+        .def("set_model", [](Database& db, const py::object& path) {
+                 std::shared_ptr<ModelHandle> m = path.is_none() ? nullptr : load_model_file(fsdecode(path));
+                 py::gil_scoped_release nogil;
+                 std::unique_lock<std::shared_mutex> lk(db.mu);
+                 db.set_model(std::move(m));
+             }, py::arg("path"),
+             "Load skani's learned-ANI regression (a gbdt-rs JSON dump) from a file; None removes it (extension over pyskani).")
+        .def_property_readonly("has_model", [](const Database& db) { return (bool)db.model; })
         .def("__enter__", [](py::object self) { return self; })
         .def("__exit__", [](Database& db, const py::object&, const py::object&, const py::object&) {
             { py::gil_scoped_release nogil; db.flush(); }
@@ -582,6 +669,7 @@ PYBIND11_MODULE(_skani, m) {
              }, py::arg("name"), py::arg("seed") = true, "Add a reference genome to the database.")
         .def("query", [](Database& db, const std::string& name, const py::args& contigs, bool seed, const py::object& learned_ani,
                          bool median, bool robust, const py::object& cutoff, bool faster_small) {
+                 warn_if_uncorrected(db, learned_ani, median, robust);
                  Sketch q = sketch_impl(db, name, contigs, seed);
                  skb_query_opts_t o{};
                  o.cutoff = cutoff.is_none() ? 0.0 : cutoff.cast<double>();
@@ -617,6 +705,7 @@ PYBIND11_MODULE(_skani, m) {
              "Add many reference genomes in one GPU batch: items = [(name, contigs), ...] (extension over pyskani).")
         .def("query_many", [](Database& db, const py::sequence& items, bool seed, const py::object& learned_ani, bool median, bool robust,
                               const py::object& cutoff, bool faster_small) {
+                 warn_if_uncorrected(db, learned_ani, median, robust);
                  std::vector<Sketch> qs = sketch_many_impl(db, items, seed);
                  skb_query_opts_t o{};
                  o.cutoff = cutoff.is_none() ? 0.0 : cutoff.cast<double>();

@@ -93,18 +93,83 @@ class TestAniEC590:
             f.result()
         assert len(db) == 11
 
-    def test_basic_returns_uncorrected_estimate(self, ec590_db, ecoli):
-        # The reference's default applies skani's learned regression (0.9939, test_ani.py:28-33).  Its weights are
-        # embedded in the skani crate and unavailable here: the default returns the uncorrected estimate.
-        hits = ec590_db.query("K12", ecoli[1])
+    @pytest.mark.xfail(reason="the reference's default applies skani's learned regression, whose weights are embedded in the "
+                              "skani crate and not part of pyskani's sources (reference tests/test_ani.py:28-33); without a "
+                              "model file the default returns the uncorrected 0.9946", strict=True)
+    def test_basic(self, ec590_db, ecoli):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            hits = ec590_db.query("K12", ecoli[1])
         assert len(hits) == 1
         assert self.close(hits[0].reference_fraction, 0.9246)
         assert self.close(hits[0].query_fraction, 0.9189)
-        assert self.close(hits[0].identity, 0.9946)
+        assert self.close(hits[0].identity, 0.9939)
 
-    def test_learned_ani_true_is_refused(self, ec590_db, ecoli):
+    def test_default_without_model_warns_and_returns_uncorrected(self, pyskani, ecoli):
+        """learned_ani=None resolves to 'apply the model' in the reference (lib.rs:611-614); without a model file the
+        uncorrected estimate comes back WITH a RuntimeWarning (raised here by turning warnings into errors)."""
+        import subprocess, sys, textwrap
+        code = textwrap.dedent("""
+            import warnings, sys
+            sys.path.insert(0, %r)
+            from tests.fixtures import ecoli_pair
+            import pyskani_b200 as pyskani
+            ec, k12, _ = ecoli_pair()
+            db = pyskani.Database()
+            assert not db.has_model
+            db.sketch('EC590', ec[:400000])
+            with warnings.catch_warnings(record=True) as w:
+                warnings.simplefilter('always')
+                a = db.query('K12', k12[:400000])
+                b = db.query('K12', k12[:400000])                      # once per process
+                c = db.query('K12', k12[:400000], learned_ani=False)   # explicit: no warning
+            assert len([x for x in w if issubclass(x.category, RuntimeWarning)]) == 1, w
+            assert [h.identity for h in a] == [h.identity for h in c] == [h.identity for h in b]
+            print('ok')
+        """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        env = {k: v for k, v in os.environ.items() if k != "PYSKANI_B200_MODEL"}
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+        assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+    def test_learned_ani_true_without_model_is_refused(self, ec590_db, ecoli):
         with pytest.raises(RuntimeError):
             ec590_db.query("K12", ecoli[1], learned_ani=True)
+
+    def test_learned_ani_with_a_model_file(self, pyskani, ecoli, tmp_path):
+        """Database(model=...) / set_model / $PYSKANI_B200_MODEL: the correction runs on the device under the reference's
+        rule (None -> c >= 70 and not median; never for robust / median) and equals the oracle's evaluator."""
+        import numpy as np
+        import oracle
+        from tests import gbdt_synth
+        path = tmp_path / "model.json"
+        text = gbdt_synth.identity_like_model(-0.035)       # ANI >= 99 %: 95 - 0.07
+        path.write_text(text)
+        db = pyskani.Database(model=str(path))
+        assert db.has_model
+        db.sketch("EC590", ecoli[0])
+        raw = db.query("K12", ecoli[1], learned_ani=False)[0]
+        r = oracle.chain(oracle.Sketch([ecoli[0]]), oracle.Sketch([ecoli[1]]))
+        want = float(oracle.learned_ani(r, oracle.Gbdt(text)))
+        assert abs(want - 0.9493) < 1e-6
+        for kw in ({}, {"learned_ani": True}):
+            h = db.query("K12", ecoli[1], **kw)[0]
+            assert h.identity == want and h.query_fraction == raw.query_fraction and h.reference_fraction == raw.reference_fraction
+        assert db.query("K12", ecoli[1], robust=True)[0].identity > 0.99       # robust / median: uncorrected
+        assert db.query("K12", ecoli[1], median=True)[0].identity > 0.99
+        assert db.query("K12", ecoli[1], learned_ani=False)[0].identity == raw.identity
+        low_c = pyskani.Database(compression=60, model=str(path))              # c < 70: None means no correction
+        low_c.sketch("EC590", ecoli[0][:500_000])
+        assert low_c.query("K12", ecoli[1][:500_000])[0].identity > 0.98
+        assert low_c.query("K12", ecoli[1][:500_000], learned_ani=True)[0].identity < 0.95
+        db.set_model(None)
+        assert not db.has_model and db.query("K12", ecoli[1], learned_ani=False)[0].identity == raw.identity
+        with pytest.raises(ValueError):
+            bad = tmp_path / "bad.json"
+            bad.write_text('{"conf": {}}')
+            db.set_model(str(bad))
+        with pytest.raises(OSError):
+            db.set_model(str(tmp_path / "missing.json"))
 
     def test_input_types(self, ec590_db, ecoli):
         k12 = ecoli[1]
