@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libskb.so")
+LIB_PATH = os.environ.get("SKB_LIB") or os.path.join(_HERE, "libskb.so")     # SKB_LIB: kernel-variant builds (tools/seed_variants.sh)
 
 SKB_OK, SKB_ERR_ARG, SKB_ERR_CUDA, SKB_ERR_NOMEM, SKB_ERR_KEY, SKB_ERR_UNSUPPORTED = range(6)
 

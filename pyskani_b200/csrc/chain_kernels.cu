@@ -112,12 +112,8 @@ __global__ void anchor_fill_kernel(const ChainBatch b) {
             const uint32_t o = off + m;
             if (o >= b.anchor_cap) break;
             const uint32_t rm = __ldg(R.meta_k + first + m);
-            b.a_qi[o] = i;
-            b.a_qp[o] = qp;
-            b.a_rp[o] = __ldg(R.pos_k + first + m);
-            b.a_meta[o] = (rm & ~1u) | ((qm ^ rm) & 1u);    // ref contig << 1 | reverse_match
-            b.a_aux[o] = 0u;                                // component size / flags and best end, accumulated by the DP kernel
-            b.a_best[o] = 0ull;
+            // (q_pos, r_pos, ref contig << 1 | reverse_match, query seed index): one 16-byte store
+            b.a_rec[o] = make_uint4(qp, __ldg(R.pos_k + first + m), (rm & ~1u) | ((qm ^ rm) & 1u), i);
         }
     }
 }
@@ -321,8 +317,7 @@ __device__ __forceinline__ void tuple_min(int32_t& sc, uint32_t& qs, uint32_t& r
 // The common path is straight-line code (selects instead of branches) so that the warp stays provably converged.
 
 template <bool WIDE>
-__device__ __forceinline__ void dp_window(const uint32_t* __restrict__ qp_a, const uint32_t* __restrict__ rp_a,
-                                          const uint32_t* __restrict__ meta_a, int32_t* f_a, uint32_t* root_a,
+__device__ __forceinline__ void dp_window(const uint4* __restrict__ rec_a, int32_t* f_a, uint32_t* root_a,
                                           const uint32_t n, const int lane, uint4* s_strip) {
     // skani's chaining constants are frozen (pyskani exposes none of them): compile-time values
     // here, shared with the host through skb_internal.cuh (ChainConsts is filled from the same constants)
@@ -334,7 +329,7 @@ __device__ __forceinline__ void dp_window(const uint32_t* __restrict__ qp_a, con
     for (uint32_t sb = 0; sb < n; sb += 32) {
         const uint32_t mine = sb + lane;
         uint32_t sq = 0, sr = 0, sm = 0;
-        if (mine < n) { sq = qp_a[mine]; sr = rp_a[mine]; sm = meta_a[mine]; }
+        if (mine < n) { const uint4 r4 = rec_a[mine]; sq = r4.x; sr = r4.y; sm = r4.z; }
         s_strip[lane] = make_uint4(sq, sr, sm, 0u);
         // g_* still holds anchor mine - 32 here: bit u of need_old = anchor sb + u must also look at distances > 32
         const uint32_t need_old = __ballot_sync(FULL, mine < n && mine >= 32u && (sq - g_qp) <= bp_band);
@@ -387,10 +382,11 @@ __device__ __forceinline__ void dp_window(const uint32_t* __restrict__ qp_a, con
                     int32_t sc = INT32_MIN;
                     if (inband) {
                         const uint32_t j = i - d;
-                        const uint32_t pq = qp_a[j];
+                        const uint4 pj = rec_a[j];
+                        const uint32_t pq = pj.x;
                         inband = (cq - pq) <= bp_band;
-                        if (inband && meta_a[j] == cm) {
-                            const uint32_t pr = rp_a[j];
+                        if (inband && pj.z == cm) {
+                            const uint32_t pr = pj.y;
                             const int32_t dq2 = (int32_t)(cq - pq);
                             const int32_t dr2 = (int32_t)(((cr - pr) ^ revmask) - revmask);
                             const int32_t gap2 = abs(dr2 - dq2);
@@ -434,38 +430,47 @@ constexpr uint32_t DP_SMEM_ANCHORS = 256;
 __device__ __forceinline__ uint32_t ldv(const uint32_t* p) { return *(volatile const uint32_t*)p; }
 __device__ __forceinline__ unsigned long long ldv(const unsigned long long* p) { return *(volatile const unsigned long long*)p; }
 
+// Anchor range of a window slot: false for unused slots and when the anchor arrays were sized too small (the host then
+// reruns the batch with the exact size).
+__device__ __forceinline__ bool window_anchors(const ChainBatch& b, uint32_t slot, uint32_t& A0, uint32_t& n) {
+    const uint32_t ws = b.win_start[slot], we = b.win_end[slot];
+    if (we <= ws) return false;
+    const PairDesc pd = b.pairs[b.win_contig[slot]];
+    A0 = b.a_off[pd.seed_off + ws];
+    const uint32_t A1 = b.a_off[pd.seed_off + we];
+    if (A1 > b.anchor_cap) return false;
+    n = A1 - A0;
+    return true;
+}
+
+// ---- warp per window: the windows the thread-per-window kernel below passes on (more than DPT_MAX_ANCHORS anchors:
+// repeat-rich regions), taken from big_list by a persistent grid
 __global__ void __launch_bounds__(DP_WARPS * 32) chain_dp_kernel(const ChainBatch b, const ChainConsts C) {
     __shared__ uint4 s_strip[DP_WARPS][32];          // the strip of 32 anchors a warp is working on; later its candidate list
     __shared__ __align__(16) uint32_t s_work[DP_WARPS][4 * DP_SMEM_ANCHORS];   // root | size+flags | best end (64 bit)
-    const int lane = threadIdx.x & 31;
-    const uint32_t slot = blockIdx.x * DP_WARPS + (threadIdx.x >> 5);
-    if (slot >= b.n_win_total) return;
-    const uint32_t ws = b.win_start[slot], we = b.win_end[slot];
-    if (we <= ws) return;                                   // unused slot
-    const PairDesc pd = b.pairs[b.win_contig[slot]];
-    const uint32_t A0 = b.a_off[pd.seed_off + ws], A1 = b.a_off[pd.seed_off + we];
-    if (A1 > b.anchor_cap) return;                          // anchor arrays were sized too small: the host reruns the batch
-    const uint32_t n = A1 - A0;
-    const uint32_t* qp_a = b.a_qp + A0; const uint32_t* rp_a = b.a_rp + A0; const uint32_t* meta_a = b.a_meta + A0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_big = *b.big_count;
+    for (uint32_t w = blockIdx.x * DP_WARPS + warp; w < n_big; w += gridDim.x * DP_WARPS) {
+    const uint32_t slot = b.big_list[w];
+    uint32_t A0 = 0, n = 0;
+    if (!window_anchors(b, slot, A0, n)) continue;
+    const uint4* rec_a = b.a_rec + A0;
     int32_t* f_a = b.a_f + A0;
-    // Per-anchor working state of the chain phases (component root, size | flags, best end).  Windows of up to
-    // DP_SMEM_ANCHORS anchors - nearly all of them - keep it in shared memory: the phases after the DP are chains of
-    // dependent scattered accesses, which cost ~30 cycles there against an L2 round trip each in the global arrays.
-    const int warp = threadIdx.x >> 5;
+    // Per-anchor working state of the chain phases (component root, size | flags, best end): shared memory for windows
+    // of up to DP_SMEM_ANCHORS anchors, the global arrays beyond
     const bool small = n <= DP_SMEM_ANCHORS;
     uint32_t* root_a = small ? s_work[warp] : b.a_root + A0;
     uint32_t* aux_a = small ? s_work[warp] + DP_SMEM_ANCHORS : b.a_aux + A0;
     unsigned long long* best_a = small ? (unsigned long long*)(s_work[warp] + 2 * DP_SMEM_ANCHORS) : b.a_best + A0;
-    if (small) {
-        for (uint32_t i = lane; i < n; i += 32) { aux_a[i] = 0u; best_a[i] = 0ull; }      // the global arrays come zeroed
-        __syncwarp();
-    }
+    for (uint32_t i = lane; i < n; i += 32) { aux_a[i] = 0u; best_a[i] = 0ull; }
+    __threadfence_block();
+    __syncwarp();
     // candidate list: at most n / min_anchors entries
     int32_t* cand_a = (small && n <= 128u * (uint32_t)max(C.min_anchors, 1)) ? (int32_t*)s_strip[warp] : f_a;
 
     // ---------------- DP
-    if ((uint64_t)n * (uint32_t)DP_ANCHOR_SCORE < (1u << 22)) dp_window<false>(qp_a, rp_a, meta_a, f_a, root_a, n, lane, s_strip[warp]);
-    else dp_window<true>(qp_a, rp_a, meta_a, f_a, root_a, n, lane, s_strip[warp]);
+    if ((uint64_t)n * (uint32_t)DP_ANCHOR_SCORE < (1u << 22)) dp_window<false>(rec_a, f_a, root_a, n, lane, s_strip[warp]);
+    else dp_window<true>(rec_a, f_a, root_a, n, lane, s_strip[warp]);
 
     // ---------------- per-component size and best end
     for (uint32_t i = lane; i < n; i += 32) {
@@ -504,9 +509,9 @@ __global__ void __launch_bounds__(DP_WARPS * 32) chain_dp_kernel(const ChainBatc
             if (ldv(&aux_a[r]) & AUX_PROCESSED) continue;
             const unsigned long long bb = ldv(&best_a[r]);
             const uint32_t bi = 0xFFFFFFFFu - (uint32_t)bb;
-            const bool rv = meta_a[r] & 1u;
-            const uint32_t rs2 = rv ? rp_a[bi] : rp_a[r];
-            tuple_min(sc, qs, rs, idx, (int32_t)(bb >> 32), qp_a[r], rs2, r);
+            const uint4 rr = rec_a[r];
+            const uint32_t rs2 = (rr.z & 1u) ? rec_a[bi].y : rr.y;
+            tuple_min(sc, qs, rs, idx, (int32_t)(bb >> 32), rr.x, rs2, r);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -517,13 +522,14 @@ __global__ void __launch_bounds__(DP_WARPS * 32) chain_dp_kernel(const ChainBatc
         const uint32_t r = idx;                                 // uniform: the best unprocessed candidate
         const unsigned long long bb = ldv(&best_a[r]);
         const uint32_t bi = 0xFFFFFFFFu - (uint32_t)bb;
-        const uint32_t cqs = qp_a[r], cqe = qp_a[bi];
+        const uint4 rec_r = rec_a[r], rec_b = rec_a[bi];
+        const uint32_t cqs = rec_r.x, cqe = rec_b.x;
         bool ov = false;
         for (uint32_t t = lane; t < ncand; t += 32) {
             const uint32_t r2 = (uint32_t)cand_a[t];
             if (!(ldv(&aux_a[r2]) & AUX_ACCEPTED)) continue;
             const uint32_t bi2 = 0xFFFFFFFFu - (uint32_t)ldv(&best_a[r2]);
-            const uint32_t lo = max(cqs, qp_a[r2]), hi = min(cqe, qp_a[bi2]);
+            const uint32_t lo = max(cqs, rec_a[r2].x), hi = min(cqe, rec_a[bi2].x);
             ov |= hi >= lo;
         }
         ov = __any_sync(FULL, ov);
@@ -532,11 +538,11 @@ __global__ void __launch_bounds__(DP_WARPS * 32) chain_dp_kernel(const ChainBatc
         __threadfence_block();
         __syncwarp();
         if (!ov) {
-            const bool rv = meta_a[r] & 1u;
-            const uint32_t crs = rv ? rp_a[bi] : rp_a[r], cre = rv ? rp_a[r] : rp_a[bi];
+            const bool rv = rec_r.z & 1u;
+            const uint32_t crs = rv ? rec_b.y : rec_r.y, cre = rv ? rec_r.y : rec_b.y;
             w_anchors += size;
-            if (cqs < w_lo) { w_lo = cqs; w_lo_qi = b.a_qi[A0 + r]; }
-            if (cqe >= w_hi) { w_hi = cqe; w_hi_qi = b.a_qi[A0 + bi]; }
+            if (cqs < w_lo) { w_lo = cqs; w_lo_qi = rec_r.w; }
+            if (cqe >= w_hi) { w_hi = cqe; w_hi_qi = rec_b.w; }
             w_covq += (cqe - cqs) + (uint32_t)C.af_ext;
             w_covr += (cre - crs) + (uint32_t)C.af_ext;
             w_chains++;
@@ -549,6 +555,250 @@ __global__ void __launch_bounds__(DP_WARPS * 32) chain_dp_kernel(const ChainBatc
         rec.cov_q = w_covq; rec.cov_r = w_covr; rec.n_chains = w_chains;
         b.win_rec[slot] = rec;
     }
+    __syncwarp();
+    }
+}
+
+// ---- thread per window: the common case.
+// A 20 kb window of a bacterial genome pair holds 10-200 anchors of which ~20 lie inside the 2 500 bp band of the current
+// one.  One THREAD walks one window: per anchor it scores the predecessors still in band, nearest first, and stops at the
+// first one outside - ~15 instructions per predecessor actually examined, against 42 warp-wide instructions per anchor
+// (32 lanes, most of them idle or out of band) in the warp-per-window formulation above.
+//   * the last DPT_RING anchors of every thread sit in a shared-memory ring laid out [slot][thread]; all threads of a
+//     warp advance through their windows in lock step (same anchor index i), so ring slot (i - d) & 31 is the same row
+//     for every lane and each LDS.128 is conflict free.  Ring entry: (q_pos, diagonal, meta, f | root << 16), where
+//     diagonal = r_pos - q_pos on the forward strand and -(r_pos + q_pos) on the reverse strand, so that
+//     dr - dq = diagonal(current) - diagonal(predecessor) on both strands: gap and dr cost three instructions;
+//   * predecessors farther back than the ring (only while the anchor 32 back is still in band: repeat-dense stretches)
+//     are read from the anchor records / f / root arrays;
+//   * component roots need no pointer jumping: the predecessor precedes the anchor, so root[i] = root[pred] is final;
+//   * per-component size and best end are kept in registers for the component of the previous anchor and spilled to the
+//     per-anchor arrays when the component changes (chains rarely interleave).
+// Windows with more than DPT_MAX_ANCHORS anchors (their f and root would not fit the 16-bit halves of the ring word, and
+// one long window would stall the other 31 lanes) are appended to big_list for the warp-per-window kernel.
+constexpr int DPT_THREADS = 64;
+constexpr uint32_t DPT_RING = 32;
+constexpr uint32_t DPT_MAX_ANCHORS = 512;
+constexpr uint32_t DPT_BINS = DPT_MAX_ANCHORS / 4;        // windows are ordered by anchor count, 4 anchors per bin
+constexpr uint32_t NO_ROOT = 0xFFFFFFFFu;
+
+// ---- windows in descending order of their anchor count (counting sort over DPT_BINS bins): the 32 windows a warp
+// walks in lock step then have nearly the same length (lanes idle 36 % of the time in slot order), and the longest
+// windows start first.  bins[0..DPT_BINS) = histogram, then cursors; bins[DPT_BINS] = number of listed windows.
+__global__ void window_bins_kernel(const ChainBatch b) {
+    __shared__ uint32_t s_bins[DPT_BINS];
+    for (uint32_t t = threadIdx.x; t < DPT_BINS; t += blockDim.x) s_bins[t] = 0u;
+    __syncthreads();
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t A0 = 0, n = 0;
+    if (slot < b.n_win_total && window_anchors(b, slot, A0, n) && n) {
+        if (n > DPT_MAX_ANCHORS) b.big_list[atomicAdd(b.big_count, 1u)] = slot;
+        else atomicAdd(&s_bins[(n - 1u) >> 2], 1u);
+    }
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < DPT_BINS; t += blockDim.x)
+        if (s_bins[t]) atomicAdd(&b.win_bins[t], s_bins[t]);
+}
+__global__ void window_bins_scan_kernel(const ChainBatch b) {      // one warp: descending exclusive scan -> cursors
+    const int lane = threadIdx.x;
+    uint32_t run = 0;
+    for (int base = (int)DPT_BINS - 32; base >= 0; base -= 32) {
+        const uint32_t idx = (uint32_t)base + 31u - (uint32_t)lane;           // lane 0 takes the largest bin of the chunk
+        const uint32_t c = b.win_bins[idx];
+        uint32_t incl = c;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+        b.win_bins[idx] = run + incl - c;
+        run += __shfl_sync(FULL, incl, 31);
+    }
+    if (lane == 0) b.win_bins[DPT_BINS] = run;
+}
+__global__ void __launch_bounds__(1024) window_order_kernel(const ChainBatch b) {
+    // one global atomic per (CTA, bin) instead of one per window: the windows of a pair fall into few bins
+    __shared__ uint32_t s_cnt[DPT_BINS], s_base[DPT_BINS];
+    for (uint32_t t = threadIdx.x; t < DPT_BINS; t += blockDim.x) s_cnt[t] = 0u;
+    __syncthreads();
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t A0 = 0, n = 0, local = 0, bin = 0;
+    const bool listed = slot < b.n_win_total && window_anchors(b, slot, A0, n) && n && n <= DPT_MAX_ANCHORS;
+    if (listed) { bin = (n - 1u) >> 2; local = atomicAdd(&s_cnt[bin], 1u); }
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < DPT_BINS; t += blockDim.x)
+        if (s_cnt[t]) s_base[t] = atomicAdd(&b.win_bins[t], s_cnt[t]);
+    __syncthreads();
+    if (listed) b.win_order[s_base[bin] + local] = slot;
+}
+
+// one predecessor from the ring against the current anchor; tq = q_pos - 1, best = max of f[j] - gap so far (> 0 to link)
+__device__ __forceinline__ void dpt_pred(const uint4 p, const uint32_t tq, const int32_t cD, const uint32_t cm, const uint32_t d,
+                                         int32_t& best, uint32_t& bestd) {
+    const uint32_t t = tq - p.x;                           // dq - 1: in band and dq >= 1  <=>  t < band (unsigned)
+    const int32_t delta = cD - (int32_t)p.y;               // dr - dq on either strand
+    const int32_t gap = abs(delta);
+    const int32_t sc = (int32_t)(p.w & 0xFFFFu) - gap;
+    // dr = dq + delta > 0  <=>  t + delta >= 0
+    if (t < DP_BP_BAND && p.z == cm && (int32_t)t + delta >= 0 && gap <= DP_MAX_GAP && sc > best) { best = sc; bestd = d; }
+}
+
+struct RootStat { uint32_t root, size, bidx; int32_t bf; };
+__device__ __forceinline__ void stat_store(const RootStat& s, uint32_t* aux_a, unsigned long long* best_a) {
+    if (s.root != NO_ROOT) {
+        aux_a[s.root] = s.size;
+        best_a[s.root] = ((unsigned long long)(uint32_t)s.bf << 32) | (0xFFFFFFFFu - s.bidx);
+    }
+}
+
+__global__ void __launch_bounds__(DPT_THREADS) chain_dp_thread_kernel(const ChainBatch b, const ChainConsts C) {
+    __shared__ uint4 s_ring[DPT_RING][DPT_THREADS];
+    __shared__ uint32_t s_rootmask[DPT_MAX_ANCHORS / 32][DPT_THREADS];     // bit i of a thread's column: anchor i is a root
+    constexpr uint32_t bp_band = DP_BP_BAND, index_band = DP_INDEX_BAND;
+    constexpr int32_t max_gap = DP_MAX_GAP, anchor_score = DP_ANCHOR_SCORE;
+    const int tid = threadIdx.x;
+    const uint32_t rank = blockIdx.x * DPT_THREADS + tid;
+    const uint32_t n_listed = b.win_bins[DPT_BINS];
+    uint32_t slot = 0, A0 = 0, n = 0;
+    if (rank < n_listed) { slot = b.win_order[rank]; window_anchors(b, slot, A0, n); }
+    const uint32_t nmax = __reduce_max_sync(FULL, n);
+    if (nmax == 0) return;
+    const uint4* rec_a = b.a_rec + A0;
+    int32_t* f_a = b.a_f + A0; uint32_t* root_a = b.a_root + A0; uint32_t* aux_a = b.a_aux + A0;
+    unsigned long long* best_a = b.a_best + A0;
+    // per-component size and best end: the components of the last two distinct roots stay in registers (a chain and the
+    // stray anchor that interrupts it), older ones are spilled to aux_a / best_a
+    RootStat sa{NO_ROOT, 0u, 0u, 0}, sb{NO_ROOT, 0u, 0u, 0};
+    uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+    if (n) nxt = rec_a[0];
+    // the ring starts out full of entries that are out of band for every anchor of the window (q_pos 2^30 bases ahead):
+    // the first anchors then run the same branch-free code as all others
+    {
+        const uint4 far = make_uint4(nxt.x + 0x40000000u, 0u, 0xFFFFFFFFu, 0u);
+#pragma unroll
+        for (uint32_t k = 0; k < DPT_RING; k++) s_ring[k][tid] = far;
+    }
+    uint32_t maskw = 0;                   // root bits of the current 32 anchors
+    // ---------------- DP, lock step over the anchor index
+    for (uint32_t i = 0; i < nmax; i++) {
+        const bool act = i < n;
+        const uint4 r = nxt;
+        if (i + 1 < n) nxt = rec_a[i + 1];                 // the next record travels while this anchor is scored
+        // pins the load here: without it the compiler sinks it to its first use, at the top of the next iteration
+        asm volatile("" : "+r"(nxt.x), "+r"(nxt.y), "+r"(nxt.z), "+r"(nxt.w));
+        const uint32_t cq = r.x, cm = r.z, tq = cq - 1u;
+        const int32_t cD = (cm & 1u) ? -(int32_t)(r.y + r.x) : (int32_t)(r.y - r.x);
+        int32_t best = 0;                 // max over valid predecessors of f[j] - gap; a link needs f[j] + 20 - gap > 20
+        uint32_t bestd = 0;
+        bool live = act;                  // predecessors are ordered by q_pos: once one is out of band, all older ones are
+#pragma unroll 1
+        for (uint32_t d0 = 1; d0 <= DPT_RING; d0 += 4) {
+            if (!__any_sync(FULL, live)) break;
+            const uint4 p0 = s_ring[(i - d0) & (DPT_RING - 1)][tid], p1 = s_ring[(i - d0 - 1) & (DPT_RING - 1)][tid];
+            const uint4 p2 = s_ring[(i - d0 - 2) & (DPT_RING - 1)][tid], p3 = s_ring[(i - d0 - 3) & (DPT_RING - 1)][tid];
+            dpt_pred(p0, tq, cD, cm, d0, best, bestd);
+            dpt_pred(p1, tq, cD, cm, d0 + 1, best, bestd);
+            dpt_pred(p2, tq, cD, cm, d0 + 2, best, bestd);
+            dpt_pred(p3, tq, cD, cm, d0 + 3, best, bestd);
+            live = live && (cq - p3.x) <= bp_band;
+        }
+        if (live && i > DPT_RING) {
+            // the whole ring is in band (repeat-dense stretch): older predecessors from the arrays, up to the index band
+            const uint32_t dend = min(i, index_band);
+            for (uint32_t d = DPT_RING + 1; d <= dend; d++) {
+                const uint4 p = rec_a[i - d];
+                const uint32_t dq = cq - p.x;
+                if (dq > bp_band) break;
+                if (dq == 0u || p.z != cm) continue;
+                const int32_t pD = (cm & 1u) ? -(int32_t)(p.y + p.x) : (int32_t)(p.y - p.x);
+                const int32_t delta = cD - pD;
+                const int32_t gap = abs(delta);
+                const int32_t sc = f_a[i - d] - gap;
+                if ((int32_t)dq + delta > 0 && gap <= max_gap && sc > best) { best = sc; bestd = d; }
+            }
+        }
+        if (act) {
+            const int32_t f = anchor_score + best;
+            uint32_t root = i;
+            if (bestd) root = bestd <= DPT_RING ? (s_ring[(i - bestd) & (DPT_RING - 1)][tid].w >> 16) : root_a[i - bestd];
+            s_ring[i & (DPT_RING - 1)][tid] = make_uint4(cq, (uint32_t)cD, cm, (uint32_t)f | (root << 16));
+            f_a[i] = f; root_a[i] = root;      // read back only beyond the ring (repeat-dense stretches)
+            if (root == i) maskw |= 1u << (i & 31u);
+            if (root != sa.root) {
+                // the other cached component becomes the current one; a third one evicts the older entry
+                const RootStat t = sa; sa = sb; sb = t;
+                if (root != sa.root) {
+                    stat_store(sa, aux_a, best_a);
+                    if (root == i) sa = RootStat{i, 0u, i, INT32_MIN};
+                    else {
+                        const unsigned long long bb = best_a[root];
+                        sa = RootStat{root, aux_a[root], 0xFFFFFFFFu - (uint32_t)bb, (int32_t)(bb >> 32)};
+                    }
+                }
+            }
+            sa.size++;
+            if (f > sa.bf) { sa.bf = f; sa.bidx = i; }      // strict: the first maximal end in DP order
+        }
+        if ((i & 31u) == 31u || i + 1 == nmax) {
+            if (act || (i >> 5) == ((n - 1u) >> 5)) s_rootmask[i >> 5][tid] = maskw;
+            maskw = 0u;
+        }
+    }
+    if (n == 0) return;
+    stat_store(sa, aux_a, best_a);
+    stat_store(sb, aux_a, best_a);
+
+    // ---------------- candidate chains: roots with enough anchors and score; the list overwrites f (no longer needed)
+    uint32_t ncand = 0;
+    for (uint32_t w = 0; w <= (n - 1u) >> 5; w++) {
+        uint32_t m = s_rootmask[w][tid];
+        while (m) {
+            const uint32_t i = (w << 5) + (uint32_t)__ffs(m) - 1u;
+            m &= m - 1u;
+            uint32_t size; int32_t score;
+            if (i == sa.root) { size = sa.size; score = sa.bf; }            // the usual case: still in registers
+            else if (i == sb.root) { size = sb.size; score = sb.bf; }
+            else { size = aux_a[i]; score = (int32_t)(best_a[i] >> 32); }
+            if (size >= (uint32_t)C.min_anchors && score >= C.min_score) f_a[ncand++] = (int32_t)i;
+        }
+    }
+    // ---------------- greedy selection without query overlap: (score desc, q start asc, r start asc, index asc)
+    uint32_t w_anchors = 0, w_lo = 0xFFFFFFFFu, w_hi = 0, w_lo_qi = 0, w_hi_qi = 0, w_covq = 0, w_covr = 0, w_chains = 0;
+    for (uint32_t round = 0; round < ncand; round++) {
+        int32_t sc = INT32_MIN; uint32_t qs = 0xFFFFFFFFu, rs = 0xFFFFFFFFu, idx = 0xFFFFFFFFu;
+        for (uint32_t t = 0; t < ncand; t++) {
+            const uint32_t r2 = (uint32_t)f_a[t];
+            if (aux_a[r2] & AUX_PROCESSED) continue;
+            const unsigned long long bb = best_a[r2];
+            const uint4 rr = rec_a[r2];
+            const uint32_t rs2 = (rr.z & 1u) ? rec_a[0xFFFFFFFFu - (uint32_t)bb].y : rr.y;
+            tuple_min(sc, qs, rs, idx, (int32_t)(bb >> 32), rr.x, rs2, r2);
+        }
+        const uint32_t rt = idx;
+        const uint32_t bi = 0xFFFFFFFFu - (uint32_t)best_a[rt];
+        const uint4 rec_r = rec_a[rt], rec_b = rec_a[bi];
+        const uint32_t cqs = rec_r.x, cqe = rec_b.x;
+        bool ov = false;
+        for (uint32_t t = 0; t < ncand && !ov; t++) {
+            const uint32_t r2 = (uint32_t)f_a[t];
+            if (!(aux_a[r2] & AUX_ACCEPTED)) continue;
+            const uint32_t bi2 = 0xFFFFFFFFu - (uint32_t)best_a[r2];
+            ov = min(cqe, rec_a[bi2].x) >= max(cqs, rec_a[r2].x);
+        }
+        const uint32_t size = aux_a[rt] & AUX_SIZE;
+        aux_a[rt] = size | AUX_PROCESSED | (ov ? 0u : AUX_ACCEPTED);
+        if (!ov) {
+            const bool rv = rec_r.z & 1u;
+            const uint32_t crs = rv ? rec_b.y : rec_r.y, cre = rv ? rec_r.y : rec_b.y;
+            w_anchors += size;
+            if (cqs < w_lo) { w_lo = cqs; w_lo_qi = rec_r.w; }
+            if (cqe >= w_hi) { w_hi = cqe; w_hi_qi = rec_b.w; }
+            w_covq += (cqe - cqs) + (uint32_t)C.af_ext;
+            w_covr += (cre - crs) + (uint32_t)C.af_ext;
+            w_chains++;
+        }
+    }
+    WindowRec rec;
+    rec.anchors = w_anchors;
+    rec.seeds = w_chains ? (w_hi_qi - w_lo_qi + 1u) : 0u;
+    rec.cov_q = w_covq; rec.cov_r = w_covr; rec.n_chains = w_chains;
+    b.win_rec[slot] = rec;
 }
 
 // ------------------------------------------------------------------ 5a. sort keys: pair << 32 | floor(ratio * 2^32)
@@ -742,9 +992,16 @@ void launch_window_walk(const ChainBatch& b, const ChainConsts& c, uint32_t max_
         g_kernel_launches++;
     }
 }
-void launch_chain_dp(const ChainBatch& b, const ChainConsts& c, cudaStream_t st) {
+void launch_chain_dp(const ChainBatch& b, const ChainConsts& c, int n_sm, cudaStream_t st) {
     if (b.n_win_total == 0) return;
-    chain_dp_kernel<<<(b.n_win_total + DP_WARPS - 1) / DP_WARPS, DP_WARPS * 32, 0, st>>>(b, c);
+    // thread per window for everything up to DPT_MAX_ANCHORS anchors; it lists the larger windows, which a persistent grid
+    // of warp-per-window CTAs then takes (the list length is only known on the device)
+    window_bins_kernel<<<(b.n_win_total + 255) / 256, 256, 0, st>>>(b);
+    window_bins_scan_kernel<<<1, 32, 0, st>>>(b);
+    window_order_kernel<<<(b.n_win_total + 1023) / 1024, 1024, 0, st>>>(b);
+    chain_dp_thread_kernel<<<(b.n_win_total + DPT_THREADS - 1) / DPT_THREADS, DPT_THREADS, 0, st>>>(b, c);
+    g_kernel_launches += 4;
+    chain_dp_kernel<<<n_sm * 4, DP_WARPS * 32, 0, st>>>(b, c);
     g_kernel_launches++;
 }
 void launch_window_keys(const ChainBatch& b, cudaStream_t st) {

@@ -1564,7 +1564,7 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
 
         std::vector<skb_hit_t> all_hits;
         const size_t n_pass = so.pass_idx.size();
-        constexpr uint64_t MAX_BATCH_SEEDS = 48ull << 20;
+        constexpr uint64_t MAX_BATCH_SEEDS = 160ull << 20;      // ~4 000 pairs of 5 Mbp genomes per batch
         size_t p0 = 0;
         while (p0 < n_pass) {
             std::vector<PairDesc> pairs;
@@ -1583,11 +1583,11 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
             }
             if (seeds >= 0x7FFFFFFFull) throw Fail{SKB_ERR_ARG, "query sketch too large for one chaining batch"};
             const uint32_t np = (uint32_t)pairs.size();
-            // The number of anchors is only known on the device.  Size the anchor arrays from an estimate (twice the
-            // smaller seed count of every pair), run the whole batch, and read the true total back together with the
+            // The number of anchors is only known on the device.  Size the anchor arrays from an estimate (1.5 x the
+            // smaller seed count of every pair, times 1.5), run the whole batch, and read the true total back together with the
             // results: one synchronisation per batch; a batch whose estimate was too small is simply run again.
             uint64_t est = 1024;
-            for (const PairDesc& pd : pairs) est += 2ull * std::min(qs[pd.q]->view.n_seeds, db->items[pd.r]->view.n_seeds);
+            for (const PairDesc& pd : pairs) { const uint64_t m = std::min(qs[pd.q]->view.n_seeds, db->items[pd.r]->view.n_seeds); est += m + m / 2; }
             if (est > 0x7FFFFFFFull) est = 0x7FFFFFFFull;
             if (const char* e = std::getenv("SKB_FORCE_ANCHOR_EST")) est = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10));   // test hook: exercises the rerun
             std::vector<PairResult> res(np);
@@ -1612,7 +1612,8 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
                 auto plan = [&](size_t bytes) { const size_t o = total; total += (bytes + 255) & ~(size_t)255; return o; };
                 const size_t o_pairs = plan(sizeof(PairDesc) * np), o_first = plan(4 * (seeds + 1)), o_cnt = plan(4 * (seeds + 1)),
                              o_aoff = plan(4 * (seeds + 2)), o_bits = plan(4 * (bit_words + 4)), o_scan = plan(scan_bytes),
-                             o_a = plan(na * 4 * 7), o_best = plan(na * 8), o_w = plan(nw * 4 * 3 + 4 * (size_t)np),
+                             o_a = plan(na * 16), o_fra = plan(na * 4 * 3), o_best = plan(na * 8), o_big = plan(4 * (nw + 4)), o_bins = plan(4 * 192), o_order = plan(4 * nw),
+                             o_w = plan(nw * 4 * 3 + 4 * (size_t)np),
                              o_rec = plan(nw * sizeof(WindowRec)), o_keys = plan(nw * 8 * 2), o_vals = plan(nw * 4 * 2),
                              o_res = plan(sizeof(PairResult) * np), o_sort = plan(sort_bytes),
                              o_groups = plan(sizeof(uint2) * groups.size()), o_total = plan(8);
@@ -1632,9 +1633,13 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
                 launch_match_count(B, st);
                 scan_match_counts(B, base + o_scan, scan_bytes, st);
                 B.anchor_cap = (uint32_t)est;
-                B.a_qi = (uint32_t*)(base + o_a); B.a_qp = B.a_qi + na; B.a_rp = B.a_qp + na; B.a_meta = B.a_rp + na;
-                B.a_f = (int32_t*)(B.a_meta + na); B.a_root = (uint32_t*)(B.a_f + na); B.a_aux = B.a_root + na;
+                B.a_rec = (uint4*)(base + o_a);
+                B.a_f = (int32_t*)(base + o_fra); B.a_root = (uint32_t*)(B.a_f + na); B.a_aux = B.a_root + na;
                 B.a_best = (unsigned long long*)(base + o_best);
+                B.big_count = (uint32_t*)(base + o_big); B.big_list = B.big_count + 4;
+                CU(cudaMemsetAsync(B.big_count, 0, 16, st));
+                B.win_bins = (uint32_t*)(base + o_bins); B.win_order = (uint32_t*)(base + o_order);
+                CU(cudaMemsetAsync(B.win_bins, 0, 4 * 192, st));
                 B.win_start = (uint32_t*)(base + o_w); B.win_end = B.win_start + nw; B.win_contig = B.win_end + nw; B.pair_nwin = B.win_contig + nw;
                 B.win_rec = (WindowRec*)(base + o_rec);
                 CU(cudaMemsetAsync(B.win_start, 0, 8 * nw, st));   // start == end == 0 marks an unused slot
@@ -1644,7 +1649,7 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
                 tq.mark("batch allocated");
                 launch_anchor_fill(B, st);
                 launch_window_walk(B, C, max_qseeds, st);
-                launch_chain_dp(B, C, st);
+                launch_chain_dp(B, C, c.n_sm, st);
                 if (C.robust || C.median) {
                     // only the trimmed mean and the median need the windows ordered by their anchors / seeds ratio
                     launch_window_keys(B, st);

@@ -238,9 +238,11 @@ struct ChainBatch {            // device pointers of one batch of pairs
     unsigned long long* a_total64;   // the same total accumulated in 64 bits (guards the 32-bit scan against wrap-around)
     // anchors
     uint32_t anchor_cap;
-    uint32_t* a_qi; uint32_t* a_qp; uint32_t* a_rp; uint32_t* a_meta;   // meta = ref contig << 1 | reverse
-    int32_t* a_f; uint32_t* a_root; uint32_t* a_aux;                    // DP score, component root, per-root size
+    uint4* a_rec;              // one 16-byte record per anchor: (q_pos, r_pos, ref contig << 1 | reverse, query seed index)
+    int32_t* a_f; uint32_t* a_root; uint32_t* a_aux;                    // DP score, component root, per-root size | flags
     unsigned long long* a_best;                                         // per-root best (score << 32 | ~index)
+    uint32_t* big_list; uint32_t* big_count;   // window slots with more anchors than the thread-per-window DP takes
+    uint32_t* win_bins; uint32_t* win_order;   // counting sort of the other windows by anchor count (descending)
     // windows
     uint32_t* win_start;       // [n_win_total] first query-seed index (pair-local) of each window
     uint32_t* win_end;         // [n_win_total] one past the last query-seed index
@@ -255,7 +257,7 @@ void launch_match_count(const ChainBatch& b, cudaStream_t st);
 void launch_anchor_fill(const ChainBatch& b, cudaStream_t st);
 uint32_t walk_group_capacity(uint32_t max_query_seeds);
 void launch_window_walk(const ChainBatch& b, const ChainConsts& c, uint32_t max_query_seeds, cudaStream_t st);
-void launch_chain_dp(const ChainBatch& b, const ChainConsts& c, cudaStream_t st);
+void launch_chain_dp(const ChainBatch& b, const ChainConsts& c, int n_sm, cudaStream_t st);
 void launch_window_keys(const ChainBatch& b, cudaStream_t st);
 void launch_ani_reduce(const ChainBatch& b, const ChainConsts& c, const uint64_t* sorted_keys,
                        const uint32_t* sorted_vals, cudaStream_t st);
