@@ -269,14 +269,13 @@ def parity_gate(args, capi, ctx, host_all, table, world, threads, oracle_db):
     del gs
     # a single-GPU database of everything on rank 0 (not timed): screen sample + reference table for N > 1
     be = parallel.CudaBackend(0, ctx=ctx)
-    full = []
-    for b0 in range(0, n_total, args.sketch_batch):
-        full += ctx.sketch_batch([[host_all.view(j)] for j in range(b0, min(n_total, b0 + args.sketch_batch))])
+    full = capi.SketchArray.concat(ctx, [ctx.sketch_batch([[host_all.view(j)] for j in range(b0, min(n_total, b0 + args.sketch_batch))])
+                                         for b0 in range(0, n_total, args.sketch_batch)])
     db = capi.Database(ctx)
     db.add_many(full)
     # (b) every screen decision of 10 queries (and the marker intersection sizes)
     q_screen = [int(x) for x in np.linspace(0, n_total - 1, 10)]
-    ok_gpu, shared_gpu = db.screen([full[q] for q in q_screen])
+    ok_gpu, shared_gpu = db.screen(capi.SketchArray.of(ctx, [full[q] for q in q_screen]))
     for i, q in enumerate(q_screen):
         for r in range(n_total):
             ok, sh = oracle.screen(oracle_db[q], oracle_db[r])
@@ -361,6 +360,8 @@ def configs1_block(args, capi, ctx, torch, stream):
 # ------------------------------------------------------------------------------------------------ the B200 arm
 def main():
     args = parse()
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keeps NCCL's version banner off stdout: rank 0 prints ONE JSON line
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -411,28 +412,30 @@ def main():
                                 (C.c_uint32 * (n + 1))(*range(n + 1))))
 
     def sketch_device(tm):
-        sk, seed_ms, tot_ms = [], 0.0, 0.0
+        parts, seed_ms, tot_ms = [], 0.0, 0.0
         for b0, b1 in batches:
-            sk += ctx.sketch_batch_device(d_ptr, np.arange(b1 - b0 + 1, dtype=np.uint32), host.offs[b0:b1], host.lens[b0:b1])
+            parts.append(ctx.sketch_batch_device(d_ptr, np.arange(b1 - b0 + 1, dtype=np.uint32), host.offs[b0:b1], host.lens[b0:b1]))
             st = ctx.stats()
             seed_ms += st.seed_ms; tot_ms += st.total_ms
         tm["seed_kernel_ms"] = seed_ms; tm["sketch_device_ms"] = tot_ms
-        return sk
+        return capi.SketchArray.concat(ctx, parts)
 
     def sketch_host(tm):
-        sk = []
+        parts = []
         for (b0, b1), (ptrs, lens, gs) in zip(batches, host_ptr_arrays):
-            out = (C.c_void_p * (b1 - b0))()
-            ctx.check(L.skb_sketch_batch(ctx._h, C.byref(params), 1, b1 - b0, gs, ptrs, lens, out))
-            sk += [capi.Sketch(ctx, out[i]) for i in range(b1 - b0)]
-        return sk
+            out = np.zeros(b1 - b0, np.uint64)
+            ctx.check(L.skb_sketch_batch(ctx._h, C.byref(params), 1, b1 - b0, gs, ptrs, lens, out.ctypes.data))
+            parts.append(capi.SketchArray(ctx, out))
+        return capi.SketchArray.concat(ctx, parts)
 
     def step(sketch_fn):
         tm = {}
         t0 = time.perf_counter()
         sk = sketch_fn(tm)
         tm["sketch_ms"] = 1e3 * (time.perf_counter() - t0)
-        table = parallel.query_and_gather(backend, sk, mine, plan, dgroup, device, None, tm)
+        # the hit table arrives on rank 0 rank after rank; ordering it by (query, ref) for the comparisons below is
+        # presentation, not part of the job (the reference returns its hits in hash-set order, lib.rs:640)
+        table = parallel.query_and_gather(backend, sk, mine, plan, dgroup, device, None, tm, sort=False)
         tm["step_wall_ms"] = 1e3 * (time.perf_counter() - t0)
         return table, tm
 
@@ -479,7 +482,7 @@ def main():
     ms_per_step, tms, table = timed(sketch_device, args.steps)
     k1 = ctx.stats().kernels_launched
     keys = [("seed_kernel_ms", "max"), ("sketch_device_ms", "max"), ("sketch_ms", "max"), ("exchange_ms", "max"), ("exchange_sizes_ms", "max"),
-            ("exchange_pack_enqueue_ms", "max"), ("exchange_allgather_ms", "max"), ("exchange_wait_adopt_ms", "max"), ("query_ms", "max"),
+            ("exchange_pack_enqueue_ms", "max"), ("exchange_allgather_ms", "max"), ("exchange_adopt_ms", "max"), ("query_ms", "max"),
             ("screen_ms", "max"), ("chain_ms", "max"), ("gather_ms", "max"), ("screened_in", "sum"), ("local_hits", "sum"),
             ("exchange_bytes_in", "max"), ("exchange_bytes_total", "max")]
     ph = phase_stats(tms, keys)
@@ -508,6 +511,7 @@ def main():
     e2e_value = pairs_total / (e2e_ms / 1e3)
 
     if rank == 0:
+        table, table_h = parallel.sort_hits(table), parallel.sort_hits(table_h)
         if table_h.shape != table.shape or not np.array_equal(table_h, table):
             raise SystemExit("host-buffer path and device-resident path returned different hit tables")
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -543,10 +547,14 @@ def main():
             "chained_pairs_per_s": ph["screened_in"] / (max(ph["chain_ms"], 1e-6) / 1e3),
             "phase_ms": {k: round(v, 4) for k, v in ph.items() if k.endswith("_ms")},
             "exchange": None if world == 1 else {
-                "ms": ph["exchange_ms"], "allgather_ms": ex_ms, "bytes_total": int(ph["exchange_bytes_total"]),
+                "ms": ph["exchange_ms"], "allgather_ms": ex_ms, "sizes_ms": ph["exchange_sizes_ms"], "pack_enqueue_ms": ph["exchange_pack_enqueue_ms"],
+                "adopt_ms": ph["exchange_adopt_ms"], "bytes_total": int(ph["exchange_bytes_total"]),
                 "bytes_in_per_gpu": int(ph["exchange_bytes_in"]), "collective": tms[-1].get("exchange_collective"),
                 "busbw_gbs": ph["exchange_bytes_in"] / (max(ex_ms, 1e-6) / 1e3) / 1e9,
-                "note": "busbw = bytes received per GPU / all-gather time (NCCL's definition for all-gather)"},
+                "note": "ms = host time until the database is usable (sizes + pack + heads + adopt); the body all-gather (allgather_ms, "
+                        "device-timed from the first collective to the end of the second) continues under the marker screen of the "
+                        "query. busbw = bytes received per GPU / allgather_ms (NCCL's definition for all-gather). Peers receive the "
+                        "reference side of every sketch only (no position-order seeds): half of the sketch bytes"},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": total_bases,
                     "d2h_bytes_per_step": int(len(table)) * C.sizeof(capi.Hit), "ms_per_step": e2e_ms,
                     "phase_ms": {k: round(v, 4) for k, v in ph_h.items()},

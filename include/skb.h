@@ -69,6 +69,7 @@ typedef struct {
     uint32_t n_contigs;    /* contigs that passed the MIN_LENGTH_CONTIG gate */
     int32_t  k, c, marker_c;
     int32_t  has_seeds;    /* sketched with seed=True */
+    int32_t  reference_only; /* received through an exchange block without the query-side arrays */
 } skb_sketch_info_t;
 
 /* Timings of the last call on this context, measured with CUDA events on the context's stream. */
@@ -112,6 +113,7 @@ int skb_sketch_batch_device(skb_ctx_t* ctx, const skb_sketch_params_t* params, i
                             const uint8_t* seq, const uint64_t* contig_offsets, const uint64_t* contig_lens,
                             skb_sketch_t** out);
 void skb_sketch_free(skb_sketch_t* s);
+void skb_sketch_free_many(uint32_t n, skb_sketch_t* const* s);   /* the same for n handles with one lock acquisition */
 int  skb_sketch_info(const skb_sketch_t* s, skb_sketch_info_t* out);
 /* Copy a sketch to host arrays (any pointer may be NULL).  Seeds come sorted by (kmer, contig, pos);
  * canonical[i] = SeedPosition.canonical; markers sorted ascending and unique (the reference keeps both in
@@ -139,22 +141,30 @@ int  skb_sketch_unpack(skb_ctx_t* ctx, const void* meta_host, uint64_t meta_byte
                        uint64_t payload_bytes, skb_sketch_t** out, uint32_t out_cap, uint32_t* n_out);
 
 /* ---- zero-copy exchange region (multi-GPU all-vs-all) ----
- * One block of sketch storage that holds one SEGMENT per rank: [descriptor | device arrays of that rank's sketches].
- * Every rank packs its own segment in place, ONE collective (all-gather with per-rank sizes, straight into this block)
- * fills the others, and the peers' sketches are then adopted as views into the block: no staging buffer, no padding to
- * the largest rank, no second device-to-device copy.  The block lives until the last adopted sketch is freed. */
+ * One block of sketch storage that holds, per rank, a HEAD segment [descriptor | marker sets | per-contig tables] and a
+ * BODY segment [seed arrays | bucket tables].  Every rank packs its own two segments in place, the caller's collectives
+ * (all-gather with per-rank sizes, straight into this block) fill the others, and the peers' sketches are then adopted
+ * as views into the block: no staging buffer, no padding, no second device-to-device copy.  Heads and bodies travel as
+ * two collectives so that the marker screen can start while the (25x larger) bodies are still on the wire.
+ * reference_only != 0 leaves out what only a QUERY needs (position-order seeds): half of the bytes; such sketches can be
+ * database members but not queries.  The block lives until the last adopted sketch is freed. */
 typedef struct skb_exchange skb_exchange_t;
-/* bytes of the segment these sketches need (a multiple of 256) and of the descriptor at its start */
-int  skb_exchange_segment_size(uint32_t n, skb_sketch_t* const* sketches, uint64_t* segment_bytes, uint64_t* meta_bytes);
+/* bytes of the two segments these sketches need (multiples of 256) and of the descriptor at the front of the head */
+int  skb_exchange_segment_size(uint32_t n, skb_sketch_t* const* sketches, int32_t reference_only, uint64_t* head_bytes,
+                               uint64_t* body_bytes, uint64_t* meta_bytes);
 int  skb_exchange_create(skb_ctx_t* ctx, uint64_t bytes, skb_exchange_t** out);
 void* skb_exchange_ptr(skb_exchange_t* ex);                    /* device address of the block */
-/* writes the segment of these sketches at `offset` (a multiple of 256); asynchronous on the context's stream */
-int  skb_exchange_pack(skb_exchange_t* ex, uint64_t offset, uint32_t n, skb_sketch_t* const* sketches);
-/* adopts the sketches of n_segments segments (offsets[i], descriptor sizes meta_bytes[i]) once their bytes have arrived
- * (the caller orders the collective before this call on the context's stream).  Handles are appended to out[] segment
- * after segment; counts[i] receives the number of sketches of segment i. */
-int  skb_exchange_adopt(skb_exchange_t* ex, uint32_t n_segments, const uint64_t* offsets, const uint64_t* meta_bytes,
-                        skb_sketch_t** out, uint32_t out_cap, uint32_t* counts);
+/* writes the two segments of these sketches at the given offsets (multiples of 256); asynchronous on the context's stream */
+int  skb_exchange_pack(skb_exchange_t* ex, uint64_t head_offset, uint64_t body_offset, uint32_t n,
+                       skb_sketch_t* const* sketches, int32_t reference_only);
+/* Orders this context behind work the caller enqueued on ANOTHER CUDA stream (the collective's): bodies == 0: the heads;
+ * the context's stream waits now (call before skb_exchange_adopt).  bodies != 0: the bodies; the wait is deferred until
+ * seed arrays of an adopted sketch are first read (chaining, export, re-packing), so screening overlaps the transfer. */
+int  skb_exchange_order_after(skb_exchange_t* ex, void* foreign_cuda_stream, int32_t bodies);
+/* adopts the sketches of n_segments peers (segment offsets as packed there, descriptor sizes meta_bytes[i]) once the
+ * heads have arrived.  Handles are appended to out[] peer after peer; counts[i] receives the number of sketches of peer i. */
+int  skb_exchange_adopt(skb_exchange_t* ex, uint32_t n_segments, const uint64_t* head_offsets, const uint64_t* body_offsets,
+                        const uint64_t* meta_bytes, skb_sketch_t** out, uint32_t out_cap, uint32_t* counts);
 void skb_exchange_free(skb_exchange_t* ex);                    /* drops the caller's reference to the block */
 
 /* ---- database: the (markers, sketches) pair a Database owns (lib.rs:132-137) ---- */

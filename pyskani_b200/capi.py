@@ -38,7 +38,7 @@ HIT_DTYPE = np.dtype([('query_index', '<u4'), ('ref_index', '<u4'), ('ani', '<f4
 class SketchInfo(C.Structure):
     _fields_ = [("n_seeds", C.c_uint64), ("n_markers", C.c_uint64), ("total_len", C.c_uint64),
                 ("n_contigs", C.c_uint32), ("k", C.c_int32), ("c", C.c_int32), ("marker_c", C.c_int32),
-                ("has_seeds", C.c_int32)]
+                ("has_seeds", C.c_int32), ("reference_only", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -51,15 +51,24 @@ class Stats(C.Structure):
 SYMBOLS = [
     "skb_ctx_create", "skb_ctx_destroy", "skb_last_error", "skb_ctx_stats", "skb_ctx_sync", "skb_ctx_stream",
     "skb_host_alloc", "skb_host_free", "skb_dev_alloc", "skb_dev_free", "skb_memcpy_h2d",
-    "skb_sketch_batch", "skb_sketch_batch_device", "skb_sketch_free", "skb_sketch_info", "skb_sketch_export",
+    "skb_sketch_batch", "skb_sketch_batch_device", "skb_sketch_free", "skb_sketch_free_many", "skb_sketch_info", "skb_sketch_export",
     "skb_sketch_import", "skb_sketch_pack_size", "skb_sketch_pack", "skb_sketch_unpack",
-    "skb_exchange_segment_size", "skb_exchange_create", "skb_exchange_ptr", "skb_exchange_pack", "skb_exchange_adopt",
+    "skb_exchange_segment_size", "skb_exchange_create", "skb_exchange_ptr", "skb_exchange_pack", "skb_exchange_order_after",
+    "skb_exchange_adopt",
     "skb_exchange_free",
     "skb_model_load_json", "skb_model_free", "skb_model_info", "skb_model_predict", "skb_db_set_model", "skb_db_create", "skb_db_destroy", "skb_db_add", "skb_db_add_many", "skb_db_replace", "skb_db_size", "skb_db_query",
     "skb_hits_free", "skb_db_screen", "skb_version",
 ]
 
 _lib = None
+
+
+def handle_array(sketches):
+    """(count, pointer usable as `skb_sketch_t* const*`, object to keep alive) for a SketchArray or any sequence of Sketch"""
+    if isinstance(sketches, SketchArray):
+        return len(sketches), sketches.handles.ctypes.data, sketches
+    arr = np.fromiter((s._h for s in sketches), np.uint64, len(sketches))
+    return len(arr), arr.ctypes.data, arr
 
 
 class SkbError(RuntimeError):
@@ -93,6 +102,7 @@ def lib():
         L.skb_sketch_batch.argtypes = [vp, C.POINTER(SketchParams), i32, u32, vp, vp, vp, vp]
         L.skb_sketch_batch_device.argtypes = [vp, C.POINTER(SketchParams), i32, u32, vp, vp, vp, vp, vp]
         L.skb_sketch_free.argtypes = [vp]
+        L.skb_sketch_free_many.argtypes = [u32, vp]
         L.skb_sketch_info.argtypes = [vp, C.POINTER(SketchInfo)]
         L.skb_sketch_export.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.skb_sketch_import.argtypes = [vp, C.POINTER(SketchParams), i32, u64, vp, vp, vp, vp, u64, vp, u32, vp,
@@ -100,12 +110,13 @@ def lib():
         L.skb_sketch_pack_size.argtypes = [u32, vp, C.POINTER(u64), C.POINTER(u64)]
         L.skb_sketch_pack.argtypes = [vp, u32, vp, vp, u64, vp, u64]
         L.skb_sketch_unpack.argtypes = [vp, vp, u64, vp, u64, vp, u32, C.POINTER(u32)]
-        L.skb_exchange_segment_size.argtypes = [u32, vp, C.POINTER(u64), C.POINTER(u64)]
+        L.skb_exchange_segment_size.argtypes = [u32, vp, i32, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+        L.skb_exchange_order_after.argtypes = [vp, vp, i32]
         L.skb_exchange_create.argtypes = [vp, u64, C.POINTER(vp)]
         L.skb_exchange_ptr.restype = vp
         L.skb_exchange_ptr.argtypes = [vp]
-        L.skb_exchange_pack.argtypes = [vp, u64, u32, vp]
-        L.skb_exchange_adopt.argtypes = [vp, u32, vp, vp, vp, u32, vp]
+        L.skb_exchange_pack.argtypes = [vp, u64, u64, u32, vp, i32]
+        L.skb_exchange_adopt.argtypes = [vp, u32, vp, vp, vp, vp, u32, vp]
         L.skb_exchange_free.argtypes = [vp]
         L.skb_model_load_json.argtypes = [vp, C.c_char_p, C.c_size_t, C.POINTER(vp)]
         L.skb_model_free.argtypes = [vp]
@@ -175,10 +186,10 @@ class Context:
         ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data if a.size else None for a in keep])
         lens = (C.c_uint64 * max(n, 1))(*[a.size for a in keep])
         gs = (C.c_uint32 * len(starts))(*starts)
-        out = (C.c_void_p * max(len(genomes), 1))()
+        out = np.zeros(max(len(genomes), 1), np.uint64)
         p = SketchParams(k, c, marker_c)
-        self.check(lib().skb_sketch_batch(self._h, C.byref(p), int(seed), len(genomes), gs, ptrs, lens, out))
-        return [Sketch(self, out[i]) for i in range(len(genomes))]
+        self.check(lib().skb_sketch_batch(self._h, C.byref(p), int(seed), len(genomes), gs, ptrs, lens, out.ctypes.data))
+        return SketchArray(self, out[:len(genomes)])
 
     def sketch_batch_device(self, seq_dev_ptr, genome_contig_start, contig_offsets, contig_lens,
                             k=15, c=125, marker_c=1000, seed=True):
@@ -186,11 +197,11 @@ class Context:
         offs = np.ascontiguousarray(contig_offsets, np.uint64)
         lens = np.ascontiguousarray(contig_lens, np.uint64)
         ng = len(gs) - 1
-        out = (C.c_void_p * max(ng, 1))()
+        out = np.zeros(max(ng, 1), np.uint64)
         p = SketchParams(k, c, marker_c)
         self.check(lib().skb_sketch_batch_device(self._h, C.byref(p), int(seed), ng, gs.ctypes.data, seq_dev_ptr,
-                                                 offs.ctypes.data, lens.ctypes.data, out))
-        return [Sketch(self, out[i]) for i in range(ng)]
+                                                 offs.ctypes.data, lens.ctypes.data, out.ctypes.data))
+        return SketchArray(self, out[:ng])
 
     def import_sketch(self, kmer, pos, contig, canonical, markers, contig_lengths, k=15, c=125, marker_c=1000,
                       has_seeds=True):
@@ -207,16 +218,14 @@ class Context:
     # ---- device-to-device transfer (multi-GPU exchange)
     def pack_size(self, sketches):
         """(payload bytes on the device, descriptor bytes on the host) that pack() needs for these sketches"""
-        n = len(sketches)
-        hs = (C.c_void_p * max(n, 1))(*[s._h for s in sketches])
+        n, hs, _keep = handle_array(sketches)
         pb, mb = C.c_uint64(), C.c_uint64()
         self.check(lib().skb_sketch_pack_size(n, hs, C.byref(pb), C.byref(mb)))
         return pb.value, mb.value
 
     def pack(self, sketches, payload_dev_ptr, payload_bytes):
         """Concatenates the sketches' device arrays into the device buffer; returns the host descriptor (uint8 array)."""
-        n = len(sketches)
-        hs = (C.c_void_p * max(n, 1))(*[s._h for s in sketches])
+        n, hs, _keep = handle_array(sketches)
         _, mb = self.pack_size(sketches)
         meta = np.zeros(mb, np.uint8)
         self.check(lib().skb_sketch_pack(self._h, n, hs, payload_dev_ptr, payload_bytes, meta.ctypes.data, mb))
@@ -226,19 +235,18 @@ class Context:
         """Rebuilds the sketches described by `meta` from a device payload (one device-to-device copy)."""
         meta = np.ascontiguousarray(meta, np.uint8)
         n = int(meta[4:8].view(np.uint32)[0]) if meta.size >= 8 else 0
-        out = (C.c_void_p * max(n, 1))()
+        out = np.zeros(max(n, 1), np.uint64)
         got = C.c_uint32()
-        self.check(lib().skb_sketch_unpack(self._h, meta.ctypes.data, meta.size, payload_dev_ptr, payload_bytes, out, n,
+        self.check(lib().skb_sketch_unpack(self._h, meta.ctypes.data, meta.size, payload_dev_ptr, payload_bytes, out.ctypes.data, n,
                                            C.byref(got)))
-        return [Sketch(self, out[i]) for i in range(got.value)]
+        return SketchArray(self, out[:got.value])
 
-    def segment_size(self, sketches):
-        """(segment bytes, descriptor bytes) of these sketches inside an exchange block"""
-        n = len(sketches)
-        hs = (C.c_void_p * max(n, 1))(*[s._h for s in sketches])
-        sb, mb = C.c_uint64(), C.c_uint64()
-        self.check(lib().skb_exchange_segment_size(n, hs, C.byref(sb), C.byref(mb)))
-        return sb.value, mb.value
+    def segment_size(self, sketches, reference_only=False):
+        """(head segment bytes, body segment bytes, descriptor bytes) of these sketches inside an exchange block"""
+        n, hs, _keep = handle_array(sketches)
+        hb, bb, mb = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.check(lib().skb_exchange_segment_size(n, hs, int(reference_only), C.byref(hb), C.byref(bb), C.byref(mb)))
+        return hb.value, bb.value, mb.value
 
     def exchange(self, nbytes):
         return Exchange(self, nbytes)
@@ -306,22 +314,26 @@ class Exchange:
     def ptr(self):
         return lib().skb_exchange_ptr(self._h)
 
-    def pack(self, offset, sketches):
-        n = len(sketches)
-        hs = (C.c_void_p * max(n, 1))(*[s._h for s in sketches])
-        self.ctx.check(lib().skb_exchange_pack(self._h, int(offset), n, hs))
+    def pack(self, head_offset, body_offset, sketches, reference_only=False):
+        n, hs, _keep = handle_array(sketches)
+        self.ctx.check(lib().skb_exchange_pack(self._h, int(head_offset), int(body_offset), n, hs, int(reference_only)))
 
-    def adopt(self, offsets, meta_bytes, max_sketches):
-        """-> list (one per segment) of lists of Sketch whose arrays are views into this block"""
-        ns = len(offsets)
-        offs = (C.c_uint64 * max(ns, 1))(*[int(o) for o in offsets])
+    def order_after(self, cuda_stream, bodies):
+        """orders the context behind work enqueued on another CUDA stream (raw handle): heads now, bodies lazily"""
+        self.ctx.check(lib().skb_exchange_order_after(self._h, C.c_void_p(int(cuda_stream)), int(bodies)))
+
+    def adopt(self, head_offsets, body_offsets, meta_bytes, max_sketches):
+        """-> list (one per peer) of lists of Sketch whose arrays are views into this block"""
+        ns = len(head_offsets)
+        ho = (C.c_uint64 * max(ns, 1))(*[int(o) for o in head_offsets])
+        bo = (C.c_uint64 * max(ns, 1))(*[int(o) for o in body_offsets])
         mbs = (C.c_uint64 * max(ns, 1))(*[int(m) for m in meta_bytes])
-        out = (C.c_void_p * max(max_sketches, 1))()
+        out = np.zeros(max(max_sketches, 1), np.uint64)
         counts = (C.c_uint32 * max(ns, 1))()
-        self.ctx.check(lib().skb_exchange_adopt(self._h, ns, offs, mbs, out, max_sketches, counts))
+        self.ctx.check(lib().skb_exchange_adopt(self._h, ns, ho, bo, mbs, out.ctypes.data, max_sketches, counts))
         res, k = [], 0
         for i in range(ns):
-            res.append([Sketch(self.ctx, out[k + j]) for j in range(counts[i])])
+            res.append(SketchArray(self.ctx, out[k:k + counts[i]]))
             k += counts[i]
         return res
 
@@ -337,16 +349,17 @@ class Exchange:
 
 
 class Sketch:
-    def __init__(self, ctx, handle):
-        self.ctx, self._h = ctx, handle
+    def __init__(self, ctx, handle, owner=None):
+        """owner: the SketchArray the handle belongs to (it frees the handle); None = this object frees it"""
+        self.ctx, self._h, self._owner = ctx, int(handle) if handle else None, owner
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and self._owner is None:
             try:
                 lib().skb_sketch_free(self._h)
             except TypeError:
                 pass
-            self._h = None
+        self._h = None
 
     def info(self):
         i = SketchInfo()
@@ -361,6 +374,64 @@ class Sketch:
         self.ctx.check(lib().skb_sketch_export(self._h, kmer.ctypes.data, pos.ctypes.data, contig.ctypes.data,
                                                canon.ctypes.data, markers.ctypes.data, cl.ctypes.data))
         return dict(kmer=kmer, pos=pos, contig=contig, canonical=canon, markers=markers, contig_lengths=cl)
+
+
+class SketchArray:
+    """The sketches one call produced: a numpy array of handles that is passed to the C ABI as it is and freed with ONE call
+    (skb_sketch_free_many) - a per-handle Python object for each of 1 000 sketches per step costs more than the query.
+    Behaves like a list of Sketch (indexing, slicing, iteration, len, +); items and slices are views that keep it alive."""
+
+    def __init__(self, ctx, handles, parents=None):
+        self.ctx = ctx
+        self.handles = np.ascontiguousarray(handles, np.uint64)
+        self._parents = parents            # None: this array owns its handles; else the owning arrays it is a view of
+
+    def __len__(self):
+        return len(self.handles)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return SketchArray(self.ctx, self.handles[i], parents=(self,))
+        return Sketch(self.ctx, self.handles[i], owner=self)
+
+    def __iter__(self):
+        return (Sketch(self.ctx, h, owner=self) for h in self.handles)
+
+    def __add__(self, other):
+        other = other if isinstance(other, SketchArray) else SketchArray.of(self.ctx, other)
+        return SketchArray(self.ctx, np.concatenate([self.handles, other.handles]), parents=(self, other))
+
+    __iadd__ = __add__
+
+    @staticmethod
+    def concat(ctx, arrays):
+        arrays = [a if isinstance(a, SketchArray) else SketchArray.of(ctx, a) for a in arrays]
+        h = np.concatenate([a.handles for a in arrays]) if arrays else np.zeros(0, np.uint64)
+        return SketchArray(ctx, h, parents=tuple(arrays))
+
+    @staticmethod
+    def gather(ctx, n, parts):
+        """n handles in a given order: parts = [(index list, SketchArray), ...]; every index appears exactly once"""
+        h = np.zeros(n, np.uint64)
+        for idxs, arr in parts:
+            h[np.asarray(idxs, np.int64)] = arr.handles
+        return SketchArray(ctx, h, parents=tuple(a for _, a in parts))
+
+    @staticmethod
+    def of(ctx, sketches):
+        """a (non-owning) array over any sequence of Sketch / SketchArray items"""
+        if isinstance(sketches, SketchArray):
+            return sketches
+        items = list(sketches)
+        return SketchArray(ctx, np.fromiter((s._h for s in items), np.uint64, len(items)), parents=tuple(items))
+
+    def __del__(self):
+        if getattr(self, "_parents", 0) is None and len(self.handles):
+            try:
+                lib().skb_sketch_free_many(len(self.handles), self.handles.ctypes.data)
+            except TypeError:
+                pass
+        self.handles = np.zeros(0, np.uint64)
 
 
 class Database:
@@ -385,11 +456,10 @@ class Database:
         return idx.value
 
     def add_many(self, sketches):
-        n = len(sketches)
-        hs = (C.c_void_p * max(n, 1))(*[s._h for s in sketches])
+        n, hs, keep = handle_array(sketches)
         idx = C.c_uint32()
         self.ctx.check(lib().skb_db_add_many(self._h, n, hs, C.byref(idx)))
-        self._keep.extend(sketches)
+        self._keep.append(sketches)
         return idx.value
 
     def set_model(self, model):
@@ -401,8 +471,7 @@ class Database:
 
     def query_array(self, queries, cutoff=0.0, learned_ani=0, median=False, robust=False, faster_small=False):
         """skb_db_query; hits as a numpy structured array (HIT_DTYPE) plus the number of screened-in pairs"""
-        n = len(queries)
-        qs = (C.c_void_p * max(n, 1))(*[q._h for q in queries])
+        n, qs, _keep = handle_array(queries)
         o = QueryOpts(cutoff, learned_ani, int(median), int(robust), int(faster_small))
         hits = C.POINTER(Hit)()
         nh, ns = C.c_uint64(0), C.c_uint64(0)
@@ -415,8 +484,7 @@ class Database:
         return out, ns.value
 
     def query(self, queries, cutoff=0.0, learned_ani=0, median=False, robust=False, faster_small=False):
-        n = len(queries)
-        qs = (C.c_void_p * max(n, 1))(*[q._h for q in queries])
+        n, qs, _keep = handle_array(queries)
         o = QueryOpts(cutoff, learned_ani, int(median), int(robust), int(faster_small))
         hits = C.POINTER(Hit)()
         nh, ns = C.c_uint64(0), C.c_uint64(0)
@@ -429,8 +497,8 @@ class Database:
         return out, ns.value
 
     def screen(self, queries, cutoff=0.8, rescue_small=True):
-        n, nr = len(queries), len(self)
-        qs = (C.c_void_p * max(n, 1))(*[q._h for q in queries])
+        nr = len(self)
+        n, qs, _keep = handle_array(queries)
         ok = np.zeros((n, nr), np.uint8); shared = np.zeros((n, nr), np.uint32)
         self.ctx.check(lib().skb_db_screen(self._h, n, qs, cutoff, int(rescue_small), ok.ctypes.data, shared.ctypes.data))
         return ok.astype(bool), shared

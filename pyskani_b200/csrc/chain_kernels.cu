@@ -665,8 +665,11 @@ __global__ void __launch_bounds__(DPT_THREADS) chain_dp_thread_kernel(const Chai
     // per-component size and best end: the components of the last two distinct roots stay in registers (a chain and the
     // stray anchor that interrupts it), older ones are spilled to aux_a / best_a
     RootStat sa{NO_ROOT, 0u, 0u, 0}, sb{NO_ROOT, 0u, 0u, 0};
-    uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
-    if (n) nxt = rec_a[0];
+    // (q_pos, r_pos, meta) of the next anchor; the record's fourth word (query seed index) is only needed for chain ends.
+    // It is deliberately NOT loaded here: as a dead destination register of a 128-bit load it gets reused as scratch,
+    // and the first write to it then waits for the whole load (write-after-write on the scoreboard).
+    uint3 nxt = make_uint3(0u, 0u, 0u);
+    if (n) { const uint2 a = *(const uint2*)rec_a; nxt = make_uint3(a.x, a.y, ((const uint32_t*)rec_a)[2]); }
     // the ring starts out full of entries that are out of band for every anchor of the window (q_pos 2^30 bases ahead):
     // the first anchors then run the same branch-free code as all others
     {
@@ -678,10 +681,13 @@ __global__ void __launch_bounds__(DPT_THREADS) chain_dp_thread_kernel(const Chai
     // ---------------- DP, lock step over the anchor index
     for (uint32_t i = 0; i < nmax; i++) {
         const bool act = i < n;
-        const uint4 r = nxt;
-        if (i + 1 < n) nxt = rec_a[i + 1];                 // the next record travels while this anchor is scored
-        // pins the load here: without it the compiler sinks it to its first use, at the top of the next iteration
-        asm volatile("" : "+r"(nxt.x), "+r"(nxt.y), "+r"(nxt.z), "+r"(nxt.w));
+        const uint3 r = nxt;
+        if (i + 1 < n) {                                   // the next record travels while this anchor is scored
+            const uint2 a = *(const uint2*)(rec_a + i + 1);
+            nxt = make_uint3(a.x, a.y, ((const uint32_t*)(rec_a + i + 1))[2]);
+        }
+        // pins the loads here: without it the compiler sinks them to their first use, at the top of the next iteration
+        asm volatile("" : "+r"(nxt.x), "+r"(nxt.y), "+r"(nxt.z));
         const uint32_t cq = r.x, cm = r.z, tq = cq - 1u;
         const int32_t cD = (cm & 1u) ? -(int32_t)(r.y + r.x) : (int32_t)(r.y - r.x);
         int32_t best = 0;                 // max over valid predecessors of f[j] - gap; a link needs f[j] + 20 - gap > 20

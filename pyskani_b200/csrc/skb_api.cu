@@ -166,18 +166,32 @@ struct DevMem {
 
 struct BatchStore {   // device arrays shared by the sketches that were produced together
     DevMem kmer_p, pos_p, meta_p, kmer_k, pos_k, meta_k, bucket, contig_seed_start, contig_len, contig_win_start, markers;
-    DevMem blob;      // sketches received through skb_sketch_unpack: every array is a slice of this one block
+    DevMem blob;      // sketches received through skb_sketch_unpack / an exchange block: every array is a slice of this one block
+    // exchange blocks: the seed arrays ("bodies") may still be arriving over NVLink while the markers are already being
+    // screened; whoever reads seed arrays first makes the context's stream wait for this event (ensure_seeds_ready)
+    cudaEvent_t body_ev = nullptr;
+    bool body_pending = false;
+    ~BatchStore() { if (body_ev) cudaEventDestroy(body_ev); }
 };
 
 struct SketchImpl {
     std::shared_ptr<Core> core;
     std::shared_ptr<BatchStore> store;
+    bool ref_only = false;     // transferred without the position-order arrays: usable as a reference, not as a query
     GenomeView view{};
     skb_sketch_info_t info{};
     std::vector<uint32_t> contig_len_host;
 };
 
 constexpr uint32_t FRAGMENT_LENGTH = 20000;   // skani::params::CHUNK_SIZE_DNA
+
+inline void ensure_seeds_ready(const SketchImpl& I) {
+    BatchStore& st = *I.store;
+    if (st.body_pending) {
+        CU(cudaStreamWaitEvent(I.core->stream, st.body_ev, 0));
+        st.body_pending = false;
+    }
+}
 
 }  // namespace skb
 
@@ -895,6 +909,18 @@ void skb_sketch_free(skb_sketch_t* s) {
     }
 }
 
+void skb_sketch_free_many(uint32_t n, skb_sketch_t* const* s) {
+    // one lock for the whole set: a database's worth of handles is released in microseconds instead of n calls
+    for (uint32_t i = 0; i < n;) {
+        if (!s[i]) { i++; continue; }
+        std::shared_ptr<Core> core = s[i]->impl ? s[i]->impl->core : nullptr;
+        if (!core) { delete s[i]; i++; continue; }
+        std::lock_guard<std::mutex> lk(core->mu);
+        cudaSetDevice(core->device);
+        for (; i < n && (!s[i] || !s[i]->impl || s[i]->impl->core == core); i++) delete s[i];
+    }
+}
+
 int skb_sketch_info(const skb_sketch_t* s, skb_sketch_info_t* out) {
     if (!s || !out) return SKB_ERR_ARG;
     *out = s->impl->info;
@@ -909,6 +935,7 @@ int skb_sketch_export(const skb_sketch_t* s, uint64_t* kmer, uint32_t* pos, uint
         Core& c = *I.core;
         // markers-only exports (Database.flush / save_markers) must not pull the seed arrays off the device
         const bool want_seeds = kmer || pos || contig || canonical;
+        if (want_seeds) ensure_seeds_ready(I);
         const uint32_t n = want_seeds ? I.view.n_seeds : 0;
         std::vector<uint32_t> k32(kmer ? n : 0), p32(pos ? n : 0), m32(contig || canonical ? n : 0);
         if (kmer) download(c, k32.data(), I.view.kmer_k, n);
@@ -1109,23 +1136,42 @@ void skb_hits_free(skb_hit_t* hits) { delete[] hits; }
 
 // ---------------------------------------------------------------- device-to-device transfer of sketches
 namespace {
-constexpr uint32_t PACK_MAGIC = 0x534B4250u;   // "SKBP"
+constexpr uint32_t PACK_MAGIC = 0x534B4251u;   // "SKBQ"
 constexpr int PACK_ARRAYS = 11;
-struct PackHeader { uint32_t magic, n; uint64_t payload_bytes; };
+// A packed set of sketches has a HEAD (descriptor, marker sets, per-contig tables: all the screen needs) and a BODY (seed
+// arrays and bucket tables: what chaining needs).  off[] of head arrays is relative to the head payload, of body arrays
+// to the body payload; skb_sketch_pack puts the body right behind the head, an exchange block keeps them in two regions
+// so that they can travel as two collectives.
+struct PackHeader { uint32_t magic, n; uint64_t head_bytes, body_bytes; uint32_t ref_only, pad; };
 struct PackSketch {
     uint64_t total_len;
     uint32_t n_seeds, n_markers, n_contigs, bucket_shift, n_buckets, win_cap;
     int32_t k, c, marker_c, has_seeds;
-    uint64_t off[PACK_ARRAYS];                 // kmer_p pos_p meta_p kmer_k pos_k meta_k bucket cstart clen cwin markers
+    uint64_t off[PACK_ARRAYS];                 // kmer_p pos_p meta_p kmer_k pos_k meta_k bucket | cstart clen cwin markers
 };
+constexpr bool pack_is_head(int a) { return a >= 7; }
 inline uint64_t pad16(uint64_t x) { return (x + 15) & ~(uint64_t)15; }
-// byte sizes of the eleven device arrays of one sketch, in PackSketch::off order
-void pack_sizes(const GenomeView& v, uint64_t* sz) {
+inline uint64_t pad256(uint64_t x) { return (x + 255) & ~(uint64_t)255; }
+// byte sizes of the eleven device arrays of one sketch, in PackSketch::off order.  ref_only leaves out what only a QUERY
+// needs (position-order seeds, per-contig seed starts): half of the bytes of a sketch.
+void pack_sizes(const GenomeView& v, bool ref_only, uint64_t* sz) {
     const uint64_t n = v.n_seeds, nc = v.n_contigs;
-    for (int i = 0; i < 6; i++) sz[i] = 4 * n;
+    for (int i = 0; i < 3; i++) sz[i] = ref_only || !v.kmer_p ? 0 : 4 * n;
+    for (int i = 3; i < 6; i++) sz[i] = 4 * n;
     sz[6] = v.bucket ? 4 * ((uint64_t)v.n_buckets + 1) : 0;
-    sz[7] = 4 * (nc + 1); sz[8] = 4 * nc; sz[9] = 4 * (nc + 1);
+    sz[7] = ref_only || !v.contig_seed_start ? 0 : 4 * (nc + 1); sz[8] = 4 * nc; sz[9] = 4 * (nc + 1);
     sz[10] = 8 * (uint64_t)v.n_markers;
+}
+void pack_totals(uint32_t n, skb_sketch_t* const* sketches, bool ref_only, uint64_t& head, uint64_t& body, uint64_t& meta) {
+    head = body = 0;
+    meta = sizeof(PackHeader) + (uint64_t)n * sizeof(PackSketch);
+    for (uint32_t i = 0; i < n; i++) {
+        if (!sketches[i]) throw Fail{SKB_ERR_ARG, "null sketch"};
+        uint64_t sz[PACK_ARRAYS];
+        pack_sizes(sketches[i]->impl->view, ref_only || sketches[i]->impl->ref_only, sz);
+        for (int a = 0; a < PACK_ARRAYS; a++) (pack_is_head(a) ? head : body) += pad16(sz[a]);
+        meta += 4 * (uint64_t)sketches[i]->impl->view.n_contigs;
+    }
 }
 }  // namespace
 
@@ -1133,15 +1179,11 @@ extern "C" {
 
 int skb_sketch_pack_size(uint32_t n, skb_sketch_t* const* sketches, uint64_t* payload_bytes, uint64_t* meta_bytes) {
     if ((n && !sketches) || !payload_bytes || !meta_bytes) return SKB_ERR_ARG;
-    uint64_t pb = 0, mb = sizeof(PackHeader) + (uint64_t)n * sizeof(PackSketch);
-    for (uint32_t i = 0; i < n; i++) {
-        if (!sketches[i]) return SKB_ERR_ARG;
-        uint64_t sz[PACK_ARRAYS];
-        pack_sizes(sketches[i]->impl->view, sz);
-        for (int a = 0; a < PACK_ARRAYS; a++) pb += pad16(sz[a]);
-        mb += 4 * (uint64_t)sketches[i]->impl->view.n_contigs;
-    }
-    *payload_bytes = pb; *meta_bytes = mb;
+    try {
+        uint64_t head = 0, body = 0, meta = 0;
+        pack_totals(n, sketches, false, head, body, meta);
+        *payload_bytes = pad256(head) + body; *meta_bytes = meta;
+    } catch (const Fail&) { return SKB_ERR_ARG; }
     return SKB_OK;
 }
 
@@ -1149,43 +1191,52 @@ int skb_sketch_pack_size(uint32_t n, skb_sketch_t* const* sketches, uint64_t* pa
 
 namespace {
 
-// Fills the host descriptor of n sketches and lists the device arrays to gather (destination offsets are relative to
-// the start of the payload).  Shared by skb_sketch_pack and skb_exchange_pack.
-void build_pack_meta(Core& c, uint32_t n, skb_sketch_t* const* sketches, uint64_t payload_bytes, char* m,
+// Fills the host descriptor of n sketches and lists the device arrays to gather: head arrays go to head_dst + off, body
+// arrays to body_dst + off.  Shared by skb_sketch_pack and skb_exchange_pack.
+void build_pack_meta(Core& c, uint32_t n, skb_sketch_t* const* sketches, bool ref_only, char* m, uint64_t head_dst, uint64_t body_dst,
                      std::vector<SegmentCopy>& segs, uint64_t& max_bytes) {
-    PackHeader hd{PACK_MAGIC, n, payload_bytes};
-    std::memcpy(m, &hd, sizeof(hd));
+    uint64_t head = 0, body = 0, meta = 0;
+    pack_totals(n, sketches, ref_only, head, body, meta);
+    bool any_ref_only = ref_only;
     PackSketch* ps = (PackSketch*)(m + sizeof(PackHeader));
     uint32_t* clens = (uint32_t*)(m + sizeof(PackHeader) + (uint64_t)n * sizeof(PackSketch));
-    uint64_t off = 0;
+    uint64_t off_h = 0, off_b = 0;
     max_bytes = 0;
     for (uint32_t i = 0; i < n; i++) {
         const SketchImpl& I = *sketches[i]->impl;
         if (I.core.get() != &c) throw Fail{SKB_ERR_ARG, "sketch belongs to another context"};
+        ensure_seeds_ready(I);
+        any_ref_only = any_ref_only || I.ref_only;
         const GenomeView& v = I.view;
         PackSketch p{};
         p.total_len = v.total_len; p.n_seeds = v.n_seeds; p.n_markers = v.n_markers; p.n_contigs = v.n_contigs;
         p.bucket_shift = v.bucket_shift; p.n_buckets = v.n_buckets; p.win_cap = v.win_cap;
         p.k = I.info.k; p.c = I.info.c; p.marker_c = I.info.marker_c; p.has_seeds = I.info.has_seeds;
         uint64_t sz[PACK_ARRAYS];
-        pack_sizes(v, sz);
+        pack_sizes(v, ref_only || I.ref_only, sz);
         const void* src[PACK_ARRAYS] = {v.kmer_p, v.pos_p, v.meta_p, v.kmer_k, v.pos_k, v.meta_k, v.bucket,
                                         v.contig_seed_start, v.contig_len, v.contig_win_start, v.markers};
         for (int a = 0; a < PACK_ARRAYS; a++) {
+            uint64_t& off = pack_is_head(a) ? off_h : off_b;
             p.off[a] = off;
-            if (sz[a]) { segs.push_back(SegmentCopy{src[a], off, sz[a]}); max_bytes = std::max(max_bytes, sz[a]); }
+            if (sz[a]) {
+                segs.push_back(SegmentCopy{src[a], (pack_is_head(a) ? head_dst : body_dst) + off, sz[a]});
+                max_bytes = std::max(max_bytes, sz[a]);
+            }
             off += pad16(sz[a]);
         }
         std::memcpy(&ps[i], &p, sizeof(p));
         if (v.n_contigs) std::memcpy(clens, I.contig_len_host.data(), 4 * (size_t)v.n_contigs);
         clens += v.n_contigs;
     }
+    PackHeader hd{PACK_MAGIC, n, head, body, any_ref_only ? 1u : 0u, 0u};
+    std::memcpy(m, &hd, sizeof(hd));
 }
 
-// Sketch handles whose arrays are views into `base` (the payload the descriptor `m` describes); `store` keeps the
+// Sketch handles whose arrays are views into the head / body payloads the descriptor `m` describes; `store` keeps the
 // memory alive.  Returns the number of sketches.
 uint32_t views_from_meta(const std::shared_ptr<Core>& core, const std::shared_ptr<BatchStore>& store, const char* m,
-                         uint64_t meta_bytes, const char* base, skb_sketch_t** out) {
+                         uint64_t meta_bytes, const char* head_base, const char* body_base, skb_sketch_t** out) {
     PackHeader hd;
     std::memcpy(&hd, m, sizeof(hd));
     if (meta_bytes < sizeof(PackHeader) + (uint64_t)hd.n * sizeof(PackSketch)) throw Fail{SKB_ERR_ARG, "truncated pack descriptor"};
@@ -1194,26 +1245,30 @@ uint32_t views_from_meta(const std::shared_ptr<Core>& core, const std::shared_pt
     uint64_t nc_total = 0;
     for (uint32_t i = 0; i < hd.n; i++) { PackSketch p; std::memcpy(&p, &ps[i], sizeof(p)); nc_total += p.n_contigs; }
     if (meta_bytes < sizeof(PackHeader) + (uint64_t)hd.n * sizeof(PackSketch) + 4 * nc_total) throw Fail{SKB_ERR_ARG, "truncated pack descriptor"};
+    const bool ref_only = hd.ref_only != 0;
     for (uint32_t i = 0; i < hd.n; i++) {
         PackSketch p;
         std::memcpy(&p, &ps[i], sizeof(p));
         GenomeView v{};
-        v.kmer_p = (const uint32_t*)(base + p.off[0]); v.pos_p = (const uint32_t*)(base + p.off[1]);
-        v.meta_p = (const uint32_t*)(base + p.off[2]); v.kmer_k = (const uint32_t*)(base + p.off[3]);
-        v.pos_k = (const uint32_t*)(base + p.off[4]); v.meta_k = (const uint32_t*)(base + p.off[5]);
-        v.bucket = (const uint32_t*)(base + p.off[6]); v.contig_seed_start = (const uint32_t*)(base + p.off[7]);
-        v.contig_len = (const uint32_t*)(base + p.off[8]); v.contig_win_start = (const uint32_t*)(base + p.off[9]);
-        v.markers = (const uint64_t*)(base + p.off[10]);
+        if (!ref_only) {
+            v.kmer_p = (const uint32_t*)(body_base + p.off[0]); v.pos_p = (const uint32_t*)(body_base + p.off[1]);
+            v.meta_p = (const uint32_t*)(body_base + p.off[2]); v.contig_seed_start = (const uint32_t*)(head_base + p.off[7]);
+        }
+        v.kmer_k = (const uint32_t*)(body_base + p.off[3]);
+        v.pos_k = (const uint32_t*)(body_base + p.off[4]); v.meta_k = (const uint32_t*)(body_base + p.off[5]);
+        v.bucket = (const uint32_t*)(body_base + p.off[6]);
+        v.contig_len = (const uint32_t*)(head_base + p.off[8]); v.contig_win_start = (const uint32_t*)(head_base + p.off[9]);
+        v.markers = (const uint64_t*)(head_base + p.off[10]);
         v.total_len = p.total_len; v.n_seeds = p.n_seeds; v.n_markers = p.n_markers; v.n_contigs = p.n_contigs;
         v.bucket_shift = p.bucket_shift; v.n_buckets = p.n_buckets; v.win_cap = p.win_cap;
         auto impl = std::make_shared<SketchImpl>();
-        impl->core = core; impl->store = store; impl->view = v;
+        impl->core = core; impl->store = store; impl->view = v; impl->ref_only = ref_only;
         impl->contig_len_host.assign(clens, clens + p.n_contigs);
         contig_quantiles(impl->contig_len_host, impl->view);
         clens += p.n_contigs;
         impl->info.n_seeds = p.n_seeds; impl->info.n_markers = p.n_markers; impl->info.total_len = p.total_len;
         impl->info.n_contigs = p.n_contigs; impl->info.k = p.k; impl->info.c = p.c; impl->info.marker_c = p.marker_c;
-        impl->info.has_seeds = p.has_seeds;
+        impl->info.has_seeds = p.has_seeds; impl->info.reference_only = ref_only ? 1 : 0;
         out[i] = new skb_sketch{impl};
     }
     return hd.n;
@@ -1228,12 +1283,12 @@ int skb_sketch_pack(skb_ctx_t* ctx, uint32_t n, skb_sketch_t* const* sketches, v
     if (!ctx || (n && !sketches) || !meta_host || (payload_bytes && !payload_dev)) return SKB_ERR_ARG;
     return guarded(ctx->core.get(), [&] {
         Core& c = *ctx->core;
-        uint64_t need_p = 0, need_m = 0;
-        if (skb_sketch_pack_size(n, sketches, &need_p, &need_m) != SKB_OK) throw Fail{SKB_ERR_ARG, "null sketch"};
-        if (payload_bytes < need_p || meta_bytes < need_m) throw Fail{SKB_ERR_ARG, "pack buffers too small (see skb_sketch_pack_size)"};
+        uint64_t head = 0, body = 0, need_m = 0;
+        pack_totals(n, sketches, false, head, body, need_m);
+        if (payload_bytes < pad256(head) + body || meta_bytes < need_m) throw Fail{SKB_ERR_ARG, "pack buffers too small (see skb_sketch_pack_size)"};
         std::vector<SegmentCopy> segs;
         uint64_t max_bytes = 0;
-        build_pack_meta(c, n, sketches, need_p, (char*)meta_host, segs, max_bytes);
+        build_pack_meta(c, n, sketches, false, (char*)meta_host, 0, pad256(head), segs, max_bytes);
         if (!segs.empty()) {
             const size_t tb = sizeof(SegmentCopy) * segs.size();
             void* d_segs = c.scratch(SLOT_PACK, tb);
@@ -1254,15 +1309,16 @@ int skb_sketch_unpack(skb_ctx_t* ctx, const void* meta_host, uint64_t meta_bytes
         PackHeader hd;
         std::memcpy(&hd, meta_host, sizeof(hd));
         if (hd.magic != PACK_MAGIC) throw Fail{SKB_ERR_ARG, "not a sketch pack descriptor"};
-        if (payload_bytes < hd.payload_bytes || (hd.payload_bytes && !payload_dev)) throw Fail{SKB_ERR_ARG, "truncated pack payload"};
+        const uint64_t total = pad256(hd.head_bytes) + hd.body_bytes;
+        if (payload_bytes < total || (total && !payload_dev)) throw Fail{SKB_ERR_ARG, "truncated pack payload"};
         *n_out = hd.n;
         if (hd.n == 0) return SKB_OK;
         if (!out || out_cap < hd.n) throw Fail{SKB_ERR_ARG, "output array too small for the packed sketches"};
         auto store = std::make_shared<BatchStore>();
-        store->blob = DevMem::persistent(ctx->core, std::max<uint64_t>(hd.payload_bytes, 16));
-        if (hd.payload_bytes)
-            CU(cudaMemcpyAsync(store->blob.p, payload_dev, hd.payload_bytes, cudaMemcpyDeviceToDevice, c.stream));
-        views_from_meta(ctx->core, store, (const char*)meta_host, meta_bytes, (const char*)store->blob.p, out);
+        store->blob = DevMem::persistent(ctx->core, std::max<uint64_t>(total, 16));
+        if (total) CU(cudaMemcpyAsync(store->blob.p, payload_dev, total, cudaMemcpyDeviceToDevice, c.stream));
+        const char* base = (const char*)store->blob.p;
+        views_from_meta(ctx->core, store, (const char*)meta_host, meta_bytes, base, base + pad256(hd.head_bytes), out);
         CU(cudaStreamSynchronize(c.stream));      // the caller may reuse the payload buffer on return
         return SKB_OK;
     });
@@ -1277,19 +1333,18 @@ struct skb_exchange {
     uint64_t bytes = 0;
 };
 
-namespace {
-inline uint64_t pad256(uint64_t x) { return (x + 255) & ~(uint64_t)255; }
-}
-
 extern "C" {
 
-int skb_exchange_segment_size(uint32_t n, skb_sketch_t* const* sketches, uint64_t* segment_bytes, uint64_t* meta_bytes) {
-    if (!segment_bytes || !meta_bytes) return SKB_ERR_ARG;
-    uint64_t pb = 0, mb = 0;
-    const int rc = skb_sketch_pack_size(n, sketches, &pb, &mb);
-    if (rc != SKB_OK) return rc;
-    *meta_bytes = mb;
-    *segment_bytes = pad256(mb) + pad256(pb);
+int skb_exchange_segment_size(uint32_t n, skb_sketch_t* const* sketches, int32_t reference_only, uint64_t* head_bytes,
+                              uint64_t* body_bytes, uint64_t* meta_bytes) {
+    if ((n && !sketches) || !head_bytes || !body_bytes || !meta_bytes) return SKB_ERR_ARG;
+    try {
+        uint64_t head = 0, body = 0, meta = 0;
+        pack_totals(n, sketches, reference_only != 0, head, body, meta);
+        *meta_bytes = meta;
+        *head_bytes = pad256(meta) + pad256(head);
+        *body_bytes = pad256(body);
+    } catch (const Fail&) { return SKB_ERR_ARG; }
     return SKB_OK;
 }
 
@@ -1317,47 +1372,70 @@ void skb_exchange_free(skb_exchange_t* ex) {
     delete ex;
 }
 
-int skb_exchange_pack(skb_exchange_t* ex, uint64_t offset, uint32_t n, skb_sketch_t* const* sketches) {
-    if (!ex || (n && !sketches) || (offset & 255)) return SKB_ERR_ARG;
+int skb_exchange_pack(skb_exchange_t* ex, uint64_t head_offset, uint64_t body_offset, uint32_t n, skb_sketch_t* const* sketches,
+                      int32_t reference_only) {
+    if (!ex || (n && !sketches) || (head_offset & 255) || (body_offset & 255)) return SKB_ERR_ARG;
     return guarded(ex->core.get(), [&] {
         Core& c = *ex->core;
-        uint64_t need_p = 0, need_m = 0;
-        if (skb_sketch_pack_size(n, sketches, &need_p, &need_m) != SKB_OK) throw Fail{SKB_ERR_ARG, "null sketch"};
-        const uint64_t seg = pad256(need_m) + pad256(need_p);
-        if (offset + seg > ex->bytes) throw Fail{SKB_ERR_ARG, "segment does not fit into the exchange block"};
-        // descriptor: built in pinned memory, copied to the head of the segment; arrays: one gather kernel
-        std::vector<char> meta(need_m);
+        uint64_t head = 0, body = 0, need_m = 0;
+        pack_totals(n, sketches, reference_only != 0, head, body, need_m);
+        const uint64_t head_payload = head_offset + pad256(need_m);
+        if (head_payload + pad256(head) > ex->bytes || body_offset + pad256(body) > ex->bytes)
+            throw Fail{SKB_ERR_ARG, "segment does not fit into the exchange block"};
+        // descriptor: built in pinned memory, copied to the front of the head segment; arrays: one gather kernel
+        const size_t meta_pad = pad256(need_m);
         std::vector<SegmentCopy> segs;
         uint64_t max_bytes = 0;
-        build_pack_meta(c, n, sketches, need_p, meta.data(), segs, max_bytes);
-        char* seg_base = (char*)ex->store->blob.p + offset;
+        std::vector<char> meta(need_m);
+        build_pack_meta(c, n, sketches, reference_only != 0, meta.data(), head_payload, body_offset, segs, max_bytes);
         const size_t tb = sizeof(SegmentCopy) * segs.size();
-        char* h = (char*)ensure_pinned(c, pad256(need_m) + tb + 64);
+        char* h = (char*)ensure_pinned(c, meta_pad + tb + 64);
         std::memcpy(h, meta.data(), need_m);
-        if (tb) std::memcpy(h + pad256(need_m), segs.data(), tb);
-        CU(cudaMemcpyAsync(seg_base, h, need_m, cudaMemcpyHostToDevice, c.stream));
+        if (tb) std::memcpy(h + meta_pad, segs.data(), tb);
+        char* blk = (char*)ex->store->blob.p;
+        CU(cudaMemcpyAsync(blk + head_offset, h, need_m, cudaMemcpyHostToDevice, c.stream));
         if (!segs.empty()) {
             void* d_segs = c.scratch(SLOT_PACK, tb);
-            CU(cudaMemcpyAsync(d_segs, h + pad256(need_m), tb, cudaMemcpyHostToDevice, c.stream));
-            launch_segment_copy((const SegmentCopy*)d_segs, (uint32_t)segs.size(), max_bytes, seg_base + pad256(need_m), c.stream);
+            CU(cudaMemcpyAsync(d_segs, h + meta_pad, tb, cudaMemcpyHostToDevice, c.stream));
+            launch_segment_copy((const SegmentCopy*)d_segs, (uint32_t)segs.size(), max_bytes, blk, c.stream);
             CU(cudaGetLastError());
         }
         // the pinned staging block is shared by later calls: wait for the two small uploads (the gather kernel may
-        // still be running; callers order their collective behind it on this stream or through skb_ctx_sync)
+        // still be running; callers order their collective behind it on this stream)
         CU(cudaEventRecord(c.ev[5], c.stream));
         CU(cudaEventSynchronize(c.ev[5]));
         return SKB_OK;
     });
 }
 
-int skb_exchange_adopt(skb_exchange_t* ex, uint32_t n_segments, const uint64_t* offsets, const uint64_t* meta_bytes,
-                       skb_sketch_t** out, uint32_t out_cap, uint32_t* counts) {
-    if (!ex || (n_segments && (!offsets || !meta_bytes || !counts))) return SKB_ERR_ARG;
+int skb_exchange_order_after(skb_exchange_t* ex, void* foreign_stream, int32_t bodies) {
+    if (!ex) return SKB_ERR_ARG;
+    return guarded(ex->core.get(), [&] {
+        Core& c = *ex->core;
+        BatchStore& st = *ex->store;
+        if (!bodies) {
+            // heads (descriptors + marker sets) have been enqueued on the caller's stream: this context waits for them now
+            CU(cudaEventRecord(c.ev[5], (cudaStream_t)foreign_stream));
+            CU(cudaStreamWaitEvent(c.stream, c.ev[5], 0));
+        } else {
+            // bodies (seed arrays): recorded now, waited for by whoever reads seed arrays of an adopted sketch first
+            if (!st.body_ev) CU(cudaEventCreateWithFlags(&st.body_ev, cudaEventDisableTiming));
+            CU(cudaEventRecord(st.body_ev, (cudaStream_t)foreign_stream));
+            st.body_pending = true;
+        }
+        return SKB_OK;
+    });
+}
+
+int skb_exchange_adopt(skb_exchange_t* ex, uint32_t n_segments, const uint64_t* head_offsets, const uint64_t* body_offsets,
+                       const uint64_t* meta_bytes, skb_sketch_t** out, uint32_t out_cap, uint32_t* counts) {
+    if (!ex || (n_segments && (!head_offsets || !body_offsets || !meta_bytes || !counts))) return SKB_ERR_ARG;
     return guarded(ex->core.get(), [&] {
         Core& c = *ex->core;
         uint64_t total_meta = 0;
         for (uint32_t i = 0; i < n_segments; i++) {
-            if ((offsets[i] & 255) || meta_bytes[i] < sizeof(PackHeader) || offsets[i] + meta_bytes[i] > ex->bytes)
+            if ((head_offsets[i] & 255) || (body_offsets[i] & 255) || meta_bytes[i] < sizeof(PackHeader) ||
+                head_offsets[i] + meta_bytes[i] > ex->bytes || body_offsets[i] > ex->bytes)
                 throw Fail{SKB_ERR_ARG, "bad exchange segment"};
             total_meta += pad256(meta_bytes[i]);
         }
@@ -1366,7 +1444,7 @@ int skb_exchange_adopt(skb_exchange_t* ex, uint32_t n_segments, const uint64_t* 
         const char* blk = (const char*)ex->store->blob.p;
         uint64_t ho = 0;
         for (uint32_t i = 0; i < n_segments; i++) {
-            CU(cudaMemcpyAsync(h + ho, blk + offsets[i], meta_bytes[i], cudaMemcpyDeviceToHost, c.stream));
+            CU(cudaMemcpyAsync(h + ho, blk + head_offsets[i], meta_bytes[i], cudaMemcpyDeviceToHost, c.stream));
             ho += pad256(meta_bytes[i]);
         }
         CU(cudaStreamSynchronize(c.stream));
@@ -1376,10 +1454,11 @@ int skb_exchange_adopt(skb_exchange_t* ex, uint32_t n_segments, const uint64_t* 
             PackHeader hd;
             std::memcpy(&hd, h + ho, sizeof(hd));
             if (hd.magic != PACK_MAGIC) throw Fail{SKB_ERR_ARG, "exchange segment does not start with a sketch descriptor (collective not finished?)"};
-            const uint64_t payload_off = offsets[i] + pad256(meta_bytes[i]);
-            if (payload_off + hd.payload_bytes > ex->bytes) throw Fail{SKB_ERR_ARG, "exchange segment exceeds the block"};
+            const uint64_t head_payload = head_offsets[i] + pad256(meta_bytes[i]);
+            if (head_payload + hd.head_bytes > ex->bytes || body_offsets[i] + hd.body_bytes > ex->bytes)
+                throw Fail{SKB_ERR_ARG, "exchange segment exceeds the block"};
             if (n_total + hd.n > out_cap || (hd.n && !out)) throw Fail{SKB_ERR_ARG, "output array too small for the adopted sketches"};
-            views_from_meta(ex->core, ex->store, h + ho, meta_bytes[i], blk + payload_off, out + n_total);
+            views_from_meta(ex->core, ex->store, h + ho, meta_bytes[i], blk + head_payload, blk + body_offsets[i], out + n_total);
             counts[i] = hd.n;
             n_total += hd.n;
             ho += pad256(meta_bytes[i]);
@@ -1534,6 +1613,7 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
             if (queries[i]->impl->core != db->core) throw Fail{SKB_ERR_ARG, "query sketch belongs to another context"};
             const auto& qi = queries[i]->impl->info;
             if (qi.k != dbi.k || qi.c != dbi.c || qi.marker_c != dbi.marker_c) throw Fail{SKB_ERR_ARG, "query sketch parameters differ from the database's"};
+            if (queries[i]->impl->ref_only) throw Fail{SKB_ERR_ARG, "this sketch was transferred as a reference only (no position-order seeds): it cannot be a query"};
             qs.push_back(queries[i]->impl); hv.push_back(queries[i]->impl->view);
         }
         Trace tq("db_query");
@@ -1564,6 +1644,11 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
 
         std::vector<skb_hit_t> all_hits;
         const size_t n_pass = so.pass_idx.size();
+        if (n_pass) {
+            // chaining reads seed arrays: sketches adopted from an exchange block may still be waiting for theirs
+            for (const auto& it : db->items) ensure_seeds_ready(*it);
+            for (const auto& q : qs) ensure_seeds_ready(*q);
+        }
         constexpr uint64_t MAX_BATCH_SEEDS = 160ull << 20;      // ~4 000 pairs of 5 Mbp genomes per batch
         size_t p0 = 0;
         while (p0 < n_pass) {

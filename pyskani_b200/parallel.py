@@ -6,12 +6,16 @@ query, so the only exchange step is the sketch database:
   1. genomes are split across ranks, balanced by total bases        (partition_by_size)
   2. every rank sketches its share on its own GPU                    (backend.sketch)
   3. sketches are exchanged ONCE, device to device, without staging  (exchange_sketches_device):
-       a. a 3-number all-gather tells every rank the segment size of every other rank
-       b. every rank allocates ONE block of sketch storage with a segment per rank and packs its own sketches into its
-          segment (skb_exchange_pack: one gather kernel)
-       c. ONE collective fills the other segments in place: ncclAllGather straight into the block when the segments
-          are (nearly) the same size, a group of per-rank broadcasts on exact sizes otherwise
-       d. the peers' sketches are adopted as views into the block (skb_exchange_adopt): no unpack copy
+       a. a 4-number all-gather tells every rank the segment sizes of every other rank
+       b. every rank allocates ONE block of sketch storage with a head segment (descriptor, marker sets) and a body
+          segment (seed arrays) per rank and packs its own sketches into its two segments (skb_exchange_pack: one
+          gather kernel); peers get what a database member needs, not the query-side arrays (half of the bytes)
+       c. two collectives fill the other segments in place - heads first, then the 25x larger bodies: ncclAllGather
+          straight into the block when the segments are (nearly) the same size, a group of per-rank broadcasts on exact
+          sizes otherwise
+       d. the peers' sketches are adopted as views into the block as soon as the heads are there (skb_exchange_adopt:
+          no unpack copy); libskb waits for the bodies only when it first reads seed arrays, so the marker screen of
+          step 4 overlaps the body transfer
      Fallback / CPU tests: an all-gather of the exported host SoA    (exchange_sketches)
   4. every rank builds the full database and queries ITS genomes against it
   5. hits are gathered on rank 0                                     (gather_hits)
@@ -101,56 +105,72 @@ class _DevBlock:
         self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
 
 
-def segment_layout(seg_bytes, uniform_slack=0.10):
-    """Offsets of the per-rank segments inside the exchange block.  Segments of (nearly) equal size are laid out at a
-    uniform stride so that ONE in-place ncclAllGather can fill the block; otherwise they are packed back to back and
-    a group of exact-size broadcasts is used.  Returns (offsets, total bytes, uniform stride or 0)."""
+def segment_layout(seg_bytes, uniform_slack=0.10, base=0):
+    """Offsets of the per-rank segments of one region of the exchange block, starting at `base`.  Segments of (nearly)
+    equal size are laid out at a uniform stride so that ONE in-place ncclAllGather can fill the region; otherwise they are
+    packed back to back and a group of exact-size broadcasts is used.  Returns (offsets, end of the region, stride or 0)."""
     world = len(seg_bytes)
-    stride = max(seg_bytes + [256])
+    stride = max(list(seg_bytes) + [256])
     if stride * world <= (1.0 + uniform_slack) * max(sum(seg_bytes), 1):
-        return [r * stride for r in range(world)], stride * world, stride
-    offs, cur = [], 0
+        return [base + r * stride for r in range(world)], base + stride * world, stride
+    offs, cur = [], base
     for s in seg_bytes:
         offs.append(cur)
         cur += s
-    return offs, max(cur, 256), 0
+    return offs, max(cur, base + 256), 0
 
 
-def exchange_sketches_device(backend, local_sketches, dist, device, timings=None):
-    """The one data-path collective, device resident: returns a list over ranks of lists of sketch handles living on this
+def _gather_region(block, offs, sizes, stride, rank, dist):
+    """one collective that fills the peers' segments of a region in place"""
+    world = len(offs)
+    if stride:
+        dist.all_gather_into_tensor(block[offs[0]:offs[0] + stride * world], block[offs[rank]:offs[rank] + stride])
+    else:
+        views = [block[offs[r]:offs[r] + sizes[r]] for r in range(world)]
+        dist.all_gather(views, views[rank])                      # exact sizes: grouped broadcasts
+
+
+def exchange_sketches_device(backend, local_sketches, dist, device, timings=None, reference_only=True):
+    """The one data-path exchange, device resident: returns a list over ranks of lists of sketch handles living on this
     rank's GPU (this rank's entry is `local_sketches` itself; the others are views into one exchange block).
-    `timings` (dict, optional) receives pack / all-gather / adopt milliseconds and the byte counts."""
+      1. a 4-number all-gather tells every rank the segment sizes of every other rank
+      2. every rank packs its sketches into its HEAD segment (descriptor, marker sets) and BODY segment (seed arrays)
+      3. collective 1 fills the heads (small), collective 2 the bodies (large); the peers' sketches are adopted as soon
+         as the heads are there, and libskb waits for the bodies only when seed arrays are first read, so the marker
+         screen of the following query runs while the bodies are still on the wire
+    reference_only: peers receive what a database member needs (half of the bytes), not what a query needs.
+    `timings` (dict, optional) receives the phase milliseconds and the byte counts."""
     import torch
     world, rank = dist.get_world_size(), dist.get_rank()
     ctx = backend.ctx
     t0 = time.perf_counter()
-    seg, mb = ctx.segment_size(local_sketches)
-    mine = torch.tensor([seg, mb, len(local_sketches)], dtype=torch.int64, device=device)
-    allsz = torch.empty(3 * world, dtype=torch.int64, device=device)
+    head, body, mb = ctx.segment_size(local_sketches, reference_only)
+    mine = torch.tensor([head, body, mb, len(local_sketches)], dtype=torch.int64, device=device)
+    allsz = torch.empty(4 * world, dtype=torch.int64, device=device)
     dist.all_gather_into_tensor(allsz, mine)
     sz = allsz.tolist()
-    segs, metas, counts = sz[0::3], sz[1::3], sz[2::3]
-    offs, total, stride = segment_layout(segs)
+    heads, bodies, metas, counts = sz[0::4], sz[1::4], sz[2::4], sz[3::4]
+    h_offs, h_end, h_stride = segment_layout(heads)
+    b_offs, total, b_stride = segment_layout(bodies, base=h_end)
     ex = ctx.exchange(total)
     t1 = time.perf_counter()
-    ex.pack(offs[rank], local_sketches)                       # asynchronous on libskb's stream
+    ex.pack(h_offs[rank], b_offs[rank], local_sketches, reference_only)        # asynchronous on libskb's stream
     lib_stream = torch.cuda.ExternalStream(ctx.stream, device=device)
     cur = torch.cuda.current_stream(device)
     ev_in, ev_a, ev_b = torch.cuda.Event(), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev_in.record(lib_stream)
-    cur.wait_event(ev_in)                                     # the collective starts when this rank's segment is packed
+    cur.wait_event(ev_in)                                     # the collectives start when this rank's segments are packed
     block = torch.as_tensor(_DevBlock(ex.ptr, total), device=device)
     ev_a.record(cur)
-    if stride:
-        dist.all_gather_into_tensor(block, block[offs[rank]:offs[rank] + stride])          # in place
-    else:
-        views = [block[offs[r]:offs[r] + segs[r]] for r in range(world)]
-        dist.all_gather(views, views[rank])                                                # exact sizes: grouped broadcasts
+    _gather_region(block, h_offs, heads, h_stride, rank, dist)
+    ex.order_after(cur.cuda_stream, bodies=False)             # libskb may read the heads from here on
+    _gather_region(block, b_offs, bodies, b_stride, rank, dist)
     ev_b.record(cur)
-    lib_stream.wait_event(ev_b)                               # libskb reads the block only after the collective
+    ex.order_after(cur.cuda_stream, bodies=True)              # ... and the bodies when it first needs seed arrays
     t2 = time.perf_counter()
     peers = [r for r in range(world) if r != rank]
-    adopted = ex.adopt([offs[r] for r in peers], [metas[r] for r in peers], sum(counts[r] for r in peers))
+    adopted = ex.adopt([h_offs[r] for r in peers], [b_offs[r] for r in peers], [metas[r] for r in peers],
+                       sum(counts[r] for r in peers))
     t3 = time.perf_counter()
     ex.close()                                                # the block now belongs to the adopted sketches
     out = [None] * world
@@ -160,22 +180,42 @@ def exchange_sketches_device(backend, local_sketches, dist, device, timings=None
     if timings is not None:
         timings["exchange_sizes_ms"] = 1e3 * (t1 - t0)
         timings["exchange_pack_enqueue_ms"] = 1e3 * (t2 - t1)
-        timings["exchange_wait_adopt_ms"] = 1e3 * (t3 - t2)
-        timings["exchange_allgather_ms"] = ev_a.elapsed_time(ev_b)        # adopt() synchronised the stream behind ev_b
-        timings["exchange_ms"] = 1e3 * (t3 - t0)
-        timings["exchange_bytes_in"] = int(sum(segs) - segs[rank])
-        timings["exchange_bytes_total"] = int(sum(segs))
-        timings["exchange_collective"] = "ncclAllGather in place (uniform stride)" if stride else "grouped ncclBroadcast on exact sizes"
+        timings["exchange_adopt_ms"] = 1e3 * (t3 - t2)
+        timings["exchange_ms"] = 1e3 * (t3 - t0)              # host time until the database is usable; bodies may still fly
+        timings["_exchange_events"] = (ev_a, ev_b)            # all-gather time is read after the step's final sync
+        timings["exchange_bytes_in"] = int(sum(heads) + sum(bodies) - heads[rank] - bodies[rank])
+        timings["exchange_bytes_total"] = int(sum(heads) + sum(bodies))
+        timings["exchange_collective"] = "%s (heads) + %s (bodies)" % (
+            "ncclAllGather in place" if h_stride else "grouped ncclBroadcast", "ncclAllGather in place" if b_stride else "grouped ncclBroadcast")
     return out
 
 
-def gather_hits(local_hits, dist, device="cpu"):
-    """hits: (n, 5) float64 rows [query_global, ref_global, ani, af_query, af_ref]; returned on rank 0 sorted by (query, ref)."""
-    flat = np.asarray(local_hits, np.float64).reshape(-1)
-    parts = _all_gather_var(flat, dist, device)
-    allh = np.concatenate(parts).reshape(-1, 5) if parts else np.zeros((0, 5))
-    order = np.lexsort((allh[:, 1], allh[:, 0]))
-    return allh[order]
+def sort_hits(table):
+    """rows ordered by (query, ref).  Every rank's rows already are, and no query is shared between ranks, so a stable sort
+    on the query column restores the global order."""
+    return table[np.argsort(table[:, 0], kind="stable")] if len(table) else table
+
+
+def gather_hits(local_hits, dist, device="cpu", sort=True):
+    """hits: (n, 5) float64 rows [query_global, ref_global, ani, af_query, af_ref]; returned on every rank, ordered by
+    (query, ref) unless sort=False (then rank after rank; the reference's own hit order is arbitrary, lib.rs:640).
+    Two collectives: the row counts, then the rows padded to the largest count."""
+    import torch
+    world = dist.get_world_size()
+    rows = np.ascontiguousarray(np.asarray(local_hits, np.float64).reshape(-1, 5))
+    cnt = torch.tensor([len(rows)], dtype=torch.int64, device=device)
+    counts = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts, cnt)
+    counts = counts.tolist()
+    m = max(counts + [1])
+    pad = torch.zeros((m, 5), dtype=torch.float64, device=device)
+    if len(rows):
+        pad[:len(rows)] = torch.from_numpy(rows).to(device)
+    allr = torch.empty((world * m, 5), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(allr, pad)
+    allr = allr.cpu().numpy().reshape(world, m, 5)
+    allh = np.concatenate([allr[r, :counts[r]] for r in range(world)]) if world else np.zeros((0, 5))
+    return sort_hits(allh) if sort else allh
 
 
 class CudaBackend:
@@ -210,7 +250,7 @@ class CudaBackend:
         """Rows (query index, ref index, ani, af_query, af_ref) as a float64 array; the queries go through skb_db_query
         in slices of at most max_pairs_per_call pairs."""
         db = self.capi.Database(self.ctx)
-        db.add_many(list(db_sketches))
+        db.add_many(db_sketches)
         nr = max(1, len(db_sketches))
         step = max(1, max_pairs_per_call // nr)
         rows, n_in, screen_ms, chain_ms = [], 0, 0.0, 0.0
@@ -232,23 +272,25 @@ class CudaBackend:
 
 
 def query_and_gather(backend, local_sketches, mine, plan, dist=None, device="cpu", query_opts=None, timings=None,
-                     import_params=None):
+                     import_params=None, sort=True):
     """Steps 3-5 for sketches that already exist on this rank: exchange, query this rank's genomes against the full
-    database, gather the hit table [query, ref, ani, af_query, af_ref] (global ids, sorted) on rank 0."""
+    database, gather the hit table [query, ref, ani, af_query, af_ref] (global ids; ordered by (query, ref) unless
+    sort=False) on rank 0."""
     query_opts = query_opts or {}
     world = dist.get_world_size() if dist is not None else 1
     rank = dist.get_rank() if dist is not None else 0
     n_total = sum(len(p) for p in plan)
     full = [None] * n_total
     on_gpu = world > 1 and hasattr(backend, "ctx") and str(device).startswith("cuda")
-    if world == 1:
+    if hasattr(backend, "ctx"):
+        # handle arrays, not per-sketch Python objects: the database of a step is assembled by index arithmetic
+        arr = backend.capi.SketchArray
+        local_sketches = arr.of(backend.ctx, local_sketches)
+        per_rank = exchange_sketches_device(backend, local_sketches, dist, device, timings) if world > 1 else [local_sketches]
+        full = arr.gather(backend.ctx, n_total, [(plan[r], per_rank[r]) for r in range(world)])
+    elif world == 1:
         for j, gi in enumerate(plan[0]):
             full[gi] = local_sketches[j]
-    elif on_gpu:
-        per_rank = exchange_sketches_device(backend, local_sketches, dist, device, timings)
-        for r, idxs in enumerate(plan):
-            for j, gi in enumerate(idxs):
-                full[gi] = per_rank[r][j]
     else:
         gathered = exchange_sketches([backend.export(s) for s in local_sketches], dist, device)
         for r, idxs in enumerate(plan):
@@ -263,14 +305,18 @@ def query_and_gather(backend, local_sketches, mine, plan, dist=None, device="cpu
         hits[:, 0] = np.asarray(mine, np.float64)[hits[:, 0].astype(np.int64)]
     t1 = time.perf_counter()
     if world == 1:
-        out = hits[np.lexsort((hits[:, 1], hits[:, 0]))]
+        out = sort_hits(hits) if sort else hits
     else:
-        allh = gather_hits(hits, dist, device)
+        allh = gather_hits(hits, dist, device, sort)
         out = allh if rank == 0 else None
     if timings is not None:
         timings["query_ms"] = 1e3 * (t1 - t0)
         timings["gather_ms"] = 1e3 * (time.perf_counter() - t1)
         timings["local_hits"] = int(len(hits))
+        ev = timings.pop("_exchange_events", None)
+        if ev is not None:
+            ev[1].synchronize()
+            timings["exchange_allgather_ms"] = ev[0].elapsed_time(ev[1])
     return out
 
 

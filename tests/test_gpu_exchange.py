@@ -26,48 +26,76 @@ def small_genomes(n_fam=4, length=250_000, seed=3000):
 
 
 def test_exchange_block_pack_and_adopt():
-    """skb_exchange_*: two 'ranks' (slices of one sketch list) pack their segments into one block; the sketches adopted
-    from the block are identical to the originals, answer queries identically and keep the block alive on their own."""
+    """skb_exchange_*: two 'ranks' (slices of one sketch list) pack their head and body segments into one block; the
+    sketches adopted from the block are identical to the originals, answer queries identically and keep the block alive on
+    their own.  Full transfer and reference-only transfer (no query-side arrays: half of the bytes)."""
     from pyskani_b200 import capi, parallel
     ctx = capi.Context(0)
     gs = ctx.sketch_batch(small_genomes())
     parts = [gs[:7], gs[7:]]
-    sizes = [ctx.segment_size(p) for p in parts]
-    assert all(s % 256 == 0 and m > 0 for s, m in sizes)
-    for uniform_slack in (10.0, -1.0):                     # uniform stride forced, then exact back-to-back segments
-        offs, total, stride = parallel.segment_layout([s for s, _ in sizes], uniform_slack)
-        assert (stride != 0) == (uniform_slack > 0)
-        ex = ctx.exchange(total)
-        for o, p in zip(offs, parts):
-            ex.pack(o, p)
-        ctx.sync()
-        got = ex.adopt(offs, [m for _, m in sizes], len(gs))
-        ex.close()                                         # adopted sketches own the block from here on
-        assert [len(x) for x in got] == [len(p) for p in parts]
-        flat = got[0] + got[1]
-        for a, b in zip(gs, flat):
-            ia, ib = a.info(), b.info()
-            assert (ia.n_seeds, ia.n_markers, ia.n_contigs, ia.total_len, ia.k, ia.c, ia.marker_c, ia.has_seeds) == \
-                   (ib.n_seeds, ib.n_markers, ib.n_contigs, ib.total_len, ib.k, ib.c, ib.marker_c, ib.has_seeds)
-            ea, eb = a.export(), b.export()
-            for key in ea:
-                assert np.array_equal(ea[key], eb[key]), key
-        db_a, db_b = capi.Database(ctx), capi.Database(ctx)
-        db_a.add_many(gs); db_b.add_many(flat)
-        ha, na = db_a.query_array(gs)
-        hb, nb = db_b.query_array(flat)
-        assert na == nb and len(ha) >= 4 * 16 and np.array_equal(ha, hb)
-        # mixed: adopted queries against the original database
-        hc, _ = db_a.query_array(flat)
-        assert np.array_equal(ha, hc)
+    db_a = capi.Database(ctx)
+    db_a.add_many(gs)
+    ha, na = db_a.query_array(gs)
+    assert len(ha) >= 4 * 16
+    full_bytes = None
+    for ref_only in (False, True):
+        sizes = [ctx.segment_size(p, ref_only) for p in parts]
+        assert all(h % 256 == 0 and b % 256 == 0 and m > 0 for h, b, m in sizes)
+        if ref_only:
+            assert sum(b for _, b, _ in sizes) < 0.6 * full_bytes          # bodies without the position-order arrays
+        else:
+            full_bytes = sum(b for _, b, _ in sizes)
+        for uniform_slack in (10.0, -1.0):                     # uniform stride forced, then exact back-to-back segments
+            h_offs, h_end, h_stride = parallel.segment_layout([h for h, _, _ in sizes], uniform_slack)
+            b_offs, total, b_stride = parallel.segment_layout([b for _, b, _ in sizes], uniform_slack, base=h_end)
+            assert (h_stride != 0) == (uniform_slack > 0) == (b_stride != 0)
+            ex = ctx.exchange(total)
+            for ho, bo, p in zip(h_offs, b_offs, parts):
+                ex.pack(ho, bo, p, ref_only)
+            # the bodies "arrive" on the context's own stream here; order_after records the event that chaining waits for
+            ex.order_after(ctx.stream, bodies=False)
+            ex.order_after(ctx.stream, bodies=True)
+            got = ex.adopt(h_offs, b_offs, [m for _, _, m in sizes], len(gs))
+            ex.close()                                         # adopted sketches own the block from here on
+            assert [len(x) for x in got] == [len(p) for p in parts]
+            flat = got[0] + got[1]
+            for a, b in zip(gs, flat):
+                ia, ib = a.info(), b.info()
+                assert (ia.n_seeds, ia.n_markers, ia.n_contigs, ia.total_len, ia.k, ia.c, ia.marker_c, ia.has_seeds) == \
+                       (ib.n_seeds, ib.n_markers, ib.n_contigs, ib.total_len, ib.k, ib.c, ib.marker_c, ib.has_seeds)
+                assert ib.reference_only == int(ref_only) and ia.reference_only == 0
+                ea, eb = a.export(), b.export()
+                for key in ea:
+                    assert np.array_equal(ea[key], eb[key]), key
+            db_b = capi.Database(ctx)
+            db_b.add_many(flat)
+            hb, nb = db_b.query_array(gs)                      # originals as queries against the adopted database
+            assert na == nb and np.array_equal(ha, hb)
+            ok_a, sh_a = db_a.screen(gs[:3])
+            ok_b, sh_b = db_b.screen(gs[:3])
+            assert np.array_equal(ok_a, ok_b) and np.array_equal(sh_a, sh_b)
+            if ref_only:
+                with pytest.raises(capi.SkbError) as e:        # reference-only sketches cannot be queries
+                    db_a.query_array(flat[:1])
+                assert e.value.code == capi.SKB_ERR_ARG
+                # ... but they can travel on: re-packed (still reference-only) and adopted again
+                h2, b2, m2 = ctx.segment_size(flat[:3], False)
+                ex2 = ctx.exchange(h2 + b2)
+                ex2.pack(0, h2, flat[:3], False)
+                (again,) = ex2.adopt([0], [h2], [m2], 3)
+                assert all(x.info().reference_only == 1 for x in again)
+                assert np.array_equal(again[1].export()["kmer"], gs[1].export()["kmer"])
+            else:
+                hc, _ = db_a.query_array(flat)                 # adopted sketches as queries
+                assert np.array_equal(ha, hc)
     # error paths: misaligned offset, segment beyond the block, garbage where a descriptor should be
     ex = ctx.exchange(1 << 16)
     with pytest.raises(capi.SkbError):
-        ex.pack(128, gs[:1])
+        ex.pack(128, 4096, gs[:1])
     with pytest.raises(capi.SkbError):
-        ex.pack(0, gs)                                     # does not fit
+        ex.pack(0, 4096, gs)                                   # does not fit
     with pytest.raises(capi.SkbError):
-        ex.adopt([0], [64], 4)                             # nothing was packed there
+        ex.adopt([0], [4096], [64], 4)                         # nothing was packed there
 
 
 def free_port():

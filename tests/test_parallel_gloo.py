@@ -109,6 +109,8 @@ def test_segment_layout():
     assert stride == 0 and offs == [0, 256, 4352] and total == 4608
     offs, total, stride = parallel.segment_layout([0, 0])
     assert total >= 256 and len(offs) == 2
+    offs, end, stride = parallel.segment_layout([512, 512], base=4096)        # a second region behind the first
+    assert offs == [4096, 4608] and end == 5120 and stride == 512
     for segs in ([512] * 8, [768, 256, 1024], [256]):
         offs, total, stride = parallel.segment_layout(segs)
         for r, (o, s) in enumerate(zip(offs, segs)):
