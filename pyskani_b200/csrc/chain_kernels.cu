@@ -647,9 +647,17 @@ __device__ __forceinline__ void stat_store(const RootStat& s, uint32_t* aux_a, u
     }
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr uint32_t DPT_STAGE = 4;          // anchor records in flight per thread (cp.async, global -> shared)
+
 __global__ void __launch_bounds__(DPT_THREADS) chain_dp_thread_kernel(const ChainBatch b, const ChainConsts C) {
     __shared__ uint4 s_ring[DPT_RING][DPT_THREADS];
-    __shared__ uint32_t s_rootmask[DPT_MAX_ANCHORS / 32][DPT_THREADS];     // bit i of a thread's column: anchor i is a root
+    __shared__ uint4 s_stage[DPT_STAGE][DPT_THREADS];     // the next anchor records of every thread, filled asynchronously
     constexpr uint32_t bp_band = DP_BP_BAND, index_band = DP_INDEX_BAND;
     constexpr int32_t max_gap = DP_MAX_GAP, anchor_score = DP_ANCHOR_SCORE;
     const int tid = threadIdx.x;
@@ -660,34 +668,37 @@ __global__ void __launch_bounds__(DPT_THREADS) chain_dp_thread_kernel(const Chai
     const uint32_t nmax = __reduce_max_sync(FULL, n);
     if (nmax == 0) return;
     const uint4* rec_a = b.a_rec + A0;
-    int32_t* f_a = b.a_f + A0; uint32_t* root_a = b.a_root + A0; uint32_t* aux_a = b.a_aux + A0;
+    // per anchor: f | root << 16 (read back only for predecessors beyond the ring; later the candidate list);
+    // root_a: the list of component roots in order of creation
+    uint32_t* fr_a = (uint32_t*)(b.a_f + A0); uint32_t* root_a = b.a_root + A0; uint32_t* aux_a = b.a_aux + A0;
     unsigned long long* best_a = b.a_best + A0;
     // per-component size and best end: the components of the last two distinct roots stay in registers (a chain and the
     // stray anchor that interrupts it), older ones are spilled to aux_a / best_a
     RootStat sa{NO_ROOT, 0u, 0u, 0}, sb{NO_ROOT, 0u, 0u, 0};
-    // (q_pos, r_pos, meta) of the next anchor; the record's fourth word (query seed index) is only needed for chain ends.
-    // It is deliberately NOT loaded here: as a dead destination register of a 128-bit load it gets reused as scratch,
-    // and the first write to it then waits for the whole load (write-after-write on the scoreboard).
-    uint3 nxt = make_uint3(0u, 0u, 0u);
-    if (n) { const uint2 a = *(const uint2*)rec_a; nxt = make_uint3(a.x, a.y, ((const uint32_t*)rec_a)[2]); }
+    uint32_t n_roots = 0;
+    // anchor records arrive through a DPT_STAGE-deep cp.async pipeline: the data comes from DRAM (~1 us away) and a
+    // register prefetch of one step is not far enough ahead; one commit group per step keeps the group count uniform
+#pragma unroll
+    for (uint32_t k = 0; k < DPT_STAGE; k++) {
+        if (k < n) cp_async16(&s_stage[k][tid], rec_a + k);
+        cp_async_commit();
+    }
+    cp_async_wait<DPT_STAGE - 1>();
     // the ring starts out full of entries that are out of band for every anchor of the window (q_pos 2^30 bases ahead):
     // the first anchors then run the same branch-free code as all others
     {
-        const uint4 far = make_uint4(nxt.x + 0x40000000u, 0u, 0xFFFFFFFFu, 0u);
+        const uint32_t q0 = n ? s_stage[0][tid].x : 0u;
+        const uint4 far = make_uint4(q0 + 0x40000000u, 0u, 0xFFFFFFFFu, 0u);
 #pragma unroll
         for (uint32_t k = 0; k < DPT_RING; k++) s_ring[k][tid] = far;
     }
-    uint32_t maskw = 0;                   // root bits of the current 32 anchors
     // ---------------- DP, lock step over the anchor index
     for (uint32_t i = 0; i < nmax; i++) {
         const bool act = i < n;
-        const uint3 r = nxt;
-        if (i + 1 < n) {                                   // the next record travels while this anchor is scored
-            const uint2 a = *(const uint2*)(rec_a + i + 1);
-            nxt = make_uint3(a.x, a.y, ((const uint32_t*)(rec_a + i + 1))[2]);
-        }
-        // pins the loads here: without it the compiler sinks them to their first use, at the top of the next iteration
-        asm volatile("" : "+r"(nxt.x), "+r"(nxt.y), "+r"(nxt.z));
+        cp_async_wait<DPT_STAGE - 1>();                    // record i has landed (groups are committed once per step)
+        const uint4 r = s_stage[i & (DPT_STAGE - 1)][tid];
+        if (i + DPT_STAGE < n) cp_async16(&s_stage[i & (DPT_STAGE - 1)][tid], rec_a + i + DPT_STAGE);
+        cp_async_commit();
         const uint32_t cq = r.x, cm = r.z, tq = cq - 1u;
         const int32_t cD = (cm & 1u) ? -(int32_t)(r.y + r.x) : (int32_t)(r.y - r.x);
         int32_t best = 0;                 // max over valid predecessors of f[j] - gap; a link needs f[j] + 20 - gap > 20
@@ -715,17 +726,18 @@ __global__ void __launch_bounds__(DPT_THREADS) chain_dp_thread_kernel(const Chai
                 const int32_t pD = (cm & 1u) ? -(int32_t)(p.y + p.x) : (int32_t)(p.y - p.x);
                 const int32_t delta = cD - pD;
                 const int32_t gap = abs(delta);
-                const int32_t sc = f_a[i - d] - gap;
+                const int32_t sc = (int32_t)(fr_a[i - d] & 0xFFFFu) - gap;
                 if ((int32_t)dq + delta > 0 && gap <= max_gap && sc > best) { best = sc; bestd = d; }
             }
         }
         if (act) {
             const int32_t f = anchor_score + best;
             uint32_t root = i;
-            if (bestd) root = bestd <= DPT_RING ? (s_ring[(i - bestd) & (DPT_RING - 1)][tid].w >> 16) : root_a[i - bestd];
-            s_ring[i & (DPT_RING - 1)][tid] = make_uint4(cq, (uint32_t)cD, cm, (uint32_t)f | (root << 16));
-            f_a[i] = f; root_a[i] = root;      // read back only beyond the ring (repeat-dense stretches)
-            if (root == i) maskw |= 1u << (i & 31u);
+            if (bestd) root = (bestd <= DPT_RING ? s_ring[(i - bestd) & (DPT_RING - 1)][tid].w : fr_a[i - bestd]) >> 16;
+            const uint32_t fr = (uint32_t)f | (root << 16);
+            s_ring[i & (DPT_RING - 1)][tid] = make_uint4(cq, (uint32_t)cD, cm, fr);
+            fr_a[i] = fr;
+            if (root == i) root_a[n_roots++] = i;
             if (root != sa.root) {
                 // the other cached component becomes the current one; a third one evicts the older entry
                 const RootStat t = sa; sa = sb; sb = t;
@@ -741,28 +753,22 @@ __global__ void __launch_bounds__(DPT_THREADS) chain_dp_thread_kernel(const Chai
             sa.size++;
             if (f > sa.bf) { sa.bf = f; sa.bidx = i; }      // strict: the first maximal end in DP order
         }
-        if ((i & 31u) == 31u || i + 1 == nmax) {
-            if (act || (i >> 5) == ((n - 1u) >> 5)) s_rootmask[i >> 5][tid] = maskw;
-            maskw = 0u;
-        }
     }
+    cp_async_wait<0>();
     if (n == 0) return;
     stat_store(sa, aux_a, best_a);
     stat_store(sb, aux_a, best_a);
 
     // ---------------- candidate chains: roots with enough anchors and score; the list overwrites f (no longer needed)
+    int32_t* f_a = (int32_t*)fr_a;
     uint32_t ncand = 0;
-    for (uint32_t w = 0; w <= (n - 1u) >> 5; w++) {
-        uint32_t m = s_rootmask[w][tid];
-        while (m) {
-            const uint32_t i = (w << 5) + (uint32_t)__ffs(m) - 1u;
-            m &= m - 1u;
-            uint32_t size; int32_t score;
-            if (i == sa.root) { size = sa.size; score = sa.bf; }            // the usual case: still in registers
-            else if (i == sb.root) { size = sb.size; score = sb.bf; }
-            else { size = aux_a[i]; score = (int32_t)(best_a[i] >> 32); }
-            if (size >= (uint32_t)C.min_anchors && score >= C.min_score) f_a[ncand++] = (int32_t)i;
-        }
+    for (uint32_t t = 0; t < n_roots; t++) {
+        const uint32_t i = root_a[t];
+        uint32_t size; int32_t score;
+        if (i == sa.root) { size = sa.size; score = sa.bf; }            // the usual case: still in registers
+        else if (i == sb.root) { size = sb.size; score = sb.bf; }
+        else { size = aux_a[i]; score = (int32_t)(best_a[i] >> 32); }
+        if (size >= (uint32_t)C.min_anchors && score >= C.min_score) f_a[ncand++] = (int32_t)i;
     }
     // ---------------- greedy selection without query overlap: (score desc, q start asc, r start asc, index asc)
     uint32_t w_anchors = 0, w_lo = 0xFFFFFFFFu, w_hi = 0, w_lo_qi = 0, w_hi_qi = 0, w_covq = 0, w_covr = 0, w_chains = 0;
