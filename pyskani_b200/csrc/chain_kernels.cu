@@ -59,37 +59,35 @@ __device__ __forceinline__ uint32_t warp_lower_bound(uint32_t lo, uint32_t hi, u
 }
 
 // ------------------------------------------------------------------ 1a. match counts
+// The query is walked in K-MER order: the 32 k-mers of a warp are neighbours in the sorted k-mer space, so their bucket
+// entries and the reference k-mers they are compared with share a few sectors (in position order every lane touched its
+// own: ~20 L1 sector lookups per query seed, the L1 tag stage was the limit).  The result goes to the seed's slot in
+// POSITION order through perm_k - one 8-byte store per MATCHED seed into the zeroed (first, count) array; the anchors
+// built from it therefore still come out sorted by (q_contig, q_pos, r_contig, r_pos): no per-pair sort.
 __global__ void match_count_kernel(const ChainBatch b) {
     const PairDesc pd = b.pairs[blockIdx.y];
     const GenomeView& Q = b.qviews[pd.q];
     const GenomeView& R = b.rviews[pd.r];
     const uint32_t nq = Q.n_seeds;
+    if (R.n_seeds == 0) return;
     const int lane = threadIdx.x & 31;
     unsigned long long total = 0;       // 64-bit anchor count of this thread's seeds (a_off is a 32-bit scan and may wrap)
-    // warp-aligned strips of 32 consecutive query seeds: the strip's "has a match" bits are one word of the bitmask
-    for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < nq; i0 += gridDim.x * blockDim.x) {
-        const uint32_t i = i0 + lane;
-        uint32_t first = 0, cnt = 0;
-        if (i < nq && R.n_seeds) {
-            const uint32_t km = __ldg(Q.kmer_p + i);
-            const uint32_t bk = km >> R.bucket_shift;
-            uint32_t lo = __ldg(R.bucket + bk), hi = __ldg(R.bucket + bk + 1);
-            const uint32_t end = hi;
-            while (lo < hi) {               // buckets hold ~8 seeds: a short search
-                uint32_t mid = (lo + hi) >> 1;
-                if (__ldg(R.kmer_k + mid) < km) lo = mid + 1; else hi = mid;
-            }
-            first = lo;
-            while (lo < end && __ldg(R.kmer_k + lo) == km) lo++;
-            cnt = lo - first;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
+        const uint32_t km = __ldg(Q.kmer_k + i);
+        const uint32_t bk = km >> R.bucket_shift;
+        uint32_t lo = __ldg(R.bucket + bk), hi = __ldg(R.bucket + bk + 1);
+        const uint32_t end = hi;
+        while (lo < hi) {               // buckets hold ~8 seeds: a short search
+            uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(R.kmer_k + mid) < km) lo = mid + 1; else hi = mid;
         }
-        if (i < nq) {
-            b.m_first[pd.seed_off + i] = first;
-            b.m_cnt[pd.seed_off + i] = cnt;
+        const uint32_t first = lo;
+        while (lo < end && __ldg(R.kmer_k + lo) == km) lo++;
+        const uint32_t cnt = lo - first;
+        if (cnt) {
+            b.m_fc[pd.seed_off + __ldg(Q.perm_k + i)] = make_uint2(first, cnt);
+            total += cnt;
         }
-        total += cnt;
-        const uint32_t bal = __ballot_sync(FULL, cnt != 0);
-        if (lane == 0) b.m_bits[pd.bits_off + (i0 >> 5)] = bal;
     }
     for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
     if (lane == 0 && total) atomicAdd(b.a_total64, total);
@@ -101,10 +99,17 @@ __global__ void anchor_fill_kernel(const ChainBatch b) {
     const GenomeView& Q = b.qviews[pd.q];
     const GenomeView& R = b.rviews[pd.r];
     const uint32_t nq = Q.n_seeds;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
-        const uint32_t cnt = b.m_cnt[pd.seed_off + i];
-        if (cnt == 0) continue;
-        const uint32_t first = b.m_first[pd.seed_off + i];
+    const int lane = threadIdx.x & 31;
+    // warp-aligned strips of 32 consecutive query seeds: the strip's "has a match" bits are one word of the bitmask the
+    // window walk reads
+    for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < nq; i0 += gridDim.x * blockDim.x) {
+        const uint32_t i = i0 + lane;
+        uint2 fc = make_uint2(0u, 0u);
+        if (i < nq) fc = b.m_fc[pd.seed_off + i];
+        const uint32_t bal = __ballot_sync(FULL, fc.y != 0u);
+        if (lane == 0) b.m_bits[pd.bits_off + (i0 >> 5)] = bal;
+        if (fc.y == 0u) continue;
+        const uint32_t first = fc.x, cnt = fc.y;
         const uint32_t off = b.a_off[pd.seed_off + i];
         const uint32_t qp = __ldg(Q.pos_p + i);
         const uint32_t qm = __ldg(Q.meta_p + i);

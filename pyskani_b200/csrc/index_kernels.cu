@@ -12,6 +12,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
+#include <thrust/iterator/transform_iterator.h>
 
 #include "skb_internal.cuh"
 
@@ -58,14 +59,16 @@ __global__ void make_seed_keys(uint32_t n, uint32_t n_genomes, const uint32_t* _
 
 __global__ void gather_kmer_order(uint32_t n, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                   const uint32_t* __restrict__ pos_p, const uint32_t* __restrict__ meta_p,
+                                  const uint32_t* __restrict__ genome_seed_start,
                                   uint32_t* __restrict__ kmer_k, uint32_t* __restrict__ pos_k,
-                                  uint32_t* __restrict__ meta_k) {
+                                  uint32_t* __restrict__ meta_k, uint32_t* __restrict__ perm_k) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t src = vals[i];
     kmer_k[i] = (uint32_t)keys[i];
     pos_k[i] = pos_p[src];
     meta_k[i] = meta_p[src];
+    if (perm_k) perm_k[i] = src - genome_seed_start[(uint32_t)(keys[i] >> 32)];      // genome-local position-order index
 }
 
 __global__ void strip_marker_keys(uint32_t n_in, const uint32_t* __restrict__ n_unique, const uint64_t* __restrict__ keys,
@@ -132,12 +135,15 @@ __global__ void iota_kernel(uint32_t* out, uint32_t n) {
     if (i < n) out[i] = i;
 }
 __global__ void gather_pos_meta(uint32_t n, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ pos_p,
-                                const uint32_t* __restrict__ meta_p, uint32_t* __restrict__ pos_k, uint32_t* __restrict__ meta_k) {
+                                const uint32_t* __restrict__ meta_p, uint32_t n_genomes, const uint32_t* __restrict__ genome_seed_start,
+                                uint32_t* __restrict__ pos_k, uint32_t* __restrict__ meta_k, uint32_t* __restrict__ perm_k) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t src = vals[i];
     pos_k[i] = pos_p[src];
     meta_k[i] = meta_p[src];
+    // a segmented sort keeps every seed inside its genome: the genome of k-order slot i is the genome of its source
+    if (perm_k) perm_k[i] = src - genome_seed_start[upper_bound_u32(genome_seed_start, n_genomes + 1, i) - 1];
 }
 
 void build_kmer_order(const IndexBuildArgs& a, void* scratch, size_t scratch_bytes, cudaStream_t st) {
@@ -155,7 +161,7 @@ void build_kmer_order(const IndexBuildArgs& a, void* scratch, size_t scratch_byt
         iota_kernel<<<(n + T - 1) / T, T, 0, st>>>(vals_in, n);
         cub::DeviceSegmentedRadixSort::SortPairs(p, cub_bytes, a.kmer_p, a.kmer_k, vals_in, vals_out, (int)n, (int)a.n_genomes,
                                                  a.genome_seed_start, a.genome_seed_start + 1, 0, 2 * a.k, st);
-        gather_pos_meta<<<(n + T - 1) / T, T, 0, st>>>(n, vals_out, a.pos_p, a.meta_p, a.pos_k, a.meta_k);
+        gather_pos_meta<<<(n + T - 1) / T, T, 0, st>>>(n, vals_out, a.pos_p, a.meta_p, a.n_genomes, a.genome_seed_start, a.pos_k, a.meta_k, a.perm_k);
         g_kernel_launches += 3;
         return;
     }
@@ -171,7 +177,7 @@ void build_kmer_order(const IndexBuildArgs& a, void* scratch, size_t scratch_byt
     const int end_bit = 32 + gbits;   // k-mer bits above 2k are zero; sorting them is harmless for k < 16
     cub::DeviceRadixSort::SortPairs(p, cub_bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0, end_bit, st);
     g_kernel_launches += 1 + (end_bit + 7) / 8;
-    gather_kmer_order<<<(n + T - 1) / T, T, 0, st>>>(n, keys_out, vals_out, a.pos_p, a.meta_p, a.kmer_k, a.pos_k, a.meta_k);
+    gather_kmer_order<<<(n + T - 1) / T, T, 0, st>>>(n, keys_out, vals_out, a.pos_p, a.meta_p, a.genome_seed_start, a.kmer_k, a.pos_k, a.meta_k, a.perm_k);
     g_kernel_launches++;
 }
 
@@ -250,7 +256,7 @@ constexpr uint32_t BUCKET_RANK_MAX = 256;   // larger buckets (low-complexity ge
 __global__ void bucket_rank_kernel(uint32_t n, uint32_t n_genomes, const BucketGenome* __restrict__ G,
                                    const uint32_t* __restrict__ bucket, const uint4* __restrict__ tmp,
                                    uint32_t* __restrict__ kmer_k, uint32_t* __restrict__ pos_k, uint32_t* __restrict__ meta_k,
-                                   uint32_t* __restrict__ overflow) {
+                                   uint32_t* __restrict__ perm_k, uint32_t* __restrict__ overflow) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const BucketGenome g = G[genome_of(G, n_genomes, t)];
@@ -267,6 +273,7 @@ __global__ void bucket_rank_kernel(uint32_t n, uint32_t n_genomes, const BucketG
     }
     const uint32_t dst = g.seed_start + s + rank;
     kmer_k[dst] = me.x; pos_k[dst] = me.z; meta_k[dst] = me.w;
+    if (perm_k) perm_k[dst] = me.y;            // genome-local index of this seed in position order
 }
 
 }  // namespace
@@ -279,8 +286,8 @@ size_t bucket_order_scratch_bytes(uint32_t n_seeds, size_t bucket_total) {
 // genomes_dev: [n_genomes] table; bucket: the store's bucket array [bucket_total]; overflow: device flag (pre-zeroed)
 void build_kmer_order_buckets(uint32_t n_seeds, uint32_t n_genomes, const BucketGenome* genomes_dev, size_t bucket_total,
                               uint32_t* counts, int counts_ready, const uint32_t* kmer_p, const uint32_t* pos_p,
-                              const uint32_t* meta_p, uint32_t* kmer_k, uint32_t* pos_k, uint32_t* meta_k, uint32_t* bucket,
-                              uint32_t* overflow, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+                              const uint32_t* meta_p, uint32_t* kmer_k, uint32_t* pos_k, uint32_t* meta_k, uint32_t* perm_k,
+                              uint32_t* bucket, uint32_t* overflow, void* scratch, size_t scratch_bytes, cudaStream_t st) {
     if (n_genomes == 0) return;
     (void)scratch_bytes;
     uint4* tmp = (uint4*)scratch;
@@ -293,7 +300,7 @@ void build_kmer_order_buckets(uint32_t n_seeds, uint32_t n_genomes, const Bucket
     bucket_scan_kernel<<<n_genomes, 1024, 0, st>>>(genomes_dev, counts, bucket);       // counts become the scatter cursors
     if (n_seeds) {
         bucket_scatter_kernel<<<(n_seeds + T - 1) / T, T, 0, st>>>(n_seeds, n_genomes, genomes_dev, kmer_p, pos_p, meta_p, counts, tmp);
-        bucket_rank_kernel<<<(n_seeds + T - 1) / T, T, 0, st>>>(n_seeds, n_genomes, genomes_dev, bucket, tmp, kmer_k, pos_k, meta_k, overflow);
+        bucket_rank_kernel<<<(n_seeds + T - 1) / T, T, 0, st>>>(n_seeds, n_genomes, genomes_dev, bucket, tmp, kmer_k, pos_k, meta_k, perm_k, overflow);
     }
     g_kernel_launches += 3;
 }
@@ -532,10 +539,12 @@ void sort_window_keys(uint32_t n, const uint64_t* keys_in, uint64_t* keys_out, c
     g_kernel_launches += 1 + (end_bit + 7) / 8;
 }
 
+struct MatchCount { __host__ __device__ __forceinline__ uint32_t operator()(const uint2& fc) const { return fc.y; } };
 void scan_match_counts(const ChainBatch& b, void* scratch, size_t scratch_bytes, cudaStream_t st) {
-    // a_off[i] = sum of m_cnt[0..i); the trailing element m_cnt[n] is zero-initialised by the caller, so
+    // a_off[i] = sum of m_fc[0..i).y; the trailing element m_fc[n] is zero-initialised by the caller, so
     // a_off[n] is the total number of anchors
-    cub::DeviceScan::ExclusiveSum(scratch, scratch_bytes, b.m_cnt, b.a_off, (int)b.n_qseeds_total + 1, st);
+    auto counts = thrust::make_transform_iterator((const uint2*)b.m_fc, MatchCount());
+    cub::DeviceScan::ExclusiveSum(scratch, scratch_bytes, counts, b.a_off, (int)b.n_qseeds_total + 1, st);
     g_kernel_launches += 2;
 }
 

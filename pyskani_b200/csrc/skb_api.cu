@@ -165,7 +165,7 @@ struct DevMem {
 };
 
 struct BatchStore {   // device arrays shared by the sketches that were produced together
-    DevMem kmer_p, pos_p, meta_p, kmer_k, pos_k, meta_k, bucket, contig_seed_start, contig_len, contig_win_start, markers;
+    DevMem kmer_p, pos_p, meta_p, kmer_k, pos_k, meta_k, perm_k, bucket, contig_seed_start, contig_len, contig_win_start, markers;
     DevMem blob;      // sketches received through skb_sketch_unpack / an exchange block: every array is a slice of this one block
     // exchange blocks: the seed arrays ("bodies") may still be arriving over NVLink while the markers are already being
     // screened; whoever reads seed arrays first makes the context's stream wait for this event (ensure_seeds_ready)
@@ -512,7 +512,7 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
         }
         // ---- k-mer order
         store->kmer_k = DevMem::persistent(core, 4 * (size_t)ns); store->pos_k = DevMem::persistent(core, 4 * (size_t)ns);
-        store->meta_k = DevMem::persistent(core, 4 * (size_t)ns);
+        store->meta_k = DevMem::persistent(core, 4 * (size_t)ns); store->perm_k = DevMem::persistent(core, 4 * (size_t)ns);
         {
             // bucket partition: histogram (built by the gather) -> per-genome scan (= the bucket tables) -> scatter -> rank
             // inside the bucket
@@ -521,8 +521,8 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             void* bscr = c.scratch(SLOT_SORT, bscr_bytes);
             build_kmer_order_buckets(ns, n_genomes, (const BucketGenome*)d_tab, bplan.total, d_bcounts, 1, store->kmer_p.as<uint32_t>(),
                                      store->pos_p.as<uint32_t>(), store->meta_p.as<uint32_t>(), store->kmer_k.as<uint32_t>(),
-                                     store->pos_k.as<uint32_t>(), store->meta_k.as<uint32_t>(), store->bucket.as<uint32_t>(), d_bover,
-                                     bscr, bscr_bytes, st);
+                                     store->pos_k.as<uint32_t>(), store->meta_k.as<uint32_t>(), store->perm_k.as<uint32_t>(),
+                                     store->bucket.as<uint32_t>(), d_bover, bscr, bscr_bytes, st);
         }
         CU(cudaStreamWaitEvent(st, c.ev[7], 0));
         CU(cudaGetLastError());                  // refused launches must not pass silently
@@ -591,6 +591,7 @@ static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_par
         v.kmer_p = store->kmer_p.as<uint32_t>() + so; v.pos_p = store->pos_p.as<uint32_t>() + so;
         v.meta_p = store->meta_p.as<uint32_t>() + so; v.kmer_k = store->kmer_k.as<uint32_t>() + so;
         v.pos_k = store->pos_k.as<uint32_t>() + so; v.meta_k = store->meta_k.as<uint32_t>() + so;
+        v.perm_k = store->perm_k.as<uint32_t>() + so;
         v.bucket = store->bucket.as<uint32_t>() + bucket_off[g];
         v.contig_seed_start = store->contig_seed_start.as<uint32_t>() + cstart_off[g];
         v.contig_win_start = cwin_base + cstart_off[g];
@@ -628,6 +629,7 @@ static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_par
             for (uint32_t g = 0; g < n_genomes; g++) ib.max_genome_seeds = std::max(ib.max_genome_seeds, seed_start[g + 1] - seed_start[g]);
             ib.kmer_p = store->kmer_p.as<uint32_t>(); ib.pos_p = store->pos_p.as<uint32_t>(); ib.meta_p = store->meta_p.as<uint32_t>();
             ib.kmer_k = store->kmer_k.as<uint32_t>(); ib.pos_k = store->pos_k.as<uint32_t>(); ib.meta_k = store->meta_k.as<uint32_t>();
+            ib.perm_k = store->perm_k.as<uint32_t>();
             ib.k = P.k;
             build_kmer_order(ib, sort_scratch, sort_bytes, st);
             launch_build_buckets(d_views.as<GenomeView>(), n_genomes, max_buckets, st);
@@ -990,6 +992,7 @@ int skb_sketch_import(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t
         store->kmer_p = DevMem::persistent(ctx->core, 4 * (size_t)n); store->pos_p = DevMem::persistent(ctx->core, 4 * (size_t)n);
         store->meta_p = DevMem::persistent(ctx->core, 4 * (size_t)n); store->kmer_k = DevMem::persistent(ctx->core, 4 * (size_t)n);
         store->pos_k = DevMem::persistent(ctx->core, 4 * (size_t)n); store->meta_k = DevMem::persistent(ctx->core, 4 * (size_t)n);
+        store->perm_k = DevMem::persistent(ctx->core, 4 * (size_t)n);
         store->markers = DevMem::persistent(ctx->core, 8 * std::max<size_t>(hmark.size(), 1));
         CU(cudaMemcpyAsync(store->kmer_p.p, hk.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(store->pos_p.p, hp.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
@@ -1004,6 +1007,7 @@ int skb_sketch_import(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t
             ib.n_genomes = 1; ib.n_seeds_total = n; ib.genome_seed_start = d_gs.as<uint32_t>(); ib.max_genome_seeds = n;
             ib.kmer_p = store->kmer_p.as<uint32_t>(); ib.pos_p = store->pos_p.as<uint32_t>(); ib.meta_p = store->meta_p.as<uint32_t>();
             ib.kmer_k = store->kmer_k.as<uint32_t>(); ib.pos_k = store->pos_k.as<uint32_t>(); ib.meta_k = store->meta_k.as<uint32_t>();
+            ib.perm_k = store->perm_k.as<uint32_t>();
             ib.k = params->k;
             build_kmer_order(ib, scratch.p, scratch.bytes, st);
             CU(cudaStreamSynchronize(st));   // host vectors above go out of scope after this call
@@ -1137,7 +1141,7 @@ void skb_hits_free(skb_hit_t* hits) { delete[] hits; }
 // ---------------------------------------------------------------- device-to-device transfer of sketches
 namespace {
 constexpr uint32_t PACK_MAGIC = 0x534B4251u;   // "SKBQ"
-constexpr int PACK_ARRAYS = 11;
+constexpr int PACK_ARRAYS = 12;
 // A packed set of sketches has a HEAD (descriptor, marker sets, per-contig tables: all the screen needs) and a BODY (seed
 // arrays and bucket tables: what chaining needs).  off[] of head arrays is relative to the head payload, of body arrays
 // to the body payload; skb_sketch_pack puts the body right behind the head, an exchange block keeps them in two regions
@@ -1147,20 +1151,20 @@ struct PackSketch {
     uint64_t total_len;
     uint32_t n_seeds, n_markers, n_contigs, bucket_shift, n_buckets, win_cap;
     int32_t k, c, marker_c, has_seeds;
-    uint64_t off[PACK_ARRAYS];                 // kmer_p pos_p meta_p kmer_k pos_k meta_k bucket | cstart clen cwin markers
+    uint64_t off[PACK_ARRAYS];                 // kmer_p pos_p meta_p perm_k kmer_k pos_k meta_k bucket | cstart clen cwin markers
 };
-constexpr bool pack_is_head(int a) { return a >= 7; }
+constexpr bool pack_is_head(int a) { return a >= 8; }
 inline uint64_t pad16(uint64_t x) { return (x + 15) & ~(uint64_t)15; }
 inline uint64_t pad256(uint64_t x) { return (x + 255) & ~(uint64_t)255; }
 // byte sizes of the eleven device arrays of one sketch, in PackSketch::off order.  ref_only leaves out what only a QUERY
 // needs (position-order seeds, per-contig seed starts): half of the bytes of a sketch.
 void pack_sizes(const GenomeView& v, bool ref_only, uint64_t* sz) {
     const uint64_t n = v.n_seeds, nc = v.n_contigs;
-    for (int i = 0; i < 3; i++) sz[i] = ref_only || !v.kmer_p ? 0 : 4 * n;
-    for (int i = 3; i < 6; i++) sz[i] = 4 * n;
-    sz[6] = v.bucket ? 4 * ((uint64_t)v.n_buckets + 1) : 0;
-    sz[7] = ref_only || !v.contig_seed_start ? 0 : 4 * (nc + 1); sz[8] = 4 * nc; sz[9] = 4 * (nc + 1);
-    sz[10] = 8 * (uint64_t)v.n_markers;
+    for (int i = 0; i < 4; i++) sz[i] = ref_only || !v.kmer_p ? 0 : 4 * n;        // what only a query needs
+    for (int i = 4; i < 7; i++) sz[i] = 4 * n;
+    sz[7] = v.bucket ? 4 * ((uint64_t)v.n_buckets + 1) : 0;
+    sz[8] = ref_only || !v.contig_seed_start ? 0 : 4 * (nc + 1); sz[9] = 4 * nc; sz[10] = 4 * (nc + 1);
+    sz[11] = 8 * (uint64_t)v.n_markers;
 }
 void pack_totals(uint32_t n, skb_sketch_t* const* sketches, bool ref_only, uint64_t& head, uint64_t& body, uint64_t& meta) {
     head = body = 0;
@@ -1214,7 +1218,7 @@ void build_pack_meta(Core& c, uint32_t n, skb_sketch_t* const* sketches, bool re
         p.k = I.info.k; p.c = I.info.c; p.marker_c = I.info.marker_c; p.has_seeds = I.info.has_seeds;
         uint64_t sz[PACK_ARRAYS];
         pack_sizes(v, ref_only || I.ref_only, sz);
-        const void* src[PACK_ARRAYS] = {v.kmer_p, v.pos_p, v.meta_p, v.kmer_k, v.pos_k, v.meta_k, v.bucket,
+        const void* src[PACK_ARRAYS] = {v.kmer_p, v.pos_p, v.meta_p, v.perm_k, v.kmer_k, v.pos_k, v.meta_k, v.bucket,
                                         v.contig_seed_start, v.contig_len, v.contig_win_start, v.markers};
         for (int a = 0; a < PACK_ARRAYS; a++) {
             uint64_t& off = pack_is_head(a) ? off_h : off_b;
@@ -1252,13 +1256,14 @@ uint32_t views_from_meta(const std::shared_ptr<Core>& core, const std::shared_pt
         GenomeView v{};
         if (!ref_only) {
             v.kmer_p = (const uint32_t*)(body_base + p.off[0]); v.pos_p = (const uint32_t*)(body_base + p.off[1]);
-            v.meta_p = (const uint32_t*)(body_base + p.off[2]); v.contig_seed_start = (const uint32_t*)(head_base + p.off[7]);
+            v.meta_p = (const uint32_t*)(body_base + p.off[2]); v.perm_k = (const uint32_t*)(body_base + p.off[3]);
+            v.contig_seed_start = (const uint32_t*)(head_base + p.off[8]);
         }
-        v.kmer_k = (const uint32_t*)(body_base + p.off[3]);
-        v.pos_k = (const uint32_t*)(body_base + p.off[4]); v.meta_k = (const uint32_t*)(body_base + p.off[5]);
-        v.bucket = (const uint32_t*)(body_base + p.off[6]);
-        v.contig_len = (const uint32_t*)(head_base + p.off[8]); v.contig_win_start = (const uint32_t*)(head_base + p.off[9]);
-        v.markers = (const uint64_t*)(head_base + p.off[10]);
+        v.kmer_k = (const uint32_t*)(body_base + p.off[4]);
+        v.pos_k = (const uint32_t*)(body_base + p.off[5]); v.meta_k = (const uint32_t*)(body_base + p.off[6]);
+        v.bucket = (const uint32_t*)(body_base + p.off[7]);
+        v.contig_len = (const uint32_t*)(head_base + p.off[9]); v.contig_win_start = (const uint32_t*)(head_base + p.off[10]);
+        v.markers = (const uint64_t*)(head_base + p.off[11]);
         v.total_len = p.total_len; v.n_seeds = p.n_seeds; v.n_markers = p.n_markers; v.n_contigs = p.n_contigs;
         v.bucket_shift = p.bucket_shift; v.n_buckets = p.n_buckets; v.win_cap = p.win_cap;
         auto impl = std::make_shared<SketchImpl>();
@@ -1695,7 +1700,7 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
                 // stream-ordered pool needed 20-150 ms to grow through the fifteen allocations this used to make
                 size_t total = 0;
                 auto plan = [&](size_t bytes) { const size_t o = total; total += (bytes + 255) & ~(size_t)255; return o; };
-                const size_t o_pairs = plan(sizeof(PairDesc) * np), o_first = plan(4 * (seeds + 1)), o_cnt = plan(4 * (seeds + 1)),
+                const size_t o_pairs = plan(sizeof(PairDesc) * np), o_fc = plan(8 * (seeds + 1)),
                              o_aoff = plan(4 * (seeds + 2)), o_bits = plan(4 * (bit_words + 4)), o_scan = plan(scan_bytes),
                              o_a = plan(na * 16), o_fra = plan(na * 4 * 3), o_best = plan(na * 8), o_big = plan(4 * (nw + 4)), o_bins = plan(4 * 192), o_order = plan(4 * nw),
                              o_w = plan(nw * 4 * 3 + 4 * (size_t)np),
@@ -1708,11 +1713,11 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
                 B.n_qseeds_total = (uint32_t)seeds; B.n_win_total = (uint32_t)wins;
                 B.pairs = (PairDesc*)(base + o_pairs);
                 CU(cudaMemcpyAsync(base + o_pairs, pairs.data(), sizeof(PairDesc) * np, cudaMemcpyHostToDevice, st));
-                B.m_first = (uint32_t*)(base + o_first); B.m_cnt = (uint32_t*)(base + o_cnt); B.a_off = (uint32_t*)(base + o_aoff);
+                B.m_fc = (uint2*)(base + o_fc); B.a_off = (uint32_t*)(base + o_aoff);
                 B.m_bits = (uint32_t*)(base + o_bits);
                 B.walk_groups = (const uint2*)(base + o_groups); B.n_walk_groups = (uint32_t)groups.size(); B.walk_group_max = group_max;
                 CU(cudaMemcpyAsync(base + o_groups, groups.data(), sizeof(uint2) * groups.size(), cudaMemcpyHostToDevice, st));
-                CU(cudaMemsetAsync(B.m_cnt + seeds, 0, 4, st));
+                CU(cudaMemsetAsync(B.m_fc, 0, 8 * (seeds + 1), st));      // only matched seeds are written
                 B.a_total64 = (unsigned long long*)(base + o_total);
                 CU(cudaMemsetAsync(B.a_total64, 0, 8, st));
                 launch_match_count(B, st);

@@ -26,6 +26,7 @@ struct GenomeView {
     const uint32_t* kmer_k;
     const uint32_t* pos_k;
     const uint32_t* meta_k;
+    const uint32_t* perm_k;        // k-order slot -> index of the same seed in position order (query side of the anchor join)
     const uint32_t* bucket;        // [n_buckets + 1] offsets into *_k by top bits of the k-mer
     const uint32_t* contig_seed_start;  // [n_contigs + 1] offsets into *_p
     const uint32_t* contig_len;    // [n_contigs]
@@ -125,6 +126,7 @@ struct IndexBuildArgs {
     const uint32_t* genome_seed_start;    // device [n_genomes+1]
     const uint32_t* kmer_p; const uint32_t* pos_p; const uint32_t* meta_p;
     uint32_t* kmer_k; uint32_t* pos_k; uint32_t* meta_k;
+    uint32_t* perm_k;                     // optional: k-order slot -> genome-local position-order index
     int k;
 };
 
@@ -141,8 +143,8 @@ size_t bucket_order_scratch_bytes(uint32_t n_seeds, size_t bucket_total);
 // seeding kernel, +47 us).  It is consumed (turned into cursors).
 void build_kmer_order_buckets(uint32_t n_seeds, uint32_t n_genomes, const BucketGenome* genomes_dev, size_t bucket_total,
                               uint32_t* counts, int counts_ready, const uint32_t* kmer_p, const uint32_t* pos_p,
-                              const uint32_t* meta_p, uint32_t* kmer_k, uint32_t* pos_k, uint32_t* meta_k, uint32_t* bucket,
-                              uint32_t* overflow, void* scratch, size_t scratch_bytes, cudaStream_t st);
+                              const uint32_t* meta_p, uint32_t* kmer_k, uint32_t* pos_k, uint32_t* meta_k, uint32_t* perm_k,
+                              uint32_t* bucket, uint32_t* overflow, void* scratch, size_t scratch_bytes, cudaStream_t st);
 
 // sorts marker keys and removes duplicates per genome; writes marker values (42-bit) to markers_out and the
 // per-genome offsets [n_genomes+1] to genome_marker_out (device)
@@ -229,8 +231,7 @@ struct ChainBatch {            // device pointers of one batch of pairs
     uint32_t n_qseeds_total;   // sum of query seeds over pairs
     uint32_t n_win_total;      // sum of window capacities over pairs
     // per query seed of each pair
-    uint32_t* m_first;         // first matching index in the reference's k-mer order
-    uint32_t* m_cnt;           // number of matches
+    uint2* m_fc;               // (first matching index in the reference's k-mer order, number of matches); zeroed per batch
     uint32_t* m_bits;          // bit i of a pair's slice = query seed i has at least one match
     const uint2* walk_groups;  // (first pair, count): consecutive pairs with the same query, walked by one CTA
     uint32_t n_walk_groups, walk_group_max;
