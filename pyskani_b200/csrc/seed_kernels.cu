@@ -82,14 +82,22 @@ __device__ __forceinline__ U64 hash_halves(U64 x) {
     b = xorshr<28>(b);
     return mul_c(b, 0x80000001u);                                     // x + (x << 31)
 }
+// EXACT: the 64-bit comparison hash < thr.  Otherwise the comparison of the high words only, hash.hi <= thr.hi: one
+// ISETP instead of two per hash (4.5 % of the ALU-pipe work of the loop).  It accepts a superset: the extra elements are
+// the keys whose hash has hi == thr.hi and lo >= thr.lo, one position in ~6e9.  Every accepted position is re-checked
+// exactly when it is written out (1 % of the positions); a false positive raises the launch's `inexact` flag and the host
+// repeats the batch with EXACT = true, so results never depend on the shortcut.
+template <bool EXACT>
 __device__ __forceinline__ bool hash_below(U64 x, uint32_t thr_lo, uint32_t thr_hi) {
     const U64 b = hash_halves(x);
-    return (((uint64_t)b.hi << 32) | b.lo) < (((uint64_t)thr_hi << 32) | thr_lo);
+    if (EXACT) return (((uint64_t)b.hi << 32) | b.lo) < (((uint64_t)thr_hi << 32) | thr_lo);
+    return b.hi <= thr_hi;
 }
 
 struct WordCtx { uint32_t w0, w1, w2, r0, r1, r2; };
 
 // masks of the 16 positions of one word: bit e of *smask / *mmask = position e is a seed / marker
+template <bool EXACT>
 __device__ __forceinline__ void eval_word(const WordCtx& c, uint32_t kmask, uint32_t kshift, uint32_t ts_lo, uint32_t ts_hi,
                                           uint32_t tm_lo, uint32_t tm_hi, uint32_t& smask, uint32_t& mmask) {
     smask = 0; mmask = 0;
@@ -107,26 +115,34 @@ __device__ __forceinline__ void eval_word(const WordCtx& c, uint32_t kmask, uint
         const uint32_t fk = flo & kmask;
         const uint32_t rk = __funnelshift_r(rlo, rhi, kshift);
         const uint32_t km = min(fk, rk);
-        if (hash_below(U64{km, 0u}, ts_lo, ts_hi)) smask |= 1u << e;
+        if (hash_below<EXACT>(U64{km, 0u}, ts_lo, ts_hi)) smask |= 1u << e;
         // marker 21-mer: canonical = min of the two 42-bit values
         const bool fsmall = (((uint64_t)fhi << 32) | flo) < (((uint64_t)rhi << 32) | rlo);
         const U64 mk{fsmall ? flo : rlo, fsmall ? fhi : rhi};
-        if (hash_below(mk, tm_lo, tm_hi)) mmask |= 1u << e;
+        if (hash_below<EXACT>(mk, tm_lo, tm_hi)) mmask |= 1u << e;
     }
 }
 
 #ifndef SKB_SEED_MINBLOCKS
 #define SKB_SEED_MINBLOCKS 3
 #endif
+constexpr uint32_t HIT_LIST_CAP = 96;      // hits of one tile that take the compact write-out (2 048 bases hold ~16 seeds, ~2 markers)
+
+template <bool EXACT>
 __global__ void __launch_bounds__(SEED_THREADS, SKB_SEED_MINBLOCKS) seed_scan_kernel(const SeedScanArgs a) {
     // Warps are independent: private packed-word and mask buffers, private output region, no block barriers.
-    __shared__ uint32_t s_pk[SEED_WARPS][TILE_WORDS + 2];
+    __shared__ uint32_t s_pk[SEED_WARPS][TILE_WORDS + 2];     // 2-bit packed words (two words of the previous tile in front)
+    __shared__ uint32_t s_rc[SEED_WARPS][TILE_WORDS + 2];     // their reverse complements: computed once, read three times
     __shared__ uint32_t s_masks[SEED_WARPS][TILE_WORDS];      // smask | mmask << 16 per word
+    __shared__ uint16_t s_hits[SEED_WARPS][2][HIT_LIST_CAP];  // (word << 4 | position) of the tile's seeds / markers, in order
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t ts_lo = (uint32_t)a.thr_seed, ts_hi = (uint32_t)(a.thr_seed >> 32);
     const uint32_t tm_lo = (uint32_t)a.thr_marker, tm_hi = (uint32_t)(a.thr_marker >> 32);
     uint32_t* pk = s_pk[warp];
+    uint32_t* rc = s_rc[warp];
     uint32_t* masks = s_masks[warp];
+    uint16_t* hits_s = s_hits[warp][0];
+    uint16_t* hits_m = s_hits[warp][1];
 
     // Regions are claimed dynamically (one atomic per chunk_tiles <= CHUNK_TILES tiles) so that no warp idles while another still
     // has a long static range in front of it; a region's place in the output depends only on its id.
@@ -192,8 +208,16 @@ __global__ void __launch_bounds__(SEED_THREADS, SKB_SEED_MINBLOCKS) seed_scan_ke
             uint4 hv = make_uint4(0, 0, 0, 0);
             if (lane < 2 && pos0 > 0) hv = ld_stream16(base - 32 + 16 * lane);      // the two words before the tile
 #pragma unroll
-            for (int j = 0; j < WORDS_PER_LANE; j++) pk[2 + j * 32 + lane] = pack16(v[j].x, v[j].y, v[j].z, v[j].w);
-            if (lane < 2) pk[lane] = pos0 > 0 ? pack16(hv.x, hv.y, hv.z, hv.w) : 0u;
+            for (int j = 0; j < WORDS_PER_LANE; j++) {
+                const uint32_t word = pack16(v[j].x, v[j].y, v[j].z, v[j].w);
+                pk[2 + j * 32 + lane] = word;
+                rc[2 + j * 32 + lane] = revcomp_word(word);
+            }
+            if (lane < 2) {
+                const uint32_t word = pos0 > 0 ? pack16(hv.x, hv.y, hv.z, hv.w) : 0u;
+                pk[lane] = word;
+                rc[lane] = revcomp_word(word);
+            }
             __syncwarp();
 
             // ---- evaluate
@@ -205,9 +229,9 @@ __global__ void __launch_bounds__(SEED_THREADS, SKB_SEED_MINBLOCKS) seed_scan_ke
                 if (16u * w < n) {
                     WordCtx c;
                     c.w2 = pk[w]; c.w1 = pk[w + 1]; c.w0 = pk[w + 2];
-                    c.r0 = revcomp_word(c.w0); c.r1 = revcomp_word(c.w1); c.r2 = revcomp_word(c.w2);
+                    c.r2 = rc[w]; c.r1 = rc[w + 1]; c.r0 = rc[w + 2];
                     uint32_t sm, mm;
-                    eval_word(c, a.kmask, a.kshift, ts_lo, ts_hi, tm_lo, tm_hi, sm, mm);
+                    eval_word<EXACT>(c, a.kmask, a.kshift, ts_lo, ts_hi, tm_lo, tm_hi, sm, mm);
                     const uint32_t left = n - 16u * w;
                     uint32_t valid = left >= 16 ? 0xFFFFu : ((1u << left) - 1u);
                     const uint32_t p0 = pos0 + 16u * w;
@@ -240,10 +264,52 @@ __global__ void __launch_bounds__(SEED_THREADS, SKB_SEED_MINBLOCKS) seed_scan_ke
                     sub_s |= (uint64_t)acc_s << (16 * j); sub_m |= (uint64_t)acc_m << (16 * j);
                     acc_s += (uint32_t)(tot_s >> (16 * j)) & 0xFFFFu; acc_m += (uint32_t)(tot_m >> (16 * j)) & 0xFFFFu;
                 }
-                // ---- ordered write-out into the warp's region
-                if (cs | cm) {
-                    const uint64_t ex_s = (is - cs) + sub_s, ex_m = (im - cm) + sub_m;   // <= 2048 per 16-bit lane
-                    const uint64_t gkey = (uint64_t)genome << 42;
+                const uint64_t ex_s = (is - cs) + sub_s, ex_m = (im - cm) + sub_m;   // <= 2048 per 16-bit lane
+                const uint64_t gkey = (uint64_t)genome << 42;
+                // ---- ordered write-out into the warp's region.
+                // Usual case: every lane drops (word, position) of its hits into a tile-wide list at its scanned offset
+                // (a few instructions per hit), then the list is worked off with ALL lanes busy and coalesced stores -
+                // in the per-lane form below 7 of 8 lanes idle while one rebuilds its k-mers.
+                const bool compact = acc_s <= HIT_LIST_CAP && acc_m <= HIT_LIST_CAP;
+                if (compact) {
+                    if (cs | cm) {
+#pragma unroll 1
+                        for (int j = 0; j < WORDS_PER_LANE; j++) {
+                            const uint32_t w = j * 32 + lane;
+                            const uint32_t mk = masks[w];
+                            uint32_t sm = mk & 0xFFFFu, mm = mk >> 16;
+                            uint32_t so = (uint32_t)(ex_s >> (16 * j)) & 0xFFFFu, mo = (uint32_t)(ex_m >> (16 * j)) & 0xFFFFu;
+                            while (sm) { hits_s[so++] = (uint16_t)((w << 4) | (uint32_t)(__ffs(sm) - 1)); sm &= sm - 1; }
+                            while (mm) { hits_m[mo++] = (uint16_t)((w << 4) | (uint32_t)(__ffs(mm) - 1)); mm &= mm - 1; }
+                        }
+                    }
+                    __syncwarp();
+                    for (uint32_t h = lane; h < acc_s; h += 32) {
+                        const uint32_t ent = hits_s[h], w = ent >> 4, e = ent & 15u;
+                        const KmerPair kp = kmers_at(pk[w], pk[w + 1], pk[w + 2], rc[w], rc[w + 1], rc[w + 2], (int)e);
+                        const uint32_t fk = (uint32_t)kp.f21 & a.kmask;
+                        const uint32_t rk = (uint32_t)(kp.r21 >> a.kshift);
+                        const bool canon = fk < rk;
+                        const uint32_t km = canon ? fk : rk;
+                        if (!EXACT && !(mm_hash64((uint64_t)km) < a.chk_seed)) atomicOr(a.overflow, 2u);
+                        const uint32_t so = cur_s + h;
+                        if (so < seed_cap) {
+                            a.kmer_r[seed_off + so] = km;
+                            a.pos_r[seed_off + so] = pos0 + 16u * w + e;
+                            a.meta_r[seed_off + so] = (cd.contig << 1) | (uint32_t)canon;
+                        } else atomicOr(a.overflow, 1u);
+                    }
+                    for (uint32_t h = lane; h < acc_m; h += 32) {
+                        const uint32_t ent = hits_m[h], w = ent >> 4, e = ent & 15u;
+                        const KmerPair kp = kmers_at(pk[w], pk[w + 1], pk[w + 2], rc[w], rc[w + 1], rc[w + 2], (int)e);
+                        const uint64_t mkr = kp.f21 < kp.r21 ? kp.f21 : kp.r21;
+                        if (!EXACT && !(mm_hash64(mkr) < a.chk_marker)) atomicOr(a.overflow, 2u);
+                        const uint32_t mo = cur_m + h;
+                        if (mo < marker_cap) a.marker_r[marker_off + mo] = gkey | mkr;
+                        else atomicOr(a.overflow, 1u);
+                    }
+                } else if (cs | cm) {
+                    // dense tiles (tiny compression factors): every lane writes its own hits
 #pragma unroll 1
                     for (int j = 0; j < WORDS_PER_LANE; j++) {
                         const uint32_t w = j * 32 + lane;
@@ -251,7 +317,7 @@ __global__ void __launch_bounds__(SEED_THREADS, SKB_SEED_MINBLOCKS) seed_scan_ke
                         uint32_t both = (mk | (mk >> 16)) & 0xFFFFu;
                         if (!both) continue;
                         const uint32_t w2 = pk[w], w1 = pk[w + 1], w0 = pk[w + 2];
-                        const uint32_t r0 = revcomp_word(w0), r1 = revcomp_word(w1), r2 = revcomp_word(w2);
+                        const uint32_t r2 = rc[w], r1 = rc[w + 1], r0 = rc[w + 2];
                         uint32_t so = cur_s + ((uint32_t)(ex_s >> (16 * j)) & 0xFFFFu);
                         uint32_t mo = cur_m + ((uint32_t)(ex_m >> (16 * j)) & 0xFFFFu);
                         const uint32_t p0 = pos0 + 16u * w;
@@ -263,18 +329,20 @@ __global__ void __launch_bounds__(SEED_THREADS, SKB_SEED_MINBLOCKS) seed_scan_ke
                                 const uint32_t fk = (uint32_t)kp.f21 & a.kmask;
                                 const uint32_t rk = (uint32_t)(kp.r21 >> a.kshift);
                                 const bool canon = fk < rk;
+                                const uint32_t km = canon ? fk : rk;
+                                if (!EXACT && !(mm_hash64((uint64_t)km) < a.chk_seed)) atomicOr(a.overflow, 2u);
                                 if (so < seed_cap) {
-                                    a.kmer_r[seed_off + so] = canon ? fk : rk;
+                                    a.kmer_r[seed_off + so] = km;
                                     a.pos_r[seed_off + so] = p0 + e;
                                     a.meta_r[seed_off + so] = (cd.contig << 1) | (uint32_t)canon;
-                                } else {
-                                    *a.overflow = 1u;
-                                }
+                                } else atomicOr(a.overflow, 1u);
                                 so++;
                             }
                             if ((mk >> (16 + e)) & 1u) {
-                                if (mo < marker_cap) a.marker_r[marker_off + mo] = gkey | (kp.f21 < kp.r21 ? kp.f21 : kp.r21);
-                                else *a.overflow = 1u;
+                                const uint64_t mkr = kp.f21 < kp.r21 ? kp.f21 : kp.r21;
+                                if (!EXACT && !(mm_hash64(mkr) < a.chk_marker)) atomicOr(a.overflow, 2u);
+                                if (mo < marker_cap) a.marker_r[marker_off + mo] = gkey | mkr;
+                                else atomicOr(a.overflow, 1u);
                                 mo++;
                             }
                         }
@@ -282,7 +350,7 @@ __global__ void __launch_bounds__(SEED_THREADS, SKB_SEED_MINBLOCKS) seed_scan_ke
                 }
                 cur_s += acc_s; cur_m += acc_m;
             }
-            __syncwarp();     // the next tile overwrites pk / masks
+            __syncwarp();     // the next tile overwrites pk / rc / masks / the hit lists
         }
     }
     if (lane == 0) {
@@ -358,7 +426,8 @@ __global__ void __launch_bounds__(256) region_gather_kernel(const RegionGatherAr
 
 void launch_seed_scan(const SeedScanArgs& a, int n_sm, cudaStream_t st) {
     if (a.n_warps == 0) return;
-    seed_scan_kernel<<<a.n_warps / SEED_WARPS, SEED_THREADS, 0, st>>>(a);
+    if (a.exact_compare) seed_scan_kernel<true><<<a.n_warps / SEED_WARPS, SEED_THREADS, 0, st>>>(a);
+    else seed_scan_kernel<false><<<a.n_warps / SEED_WARPS, SEED_THREADS, 0, st>>>(a);
     g_kernel_launches++;
 }
 

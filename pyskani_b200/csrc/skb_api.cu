@@ -409,6 +409,10 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
         uint32_t *t_kmer = nullptr, *t_pos = nullptr, *t_meta = nullptr;
         uint64_t* t_mreg = nullptr;
         uint32_t h_over = 0;
+        // exact = 0: the seeding kernel compares only the high words of hash and threshold and re-checks every hit
+        // exactly as it writes it; a position that slipped through (hash.hi == threshold.hi, lo above: one in ~6e9)
+        // raises bit 1 of the flag and the batch is repeated with the exact 64-bit comparison (SKB_SEED_EXACT=1 forces it)
+        int exact = std::getenv("SKB_SEED_EXACT") ? 1 : 0;
         for (int attempt = 0; attempt < 2; attempt++) {
             const size_t seed_store = attempt == 0 ? (size_t)n_tiles * seed_tile_cap : (size_t)seed_start[n_genomes];
             const size_t marker_store = attempt == 0 ? (size_t)n_tiles * marker_tile_cap : (size_t)marker_start[n_genomes];
@@ -424,12 +428,15 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             a.kshift = 42 - 2 * P.k;
             a.thr_seed = seed ? UINT64_MAX / (uint64_t)P.c : 0;     // seed=False keeps markers only (A.4)
             a.thr_marker = UINT64_MAX / (uint64_t)P.marker_c;
+            a.chk_seed = a.thr_seed; a.chk_marker = a.thr_marker;
+            if (std::getenv("SKB_SEED_TEST_INEXACT")) { a.chk_seed /= 2; a.chk_marker /= 2; }   // test hook: forces the exact repeat
             a.seed_tile_cap = seed_tile_cap; a.marker_tile_cap = marker_tile_cap;
             a.region_off = attempt == 0 ? nullptr : r_start;
             a.kmer_r = t_kmer; a.pos_r = t_pos; a.meta_r = t_meta; a.marker_r = t_mreg;
             a.region_seed_src = r_ssrc; a.region_marker_src = r_msrc; a.region_cnt = r_cnt;
             a.genome_region = g_region; a.genome_seed_local = g_slocal; a.genome_marker_local = g_mlocal;
             a.overflow = d_overflow;
+            a.exact_compare = (uint32_t)exact;
             CU(cudaEventRecord(c.ev[1], st));
             for (size_t li = 0; li < launches.size(); li++) {
                 const Launch& L = launches[li];
@@ -458,6 +465,11 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
                 std::memcpy(marker_start.data(), h_counts + n_genomes + 1, 4 * ((size_t)n_genomes + 1));
             }
             h_over = h_counts[2 * ((size_t)n_genomes + 1)];
+            if (h_over & 2u) {
+                if (exact) throw Fail{SKB_ERR_CUDA, "exact hash comparison flagged as inexact"};
+                exact = 1; attempt = -1;          // start over: counts and layout of this pass include a false positive
+                continue;
+            }
             if (!h_over) break;
             if (attempt == 1) throw Fail{SKB_ERR_CUDA, "seed regions overflowed twice"};
         }

@@ -75,6 +75,7 @@ struct SeedScanArgs {
     uint32_t n_warps;            // warps of this launch (grid * SEED_WARPS)
     uint32_t kmask, kshift;
     uint64_t thr_seed, thr_marker;
+    uint64_t chk_seed, chk_marker;   // thresholds of the exact re-check at write-out (= thr_*; a test hook lowers them)
     // region storage: the region of a warp whose first tile is T starts at T * seed_tile_cap (resp. marker_tile_cap)
     // and may hold (tiles of the warp) * cap records, unless explicit tables are given (retry after an overflow)
     uint32_t seed_tile_cap, marker_tile_cap;
@@ -85,7 +86,9 @@ struct SeedScanArgs {
     uint64_t* region_cnt;                                                // [n_regions + 1] exact counts, seeds | markers << 32 (also on overflow)
     uint32_t* genome_region;     // [n_genomes] region in which the genome's first tile lies (0xFFFFFFFF = no tile)
     uint32_t* genome_seed_local; uint32_t* genome_marker_local;          // [n_genomes] cursor of that region at that tile
-    uint32_t* overflow;          // set to 1 when a region was too small
+    uint32_t* overflow;          // bit 0: a region was too small; bit 1: the high-word hash comparison let a position through
+                                 // that the exact comparison rejects (the host repeats the batch with exact_compare = 1)
+    uint32_t exact_compare;      // 0: compare the high words of hash and threshold, re-check hits when they are written
 };
 
 // region_start[n_regions + 1] = exclusive scan of region_cnt (u64 lanes: seeds | markers << 32)

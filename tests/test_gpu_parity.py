@@ -131,6 +131,24 @@ def test_host_copies_merged_or_separate_give_the_same_sketch(ctx, monkeypatch):
     assert_sketch_equal(merged[0], oracle.Sketch([x.tobytes() for x in seqs[0:3]]))
 
 
+def test_sketch_hash_comparison_variants(ctx, monkeypatch):
+    """The seeding kernel compares the high words of hash and threshold and re-checks every hit exactly when it writes it;
+    a hit that fails the re-check makes the host repeat the batch with the exact 64-bit comparison.  Forced exact
+    comparison (SKB_SEED_EXACT) and a forced repeat (SKB_SEED_TEST_INEXACT halves the re-check thresholds) both give the
+    oracle's sketch, for one genome and for a ragged batch."""
+    genomes = [[rand(700_000, 61)], [rand(3_000, 62), rand(900, 63), b"ACGT" * 50], [rand(150_000, 64)]]
+    want = [oracle.Sketch(g) for g in genomes]
+    for env in ({}, {"SKB_SEED_EXACT": "1"}, {"SKB_SEED_TEST_INEXACT": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for g, o in zip(ctx.sketch_batch(genomes), want):
+            assert_sketch_equal(g, o)
+        (one,) = ctx.sketch_batch(genomes[:1], c=30, marker_c=200)
+        assert_sketch_equal(one, oracle.Sketch(genomes[0], c=30, marker_c=200))
+        for k in env:
+            monkeypatch.delenv(k)
+
+
 def test_sketch_junk_and_lowercase(ctx):
     rng = np.random.default_rng(3)
     alpha = np.frombuffer(b"ACGTacgtNnRYKM-*", np.uint8)

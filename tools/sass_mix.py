@@ -48,13 +48,15 @@ def pipe_of(op):
 
 def kernel_sass(obj, name):
     out = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout
-    cur, keep = None, []
+    cur, keep, chosen = None, [], None
     for line in out.splitlines():
         m = re.search(r"Function : (\S+)", line)
         if m:
             cur = m.group(1)
+            if chosen is None and name in cur:
+                chosen = cur               # the first match only: template instances share a name prefix
             continue
-        if cur and name in cur:
+        if cur and cur == chosen:
             m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", line)
             if m:
                 keep.append((int(m.group(1), 16), m.group(2).strip()))
@@ -65,7 +67,7 @@ def kernel_sass(obj, name):
 
 def main():
     obj = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "pyskani_b200", "csrc", "seed_kernels.o")
-    name = sys.argv[2] if len(sys.argv) > 2 else "seed_scan_kernel"
+    name = sys.argv[2] if len(sys.argv) > 2 else "seed_scan_kernelILb0"      # <false>: the high-word comparison variant
     units = int(sys.argv[3]) if len(sys.argv) > 3 else 16
     ins = kernel_sass(obj, name)
     addr_index = {a: i for i, (a, _) in enumerate(ins)}
