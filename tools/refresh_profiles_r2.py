@@ -30,9 +30,9 @@ step = L[ends[2] + 1:ends[5] + 1]
 
 
 def short(n):
-    if 'RadixSort' in n: return 'CUB radix sort (marker index postings)'
-    if 'Scan' in n: return 'CUB scan (anchor offsets, region counts)'
-    if 'Select' in n or 'Compact' in n: return 'CUB select'
+    if 'DeviceRadixSort' in n or 'RadixSort' in n and 'skb::' not in n.split('(')[0]: return 'CUB radix sort (marker index postings)'
+    if 'DeviceScan' in n: return 'CUB scan (anchor offsets, region counts)'
+    if 'DeviceSelect' in n or 'DeviceCompact' in n: return 'CUB select'
     m = re.search(r'skb::(?:<unnamed>::)?(\w+)', n)
     if m: return m.group(1)
     return 'CUB other'
