@@ -76,6 +76,9 @@ typedef struct {
 typedef struct {
     float h2d_ms, seed_ms, index_ms, screen_ms, chain_ms, total_ms;
     uint64_t kernels_launched;   /* cumulative count of this library's kernel launches */
+    /* skb_sketch_batch: bytes that crossed the host->device link as ASCII and as 2-bit words (4 bases per byte; large
+     * batches are partly compacted by host threads before the copy, see skb_ctx_set_host_threads) */
+    uint64_t h2d_raw_bytes, h2d_packed_bytes;
 } skb_stats_t;
 
 /* ---- context ---- */
@@ -86,6 +89,12 @@ int  skb_ctx_stats(const skb_ctx_t* ctx, skb_stats_t* out);
 int  skb_ctx_sync(skb_ctx_t* ctx);
 /* CUDA stream all work of this context is enqueued on (a cudaStream_t), for event timing by callers */
 void* skb_ctx_stream(skb_ctx_t* ctx);
+/* Host threads of the ingest pipeline of skb_sketch_batch (host buffers).  Batches of 64 MB and more travel two ways at
+ * once: the copy engine pulls chunks of ASCII out of the caller's memory while n - 1 threads compact other chunks to
+ * 2-bit words (4:1) in pinned staging memory and one thread feeds the copy engine; the seeding kernel reads either form
+ * and produces bit-identical sketches.  n = 0 or 1: every byte travels as ASCII; n < 0: default = SKB_HOST_THREADS, else
+ * min(32, usable CPUs / LOCAL_WORLD_SIZE).  SKB_INGEST=raw|pack|mix overrides the policy (test hook). */
+int  skb_ctx_set_host_threads(skb_ctx_t* ctx, int32_t n);
 
 /* pinned host staging memory (so that callers can keep inputs where an async H2D copy can reach them) */
 int  skb_host_alloc(skb_ctx_t* ctx, size_t bytes, void** out);

@@ -44,12 +44,13 @@ class SketchInfo(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("seed_ms", C.c_float), ("index_ms", C.c_float),
                 ("screen_ms", C.c_float), ("chain_ms", C.c_float), ("total_ms", C.c_float),
-                ("kernels_launched", C.c_uint64)]
+                ("kernels_launched", C.c_uint64), ("h2d_raw_bytes", C.c_uint64), ("h2d_packed_bytes", C.c_uint64)]
 
 
 # every symbol include/skb.h declares (tests/test_abi.py checks the library exports all of them)
 SYMBOLS = [
     "skb_ctx_create", "skb_ctx_destroy", "skb_last_error", "skb_ctx_stats", "skb_ctx_sync", "skb_ctx_stream",
+    "skb_ctx_set_host_threads",
     "skb_host_alloc", "skb_host_free", "skb_dev_alloc", "skb_dev_free", "skb_memcpy_h2d",
     "skb_sketch_batch", "skb_sketch_batch_device", "skb_sketch_free", "skb_sketch_free_many", "skb_sketch_info", "skb_sketch_export",
     "skb_sketch_import", "skb_sketch_pack_size", "skb_sketch_pack", "skb_sketch_unpack",
@@ -94,6 +95,7 @@ def lib():
         L.skb_ctx_sync.argtypes = [vp]
         L.skb_ctx_stream.restype = vp
         L.skb_ctx_stream.argtypes = [vp]
+        L.skb_ctx_set_host_threads.argtypes = [vp, i32]
         L.skb_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
         L.skb_host_free.argtypes = [vp, vp]
         L.skb_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
@@ -173,6 +175,10 @@ class Context:
     @property
     def stream(self):
         return lib().skb_ctx_stream(self._h)
+
+    def set_host_threads(self, n):
+        """Threads of the host ingest pipeline of sketch calls on host buffers (0/1: all bytes travel as ASCII; < 0: default)."""
+        self.check(lib().skb_ctx_set_host_threads(self._h, int(n)))
 
     # ---- sketching
     def sketch_batch(self, genomes, k=15, c=125, marker_c=1000, seed=True):

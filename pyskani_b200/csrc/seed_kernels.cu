@@ -128,7 +128,15 @@ __device__ __forceinline__ void eval_word(const WordCtx& c, uint32_t kmask, uint
 #endif
 constexpr uint32_t HIT_LIST_CAP = 96;      // hits of one tile that take the compact write-out (2 048 bases hold ~16 seeds, ~2 markers)
 
-template <bool EXACT>
+__device__ __forceinline__ uint32_t ld_stream4(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// PACKED: the launch's input already consists of 2-bit words (host_pack.h: chunks that the host compacted before the
+// PCIe link); word i of a contig sits at byte offset seq_off / 4 + 4 i of a.seq.  Everything after the load is shared.
+template <bool EXACT, bool PACKED>
 __global__ void __launch_bounds__(SEED_THREADS, SKB_SEED_MINBLOCKS) seed_scan_kernel(const SeedScanArgs a) {
     // Warps are independent: private packed-word and mask buffers, private output region, no block barriers.
     __shared__ uint32_t s_pk[SEED_WARPS][TILE_WORDS + 2];     // 2-bit packed words (two words of the previous tile in front)
@@ -197,6 +205,23 @@ __global__ void __launch_bounds__(SEED_THREADS, SKB_SEED_MINBLOCKS) seed_scan_ke
                 a.genome_marker_local[genome] = cur_m;
             }
 
+            if (PACKED) {
+                // ---- load: word j*32 + lane for j = 0..3 (each warp load covers 128 contiguous bytes)
+                const uint32_t* wbase = reinterpret_cast<const uint32_t*>(a.seq + (cd.seq_off >> 2)) + (pos0 >> 4);
+                uint32_t v[WORDS_PER_LANE];
+#pragma unroll
+                for (int j = 0; j < WORDS_PER_LANE; j++) {
+                    const uint32_t w = j * 32 + lane;
+                    v[j] = 16u * w < n ? ld_stream4(wbase + w) : 0u;
+                }
+                const uint32_t hv = (lane < 2 && pos0 > 0) ? ld_stream4(wbase - 2 + lane) : 0u;   // the two words before the tile
+#pragma unroll
+                for (int j = 0; j < WORDS_PER_LANE; j++) {
+                    pk[2 + j * 32 + lane] = v[j];
+                    rc[2 + j * 32 + lane] = revcomp_word(v[j]);
+                }
+                if (lane < 2) { pk[lane] = hv; rc[lane] = revcomp_word(hv); }
+            } else {
             // ---- load + pack: word j*32 + lane for j = 0..3 (each warp load covers 512 contiguous bytes)
             uint4 v[WORDS_PER_LANE];
 #pragma unroll
@@ -217,6 +242,7 @@ __global__ void __launch_bounds__(SEED_THREADS, SKB_SEED_MINBLOCKS) seed_scan_ke
                 const uint32_t word = pos0 > 0 ? pack16(hv.x, hv.y, hv.z, hv.w) : 0u;
                 pk[lane] = word;
                 rc[lane] = revcomp_word(word);
+            }
             }
             __syncwarp();
 
@@ -426,8 +452,14 @@ __global__ void __launch_bounds__(256) region_gather_kernel(const RegionGatherAr
 
 void launch_seed_scan(const SeedScanArgs& a, int n_sm, cudaStream_t st) {
     if (a.n_warps == 0) return;
-    if (a.exact_compare) seed_scan_kernel<true><<<a.n_warps / SEED_WARPS, SEED_THREADS, 0, st>>>(a);
-    else seed_scan_kernel<false><<<a.n_warps / SEED_WARPS, SEED_THREADS, 0, st>>>(a);
+    const dim3 grid(a.n_warps / SEED_WARPS), block(SEED_THREADS);
+    if (a.packed) {
+        if (a.exact_compare) seed_scan_kernel<true, true><<<grid, block, 0, st>>>(a);
+        else seed_scan_kernel<false, true><<<grid, block, 0, st>>>(a);
+    } else {
+        if (a.exact_compare) seed_scan_kernel<true, false><<<grid, block, 0, st>>>(a);
+        else seed_scan_kernel<false, false><<<grid, block, 0, st>>>(a);
+    }
     g_kernel_launches++;
 }
 

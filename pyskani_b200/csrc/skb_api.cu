@@ -5,11 +5,17 @@
 // an unbounded release threshold, so scratch is recycled between calls instead of hitting cudaMalloc.
 // There is deliberately no CPU implementation of any step in this file.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <climits>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <deque>
+#include <functional>
 
+#include "host_pack.h"
 #include "skb_internal.cuh"
 #include "slab_pool.h"
 
@@ -57,16 +63,25 @@ struct Core {
     cudaStream_t copy_stream = nullptr;       // host->device copies of skb_sketch_batch run here, ahead of the kernels
     cudaStream_t aux_stream = nullptr;        // marker-set build of a batch, beside the k-mer order build on `stream`
     std::vector<cudaEvent_t> ev_pool;         // "chunk is on the device" events (timing disabled)
+    // ingest pipeline of large host batches (host_pack.h): worker threads + pinned staging for the 2-bit chunks
+    std::unique_ptr<HostTeam> team;
+    int host_threads = -1;                    // -1: default (SKB_HOST_THREADS, else min(32, cpus / LOCAL_WORLD_SIZE)); 0: off
+    void* pack_stage = nullptr;               // pinned, mirrors the device layout of a batch at a quarter of its size
+    size_t pack_stage_bytes = 0;
+    void* raw_stage = nullptr;                // pinned staging of the pipeline's DMA thread for small contigs
     cudaEvent_t pool_event(size_t i) {
         while (ev_pool.size() <= i) {
             cudaEvent_t e;
-            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) return nullptr;   // waited for by the ingest feeder: sleep, do not spin
             ev_pool.push_back(e);
         }
         return ev_pool[i];
     }
     ~Core() {
+        team.reset();
         cudaSetDevice(device);
+        if (pack_stage) cudaFreeHost(pack_stage);
+        if (raw_stage) cudaFreeHost(raw_stage);
         if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
         if (aux_stream) { cudaStreamSynchronize(aux_stream); cudaStreamDestroy(aux_stream); }
         if (stream) cudaStreamSynchronize(stream);
@@ -125,7 +140,7 @@ void* Core::scratch(int slot, size_t bytes) {
     }
     return b.p;
 }
-enum { SLOT_SEQ = 0, SLOT_KMER, SLOT_POS, SLOT_META, SLOT_MKEYS, SLOT_STATUS, SLOT_SORT, SLOT_MARK, SLOT_GS, SLOT_GM, SLOT_DESC, SLOT_MKEYS2, SLOT_RSCAN, SLOT_GM_IN, SLOT_BTAB, SLOT_BCOUNT, SLOT_CHAIN, SLOT_MIDX, SLOT_PACK };
+enum { SLOT_SEQ = 0, SLOT_KMER, SLOT_POS, SLOT_META, SLOT_MKEYS, SLOT_STATUS, SLOT_SORT, SLOT_MARK, SLOT_GS, SLOT_GM, SLOT_DESC, SLOT_MKEYS2, SLOT_RSCAN, SLOT_GM_IN, SLOT_BTAB, SLOT_BCOUNT, SLOT_CHAIN, SLOT_MIDX, SLOT_PACK, SLOT_SEQPK };
 
 // stream-ordered device buffer
 struct DevMem {
@@ -308,11 +323,14 @@ static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_par
 
 // A chunk of the batch whose bytes become available on the device when `ready` fires (host->device pipelining):
 // flat contigs [previous contig_end, contig_end).
-struct ChunkPlan { uint32_t contig_end; cudaEvent_t ready; };
+// host_wait (optional): blocks the calling thread until `ready` has been RECORDED by the ingest pipeline's threads (a
+// stream wait on an event that was never recorded would be a no-op) and tells in which form the chunk arrived:
+// 0 = ASCII in seq_dev, 1 = 2-bit words in seq_packed_dev.
+struct ChunkPlan { uint32_t contig_end; cudaEvent_t ready; std::function<int()> host_wait; };
 
 static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_params_t& P, int seed, uint32_t n_genomes,
                         const uint32_t* gstart, const uint8_t* seq_dev, const uint64_t* offs, const uint64_t* lens,
-                        skb_sketch_t** out, const std::vector<ChunkPlan>* plan = nullptr) {
+                        skb_sketch_t** out, const std::vector<ChunkPlan>* plan = nullptr, const uint8_t* seq_packed_dev = nullptr) {
     Core& c = *core;
     cudaStream_t st = c.stream;
     Trace t2("sketch_core");
@@ -361,10 +379,10 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
         table_upload(c, d_descs, descs.data(), sizeof(ContigDesc) * descs.size());
         t2.mark("descs uploaded");
         // ---- launch plan: one launch per copy chunk (or one for everything); every warp of a launch owns a region
-        struct Launch { uint32_t d0, d1, tile_base, n_tiles, n_warps, n_chunks, chunk_tiles, region_base; cudaEvent_t ready; };
+        struct Launch { uint32_t d0, d1, tile_base, n_tiles, n_warps, n_chunks, chunk_tiles, region_base; cudaEvent_t ready; const ChunkPlan* chunk; };
         std::vector<Launch> launches;
         uint32_t n_regions = 0;
-        auto add_launch = [&](uint32_t d0, uint32_t d1, cudaEvent_t ready) {
+        auto add_launch = [&](uint32_t d0, uint32_t d1, cudaEvent_t ready, const ChunkPlan* chunk = nullptr) {
             if (d1 <= d0) return;
             Launch L{};
             L.d0 = d0; L.d1 = d1; L.tile_base = descs[d0].tile_start;
@@ -375,15 +393,15 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             L.chunk_tiles = std::max<uint32_t>(1, std::min<uint32_t>(CHUNK_TILES, n_tiles / (2 * all_warps)));   // by the size of the whole call
             L.n_chunks = (L.n_tiles + L.chunk_tiles - 1) / L.chunk_tiles;
             uint32_t grid = std::min<uint32_t>((uint32_t)c.n_sm * 4u, (L.n_chunks + SEED_WARPS - 1) / SEED_WARPS);
-            L.n_warps = grid * SEED_WARPS; L.region_base = n_regions; L.ready = ready;
+            L.n_warps = grid * SEED_WARPS; L.region_base = n_regions; L.ready = ready; L.chunk = chunk;
             n_regions += L.n_chunks;
             launches.push_back(L);
         };
         if (plan && plan->size() > 1) {
             uint32_t d0 = 0;
-            for (size_t ch = 0; ch < plan->size(); ch++) { add_launch(d0, chunk_desc_end[ch], (*plan)[ch].ready); d0 = chunk_desc_end[ch]; }
+            for (size_t ch = 0; ch < plan->size(); ch++) { add_launch(d0, chunk_desc_end[ch], (*plan)[ch].ready, &(*plan)[ch]); d0 = chunk_desc_end[ch]; }
         } else {
-            add_launch(0, (uint32_t)descs.size(), plan && plan->size() == 1 ? (*plan)[0].ready : nullptr);
+            add_launch(0, (uint32_t)descs.size(), plan && plan->size() == 1 ? (*plan)[0].ready : nullptr, plan && plan->size() == 1 ? &(*plan)[0] : nullptr);
         }
 
         // ---- region bookkeeping (device): counts, storage offsets, scans, per-genome records, overflow flag
@@ -440,8 +458,10 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             CU(cudaEventRecord(c.ev[1], st));
             for (size_t li = 0; li < launches.size(); li++) {
                 const Launch& L = launches[li];
+                const int packed = L.chunk && L.chunk->host_wait ? L.chunk->host_wait() : 0;
                 if (L.ready) CU(cudaStreamWaitEvent(st, L.ready, 0));
                 SeedScanArgs b2 = a;
+                if (packed) { b2.seq = seq_packed_dev; b2.packed = 1; }
                 b2.n_chunks = L.n_chunks; b2.chunk_tiles = L.chunk_tiles; b2.chunk_counter = d_claim + li;
                 b2.contigs = d_descs + L.d0; b2.n_contigs = L.d1 - L.d0;
                 b2.tile_base = L.tile_base; b2.n_tiles = L.n_tiles; b2.n_warps = L.n_warps; b2.region_base = L.region_base;
@@ -546,6 +566,190 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
         finish_batch(core, P, seed, n_genomes, contig_lens, store, seed_start, marker_start, nullptr, out);
     }
     t2.mark("finish_batch done");
+}
+
+
+// ------------------------------------------------------------------------------------------------ host ingest pipeline
+// Large host batches reach the device through two concurrent routes (host_pack.h): the copy engine pulls chunks of
+// plain ASCII out of the caller's memory, and a team of threads compacts other chunks to 2-bit words in pinned staging
+// memory, from where a quarter of the bytes crosses the link.  Chunks (runs of whole contigs, ~16 MB) are claimed in
+// order from one counter by whichever route is free, so the split adapts to the host: PCIe rate against pack rate.
+// The calling thread meanwhile launches the seeding kernel of every chunk in order (sketch_core), variant by arrival form.
+
+// DMA of ASCII contigs into the device layout: large contigs straight from the caller's memory (adjacent ones that keep
+// the device displacement merged into one copy), small ones through a pinned staging block.
+struct RawCopier {
+    static constexpr uint64_t DIRECT = 1 << 18;
+    static constexpr size_t STAGE = (size_t)8 << 20;
+    Core& c; cudaStream_t cs; uint8_t* d_seq; bool merge;
+    char* stage = nullptr; size_t used = 0; uint64_t stage_dev0 = 0;
+    const uint8_t* run_src = nullptr; uint64_t run_dst = 0, run_bytes = 0;
+    uint64_t bytes = 0;
+    RawCopier(Core& c_, cudaStream_t cs_, uint8_t* d, char* stage_) : c(c_), cs(cs_), d_seq(d), merge(std::getenv("SKB_NO_COPY_MERGE") == nullptr), stage(stage_) {}
+    void flush_run() {
+        if (run_bytes) {
+            CU(cudaMemcpyAsync((char*)d_seq + run_dst, run_src, run_bytes, cudaMemcpyHostToDevice, cs));
+            run_bytes = 0;
+        }
+    }
+    void flush_stage() {
+        if (used) {
+            CU(cudaMemcpyAsync((char*)d_seq + stage_dev0, stage, used, cudaMemcpyHostToDevice, cs));
+            CU(cudaStreamSynchronize(cs));            // the staging block is reused
+            used = 0;
+        }
+    }
+    void add(const uint8_t* src, uint64_t len, uint64_t off) {
+        bytes += len;
+        if (len >= DIRECT) {
+            // (the <= 31 padding bytes between merged contigs are copied along; they lie between two valid buffers on pages
+            // that hold valid bytes, and the kernels never interpret bytes outside a contig)
+            const bool adjacent = merge && run_bytes && off >= run_dst + run_bytes && off - (run_dst + run_bytes) < 32 &&
+                                  (int64_t)(src - run_src) == (int64_t)(off - run_dst);
+            if (adjacent) run_bytes = off - run_dst + len;
+            else { flush_run(); run_src = src; run_dst = off; run_bytes = len; }
+        } else {
+            const uint64_t span = align16(len) + 16;
+            if (used && (used + span > STAGE || stage_dev0 + used != off)) flush_stage();
+            if (!used) stage_dev0 = off;
+            std::memcpy(stage + used, src, len);
+            used += span;
+        }
+    }
+    void flush() { flush_run(); flush_stage(); }
+};
+
+struct Ingest {
+    enum { MIX = 0, PACK_ONLY = 1 };
+    static constexpr size_t PIECE_BASES = (size_t)1 << 20;     // unit of work of a packing thread (a multiple of 16)
+    static constexpr unsigned RAW_DEPTH = 2;                     // ASCII chunks the copy engine may have queued
+    struct Chunk { uint32_t c0, c1; cudaEvent_t ev; int mode; bool done; };
+    struct Piece { const uint8_t* src; size_t n; uint32_t* dst; uint32_t chunk; };
+
+    Core& c;
+    const uint8_t* const* contigs; const uint64_t* lens; const uint64_t* offs;     // flat contig arrays; offs = ASCII device layout
+    uint8_t* d_seq; uint8_t* d_pk; char* stage_pk; char* stage_raw;
+    int policy;
+    std::vector<Chunk> chunks;
+    std::atomic<uint32_t> next_chunk{0};
+    std::atomic<bool> abort{false};
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Piece> queue;
+    std::vector<uint32_t> remaining;
+    int err = 0; std::string err_msg;
+    uint64_t raw_bytes = 0, packed_bytes = 0;      // bytes that crossed the link in either form (guarded by mu)
+
+    Ingest(Core& c_, const uint8_t* const* ct, const uint64_t* ln, const uint64_t* of, uint8_t* dseq, uint8_t* dpk, char* spk, char* sraw, int pol)
+        : c(c_), contigs(ct), lens(ln), offs(of), d_seq(dseq), d_pk(dpk), stage_pk(spk), stage_raw(sraw), policy(pol) {}
+
+    // calling thread: block until chunk ch is on its way (its event is recorded); returns the arrival form
+    int wait(uint32_t ch) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return chunks[ch].done || err; });
+        if (err) throw Fail{err, err_msg};
+        return chunks[ch].mode;
+    }
+    void fail(int code, const std::string& msg) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!err) { err = code; err_msg = msg; }
+        abort.store(true);
+        cv.notify_all();
+    }
+    void mark_done(uint32_t ch, int mode, uint64_t link_bytes) {
+        CU(cudaEventRecord(chunks[ch].ev, c.copy_stream));
+        std::lock_guard<std::mutex> lk(mu);
+        chunks[ch].mode = mode; chunks[ch].done = true;
+        (mode ? packed_bytes : raw_bytes) += link_bytes;
+        cv.notify_all();
+    }
+    bool kept(uint32_t i) const { return lens[i] >= SKB_MIN_LENGTH_CONTIG; }
+
+    // ---- route 1: ASCII by DMA (one thread)
+    void feed_raw() {
+        RawCopier rc(c, c.copy_stream, d_seq, stage_raw);
+        std::deque<uint32_t> outstanding;
+        while (!abort.load()) {
+            if (outstanding.size() >= RAW_DEPTH) { CU(cudaEventSynchronize(chunks[outstanding.front()].ev)); outstanding.pop_front(); }
+            const uint32_t ch = next_chunk.fetch_add(1);
+            if (ch >= chunks.size()) break;
+            const uint64_t before = rc.bytes;
+            for (uint32_t i = chunks[ch].c0; i < chunks[ch].c1; i++) if (kept(i)) rc.add(contigs[i], lens[i], offs[i]);
+            rc.flush();
+            mark_done(ch, 0, rc.bytes - before);
+            outstanding.push_back(ch);
+        }
+    }
+    // ---- route 2: 2-bit words through pinned staging (all other threads)
+    void finish_packed(uint32_t ch) {
+        uint32_t first = chunks[ch].c0, last = chunks[ch].c1;
+        while (first < last && !kept(first)) first++;
+        while (last > first && !kept(last - 1)) last--;
+        uint64_t bytes = 0;
+        if (first < last) {
+            const uint64_t b0 = offs[first] / 4, b1 = (offs[last - 1] + align16(lens[last - 1])) / 4;     // contiguous: the staging mirrors the device layout
+            bytes = b1 - b0;
+            CU(cudaMemcpyAsync(d_pk + b0, stage_pk + b0, bytes, cudaMemcpyHostToDevice, c.copy_stream));
+        }
+        mark_done(ch, 1, bytes);
+    }
+    void pack_loop() {
+        while (!abort.load()) {
+            Piece p{};
+            bool have = false, empty_chunk = false;
+            uint32_t claimed = 0;
+            {
+                // taking a piece and, when none is left, claiming the next chunk happen under one lock: at most one
+                // chunk beyond the queue is ever claimed for packing, the rest stays available to the copy engine
+                std::lock_guard<std::mutex> lk(mu);
+                if (!queue.empty()) { p = queue.front(); queue.pop_front(); have = true; }
+                else {
+                    claimed = next_chunk.fetch_add(1);
+                    if (claimed >= chunks.size()) break;
+                    uint32_t n_pieces = 0;
+                    for (uint32_t i = chunks[claimed].c0; i < chunks[claimed].c1; i++) {
+                        if (!kept(i)) continue;
+                        uint32_t* dst = reinterpret_cast<uint32_t*>(stage_pk + offs[i] / 4);
+                        for (uint64_t o = 0; o < lens[i]; o += PIECE_BASES) {
+                            queue.push_back(Piece{contigs[i] + o, (size_t)std::min<uint64_t>(PIECE_BASES, lens[i] - o), dst + o / 16, claimed});
+                            n_pieces++;
+                        }
+                    }
+                    remaining[claimed] = n_pieces;
+                    if (n_pieces) { p = queue.front(); queue.pop_front(); have = true; }
+                    else empty_chunk = true;
+                }
+            }
+            if (empty_chunk) { finish_packed(claimed); continue; }
+            if (!have) continue;
+            host_pack_bases(p.src, p.n, p.dst);
+            bool last;
+            { std::lock_guard<std::mutex> lk(mu); last = --remaining[p.chunk] == 0; }
+            if (last) finish_packed(p.chunk);
+        }
+    }
+    void worker(unsigned id) {
+        try {
+            if (id == 0 && policy == MIX) feed_raw();
+            pack_loop();          // the feeding thread helps with what is left once every chunk is claimed
+        } catch (const Fail& f) {
+            fail(f.code, f.msg);
+        } catch (const std::exception& e) {
+            fail(SKB_ERR_CUDA, e.what());
+        }
+    }
+};
+
+// thread count of the ingest pipeline of this context (0 = pipeline off)
+static unsigned resolve_host_threads(const Core& c) {
+    if (c.host_threads >= 0) return (unsigned)c.host_threads;
+    if (const char* e = std::getenv("SKB_HOST_THREADS")) return (unsigned)std::max(0, std::atoi(e));
+    unsigned cpus = host_cpu_count();
+    // one process per GPU sharing the host's cores (torchrun exports LOCAL_WORLD_SIZE)
+    if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) { const int w = std::atoi(e); if (w > 1) cpus = std::max(1u, cpus / (unsigned)w); }
+    // the calling thread spins in its stream synchronisations and the feeding thread sleeps in its event waits: one
+    // feeder + (cpus - 1) packing threads keep every core busy
+    return std::min(32u, cpus);
 }
 
 static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_params_t& P, int seed,
@@ -734,6 +938,12 @@ int skb_ctx_sync(skb_ctx_t* ctx) {
     return guarded(ctx->core.get(), [&] { CU(cudaStreamSynchronize(ctx->core->stream)); return SKB_OK; });
 }
 void* skb_ctx_stream(skb_ctx_t* ctx) { return ctx ? (void*)ctx->core->stream : nullptr; }
+int skb_ctx_set_host_threads(skb_ctx_t* ctx, int32_t n) {
+    if (!ctx) return SKB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->core->mu);
+    ctx->core->host_threads = n < 0 ? -1 : std::min<int32_t>(n, 256);
+    return SKB_OK;
+}
 
 int skb_host_alloc(skb_ctx_t* ctx, size_t bytes, void** out) {
     if (!ctx || !out) return SKB_ERR_ARG;
@@ -805,37 +1015,18 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
         CU(cudaStreamWaitEvent(cs, c.ev[5], 0));          // d_seq's allocation is ordered on `st`
         cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr;
         if (tr.on) { cudaEventCreate(&ev_c0); cudaEventCreate(&ev_c1); cudaEventRecord(ev_c0, cs); }
-        constexpr uint64_t DIRECT = 1 << 18;
-        constexpr size_t STAGE = (size_t)8 << 20;
-        constexpr uint64_t CHUNK = (uint64_t)16 << 20;      // granularity of copy -> seeding hand-over
+        uint64_t CHUNK = (uint64_t)16 << 20;                // granularity of copy -> seeding hand-over
+        if (const char* e = std::getenv("SKB_CHUNK_KB")) CHUNK = std::max<uint64_t>(1, (uint64_t)std::atoll(e)) << 10;   // test hook
         constexpr uint64_t SUB = (uint64_t)192 << 20;       // genomes are indexed in sub-batches of about this size
         constexpr uint64_t SUB_MAX = (uint64_t)1536 << 20;  // upper bound of a sub-batch (the batch limit is 2^31 bases)
-        // All copies are enqueued up front.  The batch is then processed in sub-batches (whole genomes): while the
-        // index of sub-batch i is built, the copies of the later sub-batches keep the PCIe link busy, so only the
-        // last sub-batch's index build is exposed after the final byte has arrived.
+        constexpr uint64_t INGEST_MIN = (uint64_t)64 << 20; // smaller calls are not worth waking the thread team for
+        // The batch is processed in sub-batches (whole genomes): while the index of sub-batch i is built, the copies of
+        // the later sub-batches keep the PCIe link busy, so only the last sub-batch's index build is exposed after the
+        // final byte has arrived.
         struct SubBatch { uint32_t g0, g1; std::vector<ChunkPlan> plan; };
         std::vector<SubBatch> subs;
-        size_t n_events = 0;
-        char* stage = nullptr; size_t used = 0; uint64_t stage_dev0 = 0;
-        // Large contigs that follow each other in host memory with the same displacement as in the device layout
-        // (a caller holding its records in one buffer, 16-byte aligned) travel as ONE copy: 101 separate 5 MB copies
-        // kept the link at 52 instead of 55 GB/s.  The <= 31 padding bytes in between are copied along; they lie between
-        // two valid buffers on pages that hold valid bytes, and the kernels never interpret bytes outside a contig.
-        const uint8_t* run_src = nullptr; uint64_t run_dst = 0, run_bytes = 0;
-        const bool merge_copies = std::getenv("SKB_NO_COPY_MERGE") == nullptr;
-        auto flush_run = [&] {
-            if (run_bytes) {
-                CU(cudaMemcpyAsync((char*)d_seq + run_dst, run_src, run_bytes, cudaMemcpyHostToDevice, cs));
-                run_bytes = 0;
-            }
-        };
-        auto flush = [&] {
-            if (used) {
-                CU(cudaMemcpyAsync((char*)d_seq + stage_dev0, stage, used, cudaMemcpyHostToDevice, cs));
-                CU(cudaStreamSynchronize(cs));            // the staging block is reused
-                used = 0;
-            }
-        };
+        struct ChunkRange { uint32_t c0, c1; };
+        std::vector<ChunkRange> ranges;                     // flat contig range of every chunk, in order
         uint64_t kept_bytes = 0;
         for (uint32_t i = 0; i < n_contigs; i++) if (contig_lens[i] >= SKB_MIN_LENGTH_CONTIG) kept_bytes += contig_lens[i];
         // cut points (cumulative bytes): equal parts of about SUB bytes (measured best on B200 among head/tail splits:
@@ -846,54 +1037,118 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
             cuts.clear();
             for (const char* p = e; *p;) { char* end; const double mb = std::strtod(p, &end); if (end == p) break; cuts.push_back((uint64_t)(mb * 1048576.0)); p = *end ? end + 1 : end; }
         }
-        uint64_t in_chunk = 0, in_sub = 0, done_bytes = 0;
-        SubBatch cur_sub{0, 0, {}};
-        auto close_chunk = [&](uint32_t contig_end) {
-            flush_run();
-            flush();
-            cudaEvent_t e = c.pool_event(n_events++);
-            if (!e) throw Fail{SKB_ERR_CUDA, "cannot create an event"};
-            CU(cudaEventRecord(e, cs));
-            cur_sub.plan.push_back(ChunkPlan{contig_end, e});
-            in_chunk = 0;
-        };
-        for (uint32_t g = 0; g < n_genomes; g++) {
-            for (uint32_t i = genome_contig_start[g]; i < genome_contig_start[g + 1]; i++) {
-                const uint64_t len = contig_lens[i];
-                if (len < SKB_MIN_LENGTH_CONTIG) continue;
-                if (len >= DIRECT) {
-                    const bool adjacent = merge_copies && run_bytes && offs[i] >= run_dst + run_bytes && offs[i] - (run_dst + run_bytes) < 32 &&
-                                          (int64_t)(contigs[i] - run_src) == (int64_t)(offs[i] - run_dst);
-                    if (adjacent) run_bytes = offs[i] - run_dst + len;
-                    else { flush_run(); run_src = contigs[i]; run_dst = offs[i]; run_bytes = len; }
-                } else {
-                    if (!stage) stage = (char*)ensure_pinned(c, STAGE);
-                    const uint64_t span = align16(len) + 16;
-                    if (used && (used + span > STAGE || stage_dev0 + used != offs[i])) flush();
-                    if (!used) stage_dev0 = offs[i];
-                    std::memcpy(stage + used, contigs[i], len);
-                    used += span;
+        {
+            uint64_t in_chunk = 0, in_sub = 0, done_bytes = 0;
+            uint32_t chunk_c0 = 0;
+            SubBatch cur_sub{0, 0, {}};
+            auto close_chunk = [&](uint32_t contig_end) {
+                cudaEvent_t e = c.pool_event(ranges.size());
+                if (!e) throw Fail{SKB_ERR_CUDA, "cannot create an event"};
+                ranges.push_back(ChunkRange{chunk_c0, contig_end});
+                cur_sub.plan.push_back(ChunkPlan{contig_end, e, nullptr});
+                chunk_c0 = contig_end;
+                in_chunk = 0;
+            };
+            for (uint32_t g = 0; g < n_genomes; g++) {
+                for (uint32_t i = genome_contig_start[g]; i < genome_contig_start[g + 1]; i++) {
+                    const uint64_t len = contig_lens[i];
+                    if (len < SKB_MIN_LENGTH_CONTIG) continue;
+                    in_chunk += len; in_sub += len; done_bytes += len;
+                    if (in_chunk >= CHUNK && i + 1 < genome_contig_start[g + 1]) close_chunk(i + 1);
                 }
-                in_chunk += len; in_sub += len; done_bytes += len;
-                if (in_chunk >= CHUNK && i + 1 < genome_contig_start[g + 1]) close_chunk(i + 1);
-            }
-            const bool last = g + 1 == n_genomes;
-            const bool end_sub = last || (subs.size() < cuts.size() && done_bytes >= cuts[subs.size()]) || in_sub >= SUB_MAX;
-            if (in_chunk >= CHUNK || end_sub) close_chunk(genome_contig_start[g + 1]);
-            if (end_sub) {
-                cur_sub.g1 = g + 1;
-                subs.push_back(std::move(cur_sub));
-                cur_sub = SubBatch{g + 1, g + 1, {}};
-                in_sub = 0;
+                const bool last = g + 1 == n_genomes;
+                const bool end_sub = last || (subs.size() < cuts.size() && done_bytes >= cuts[subs.size()]) || in_sub >= SUB_MAX;
+                if (in_chunk >= CHUNK || end_sub) close_chunk(genome_contig_start[g + 1]);
+                if (end_sub) {
+                    cur_sub.g1 = g + 1;
+                    subs.push_back(std::move(cur_sub));
+                    cur_sub = SubBatch{g + 1, g + 1, {}};
+                    in_sub = 0;
+                }
             }
         }
-        if (tr.on) cudaEventRecord(ev_c1, cs);
-        tr.mark("copies enqueued");
+        // ---- how the bytes travel
+        const char* ingest_env = std::getenv("SKB_INGEST");      // raw | pack | mix (default)
+        const bool want_raw = ingest_env && std::strcmp(ingest_env, "raw") == 0;
+        const unsigned n_threads = want_raw ? 0 : resolve_host_threads(c);
+        const bool pipelined = n_threads >= 2 && ranges.size() >= 2 && (kept_bytes >= INGEST_MIN || ingest_env != nullptr);
         float seed_ms = 0;
-        for (SubBatch& sb : subs) {
-            sketch_core(ctx->core, *params, seed, sb.g1 - sb.g0, genome_contig_start + sb.g0, d_seq, offs.data(), contig_lens,
-                        out + sb.g0, &sb.plan);
-            seed_ms += elapsed(c.ev[1], c.ev[2]);
+        uint64_t link_raw = 0, link_packed = 0;
+        if (!pipelined) {
+            // all copies are enqueued up front by this thread
+            RawCopier rc(c, cs, d_seq, nullptr);
+            for (uint32_t i = 0; i < n_contigs && !rc.stage; i++)
+                if (contig_lens[i] >= SKB_MIN_LENGTH_CONTIG && contig_lens[i] < RawCopier::DIRECT) rc.stage = (char*)ensure_pinned(c, RawCopier::STAGE);
+            size_t ch = 0;
+            for (SubBatch& sb : subs)
+                for (ChunkPlan& cp : sb.plan) {
+                    for (uint32_t i = ranges[ch].c0; i < ranges[ch].c1; i++)
+                        if (contig_lens[i] >= SKB_MIN_LENGTH_CONTIG) rc.add(contigs[i], contig_lens[i], offs[i]);
+                    rc.flush();
+                    CU(cudaEventRecord(cp.ready, cs));
+                    ch++;
+                }
+            link_raw = rc.bytes;
+            if (tr.on) cudaEventRecord(ev_c1, cs);
+            tr.mark("copies enqueued");
+            for (SubBatch& sb : subs) {
+                sketch_core(ctx->core, *params, seed, sb.g1 - sb.g0, genome_contig_start + sb.g0, d_seq, offs.data(), contig_lens,
+                            out + sb.g0, &sb.plan);
+                seed_ms += elapsed(c.ev[1], c.ev[2]);
+            }
+        } else {
+            if (!c.team || c.team->size() != n_threads) {
+                c.team.reset();
+                const int dev = c.device;
+                c.team.reset(new HostTeam(n_threads, [dev] { cudaSetDevice(dev); }));
+            }
+            uint8_t* d_pk = (uint8_t*)c.scratch(SLOT_SEQPK, cur / 4 + 64);
+            if (c.pack_stage_bytes < cur / 4 + 64) {
+                if (c.pack_stage) { CU(cudaStreamSynchronize(cs)); cudaFreeHost(c.pack_stage); c.pack_stage = nullptr; c.pack_stage_bytes = 0; }
+                const size_t want = cur / 4 + cur / 32 + 4096;
+                CU(cudaHostAlloc(&c.pack_stage, want, cudaHostAllocDefault));
+                c.pack_stage_bytes = want;
+            }
+            if (!c.raw_stage) CU(cudaHostAlloc(&c.raw_stage, RawCopier::STAGE, cudaHostAllocDefault));
+            char* stage_raw = (char*)c.raw_stage;
+            CU(cudaEventRecord(c.ev[5], st));
+            CU(cudaStreamWaitEvent(cs, c.ev[5], 0));      // d_pk's allocation is ordered on `st` as well
+            const int policy = ingest_env && std::strcmp(ingest_env, "pack") == 0 ? Ingest::PACK_ONLY : Ingest::MIX;
+            Ingest ing(c, contigs, contig_lens, offs.data(), d_seq, d_pk, (char*)c.pack_stage, stage_raw, policy);
+            ing.chunks.resize(ranges.size());
+            ing.remaining.assign(ranges.size(), 0);
+            {
+                size_t ch = 0;
+                for (SubBatch& sb : subs)
+                    for (ChunkPlan& cp : sb.plan) {
+                        ing.chunks[ch] = Ingest::Chunk{ranges[ch].c0, ranges[ch].c1, cp.ready, 0, false};
+                        const uint32_t id = (uint32_t)ch;
+                        Ingest* pi = &ing;
+                        cp.host_wait = [pi, id] { return pi->wait(id); };
+                        ch++;
+                    }
+            }
+            // the team must have left `ing` before this frame unwinds, whatever happens below
+            struct TeamGuard {
+                Ingest& ing; HostTeam& team; bool finished;
+                ~TeamGuard() { if (!finished) ing.abort.store(true); team.wait(); }
+            };
+            c.team->launch([&ing](unsigned id) { ing.worker(id); });
+            {
+                TeamGuard guard{ing, *c.team, false};
+                tr.mark("ingest team started");
+                for (SubBatch& sb : subs) {
+                    sketch_core(ctx->core, *params, seed, sb.g1 - sb.g0, genome_contig_start + sb.g0, d_seq, offs.data(), contig_lens,
+                                out + sb.g0, &sb.plan, d_pk);
+                    seed_ms += elapsed(c.ev[1], c.ev[2]);
+                }
+                guard.finished = true;                     // every chunk was consumed above: the team is leaving on its own
+            }
+            if (ing.err) throw Fail{ing.err, ing.err_msg};
+            link_raw = ing.raw_bytes; link_packed = ing.packed_bytes;
+            if (tr.on) cudaEventRecord(ev_c1, cs);
+            if (tr.on) std::fprintf(stderr, "[skb] sketch_batch: ingest by %u threads (%s): %.1f MB as ASCII, %.1f MB as 2-bit words (= %.1f MB of bases)\n",
+                                    n_threads, host_pack_isa(), link_raw / 1048576.0, link_packed / 1048576.0, link_packed * 4 / 1048576.0);
         }
         tr.mark("sketch_core done");
         CU(cudaEventRecord(c.ev[4], st));
@@ -905,6 +1160,7 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
             std::fprintf(stderr, "[skb] sketch_batch: copy stream busy %.3f ms, started %.3f ms after the call's first event\n", cms, lead);
             cudaEventDestroy(ev_c0); cudaEventDestroy(ev_c1);
         }
+        c.stats.h2d_raw_bytes = link_raw; c.stats.h2d_packed_bytes = link_packed;
         c.stats.h2d_ms = 0; c.stats.seed_ms = seed_ms;     // seeding launches wait on the copies: this includes PCIe time
         c.stats.total_ms = elapsed(c.ev[0], c.ev[4]); c.stats.index_ms = c.stats.total_ms - seed_ms;
         return SKB_OK;

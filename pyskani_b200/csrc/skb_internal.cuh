@@ -89,6 +89,7 @@ struct SeedScanArgs {
     uint32_t* overflow;          // bit 0: a region was too small; bit 1: the high-word hash comparison let a position through
                                  // that the exact comparison rejects (the host repeats the batch with exact_compare = 1)
     uint32_t exact_compare;      // 0: compare the high words of hash and threshold, re-check hits when they are written
+    uint32_t packed;             // 1: seq holds 2-bit words (contig at byte seq_off / 4) instead of ASCII (contig at byte seq_off)
 };
 
 // region_start[n_regions + 1] = exclusive scan of region_cnt (u64 lanes: seeds | markers << 32)

@@ -131,6 +131,39 @@ def test_host_copies_merged_or_separate_give_the_same_sketch(ctx, monkeypatch):
     assert_sketch_equal(merged[0], oracle.Sketch([x.tobytes() for x in seqs[0:3]]))
 
 
+def test_ingest_routes_give_the_same_sketch(ctx, monkeypatch):
+    """Large host batches reach the device partly as ASCII (copy engine) and partly as 2-bit words compacted by host threads
+    (host_pack.h); which chunk takes which route depends on timing.  Every policy - all ASCII, all compacted, mixed, the
+    pipeline switched off - must give the oracle's sketches bit for bit: ragged genomes, contigs below the 500 bp gate, small
+    contigs that go through staging, junk bytes, lower case, lengths that are not multiples of 16."""
+    monkeypatch.setenv("SKB_CHUNK_KB", "256")            # many chunks out of a few MB
+    junk = bytearray(rand(600_000, 711))
+    junk[1000:1400] = b"N" * 400
+    junk[5000:5003] = b"\n-*"
+    genomes = [[rand(1_200_003, 701)], [rand(70_001, 702), rand(499, 703), rand(9_000, 704).lower(), rand(300_000, 705)],
+               [bytes(junk)], [rand(501, 706)], [rand(2_000_000, 707), rand(333_333, 708)], [rand(40_000, 709)] * 3]
+    want = [oracle.Sketch(g) for g in genomes]
+    seen_packed = seen_raw = False
+    for policy, threads in (("raw", -1), ("pack", 4), ("mix", 3), ("mix", 8), ("pack", 2), ("mix", 1)):
+        monkeypatch.setenv("SKB_INGEST", policy)
+        ctx.set_host_threads(threads)
+        for rep in range(2):
+            got = ctx.sketch_batch(genomes)
+            st = ctx.stats()
+            for g, o in zip(got, want):
+                assert_sketch_equal(g, o)
+            if policy == "pack" and threads >= 2:
+                assert st.h2d_raw_bytes == 0 and st.h2d_packed_bytes > 0
+            if policy == "raw" or threads < 2:
+                assert st.h2d_packed_bytes == 0 and st.h2d_raw_bytes > 0
+            seen_packed |= st.h2d_packed_bytes > 0
+            seen_raw |= st.h2d_raw_bytes > 0
+        (one,) = ctx.sketch_batch(genomes[4:5], c=30, marker_c=200)
+        assert_sketch_equal(one, oracle.Sketch(genomes[4], c=30, marker_c=200))
+    ctx.set_host_threads(-1)
+    assert seen_packed and seen_raw
+
+
 def test_sketch_hash_comparison_variants(ctx, monkeypatch):
     """The seeding kernel compares the high words of hash and threshold and re-checks every hit exactly when it writes it;
     a hit that fails the re-check makes the host repeat the batch with the exact 64-bit comparison.  Forced exact
