@@ -42,6 +42,27 @@ ALG_BYTES_PER_BASE = 1.0 + 16.0 / 125.0 + 8.0 / 1000.0   # 1 B r
 METRIC = "ANI pairs/s, all-vs-all (sketch + exchange + screen + chain + ANI)"
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The driver reads ONE JSON line from stdout.  Libraries loaded later (NCCL's version banner, a warning of the CUDA
+    runtime) write to file descriptor 1 on their own, so the descriptor is pointed at stderr for the whole run and the result
+    line goes through a private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    fd = _JSON_FD if _JSON_FD is not None else 1
+    while data:
+        data = data[os.write(fd, data):]
+
+
 def workload_string(a):
     return ("configs[2]: all-vs-all of %d synthetic %d bp genomes (%d families x %d: root + mutants at 1-15%% divergence, indels)"
             % (a.families * a.members, a.genome_len, a.families, a.members))
@@ -245,7 +266,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ parity gate
@@ -360,6 +381,7 @@ def configs1_block(args, capi, ctx, torch, stream):
 # ------------------------------------------------------------------------------------------------ the B200 arm
 def main():
     args = parse()
+    claim_stdout()
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"          # keeps NCCL's version banner off stdout: rank 0 prints ONE JSON line
     rank = int(os.environ.get("RANK", "0"))
@@ -607,7 +629,7 @@ def main():
             del odb
         if not args.skip_configs1:
             line["configs1"] = configs1_block(args, capi, ctx, torch, stream)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -196,25 +196,34 @@ def sort_hits(table):
     return table[np.argsort(table[:, 0], kind="stable")] if len(table) else table
 
 
+_GATHER_ROWS = {}       # world size -> rows every rank sends per gather (grows when a rank had more)
+
+
 def gather_hits(local_hits, dist, device="cpu", sort=True):
     """hits: (n, 5) float64 rows [query_global, ref_global, ani, af_query, af_ref]; returned on every rank, ordered by
     (query, ref) unless sort=False (then rank after rank; the reference's own hit order is arbitrary, lib.rs:640).
-    Two collectives: the row counts, then the rows padded to the largest count."""
+    ONE collective and one host round trip in the steady state: every rank sends a fixed-capacity block whose first row holds
+    its row count; the capacity is remembered per world size and, if some rank had more rows than fit, all ranks see that in
+    the counts and repeat the collective with a larger capacity (every rank takes the same decision from the same data)."""
     import torch
     world = dist.get_world_size()
     rows = np.ascontiguousarray(np.asarray(local_hits, np.float64).reshape(-1, 5))
-    cnt = torch.tensor([len(rows)], dtype=torch.int64, device=device)
-    counts = torch.empty(world, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(counts, cnt)
-    counts = counts.tolist()
-    m = max(counts + [1])
-    pad = torch.zeros((m, 5), dtype=torch.float64, device=device)
-    if len(rows):
-        pad[:len(rows)] = torch.from_numpy(rows).to(device)
-    allr = torch.empty((world * m, 5), dtype=torch.float64, device=device)
-    dist.all_gather_into_tensor(allr, pad)
-    allr = allr.cpu().numpy().reshape(world, m, 5)
-    allh = np.concatenate([allr[r, :counts[r]] for r in range(world)]) if world else np.zeros((0, 5))
+    cap = _GATHER_ROWS.get(world, 1024)
+    while True:
+        block = np.zeros((cap + 1, 5), np.float64)
+        block[0, 0] = len(rows)
+        k = min(len(rows), cap)
+        block[1:1 + k] = rows[:k]
+        send = torch.from_numpy(block).to(device)
+        allr = torch.empty((world * (cap + 1), 5), dtype=torch.float64, device=device)
+        dist.all_gather_into_tensor(allr, send)
+        allr = allr.cpu().numpy().reshape(world, cap + 1, 5)
+        counts = [int(allr[r, 0, 0]) for r in range(world)]
+        if max(counts) <= cap:
+            break
+        cap = 1 << int(np.ceil(np.log2(max(counts) * 1.25)))
+        _GATHER_ROWS[world] = cap
+    allh = np.concatenate([allr[r, 1:1 + counts[r]] for r in range(world)]) if world else np.zeros((0, 5))
     return sort_hits(allh) if sort else allh
 
 

@@ -73,8 +73,15 @@ def _worker(rank, world, port, q):
     be = OracleBackend()
     be.genomes = genomes
     table = parallel.all_vs_all(genomes, be, dist=dist, device="cpu")
+    # the hit gather with uneven, empty and over-capacity row counts (one collective, repeated when a rank had more rows
+    # than the remembered capacity)
+    gathers = []
+    for n0, n1 in ((5, 0), (0, 0), (3000, 7), (10, 2500)):
+        n = n0 if rank == 0 else n1
+        rows = np.arange(5 * n, dtype=np.float64).reshape(n, 5) + 1e6 * rank
+        gathers.append(parallel.gather_hits(rows, dist, "cpu", sort=False))
     if rank == 0:
-        q.put(table)
+        q.put((table, gathers, dict(parallel._GATHER_ROWS)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -148,10 +155,14 @@ def test_two_ranks_equal_one_rank():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    table = q.get(timeout=180)
+    table, gathers, caps = q.get(timeout=180)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    for (n0, n1), g in zip(((5, 0), (0, 0), (3000, 7), (10, 2500)), gathers):
+        want = np.concatenate([np.arange(5 * n0, dtype=np.float64).reshape(n0, 5), np.arange(5 * n1, dtype=np.float64).reshape(n1, 5) + 1e6])
+        assert g.shape == want.shape and np.array_equal(g, want)
+    assert caps[2] >= 3000
     assert table.shape == single.shape
     assert np.array_equal(table[:, :2], single[:, :2])
     assert np.allclose(table[:, 2:], single[:, 2:], rtol=0, atol=0)
