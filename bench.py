@@ -78,6 +78,8 @@ def parse():
     ap.add_argument("--families", type=int, default=100)
     ap.add_argument("--members", type=int, default=10)
     ap.add_argument("--sketch-batch", type=int, default=250, help="genomes per skb_sketch_batch call")
+    ap.add_argument("--e2e-batch", type=int, default=0, help="genomes per skb_sketch_batch call of the host-buffer run (default: --sketch-batch)")
+    ap.add_argument("--no-pipeline", action="store_true", help="host-buffer run at 1 GPU: query only after every batch is sketched")
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries of the CPU sample (default: about 96, a multiple of the threads)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -427,7 +429,9 @@ def main():
     batches = [(b0, min(n_mine, b0 + args.sketch_batch)) for b0 in range(0, n_mine, args.sketch_batch)]
     params = capi.SketchParams(15, 125, 1000)
     host_ptr_arrays = []
-    for b0, b1 in batches:
+    eb = args.e2e_batch or args.sketch_batch
+    batches_h = [(b0, min(n_mine, b0 + eb)) for b0 in range(0, n_mine, eb)]
+    for b0, b1 in batches_h:
         n = b1 - b0
         host_ptr_arrays.append(((C.c_void_p * n)(*[h_ptr + int(host.offs[j]) for j in range(b0, b1)]),
                                 (C.c_uint64 * n)(*[int(host.lens[j]) for j in range(b0, b1)]),
@@ -444,16 +448,48 @@ def main():
 
     def sketch_host(tm):
         parts, raw, packed = [], 0, 0
-        for (b0, b1), (ptrs, lens, gs) in zip(batches, host_ptr_arrays):
-            out = np.zeros(b1 - b0, np.uint64)
-            ctx.check(L.skb_sketch_batch(ctx._h, C.byref(params), 1, b1 - b0, gs, ptrs, lens, out.ctypes.data))
-            parts.append(capi.SketchArray(ctx, out))
-            st = ctx.stats()
-            raw += st.h2d_raw_bytes; packed += st.h2d_packed_bytes
-        tm["h2d_ascii_bytes"] = float(raw); tm["h2d_packed_bytes"] = float(packed)
+        for part in sketch_host_batches(tm):
+            parts.append(part)
         return capi.SketchArray.concat(ctx, parts)
 
+    def sketch_host_batches(tm):
+        """the host-buffer sketch calls, one batch per iteration"""
+        raw, packed = 0, 0
+        for (b0, b1), (ptrs, lens, gs) in zip(batches_h, host_ptr_arrays):
+            out = np.zeros(b1 - b0, np.uint64)
+            ctx.check(L.skb_sketch_batch(ctx._h, C.byref(params), 1, b1 - b0, gs, ptrs, lens, out.ctypes.data))
+            st = ctx.stats()
+            raw += st.h2d_raw_bytes; packed += st.h2d_packed_bytes
+            tm["h2d_ascii_bytes"] = float(raw); tm["h2d_packed_bytes"] = float(packed)
+            yield capi.SketchArray(ctx, out)
+
+    # one GPU, host buffers: the queries of a batch run on a second context of the same device while the next batch is
+    # still crossing PCIe (parallel.all_vs_all_pipelined); with several ranks the exchange comes first
+    pipelined = world == 1 and not args.no_pipeline and len(batches_h) > 1
+    backend_q = parallel.CudaBackend(local_rank, ctx=capi.Context(local_rank)) if pipelined else None
+    if os.environ.get("BENCH_TEAM"):
+        ctx.set_host_threads(int(os.environ["BENCH_TEAM"]))      # tuning hook: threads of the ingest team
+    elif pipelined:
+        # the query thread spins on its own waits: one CPU less for the ingest team (measured: 16 -> 15 threads, -4 ms)
+        ctx.set_host_threads(max(2, min(32, len(os.sched_getaffinity(0))) - 1))
+    if pipelined and not os.environ.get("BENCH_NO_PRIORITY"):
+        ctx.set_priority(True)          # seeding / index kernels go ahead of the query context's
+        stream = torch.cuda.ExternalStream(ctx.stream, device=device)
+
+    def step_pipelined(_unused):
+        tm = {}
+        t0 = time.perf_counter()
+        table = parallel.all_vs_all_pipelined(sketch_host_batches(tm), backend_q, timings=tm, sort=False)
+        if len(table):
+            ids = np.asarray(mine, np.float64)
+            table[:, 0] = ids[table[:, 0].astype(np.int64)]
+            table[:, 1] = ids[table[:, 1].astype(np.int64)]
+        tm["step_wall_ms"] = 1e3 * (time.perf_counter() - t0)
+        return table, tm
+
     def step(sketch_fn):
+        if sketch_fn is sketch_host and pipelined:
+            return step_pipelined(None)
         tm = {}
         t0 = time.perf_counter()
         sk = sketch_fn(tm)
@@ -586,6 +622,10 @@ def main():
                     "d2h_bytes_per_step": int(len(table)) * C.sizeof(capi.Hit), "ms_per_step": e2e_ms,
                     "phase_ms": {k: round(v, 4) for k, v in ph_h.items() if k.endswith("_ms")},
                     "host_input_bytes_per_step": total_bases,
+                    "sketch_batch": eb,
+                    "pipeline": ("queries of a sketched batch (new batch x database so far, both directions) run on a second context "
+                                 "of the same device under the ingest of the next batch; phase_ms.query_ms is what was left after "
+                                 "the last batch") if pipelined else "sketch all, then query",
                     "ingest": {"h2d_ascii_bytes": int(ph_h["h2d_ascii_bytes"]), "h2d_packed_bytes": int(ph_h["h2d_packed_bytes"]),
                                "bases_sent_packed": int(4 * ph_h["h2d_packed_bytes"]),
                                "note": "skb_sketch_batch moves large host batches two ways at once: the copy engine pulls chunks of "

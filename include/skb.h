@@ -11,7 +11,10 @@
  * by the caller and released with the matching *_free / *_destroy; hit arrays are library-allocated
  * and released with skb_hits_free.
  * Threading: a context serialises its own calls with an internal mutex (the reference guards its
- * state with RwLocks, lib.rs:135-136).  Use one context per GPU.
+ * state with RwLocks, lib.rs:135-136).  One context per GPU is the normal arrangement.  Two contexts on the SAME device run
+ * concurrently (own stream, own scratch): a database of one may hold, and be queried with, finished sketches of the other,
+ * which is how an all-vs-all hides its queries under the host->device ingest of the next sketch batch
+ * (pyskani_b200/parallel.py: all_vs_all_pipelined).
  */
 #ifndef SKB_H
 #define SKB_H
@@ -95,6 +98,12 @@ void* skb_ctx_stream(skb_ctx_t* ctx);
  * and produces bit-identical sketches.  n = 0 or 1: every byte travels as ASCII; n < 0: default = SKB_HOST_THREADS, else
  * min(32, usable CPUs / LOCAL_WORLD_SIZE).  SKB_INGEST=raw|pack|mix overrides the policy (test hook). */
 int  skb_ctx_set_host_threads(skb_ctx_t* ctx, int32_t n);
+/* Two contexts sharing one device (a pipelined all-vs-all sketches on one and queries on the other, each fed by its own
+ * host thread): high != 0 gives the context's compute streams the HIGHEST scheduling priority of the device, so its kernels
+ * do not queue behind the other context's (0: back to the default, the lowest).  Call it between, not during, other calls;
+ * skb_ctx_stream() changes.  (Sleeping instead of spinning waits were measured for either side and cost more than the CPU
+ * they free: DESIGN.md section 7.) */
+int  skb_ctx_set_priority(skb_ctx_t* ctx, int32_t high);
 
 /* pinned host staging memory (so that callers can keep inputs where an async H2D copy can reach them) */
 int  skb_host_alloc(skb_ctx_t* ctx, size_t bytes, void** out);

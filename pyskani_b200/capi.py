@@ -50,7 +50,7 @@ class Stats(C.Structure):
 # every symbol include/skb.h declares (tests/test_abi.py checks the library exports all of them)
 SYMBOLS = [
     "skb_ctx_create", "skb_ctx_destroy", "skb_last_error", "skb_ctx_stats", "skb_ctx_sync", "skb_ctx_stream",
-    "skb_ctx_set_host_threads",
+    "skb_ctx_set_host_threads", "skb_ctx_set_priority",
     "skb_host_alloc", "skb_host_free", "skb_dev_alloc", "skb_dev_free", "skb_memcpy_h2d",
     "skb_sketch_batch", "skb_sketch_batch_device", "skb_sketch_free", "skb_sketch_free_many", "skb_sketch_info", "skb_sketch_export",
     "skb_sketch_import", "skb_sketch_pack_size", "skb_sketch_pack", "skb_sketch_unpack",
@@ -96,6 +96,7 @@ def lib():
         L.skb_ctx_stream.restype = vp
         L.skb_ctx_stream.argtypes = [vp]
         L.skb_ctx_set_host_threads.argtypes = [vp, i32]
+        L.skb_ctx_set_priority.argtypes = [vp, i32]
         L.skb_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
         L.skb_host_free.argtypes = [vp, vp]
         L.skb_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
@@ -175,6 +176,10 @@ class Context:
     @property
     def stream(self):
         return lib().skb_ctx_stream(self._h)
+
+    def set_priority(self, high=True):
+        """Highest stream priority for this context's kernels: those of other contexts of the device only fill its gaps."""
+        self.check(lib().skb_ctx_set_priority(self._h, 1 if high else 0))
 
     def set_host_threads(self, n):
         """Threads of the host ingest pipeline of sketch calls on host buffers (0/1: all bytes travel as ASCII; < 0: default)."""

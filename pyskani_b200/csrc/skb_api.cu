@@ -44,6 +44,8 @@ using SlabPool = SlabPoolT<CudaRawAlloc, CudaRawFree>;
 struct Core {
     int device = 0;
     SlabPool slabs;
+    std::mutex slab_mu;       // sketches may be released by a thread that works on ANOTHER context of the same device (a
+                              // database there holds the last reference): the pool has its own lock
     int n_sm = 148;
     cudaStream_t stream = nullptr;
     std::mutex mu;
@@ -156,6 +158,7 @@ struct DevMem {
         DevMem m;
         m.bytes = n; m.core = c;
         if (n) {
+            std::lock_guard<std::mutex> lk(c->slab_mu);
             m.p = c->slabs.alloc(n, &m.slab);
             if (!m.p) throw Fail{SKB_ERR_NOMEM, "out of device memory for sketch storage"};
         }
@@ -170,7 +173,7 @@ struct DevMem {
     }
     void release() {
         if (p && core) {
-            if (slab) core->slabs.free(slab, p, bytes);
+            if (slab) { std::lock_guard<std::mutex> lk(core->slab_mu); core->slabs.free(slab, p, bytes); }
             else { cudaSetDevice(core->device); cudaFreeAsync(p, core->stream); }
         }
         p = nullptr; bytes = 0; slab = nullptr;
@@ -938,6 +941,22 @@ int skb_ctx_sync(skb_ctx_t* ctx) {
     return guarded(ctx->core.get(), [&] { CU(cudaStreamSynchronize(ctx->core->stream)); return SKB_OK; });
 }
 void* skb_ctx_stream(skb_ctx_t* ctx) { return ctx ? (void*)ctx->core->stream : nullptr; }
+int skb_ctx_set_priority(skb_ctx_t* ctx, int32_t high) {
+    if (!ctx) return SKB_ERR_ARG;
+    return guarded(ctx->core.get(), [&] {
+        Core& c = *ctx->core;
+        int least = 0, greatest = 0;              // numerically lower = higher priority; streams are created with `least`
+        CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        for (cudaStream_t* sp : {&c.stream, &c.aux_stream}) {
+            CU(cudaStreamSynchronize(*sp));
+            cudaStream_t fresh = nullptr;
+            CU(cudaStreamCreateWithPriority(&fresh, cudaStreamNonBlocking, high ? greatest : least));
+            cudaStreamDestroy(*sp);
+            *sp = fresh;
+        }
+        return SKB_OK;
+    });
+}
 int skb_ctx_set_host_threads(skb_ctx_t* ctx, int32_t n) {
     if (!ctx) return SKB_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->core->mu);
@@ -1303,7 +1322,7 @@ void skb_db_destroy(skb_db_t* db) {
 int skb_db_add(skb_db_t* db, skb_sketch_t* s, uint32_t* index_out) {
     if (!db || !s) return SKB_ERR_ARG;
     return guarded(db->core.get(), [&] {
-        if (s->impl->core != db->core) throw Fail{SKB_ERR_ARG, "sketch belongs to another context"};
+        if (s->impl->core->device != db->core->device) throw Fail{SKB_ERR_ARG, "sketch belongs to a context of another device"};
         if (!db->items.empty()) {
             const auto& a = db->items[0]->info; const auto& b = s->impl->info;
             if (a.k != b.k || a.c != b.c || a.marker_c != b.marker_c) throw Fail{SKB_ERR_ARG, "sketch parameters differ from the database's"};
@@ -1319,7 +1338,7 @@ int skb_db_add_many(skb_db_t* db, uint32_t n, skb_sketch_t* const* sketches, uin
     return guarded(db->core.get(), [&] {
         for (uint32_t i = 0; i < n; i++) {
             if (!sketches[i]) throw Fail{SKB_ERR_ARG, "null sketch"};
-            if (sketches[i]->impl->core != db->core) throw Fail{SKB_ERR_ARG, "sketch belongs to another context"};
+            if (sketches[i]->impl->core->device != db->core->device) throw Fail{SKB_ERR_ARG, "sketch belongs to a context of another device"};
             const auto& a0 = db->items.empty() ? sketches[0]->impl->info : db->items[0]->info;
             const auto& b0 = sketches[i]->impl->info;
             if (a0.k != b0.k || a0.c != b0.c || a0.marker_c != b0.marker_c) throw Fail{SKB_ERR_ARG, "sketch parameters differ from the database's"};
@@ -1334,7 +1353,7 @@ int skb_db_replace(skb_db_t* db, uint32_t index, skb_sketch_t* s) {
     if (!db || !s) return SKB_ERR_ARG;
     return guarded(db->core.get(), [&] {
         if (index >= db->items.size()) throw Fail{SKB_ERR_KEY, "no sketch at this index"};
-        if (s->impl->core != db->core) throw Fail{SKB_ERR_ARG, "sketch belongs to another context"};
+        if (s->impl->core->device != db->core->device) throw Fail{SKB_ERR_ARG, "sketch belongs to a context of another device"};
         const auto& a = db->items[0]->info; const auto& b = s->impl->info;
         if (db->items.size() > 1 && (a.k != b.k || a.c != b.c || a.marker_c != b.marker_c)) throw Fail{SKB_ERR_ARG, "sketch parameters differ from the database's"};
         CU(cudaStreamSynchronize(db->core->stream));     // nothing in flight may still read the old sketch's arrays
@@ -1854,7 +1873,7 @@ int skb_db_screen(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries
         std::vector<GenomeView> hv;
         for (uint32_t i = 0; i < n_queries; i++) {
             if (!queries[i]) throw Fail{SKB_ERR_ARG, "null query sketch"};
-            if (queries[i]->impl->core != db->core) throw Fail{SKB_ERR_ARG, "query sketch belongs to another context"};
+            if (queries[i]->impl->core->device != db->core->device) throw Fail{SKB_ERR_ARG, "query sketch belongs to a context of another device"};
             qs.push_back(queries[i]->impl); hv.push_back(queries[i]->impl->view);
         }
         DevMem d_q(db->core, sizeof(GenomeView) * std::max<uint32_t>(n_queries, 1));
@@ -1883,7 +1902,7 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
         std::vector<GenomeView> hv;
         for (uint32_t i = 0; i < n_queries; i++) {
             if (!queries[i]) throw Fail{SKB_ERR_ARG, "null query sketch"};
-            if (queries[i]->impl->core != db->core) throw Fail{SKB_ERR_ARG, "query sketch belongs to another context"};
+            if (queries[i]->impl->core->device != db->core->device) throw Fail{SKB_ERR_ARG, "query sketch belongs to a context of another device"};
             const auto& qi = queries[i]->impl->info;
             if (qi.k != dbi.k || qi.c != dbi.c || qi.marker_c != dbi.marker_c) throw Fail{SKB_ERR_ARG, "query sketch parameters differ from the database's"};
             if (queries[i]->impl->ref_only) throw Fail{SKB_ERR_ARG, "this sketch was transferred as a reference only (no position-order seeds): it cannot be a query"};

@@ -340,3 +340,77 @@ def all_vs_all(genomes, backend, dist=None, device="cpu", sketch_params=None, qu
     mine = plan[rank]
     local = backend.sketch([genomes[i] for i in mine], **sketch_params)
     return query_and_gather(backend, local, mine, plan, dist, device, query_opts, timings, import_params=sketch_params)
+
+
+def all_vs_all_pipelined(sketch_batches, query_backend, query_opts=None, timings=None, sort=True):
+    """Single-GPU all-vs-all whose queries run UNDER the host->device ingest of the following sketch batches.
+
+    sketch_batches: an iterable that yields the sketches of one batch after the other (capi.SketchArray or lists of Sketch;
+    typically a generator whose body calls skb_sketch_batch on host buffers through the SKETCHING context - the caller's
+    thread is inside that call, with the GIL released, most of the time).  query_backend: a CudaBackend on a SECOND context
+    of the same device (own stream, own scratch), so that its kernels fill the gaps the GPU has while PCIe and the host's
+    compaction threads set the pace.  A pair (i, j) is computable as soon as both genomes are sketched; when batch k arrives
+    a worker thread runs
+        queries = batches 0..k-1, database = batch k        and        queries = batch k, database = batches 0..k
+    which covers every ordered pair exactly once.  Only the two calls of the LAST batch are exposed after the ingest ends.
+    Returns the (n, 5) table [query, ref, ani, af_query, af_ref] with global indices in arrival order of the genomes
+    (ordered by (query, ref) unless sort=False)."""
+    import queue
+    import threading
+    query_opts = dict(query_opts or {})
+    arr = query_backend.capi.SketchArray
+    q = queue.Queue()
+    rows, err = [], []
+    stats = {}
+
+    def work():
+        try:
+            done, base = [], 0
+            while True:
+                part = q.get()
+                if part is None:
+                    return
+                part = arr.of(query_backend.ctx, part)
+                n = len(part)
+                if n == 0:
+                    continue
+                if done:
+                    old = arr.concat(query_backend.ctx, done)
+                    h = np.asarray(query_backend.query(part, old, stats=stats, **query_opts), np.float64).reshape(-1, 5)
+                    if len(h):
+                        h[:, 1] += base
+                        rows.append(h)
+                done.append(part)
+                full = arr.concat(query_backend.ctx, done)
+                h = np.asarray(query_backend.query(full, part, stats=stats, **query_opts), np.float64).reshape(-1, 5)
+                if len(h):
+                    h[:, 0] += base
+                    rows.append(h)
+                base += n
+        except BaseException as e:          # surfaced on the caller's thread
+            err.append(e)
+
+    t = threading.Thread(target=work, name="skb-query")
+    t.start()
+    t0 = time.perf_counter()
+    try:
+        for part in sketch_batches:
+            q.put(part)
+            if err:
+                break
+    finally:
+        t1 = time.perf_counter()
+        q.put(None)
+        t.join()
+    t2 = time.perf_counter()
+    if err:
+        raise err[0]
+    table = np.concatenate(rows) if rows else np.zeros((0, 5))
+    if timings is not None:
+        timings.update(stats)
+        timings["sketch_ms"] = 1e3 * (t1 - t0)          # the ingest-bound part; queries of earlier batches ran under it
+        timings["query_ms"] = 1e3 * (t2 - t1)           # what was left of the queries once the last batch was sketched
+        timings["exchange_ms"] = 0.0
+        timings["gather_ms"] = 0.0
+        timings["local_hits"] = int(len(table))
+    return sort_hits(table) if sort else table

@@ -129,6 +129,37 @@ def _nccl_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def test_pipelined_all_vs_all_equals_the_plain_one():
+    """parallel.all_vs_all_pipelined: sketch batches arrive one after the other on one context while a worker thread queries
+    them on a SECOND context of the same device (new batch x database so far, both directions).  The table must equal the
+    plain all-vs-all of the same genomes, for several batch splits (incl. an empty batch and a single one), and sketches of
+    one context must be usable in a database of the other."""
+    from pyskani_b200 import capi, parallel
+    ctx_s, ctx_q = capi.Context(0), capi.Context(0)
+    genomes = small_genomes(n_fam=5)
+    gs = ctx_s.sketch_batch(genomes)
+    db = capi.Database(ctx_s)
+    db.add_many(gs)
+    h, _ = db.query_array(gs)
+    want = np.zeros((len(h), 5))
+    want[:, 0] = h["query_index"]; want[:, 1] = h["ref_index"]; want[:, 2] = h["ani"]; want[:, 3] = h["af_query"]; want[:, 4] = h["af_ref"]
+    want = parallel.sort_hits(want)
+    assert len(want) >= 5 * 16
+    bq = parallel.CudaBackend(0, ctx=ctx_q)
+    for cuts in ([0, 7, 12, len(genomes)], [0, len(genomes)], [0, 1, 1, 9, len(genomes)], [0, 3, 6, 9, 12, 15, 18, len(genomes)]):
+        def batches():
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                yield ctx_s.sketch_batch(genomes[a:b])          # sketched while the worker queries the earlier ones
+        tm = {}
+        got = parallel.all_vs_all_pipelined(batches(), bq, timings=tm)
+        assert got.shape == want.shape and np.array_equal(got, want), cuts
+        assert tm["local_hits"] == len(want) and tm["screened_in"] >= len(want)
+    # an error on the worker thread reaches the caller
+    other = ctx_s.sketch_batch(genomes[:2], c=30)
+    with pytest.raises(capi.SkbError):
+        parallel.all_vs_all_pipelined(iter([gs[:3], other]), bq)
+
+
 def test_two_gpu_all_vs_all_equals_single_gpu():
     """The north-star split over NCCL: partition, sketch, exchange (pack + all-gather into the block + adopt), query own
     slice, gather hits.  The 2-GPU hit table must equal the single-GPU table bit for bit."""
