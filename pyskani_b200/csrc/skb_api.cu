@@ -749,7 +749,16 @@ static unsigned resolve_host_threads(const Core& c) {
     if (const char* e = std::getenv("SKB_HOST_THREADS")) return (unsigned)std::max(0, std::atoi(e));
     unsigned cpus = host_cpu_count();
     // one process per GPU sharing the host's cores (torchrun exports LOCAL_WORLD_SIZE)
-    if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) { const int w = std::atoi(e); if (w > 1) cpus = std::max(1u, cpus / (unsigned)w); }
+    if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) {
+        const int w = std::atoi(e);
+        if (w > 1) {
+            cpus = std::max(1u, cpus / (unsigned)w);
+            // eight ranks on a 32-CPU host: 3 packing threads per rank beside 8 spinning callers and NCCL's proxies packed 5 % of
+            // the bytes and cost 4 % of the step (33.6 against 31.7 ms, gpurun_out/r2g_bench_n8*.json): below 8 CPUs per rank
+            // every byte travels as ASCII
+            if (cpus < 8) return 0;
+        }
+    }
     // the calling thread spins in its stream synchronisations and the feeding thread sleeps in its event waits: one
     // feeder + (cpus - 1) packing threads keep every core busy
     return std::min(32u, cpus);
