@@ -157,7 +157,7 @@ class Context:
         if self._h:
             try:
                 lib().skb_ctx_destroy(self._h)
-            except TypeError:      # interpreter shutdown: module globals are already gone
+            except (TypeError, ImportError, AttributeError):    # interpreter shutdown: the library may already be gone      # interpreter shutdown: module globals are already gone
                 pass
             self._h = None
 
@@ -308,7 +308,7 @@ class Model:
         if getattr(self, "_h", None):
             try:
                 lib().skb_model_free(self._h)
-            except TypeError:
+            except (TypeError, ImportError, AttributeError):    # interpreter shutdown: the library may already be gone
                 pass
             self._h = None
 
@@ -352,7 +352,7 @@ class Exchange:
         if getattr(self, "_h", None):
             try:
                 lib().skb_exchange_free(self._h)
-            except TypeError:
+            except (TypeError, ImportError, AttributeError):    # interpreter shutdown: the library may already be gone
                 pass
             self._h = None
 
@@ -368,7 +368,7 @@ class Sketch:
         if getattr(self, "_h", None) and self._owner is None:
             try:
                 lib().skb_sketch_free(self._h)
-            except TypeError:
+            except (TypeError, ImportError, AttributeError):    # interpreter shutdown: the library may already be gone
                 pass
         self._h = None
 
@@ -440,7 +440,7 @@ class SketchArray:
         if getattr(self, "_parents", 0) is None and len(self.handles):
             try:
                 lib().skb_sketch_free_many(len(self.handles), self.handles.ctypes.data)
-            except TypeError:
+            except (TypeError, ImportError, AttributeError):    # interpreter shutdown: the library may already be gone
                 pass
         self.handles = np.zeros(0, np.uint64)
 
@@ -456,7 +456,7 @@ class Database:
         if getattr(self, "_h", None):
             try:
                 lib().skb_db_destroy(self._h)
-            except TypeError:
+            except (TypeError, ImportError, AttributeError):    # interpreter shutdown: the library may already be gone
                 pass
             self._h = None
 

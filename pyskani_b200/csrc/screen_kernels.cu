@@ -10,9 +10,11 @@
 //     postings; a CTA looks a query's markers up once and counts per reference in shared memory.
 // The pass/fail decision (count > screen_val^21 * |smaller|, or the small-genome rescue) is a second tiny kernel so that
 // the comparison is one IEEE multiply + compare, identical to the oracle's.
+#include <algorithm>
 #include <cstdlib>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include "skb_internal.cuh"
 
 namespace skb {
@@ -297,16 +299,21 @@ __global__ void __launch_bounds__(JOIN_THREADS) marker_join_kernel(const GenomeV
                                                                     const uint32_t* __restrict__ vals,
                                                                     const uint32_t* __restrict__ bucket, uint32_t shift,
                                                                     uint32_t n_refs, uint32_t tile, uint32_t* __restrict__ count) {
+    // gridDim.z > 1: the query's markers are divided among that many CTAs (few queries would otherwise leave most SMs
+    // without a CTA, and a CTA's 5 000 dependent lookups take as long whether 125 or 1 000 of them run); the partial counts
+    // are then ADDED to the zeroed matrix
     extern __shared__ uint32_t s_cnt[];
     const uint32_t t0 = blockIdx.x * tile, tn = min(tile, n_refs - t0);
     const GenomeView& Q = queries[blockIdx.y];
     for (uint32_t i = threadIdx.x; i < tn; i += JOIN_THREADS) s_cnt[i] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const uint32_t nm = Q.n_markers;
+    const uint32_t m_all = Q.n_markers;
+    const uint32_t per = ((m_all + gridDim.z - 1) / gridDim.z + 31u) & ~31u;         // markers of this CTA's part
+    const uint32_t m0 = min(m_all, blockIdx.z * per), nm = min(m_all, m0 + per);
     // a warp takes 32 consecutive query markers: every lane finds its own first posting, then the warp walks the
     // posting run of each marker that has one with coalesced loads
-    for (uint32_t base = (threadIdx.x >> 5) * 32; base < nm; base += JOIN_THREADS) {
+    for (uint32_t base = m0 + (threadIdx.x >> 5) * 32; base < nm; base += JOIN_THREADS) {
         const uint32_t i = base + (uint32_t)lane;
         uint64_t m = ~0ull; uint32_t lo = 0, hi = 0;
         if (i < nm) {
@@ -337,34 +344,99 @@ __global__ void __launch_bounds__(JOIN_THREADS) marker_join_kernel(const GenomeV
     }
     __syncthreads();
     uint32_t* row = count + (size_t)blockIdx.y * n_refs + t0;
-    for (uint32_t i = threadIdx.x; i < tn; i += JOIN_THREADS) row[i] = s_cnt[i];
+    if (gridDim.z == 1) {
+        for (uint32_t i = threadIdx.x; i < tn; i += JOIN_THREADS) row[i] = s_cnt[i];
+    } else {
+        for (uint32_t i = threadIdx.x; i < tn; i += JOIN_THREADS) if (s_cnt[i]) atomicAdd(&row[i], s_cnt[i]);
+    }
 }
 
 }  // namespace
 
-size_t marker_index_scratch_bytes(uint32_t n_postings) {
-    size_t sort_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
-                                    (uint32_t*)nullptr, (int)n_postings, 0, MARKER_BITS);
-    return (((size_t)n_postings * 8 + 255) & ~(size_t)255) + (((size_t)n_postings * 4 + 255) & ~(size_t)255) + sort_bytes + 256;
+constexpr uint32_t MIDX_BUCKET_CAP = 96;      // largest bucket the partition path ranks by comparison
+
+namespace {
+
+// ---- index build by bucket partition (round 2): histogram of the top bits -> scan (= the bucket table) -> scatter with a
+// cursor per bucket -> every posting ranks itself inside its bucket by (marker, genome).  The result is the array a stable
+// radix sort by marker produces (postings are generated genome after genome), at a third of its cost: the sort makes six
+// passes over 12 bytes per posting, and at 5 M postings each pass is latency-, not bandwidth-bound.
+__global__ void marker_hist_kernel(const GenomeView* __restrict__ refs, uint32_t shift, uint32_t* __restrict__ cnt) {
+    const GenomeView& R = refs[blockIdx.x];
+    for (uint32_t i = threadIdx.x; i < R.n_markers; i += blockDim.x) atomicAdd(&cnt[(uint32_t)(R.markers[i] >> shift)], 1u);
+}
+__global__ void marker_scatter_kernel(const GenomeView* __restrict__ refs, uint32_t shift, const uint32_t* __restrict__ bucket,
+                                      uint32_t* __restrict__ cursor, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t g = blockIdx.x;
+    const GenomeView& R = refs[g];
+    for (uint32_t i = threadIdx.x; i < R.n_markers; i += blockDim.x) {
+        const uint64_t m = R.markers[i];
+        const uint32_t b = (uint32_t)(m >> shift);
+        const uint32_t slot = bucket[b] + atomicAdd(&cursor[b], 1u);
+        keys[slot] = m; vals[slot] = g;
+    }
+}
+__global__ void marker_rank_kernel(uint32_t n, const uint64_t* __restrict__ k_in, const uint32_t* __restrict__ v_in,
+                                   const uint32_t* __restrict__ bucket, uint32_t shift, uint64_t* __restrict__ keys,
+                                   uint32_t* __restrict__ vals, uint32_t* __restrict__ overflow) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t k = k_in[j];
+    const uint32_t v = v_in[j];
+    const uint32_t b = (uint32_t)(k >> shift);
+    const uint32_t lo = __ldg(bucket + b), hi = __ldg(bucket + b + 1);
+    if (hi - lo > MIDX_BUCKET_CAP) { *overflow = 1u; return; }          // the host falls back to the radix sort
+    uint32_t rank = 0;
+    for (uint32_t t = lo; t < hi; t++) {
+        const uint64_t kt = k_in[t];
+        rank += (kt < k || (kt == k && v_in[t] < v)) ? 1u : 0u;
+    }
+    keys[lo + rank] = k; vals[lo + rank] = v;
 }
 
+}  // namespace
+
+size_t marker_index_scratch_bytes(uint32_t n_postings, uint32_t n_buckets) {
+    size_t sort_bytes = 0, scan_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)n_postings, 0, MARKER_BITS);
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_buckets + 1);
+    return (((size_t)n_postings * 8 + 255) & ~(size_t)255) + (((size_t)n_postings * 4 + 255) & ~(size_t)255) +
+           2 * (((size_t)n_buckets * 4 + 8 + 255) & ~(size_t)255) + 256 + std::max(sort_bytes, scan_bytes) + 256;
+}
+
+// overflow (device, 4 bytes): set when a bucket was too large for the partition path; the caller then calls again with
+// use_sort = true.  Everything is asynchronous on `st`.
 void build_marker_index(const GenomeView* refs, uint32_t n_refs, const uint32_t* genome_off, uint32_t n_postings,
                         uint64_t* keys, uint32_t* vals, uint32_t* bucket, uint32_t shift, uint32_t n_buckets,
-                        void* scratch, size_t scratch_bytes, cudaStream_t st) {
+                        void* scratch, size_t scratch_bytes, bool use_sort, uint32_t* overflow, cudaStream_t st) {
     if (n_refs == 0) return;
     char* p = (char*)scratch;
     uint64_t* k_in = (uint64_t*)p; p += ((size_t)n_postings * 8 + 255) & ~(size_t)255;
     uint32_t* v_in = (uint32_t*)p; p += ((size_t)n_postings * 4 + 255) & ~(size_t)255;
-    size_t sort_bytes = scratch_bytes - (size_t)(p - (char*)scratch);
-    marker_postings_kernel<<<n_refs, 256, 0, st>>>(refs, genome_off, k_in, v_in);
-    g_kernel_launches++;
-    if (n_postings) {
-        cub::DeviceRadixSort::SortPairs(p, sort_bytes, k_in, keys, v_in, vals, (int)n_postings, 0, MARKER_BITS, st);
-        g_kernel_launches += 2 * ((MARKER_BITS + 7) / 8);
+    uint32_t* cnt = (uint32_t*)p; p += ((size_t)n_buckets * 4 + 8 + 255) & ~(size_t)255;
+    uint32_t* cursor = (uint32_t*)p; p += ((size_t)n_buckets * 4 + 8 + 255) & ~(size_t)255;
+    p += 256;
+    size_t tmp_bytes = scratch_bytes - (size_t)(p - (char*)scratch);
+    if (use_sort) {
+        marker_postings_kernel<<<n_refs, 256, 0, st>>>(refs, genome_off, k_in, v_in);
+        g_kernel_launches++;
+        if (n_postings) {
+            cub::DeviceRadixSort::SortPairs(p, tmp_bytes, k_in, keys, v_in, vals, (int)n_postings, 0, MARKER_BITS, st);
+            g_kernel_launches += 2 * ((MARKER_BITS + 7) / 8);
+        }
+        marker_index_buckets_kernel<<<(n_buckets + 1 + 255) / 256, 256, 0, st>>>(keys, n_postings, shift, n_buckets, bucket);
+        g_kernel_launches++;
+        return;
     }
-    marker_index_buckets_kernel<<<(n_buckets + 1 + 255) / 256, 256, 0, st>>>(keys, n_postings, shift, n_buckets, bucket);
-    g_kernel_launches++;
+    cudaMemsetAsync(cnt, 0, 4 * ((size_t)n_buckets + 1), st);
+    cudaMemsetAsync(cursor, 0, 4 * ((size_t)n_buckets + 1), st);
+    cudaMemsetAsync(overflow, 0, 4, st);
+    marker_hist_kernel<<<n_refs, 256, 0, st>>>(refs, shift, cnt);
+    cub::DeviceScan::ExclusiveSum(p, tmp_bytes, cnt, bucket, (int)n_buckets + 1, st);
+    marker_scatter_kernel<<<n_refs, 256, 0, st>>>(refs, shift, bucket, cursor, k_in, v_in);
+    if (n_postings) marker_rank_kernel<<<(n_postings + 255) / 256, 256, 0, st>>>(n_postings, k_in, v_in, bucket, shift, keys, vals, overflow);
+    g_kernel_launches += 5;
 }
 
 void launch_marker_join(const GenomeView* queries, uint32_t n_queries, uint32_t n_refs, const uint64_t* keys,
@@ -373,7 +445,12 @@ void launch_marker_join(const GenomeView* queries, uint32_t n_queries, uint32_t 
     const uint32_t tile = n_refs < 32768u ? n_refs : 32768u;
     const size_t smem = (size_t)tile * 4;
     cudaFuncSetAttribute(marker_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4);   // per launch: the attribute belongs to the current device
-    dim3 grid((n_refs + tile - 1) / tile, n_queries);
+    const uint32_t tiles = (n_refs + tile - 1) / tile;
+    // at least ~4 CTAs per SM: split the markers of each query when there are few queries
+    uint32_t splits = 1;
+    if ((uint64_t)tiles * n_queries < 592) splits = (uint32_t)std::min<uint64_t>(16, (592 + (uint64_t)tiles * n_queries - 1) / ((uint64_t)tiles * n_queries));
+    if (splits > 1) cudaMemsetAsync(count, 0, sizeof(uint32_t) * (size_t)n_queries * n_refs, st);
+    dim3 grid(tiles, n_queries, splits);
     marker_join_kernel<<<grid, JOIN_THREADS, smem, st>>>(queries, keys, vals, bucket, shift, n_refs, tile, count);
     g_kernel_launches++;
 }

@@ -1808,12 +1808,21 @@ bool db_marker_index(skb_db& db, const GenomeView* d_r) {
     db.idx_vals = DevMem::persistent(db.core, 4 * total);
     db.idx_bucket = DevMem::persistent(db.core, 4 * ((size_t)nb + 1));
     const size_t off_bytes = (4 * ((size_t)nr + 1) + 255) & ~(size_t)255;
-    const size_t scr_bytes = marker_index_scratch_bytes((uint32_t)total);
-    char* scr = (char*)c.scratch(SLOT_MIDX, off_bytes + scr_bytes);
+    const size_t scr_bytes = marker_index_scratch_bytes((uint32_t)total, nb);
+    char* scr = (char*)c.scratch(SLOT_MIDX, off_bytes + 256 + scr_bytes);
+    uint32_t* d_over = (uint32_t*)(scr + off_bytes);
     CU(cudaMemcpyAsync(scr, off.data(), 4 * ((size_t)nr + 1), cudaMemcpyHostToDevice, c.stream));
-    build_marker_index(d_r, nr, (const uint32_t*)scr, (uint32_t)total, db.idx_keys.as<uint64_t>(), db.idx_vals.as<uint32_t>(),
-                       db.idx_bucket.as<uint32_t>(), db.idx_shift, nb, scr + off_bytes, scr_bytes, c.stream);
-    CU(cudaStreamSynchronize(c.stream));      // `off` is pageable host memory
+    // bucket partition first; a bucket beyond its capacity (many genomes sharing the same markers) falls back to the sort
+    bool use_sort = std::getenv("SKB_MIDX_SORT") != nullptr;       // test hook
+    for (int attempt = 0; attempt < 2; attempt++) {
+        build_marker_index(d_r, nr, (const uint32_t*)scr, (uint32_t)total, db.idx_keys.as<uint64_t>(), db.idx_vals.as<uint32_t>(),
+                           db.idx_bucket.as<uint32_t>(), db.idx_shift, nb, scr + off_bytes + 256, scr_bytes, use_sort, d_over, c.stream);
+        uint32_t over = 0;
+        if (!use_sort) download(c, &over, d_over, 1);
+        CU(cudaStreamSynchronize(c.stream));      // `off` is pageable host memory
+        if (!over) break;
+        use_sort = true;
+    }
     db.idx_postings = (uint32_t)total;
     return true;
 }
@@ -1833,22 +1842,26 @@ void run_screen(skb_db& db, const std::vector<std::shared_ptr<SketchImpl>>& quer
     const size_t n = (size_t)nq * nr;
     if (n == 0) return;
     if (n >= 0x7FFFFFFFull) throw Fail{SKB_ERR_ARG, "more than 2^31 pairs in one call; split the queries"};
+    Trace ts("screen");
     const GenomeView* d_r = db_views(db);
     DevMem d_count(db.core, 4 * n), d_pass(db.core, n);
+    ts.mark("views + buffers");
     std::vector<uint32_t> qm(nq);
     for (uint32_t i = 0; i < nq; i++) qm[i] = queries[i]->view.n_markers;
     // large pair matrices go through the database's marker index, small ones through the pairwise kernels
     // (SKB_SCREEN_MODE=index|pairwise forces one of them: used by the parity tests)
     bool use_index = n >= 16384;
     if (const char* e = std::getenv("SKB_SCREEN_MODE")) use_index = std::strcmp(e, "index") == 0;
-    if (use_index && db_marker_index(db, d_r))
+    if (use_index && db_marker_index(db, d_r)) {
+        ts.mark("marker index ready");
         launch_marker_join(d_q, nq, nr, db.idx_keys.as<uint64_t>(), db.idx_vals.as<uint32_t>(), db.idx_bucket.as<uint32_t>(),
                            db.idx_shift, d_count.as<uint32_t>(), st);
-    else
+    } else
         launch_marker_screen(d_q, nq, d_r, nr, d_count.as<uint32_t>(), qm.data(), c.n_sm, st);
     launch_screen_decide(d_q, nq, d_r, nr, d_count.as<uint32_t>(), pow21(screen_val), screen_val == 0.0, rescue_small,
                          d_pass.as<uint8_t>(), st);
     CU(cudaGetLastError());
+    ts.mark("join + decide enqueued");
     if (pass_host) download(c, pass_host, d_pass.as<uint8_t>(), n);
     if (shared_host) download(c, shared_host, d_count.as<uint32_t>(), n);
     if (out && n <= (1u << 16)) {
@@ -1864,10 +1877,12 @@ void run_screen(skb_db& db, const std::vector<std::shared_ptr<SketchImpl>>& quer
         uint32_t cnt = 0;
         download(c, &cnt, d_cnt, 1);
         CU(cudaStreamSynchronize(st));
+        ts.mark("survivor count on the host");
         out->pass_idx.resize(cnt);
         download(c, out->pass_idx.data(), d_idx.as<uint32_t>(), cnt);
     }
     CU(cudaStreamSynchronize(st));
+    ts.mark("done");
 }
 
 }  // namespace

@@ -177,11 +177,11 @@ void launch_screen_decide(const GenomeView* queries, uint32_t n_queries, const G
 
 constexpr int MARKER_BITS = 42;   // a marker is a canonical 21-mer
 // marker index of a database: all (marker, genome) postings sorted by marker + bucket table on the top bits
-size_t marker_index_scratch_bytes(uint32_t n_postings);
+size_t marker_index_scratch_bytes(uint32_t n_postings, uint32_t n_buckets);
+// use_sort = false: bucket partition (may raise *overflow when a bucket is too large: call again with use_sort = true)
 void build_marker_index(const GenomeView* refs, uint32_t n_refs, const uint32_t* genome_off, uint32_t n_postings,
                         uint64_t* keys, uint32_t* vals, uint32_t* bucket, uint32_t shift, uint32_t n_buckets,
-                        void* scratch, size_t scratch_bytes, cudaStream_t st);
-// count[q * n_refs + r] through the index (same values as launch_marker_screen)
+                        void* scratch, size_t scratch_bytes, bool use_sort, uint32_t* overflow, cudaStream_t st);
 void launch_marker_join(const GenomeView* queries, uint32_t n_queries, uint32_t n_refs, const uint64_t* keys,
                         const uint32_t* vals, const uint32_t* bucket, uint32_t shift, uint32_t* count, cudaStream_t st);
 

@@ -287,6 +287,46 @@ def test_screen_modes_match_oracle(ctx, monkeypatch, mode):
     assert hits_a == hits_b and n_a == n_b
 
 
+def test_marker_index_build_paths(ctx, monkeypatch):
+    """The database's marker index is built by bucket partition (histogram, scan, scatter, rank inside the bucket); a bucket
+    beyond the rank kernel's capacity - here 110 identical genomes, so every marker has 110 postings - makes the build fall
+    back to the radix sort.  Partition, forced sort and the pairwise kernels give the same counts and decisions (= the
+    oracle's), with many queries and with few (where the join divides a query's markers among several CTAs)."""
+    from pyskani_b200 import capi
+    fams = []
+    for f in range(3):
+        fams += make_family(4, 250_000, 340 + f, [0.01, 0.05, 0.12, 0.22])
+    contigs = [[g.tobytes()] for g in fams]
+    clone = synth.random_genome(80_000, 399).tobytes()
+    few = ctx.sketch_batch(contigs)
+    many = ctx.sketch_batch(contigs + [[clone]] * 110)
+    os_few = [oracle.Sketch(c) for c in contigs]
+    o_clone = oracle.Sketch([clone])
+    for name, gs in (("no overflow", few), ("overflow -> sort", many)):
+        results = {}
+        for mode, env in (("partition", {"SKB_SCREEN_MODE": "index"}), ("sort", {"SKB_SCREEN_MODE": "index", "SKB_MIDX_SORT": "1"}),
+                          ("pairwise", {"SKB_SCREEN_MODE": "pairwise"})):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            db = capi.Database(ctx)
+            db.add_many(gs)
+            results[mode] = [db.screen(gs[:3], 0.8, True), db.screen(gs, 0.8, True), db.screen(gs[5:6], 0.95, False)]
+            for k in env:
+                monkeypatch.delenv(k)
+        for mode in ("sort", "pairwise"):
+            for (ok_a, sh_a), (ok_b, sh_b) in zip(results["partition"], results[mode]):
+                assert np.array_equal(ok_a, ok_b) and np.array_equal(sh_a, sh_b), (name, mode)
+        ok, shared = results["partition"][1]
+        for i in (0, 5, len(os_few) - 1):
+            for j in range(len(os_few)):
+                want_ok, want_shared = oracle.screen(os_few[i], os_few[j], 0.8, True)
+                assert shared[i, j] == want_shared and ok[i, j] == want_ok, (name, i, j)
+        if len(gs) > len(few):
+            want_ok, want_shared = oracle.screen(o_clone, o_clone, 0.8, True)
+            n0 = len(contigs)
+            assert (shared[n0:, n0:] == want_shared).all() and ok[n0:, n0:].all() == bool(want_ok)
+
+
 # ------------------------------------------------------------------ chain / ANI
 def check_hits(hits, oq, orefs, cutoff=0.8, rescue=True, **flags):
     idx, res, n_in = oracle.query(oq, orefs, cutoff, rescue, oracle.default_params(**flags))
