@@ -79,12 +79,15 @@ def parse():
     ap.add_argument("--members", type=int, default=10)
     ap.add_argument("--sketch-batch", type=int, default=250, help="genomes per skb_sketch_batch call")
     ap.add_argument("--e2e-batch", type=int, default=0, help="genomes per skb_sketch_batch call of the host-buffer run (default: --sketch-batch)")
-    ap.add_argument("--no-pipeline", action="store_true", help="host-buffer run at 1 GPU: query only after every batch is sketched")
+    ap.add_argument("--pipeline", action="store_true",
+                    help="host-buffer run at 1 GPU through parallel.all_vs_all_pipelined (queries on a second context under the "
+                         "ingest of the next batch); off by default: it gained 3 ms on one box and lost 3-9 ms on two others")
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries of the CPU sample (default: about 96, a multiple of the threads)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--skip-configs1", action="store_true")
+    ap.add_argument("--skip-python-api", action="store_true")
     ap.add_argument("--n-refs", type=int, default=100, help="configs[1] block: mutated copies")
     return ap.parse_args()
 
@@ -381,6 +384,42 @@ def configs1_block(args, capi, ctx, torch, stream):
 
 
 # ------------------------------------------------------------------------------------------------ the B200 arm
+def python_api_block(args, host, n_total, want_hits):
+    """The same all-vs-all through the pyskani-compatible extension, as a Python caller would run it: genomes are `bytes`
+    objects (pageable memory), Database.sketch_many(...) then Database.query_many(...) - which, like the reference's
+    query(), sketches every query genome again - plus a sample of the reference's own one-genome call, Database.query()."""
+    import pyskani_b200 as pyskani
+    items = [("g%d" % j, host.view(j).tobytes()) for j in range(n_total)]
+    best, n_hits = None, 0
+    for _ in range(2):
+        db = pyskani.Database()
+        t0 = time.perf_counter()
+        db.sketch_many(items)
+        t1 = time.perf_counter()
+        hits = db.query_many(items, learned_ani=False)
+        t2 = time.perf_counter()
+        n_hits = sum(len(h) for h in hits)
+        if best is None or t2 - t0 < best[0]:
+            best = (t2 - t0, t1 - t0, t2 - t1)
+        if _ == 0:
+            lat = []
+            for j in range(0, min(n_total, 24)):
+                ta = time.perf_counter()
+                db.query(items[j][0], items[j][1], learned_ani=False)
+                lat.append(time.perf_counter() - ta)
+        del db
+    if n_hits != want_hits:
+        raise SystemExit("the extension returned %d hits, the C ABI path %d" % (n_hits, want_hits))
+    return {"value": n_total * n_total / best[0], "unit": "pairs/s", "ms_per_step": 1e3 * best[0],
+            "sketch_many_ms": 1e3 * best[1], "query_many_ms": 1e3 * best[2], "hits": n_hits,
+            "host_bytes_per_step": 2 * int(sum(len(b) for _, b in items)),
+            "single_query_call_ms": 1e3 * float(np.median(lat)),
+            "note": "pyskani_b200.Database.sketch_many + query_many on Python bytes (pageable host memory); query_many sketches the "
+                    "1 000 query genomes again, as the reference's query() does, so 10 GB of ASCII are ingested per step; "
+                    "single_query_call_ms = median of Database.query(name, bytes) against the 1 000-genome database (the "
+                    "reference's own call pattern: sketch one genome, screen 1 000, chain ~9)"}
+
+
 def main():
     args = parse()
     claim_stdout()
@@ -465,7 +504,7 @@ def main():
 
     # one GPU, host buffers: the queries of a batch run on a second context of the same device while the next batch is
     # still crossing PCIe (parallel.all_vs_all_pipelined); with several ranks the exchange comes first
-    pipelined = world == 1 and not args.no_pipeline and len(batches_h) > 1
+    pipelined = world == 1 and args.pipeline and len(batches_h) > 1
     backend_q = parallel.CudaBackend(local_rank, ctx=capi.Context(local_rank)) if pipelined else None
     if os.environ.get("BENCH_TEAM"):
         ctx.set_host_threads(int(os.environ["BENCH_TEAM"]))      # tuning hook: threads of the ingest team
@@ -669,6 +708,8 @@ def main():
             del odb
         if not args.skip_configs1:
             line["configs1"] = configs1_block(args, capi, ctx, torch, stream)
+        if world == 1 and not args.skip_python_api:
+            line["python_api"] = python_api_block(args, host, n_total, int(len(table)))
         emit(line)
     if world > 1:
         dist.barrier()

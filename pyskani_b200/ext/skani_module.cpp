@@ -498,12 +498,28 @@ std::vector<Sketch> sketch_many_impl(Database& db, const py::sequence& items, bo
     const uint32_t n = (uint32_t)out.size();
     std::vector<skb_sketch_t*> handles(n, nullptr);
     skb_sketch_params_t p{(int32_t)db.params.k, (int32_t)db.params.c, (int32_t)db.params.marker_c};
-    int rc;
+    int rc = SKB_OK;
     {
+        // one GPU batch holds fewer than 2^31 bases: a long list goes down in slices of about 1.25 G bases (whole genomes)
         py::gil_scoped_release nogil;
-        rc = skb_sketch_batch(global_ctx(), &p, seed ? 1 : 0, n, gstart.data(), ptrs.data(), lens.data(), handles.data());
+        constexpr uint64_t SLICE_BASES = 1250ull << 20;
+        for (uint32_t g0 = 0; g0 < n && rc == SKB_OK;) {
+            uint32_t g1 = g0;
+            uint64_t bases = 0;
+            while (g1 < n) {
+                uint64_t b = 0;
+                for (uint32_t ci = gstart[g1]; ci < gstart[g1 + 1]; ci++) b += lens[ci];
+                if (g1 > g0 && bases + b > SLICE_BASES) break;
+                bases += b; g1++;
+            }
+            std::vector<uint32_t> gs(g1 - g0 + 1);
+            for (uint32_t g = g0; g <= g1; g++) gs[g - g0] = gstart[g] - gstart[g0];
+            rc = skb_sketch_batch(global_ctx(), &p, seed ? 1 : 0, g1 - g0, gs.data(), ptrs.data() + gstart[g0], lens.data() + gstart[g0],
+                                  handles.data() + g0);
+            g0 = g1;
+        }
     }
-    for (uint32_t g = 0; g < n; g++) { out[g].handle = std::make_shared<SketchHandle>(); out[g].handle->h = handles[g]; }
+    for (uint32_t g = 0; g < n; g++) if (handles[g]) { out[g].handle = std::make_shared<SketchHandle>(); out[g].handle->h = handles[g]; }
     check(global_ctx(), rc);
     return out;
 }
