@@ -1096,7 +1096,7 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
             }
         }
         // ---- how the bytes travel
-        const char* ingest_env = std::getenv("SKB_INGEST");      // raw | pack | mix (default)
+        const char* ingest_env = std::getenv("SKB_INGEST");      // raw | pack | mix | auto (= unset, but also for small batches)
         const bool want_raw = ingest_env && std::strcmp(ingest_env, "raw") == 0;
         const unsigned n_threads = want_raw ? 0 : resolve_host_threads(c);
         const bool pipelined = n_threads >= 2 && ranges.size() >= 2 && (kept_bytes >= INGEST_MIN || ingest_env != nullptr);
@@ -1141,7 +1141,21 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
             char* stage_raw = (char*)c.raw_stage;
             CU(cudaEventRecord(c.ev[5], st));
             CU(cudaStreamWaitEvent(cs, c.ev[5], 0));      // d_pk's allocation is ordered on `st` as well
-            const int policy = ingest_env && std::strcmp(ingest_env, "pack") == 0 ? Ingest::PACK_ONLY : Ingest::MIX;
+            int policy = ingest_env && std::strcmp(ingest_env, "pack") == 0 ? Ingest::PACK_ONLY : Ingest::MIX;
+            if (policy == Ingest::MIX && (!ingest_env || std::strcmp(ingest_env, "auto") == 0)) {
+                // Pageable sources (Python bytes) never take the DMA route: the driver stages such a copy through its own
+                // buffers at a fraction of the link rate and holds the stream's lock meanwhile, which stalls the copies the
+                // packing threads enqueue (measured through the extension: 23 GB/s with the DMA route).  The
+                // packing threads read pageable memory as fast as pinned memory.
+                for (const ChunkRange& r : ranges) {
+                    uint32_t i = r.c0;
+                    while (i < r.c1 && contig_lens[i] < SKB_MIN_LENGTH_CONTIG) i++;
+                    if (i == r.c1) continue;
+                    cudaPointerAttributes at{};
+                    if (cudaPointerGetAttributes(&at, contigs[i]) != cudaSuccess) { cudaGetLastError(); policy = Ingest::PACK_ONLY; break; }
+                    if (at.type == cudaMemoryTypeUnregistered) { policy = Ingest::PACK_ONLY; break; }
+                }
+            }
             Ingest ing(c, contigs, contig_lens, offs.data(), d_seq, d_pk, (char*)c.pack_stage, stage_raw, policy);
             ing.chunks.resize(ranges.size());
             ing.remaining.assign(ranges.size(), 0);

@@ -160,6 +160,37 @@ def test_ingest_routes_give_the_same_sketch(ctx, monkeypatch):
             seen_raw |= st.h2d_raw_bytes > 0
         (one,) = ctx.sketch_batch(genomes[4:5], c=30, marker_c=200)
         assert_sketch_equal(one, oracle.Sketch(genomes[4], c=30, marker_c=200))
+    # the automatic policy: pageable sources (these bytes objects) are left to the packing threads altogether, pinned ones
+    # are shared between the copy engine and the packing threads
+    monkeypatch.setenv("SKB_INGEST", "auto")
+    ctx.set_host_threads(4)
+    got = ctx.sketch_batch(genomes)
+    st = ctx.stats()
+    assert st.h2d_raw_bytes == 0 and st.h2d_packed_bytes > 0
+    for g, o in zip(got, want):
+        assert_sketch_equal(g, o)
+    import ctypes as C
+    flat = [c for g in genomes for c in g]
+    total = sum((len(c) + 15) // 16 * 16 + 16 for c in flat) + 64
+    hp = ctx.host_alloc(total)
+    try:
+        arr = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), shape=(total,))
+        views, off = [], 16
+        for g in genomes:
+            vg = []
+            for c in g:
+                arr[off:off + len(c)] = np.frombuffer(c, np.uint8)
+                vg.append(arr[off:off + len(c)])
+                off += (len(c) + 15) // 16 * 16 + 16
+            views.append(vg)
+        for rep in range(3):
+            got = ctx.sketch_batch(views)
+            st = ctx.stats()
+            seen_raw |= st.h2d_raw_bytes > 0
+            for g, o in zip(got, want):
+                assert_sketch_equal(g, o)
+    finally:
+        ctx.host_free(hp)
     ctx.set_host_threads(-1)
     assert seen_packed and seen_raw
 
