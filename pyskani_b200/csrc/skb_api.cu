@@ -1979,7 +1979,19 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
             for (const auto& it : db->items) ensure_seeds_ready(*it);
             for (const auto& q : qs) ensure_seeds_ready(*q);
         }
-        constexpr uint64_t MAX_BATCH_SEEDS = 160ull << 20;      // ~4 000 pairs of 5 Mbp genomes per batch
+        // Query seeds per chaining batch: large batches amortise the ~25 launches, the kernel tails and the host round trip
+        // of a batch (10^6-pair all-vs-all, 354 M query seeds: 10.9 ms in three batches of <= 160 M, 10.2 ms in one).  A batch
+        // needs ~12 B per query seed + ~54 B per seed for the anchor arrays (1.5 anchors per seed reserved): up to 384 M seeds
+        // = 25 GB, but never more than half of the memory that is free (plus what the context's chaining arena holds already).
+        uint64_t MAX_BATCH_SEEDS = 384ull << 20;
+        {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+                const uint64_t budget = ((uint64_t)free_b + c.arena[SLOT_CHAIN].bytes) / 2;
+                MAX_BATCH_SEEDS = std::min<uint64_t>(MAX_BATCH_SEEDS, std::max<uint64_t>(budget / 72, 16ull << 20));
+            } else cudaGetLastError();
+            if (const char* e = std::getenv("SKB_CHAIN_BATCH_MSEEDS")) MAX_BATCH_SEEDS = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10)) << 20;   // tuning / test hook
+        }
         size_t p0 = 0;
         while (p0 < n_pass) {
             std::vector<PairDesc> pairs;

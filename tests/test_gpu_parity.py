@@ -445,8 +445,9 @@ def test_fragmented_query_vs_oracle(ctx):
     assert len(hits) == 3
 
 
-def test_all_vs_all_small(ctx):
-    """BASELINE.json config 3 at reduced size: families of related genomes, every ordered pair."""
+def test_all_vs_all_small(ctx, monkeypatch):
+    """BASELINE.json config 3 at reduced size: families of related genomes, every ordered pair; the same in many small
+    chaining batches (the batch size follows the free device memory and is normally far above this workload)."""
     from pyskani_b200 import capi
     genomes = []
     for f in range(4):
@@ -464,6 +465,14 @@ def test_all_vs_all_small(ctx):
     assert total_in == n_in
     # only intra-family pairs can pass the screen
     assert all(h[0] // 4 == h[1] // 4 for h in hits)
+    monkeypatch.setenv("SKB_CHAIN_BATCH_MSEEDS", "1")           # <= 2^20 query seeds per batch: 64 pairs -> several batches
+    big = ctx.sketch_batch([[synth.random_genome(2_000_000, 75).tobytes()], [synth.mutate(synth.random_genome(2_000_000, 75), 0.03, 76).tobytes()]])
+    db2 = capi.Database(ctx)
+    db2.add_many(list(gs) + list(big))
+    hits_small, n_small = db2.query(list(gs) + list(big))
+    monkeypatch.delenv("SKB_CHAIN_BATCH_MSEEDS")
+    hits_one, n_one = db2.query(list(gs) + list(big))
+    assert hits_small == hits_one and n_small == n_one and n_one >= n_in + 4
 
 
 def test_walk_groups(ctx, monkeypatch):
