@@ -554,6 +554,8 @@ def main():
         for _ in range(steps):
             table, tm = step(sketch_fn)
             tms.append(tm)
+            if os.environ.get("BENCH_STEP_LOG") and rank == 0:
+                print("step: " + " ".join("%s=%.2f" % (k, v) for k, v in tm.items() if k.endswith("_ms")), file=sys.stderr, flush=True)
         e1.record(stream)
         barrier()
         wall_ms = 1e3 * (time.perf_counter() - t0)

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--genome-len", type=int, default=5_000_000)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--threads", default="4,8,12,14,15,16")
+    ap.add_argument("--only", default="", help="run only this policy (raw | pack | mix)")
     a = ap.parse_args()
     from pyskani_b200 import capi
     import workload
@@ -60,12 +61,15 @@ def main():
         print("%-5s threads %2d: %7.2f ms  %6.1f GB/s of ASCII input   (link: %6.1f MB ASCII + %6.1f MB packed)"
               % (policy, threads, 1e3 * best, bases / best / 1e9, raw / 1e6, packed / 1e6), flush=True)
 
-    run("raw", 0)
+    if a.only in ("", "raw"):
+        run("raw", 0)
     for t in [int(x) for x in a.threads.split(",")]:
         if t > max(2, cpus):
             continue
-        run("pack", t)
-        run("mix", t)
+        if a.only in ("", "pack"):
+            run("pack", t)
+        if a.only in ("", "mix"):
+            run("mix", t)
     os.environ.pop("SKB_INGEST", None)
 
 

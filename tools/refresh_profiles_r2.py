@@ -13,24 +13,30 @@ def capture(fn, *a):
     return buf.getvalue()
 
 
-WL = "python bench.py --steps 1 --warmup 1 (all-vs-all of 1 000 x 5 Mbp genomes on one B200: 4 sketch calls of 250 genomes, 3 chaining batches per step)"
-for k in ["seed_scan_kernel", "chain_dp_thread_kernel", "match_count_kernel", "anchor_fill_kernel", "window_walk_smem_kernel", "marker_join_kernel"]:
+WL = "python bench.py --steps 1 --warmup 1 (all-vs-all of 1 000 x 5 Mbp genomes on one B200: 4 sketch calls of 250 genomes, one chaining batch per step)"
+rep = os.path.join(G, "r2_seed_scan_packed.ncu-rep")
+if os.path.exists(rep):
+    open(os.path.join(P, "r2_seed_scan_kernel_packed_ncu_full.txt"), "w").write(
+        capture(S.full, rep, "ncu --set full --clock-control none --import-source on -k regex:seed_scan_kernel -s 20 -c 1: SKB_INGEST=pack python "
+                             "tools/ingest_sweep.py --only pack (seed_scan_kernel<false, true>: the launch of one ~16 MB chunk that the host "
+                             "threads compacted to 2-bit words; launches of this path are small and wait for their chunk); round 2"))
+for k in ["seed_scan_kernel", "chain_dp_thread_kernel", "match_count_kernel", "anchor_fill_kernel", "window_walk_smem_kernel", "marker_join_kernel", "marker_rank_kernel"]:
     rep = os.path.join(G, "r2_%s.ncu-rep" % k)
     if os.path.exists(rep):
         open(os.path.join(P, "r2_%s_ncu_full.txt" % k), "w").write(
             capture(S.full, rep, "ncu --set full --clock-control none --import-source on -k regex:%s -s 1 -c 1: %s; round 2" % (k, WL)))
 
-# one device-resident step cut from the launch list (steps end with the third ani_reduce launch)
+# one device-resident step cut from the launch list (every step ends with its ani_reduce launch: one chaining batch per step)
 rows = list(csv.reader(open(os.path.join(G, "r2_launches_allvsall.csv"))))
 hi = [i for i, r in enumerate(rows) if 'Kernel Name' in r][0]
 H = rows[hi]; kn, mv, mn = H.index('Kernel Name'), H.index('Metric Value'), H.index('Metric Name')
 L = [(r[kn], float(r[mv].replace(',', '')) / 1e3) for r in rows[hi + 1:] if len(r) > mv and r[mn] == 'gpu__time_duration.sum']
 ends = [i for i, (n, t) in enumerate(L) if 'ani_reduce' in n]
-step = L[ends[2] + 1:ends[5] + 1]
+step = L[ends[0] + 1:ends[1] + 1]
 
 
 def short(n):
-    if 'DeviceRadixSort' in n or 'RadixSort' in n and 'skb::' not in n.split('(')[0]: return 'CUB radix sort (marker index postings)'
+    if 'DeviceRadixSort' in n or 'RadixSort' in n and 'skb::' not in n.split('(')[0]: return 'CUB radix sort'
     if 'DeviceScan' in n: return 'CUB scan (anchor offsets, region counts)'
     if 'DeviceSelect' in n or 'DeviceCompact' in n: return 'CUB select'
     m = re.search(r'skb::(?:<unnamed>::)?(\w+)', n)
@@ -83,10 +89,11 @@ for src, dst in (("r2_bench_n1.json", "r2_bench_line_n1.json"), ("r2_bench_refer
 mem = open(os.path.join(G, "r2_memcheck.log")).read().strip().splitlines()
 race = open(os.path.join(G, "r2_racecheck.log")).read().strip().splitlines()
 open(os.path.join(P, "r2_sanitizer.txt"), "w").write(
-    "# compute-sanitizer on the GPU parity tests (B200, round 2: after the thread-per-window DP, the k-order anchor join, the exchange\n"
-    "# block, the learned-ANI evaluator and the seeding changes); commands in tools/profile_round2.sh\n"
+    "# compute-sanitizer on the GPU parity tests (B200, end of round 2: thread-per-window DP, k-order anchor join, exchange block,\n"
+    "# learned-ANI evaluator, seeding changes, packed-input seeding variant + host ingest, bucket-partition marker index, split join,\n"
+    "# pipelined all-vs-all on two contexts); commands in tools/profile_round2.sh\n"
     "memcheck : tests/test_gpu_parity.py tests/test_gpu_exchange.py tests/test_gpu_learned_ani.py -k 'not ecoli and not mutant_series and not large_genomes and not two_gpu'\n"
     "           -> %s ; %s\n"
-    "racecheck: tests/test_gpu_parity.py tests/test_gpu_learned_ani.py -k 'ragged or fragmented or walk_groups or all_vs_all_small or repeat_rich or hash_comparison or query_with_model'\n"
+    "racecheck: tests/test_gpu_parity.py tests/test_gpu_learned_ani.py -k 'ragged or fragmented or walk_groups or all_vs_all_small or repeat_rich or hash_comparison or query_with_model or marker_index_build or screen_modes'\n"
     "           -> %s ; %s\n" % (mem[-2].strip(), mem[-1].strip("= "), race[-2].strip(), race[-1].strip("= ")))
 print(open(os.path.join(P, "r2_launches_allvsall.txt")).read())
