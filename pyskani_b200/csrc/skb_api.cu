@@ -67,6 +67,7 @@ struct Core {
     std::vector<cudaEvent_t> ev_pool;         // "chunk is on the device" events (timing disabled)
     // ingest pipeline of large host batches (host_pack.h): worker threads + pinned staging for the 2-bit chunks
     std::unique_ptr<HostTeam> team;
+    uint64_t chain_batch_seeds = 160ull << 20;   // query seeds per chaining batch (set from the device's memory size)
     int host_threads = -1;                    // -1: default (SKB_HOST_THREADS, else min(32, cpus / LOCAL_WORLD_SIZE)); 0: off
     void* pack_stage = nullptr;               // pinned, mirrors the device layout of a batch at a quarter of its size
     size_t pack_stage_bytes = 0;
@@ -924,6 +925,7 @@ int skb_ctx_create(int device, skb_ctx_t** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SKB_ERR_CUDA;
     core->n_sm = prop.multiProcessorCount;
+    core->chain_batch_seeds = std::min<uint64_t>(384ull << 20, std::max<uint64_t>(16ull << 20, (uint64_t)((double)prop.totalGlobalMem * 0.15 / 72.0)));
     if (cudaStreamCreateWithFlags(&core->stream, cudaStreamNonBlocking) != cudaSuccess) return SKB_ERR_CUDA;
     if (cudaStreamCreateWithFlags(&core->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return SKB_ERR_CUDA;
     if (cudaStreamCreateWithFlags(&core->aux_stream, cudaStreamNonBlocking) != cudaSuccess) return SKB_ERR_CUDA;
@@ -1980,18 +1982,12 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
             for (const auto& q : qs) ensure_seeds_ready(*q);
         }
         // Query seeds per chaining batch: large batches amortise the ~25 launches, the kernel tails and the host round trip
-        // of a batch (10^6-pair all-vs-all, 354 M query seeds: 10.9 ms in three batches of <= 160 M, 10.2 ms in one).  A batch
+        // of a batch (10^6-pair all-vs-all, 354 M query seeds: 10.9 ms in three batches of <= 160 M, 10.4 ms in one).  A batch
         // needs ~12 B per query seed + ~54 B per seed for the anchor arrays (1.5 anchors per seed reserved): up to 384 M seeds
-        // = 25 GB, but never more than half of the memory that is free (plus what the context's chaining arena holds already).
-        uint64_t MAX_BATCH_SEEDS = 384ull << 20;
-        {
-            size_t free_b = 0, total_b = 0;
-            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-                const uint64_t budget = ((uint64_t)free_b + c.arena[SLOT_CHAIN].bytes) / 2;
-                MAX_BATCH_SEEDS = std::min<uint64_t>(MAX_BATCH_SEEDS, std::max<uint64_t>(budget / 72, 16ull << 20));
-            } else cudaGetLastError();
-            if (const char* e = std::getenv("SKB_CHAIN_BATCH_MSEEDS")) MAX_BATCH_SEEDS = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10)) << 20;   // tuning / test hook
-        }
+        // = 25 GB, bounded by 15 % of the device's memory (read once, when the context is created: cudaMemGetInfo costs up to
+        // 15 ms per call on some boxes) and halved for good whenever the arena cannot be allocated.
+        uint64_t MAX_BATCH_SEEDS = c.chain_batch_seeds;
+        if (const char* e = std::getenv("SKB_CHAIN_BATCH_MSEEDS")) MAX_BATCH_SEEDS = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10)) << 20;   // tuning / test hook
         size_t p0 = 0;
         while (p0 < n_pass) {
             std::vector<PairDesc> pairs;
@@ -2031,6 +2027,7 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
             }
             const size_t nw = std::max<uint64_t>(wins, 1);
             const size_t scan_bytes = scan_scratch_bytes((uint32_t)seeds + 1), sort_bytes = sort_pairs_scratch_bytes((uint32_t)wins);
+            bool retry_smaller = false;
             for (int attempt = 0; attempt < 2; attempt++) {
                 const size_t na = (size_t)est;
                 // every transient array of the batch is carved out of ONE grow-only block of the context: a cold
@@ -2044,7 +2041,19 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
                              o_rec = plan(nw * sizeof(WindowRec)), o_keys = plan(nw * 8 * 2), o_vals = plan(nw * 4 * 2),
                              o_res = plan(sizeof(PairResult) * np), o_sort = plan(sort_bytes),
                              o_groups = plan(sizeof(uint2) * groups.size()), o_total = plan(8);
-                char* base = (char*)c.scratch(SLOT_CHAIN, total);
+                char* base = nullptr;
+                try {
+                    base = (char*)c.scratch(SLOT_CHAIN, total);
+                } catch (const Fail& f) {
+                    // no room for a batch of this size (other tenants of the device, a huge database): halve the batch size
+                    // of this context for good and plan the remaining pairs again
+                    if (f.code != SKB_ERR_NOMEM || np <= 1) throw;
+                    cudaGetLastError();
+                    c.chain_batch_seeds = std::max<uint64_t>(1ull << 20, std::min(c.chain_batch_seeds, seeds) / 2);
+                    MAX_BATCH_SEEDS = c.chain_batch_seeds;
+                    retry_smaller = true;
+                    break;
+                }
                 ChainBatch B{};
                 B.qviews = d_q.as<GenomeView>(); B.rviews = d_r; B.n_pairs = np;
                 B.n_qseeds_total = (uint32_t)seeds; B.n_win_total = (uint32_t)wins;
@@ -2105,6 +2114,7 @@ int skb_db_query(skb_db_t* db, uint32_t n_queries, skb_sketch_t* const* queries,
                 if (attempt == 1) throw Fail{SKB_ERR_CUDA, "anchor arrays overflowed twice"};
                 est = n_anchors;
             }
+            if (retry_smaller) continue;       // plan again from p0 with the smaller batch size
             for (uint32_t i = 0; i < np; i++) {
                 if (res[i].ani > 0.1f) {   // reference lib.rs:654
                     skb_hit_t h{};
