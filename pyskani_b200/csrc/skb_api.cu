@@ -133,8 +133,15 @@ uint32_t* Core::pinned_counts(size_t words) {
     return pinned_cnt;
 }
 
+enum { SLOT_SEQ = 0, SLOT_KMER, SLOT_POS, SLOT_META, SLOT_MKEYS, SLOT_STATUS, SLOT_SORT, SLOT_MARK, SLOT_GS, SLOT_GM, SLOT_DESC, SLOT_MKEYS2, SLOT_RSCAN, SLOT_GM_IN, SLOT_BTAB, SLOT_BCOUNT, SLOT_CHAIN, SLOT_MIDX, SLOT_PACK, SLOT_SEQPK };
+
 void* Core::scratch(int slot, size_t bytes) {
     Block& b = arena[slot];
+    if (slot == SLOT_CHAIN && bytes > ((size_t)1 << 20)) {
+        // test hook: pretend the device has no room for a chaining arena above this many MB (exercises the smaller-batch retry)
+        if (const char* e = std::getenv("SKB_TEST_CHAIN_ARENA_MB"))
+            if (bytes > ((size_t)std::strtoull(e, nullptr, 10) << 20)) throw Fail{SKB_ERR_NOMEM, "chaining arena above the test limit"};
+    }
     if (b.bytes < bytes) {
         if (b.p) { CU(cudaStreamSynchronize(stream)); CU(cudaStreamSynchronize(copy_stream)); CU(cudaStreamSynchronize(aux_stream)); CU(cudaFree(b.p)); b.p = nullptr; b.bytes = 0; }
         const size_t want = bytes + bytes / 8 + 4096;
@@ -143,7 +150,6 @@ void* Core::scratch(int slot, size_t bytes) {
     }
     return b.p;
 }
-enum { SLOT_SEQ = 0, SLOT_KMER, SLOT_POS, SLOT_META, SLOT_MKEYS, SLOT_STATUS, SLOT_SORT, SLOT_MARK, SLOT_GS, SLOT_GM, SLOT_DESC, SLOT_MKEYS2, SLOT_RSCAN, SLOT_GM_IN, SLOT_BTAB, SLOT_BCOUNT, SLOT_CHAIN, SLOT_MIDX, SLOT_PACK, SLOT_SEQPK };
 
 // stream-ordered device buffer
 struct DevMem {

@@ -473,6 +473,16 @@ def test_all_vs_all_small(ctx, monkeypatch):
     monkeypatch.delenv("SKB_CHAIN_BATCH_MSEEDS")
     hits_one, n_one = db2.query(list(gs) + list(big))
     assert hits_small == hits_one and n_small == n_one and n_one >= n_in + 4
+    # a chaining arena that cannot be allocated halves the batch size of the context and the remaining pairs are planned again
+    from pyskani_b200 import capi as _capi
+    tight = _capi.Context(0)
+    gt = tight.sketch_batch(contigs)
+    dbt = _capi.Database(tight)
+    dbt.add_many(gt)
+    monkeypatch.setenv("SKB_TEST_CHAIN_ARENA_MB", "12")
+    hits_tight, n_tight = dbt.query(gt)
+    monkeypatch.delenv("SKB_TEST_CHAIN_ARENA_MB")
+    assert (hits_tight, n_tight) == (hits, n_in)
 
 
 def test_walk_groups(ctx, monkeypatch):
