@@ -72,6 +72,10 @@ struct Core {
     void* pack_stage = nullptr;               // pinned, mirrors the device layout of a batch at a quarter of its size
     size_t pack_stage_bytes = 0;
     void* raw_stage = nullptr;                // pinned staging of the pipeline's DMA thread for small contigs
+    // which route pinned sources take is learned per context: best recent input GB/s of the mixed policy [0] and of
+    // packing every chunk [1]; the faster one is used, the other re-measured every 16th large call
+    double ingest_rate[2] = {0.0, 0.0};
+    uint32_t ingest_calls = 0;
     cudaEvent_t pool_event(size_t i) {
         while (ev_pool.size() <= i) {
             cudaEvent_t e;
@@ -766,9 +770,9 @@ static unsigned resolve_host_threads(const Core& c) {
             if (cpus < 8) return 0;
         }
     }
-    // the calling thread spins in its stream synchronisations and the feeding thread sleeps in its event waits: one
-    // feeder + (cpus - 1) packing threads keep every core busy
-    return std::min(32u, cpus);
+    // the calling thread spins in its stream synchronisations: it keeps one CPU, the team gets the others (with 16 CPUs,
+    // 16 packing threads reach 80 GB/s, 15 reach 102 GB/s: profiles/r2_ingest_sweep.txt)
+    return std::max(2u, std::min(32u, cpus) - 1u);
 }
 
 static void finish_batch(const std::shared_ptr<Core>& core, const skb_sketch_params_t& P, int seed,
@@ -1164,6 +1168,23 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
                     if (at.type == cudaMemoryTypeUnregistered) { policy = Ingest::PACK_ONLY; break; }
                 }
             }
+            // Pinned sources: both routes at once (MIX) or every chunk through the packing threads (PACK_ONLY)?  With enough
+            // threads the host's memory system, not PCIe, is the limit, and the DMA route's reads then only slow the packing
+            // threads down (16-CPU bench box: 13.2 ms mixed, 12.2 ms packed per 1.25 GB; with 4 threads 16.3 against 23.7 ms).
+            // Which one wins depends on the host, so it is measured: the first two large calls try one each, later calls take
+            // the faster and re-measure the other now and then.  The sketches do not depend on the choice.
+            bool learned_policy = false;
+            if (policy == Ingest::MIX && !ingest_env) {
+                learned_policy = true;
+                if (c.ingest_rate[0] == 0.0) policy = Ingest::MIX;
+                else if (c.ingest_rate[1] == 0.0) policy = Ingest::PACK_ONLY;
+                else {
+                    const int best = c.ingest_rate[1] > c.ingest_rate[0] ? Ingest::PACK_ONLY : Ingest::MIX;
+                    policy = (c.ingest_calls % 16 == 15) ? 1 - best : best;
+                }
+                c.ingest_calls++;
+            }
+            const auto ingest_t0 = std::chrono::steady_clock::now();
             Ingest ing(c, contigs, contig_lens, offs.data(), d_seq, d_pk, (char*)c.pack_stage, stage_raw, policy);
             ing.chunks.resize(ranges.size());
             ing.remaining.assign(ranges.size(), 0);
@@ -1196,6 +1217,13 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
             }
             if (ing.err) throw Fail{ing.err, ing.err_msg};
             link_raw = ing.raw_bytes; link_packed = ing.packed_bytes;
+            if (learned_policy) {
+                const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - ingest_t0).count();
+                const double rate = (double)kept_bytes / std::max(sec, 1e-6) / 1e9;
+                // disturbances only ever make a call slower: remember the best recent rate of each policy (slowly forgotten)
+                double& r = c.ingest_rate[policy];
+                r = std::max(0.97 * r, rate);
+            }
             if (tr.on) cudaEventRecord(ev_c1, cs);
             if (tr.on) std::fprintf(stderr, "[skb] sketch_batch: ingest by %u threads (%s): %.1f MB as ASCII, %.1f MB as 2-bit words (= %.1f MB of bases)\n",
                                     n_threads, host_pack_isa(), link_raw / 1048576.0, link_packed / 1048576.0, link_packed * 4 / 1048576.0);
