@@ -72,9 +72,9 @@ struct Core {
     void* pack_stage = nullptr;               // pinned, mirrors the device layout of a batch at a quarter of its size
     size_t pack_stage_bytes = 0;
     void* raw_stage = nullptr;                // pinned staging of the pipeline's DMA thread for small contigs
-    // which route pinned sources take is learned per context: best recent input GB/s of the mixed policy [0] and of
-    // packing every chunk [1]; the faster one is used, the other re-measured every 16th large call
-    double ingest_rate[2] = {0.0, 0.0};
+    // which route pinned sources take is learned per context: best recent input GB/s of the mixed policy [0], of packing
+    // every chunk [1] and of plain copies [2]; the fastest is used, the others re-measured in turn every 16th large call
+    double ingest_rate[3] = {0.0, 0.0, 0.0};
     uint32_t ingest_calls = 0;
     cudaEvent_t pool_event(size_t i) {
         while (ev_pool.size() <= i) {
@@ -1111,7 +1111,45 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
         const char* ingest_env = std::getenv("SKB_INGEST");      // raw | pack | mix | auto (= unset, but also for small batches)
         const bool want_raw = ingest_env && std::strcmp(ingest_env, "raw") == 0;
         const unsigned n_threads = want_raw ? 0 : resolve_host_threads(c);
-        const bool pipelined = n_threads >= 2 && ranges.size() >= 2 && (kept_bytes >= INGEST_MIN || ingest_env != nullptr);
+        bool pipelined = n_threads >= 2 && ranges.size() >= 2 && (kept_bytes >= INGEST_MIN || ingest_env != nullptr);
+        // Large batches without a forced policy: pageable sources (Python bytes) are left to the packing threads altogether -
+        // the driver stages a pageable copy through its own buffers at a fraction of the link rate and holds the stream's lock
+        // meanwhile, which stalls the copies the packing threads enqueue (through the extension: 23 GB/s with the DMA route,
+        // 80 GB/s without).  For pinned sources the context LEARNS which of three policies is fastest on this host: both
+        // routes at once [0], every chunk packed [1], or plain copies without the team [2].  With enough threads the host's
+        // memory system, not PCIe, is the limit and the DMA route's reads only slow the packing threads down (16-CPU box,
+        // 1.25 GB: 13.2 ms mixed, 12.2 ms packed, 24.5 ms copied); with 4 threads 16.3 / 23.7 / 24.5 ms; with several ranks on
+        // a host whose PCIe or memory fabric is already saturated by the copies, the team only costs.  The first three large
+        // calls try one policy each, later calls take the one with the best recent rate and re-measure the others in turn
+        // every 16th call.  The sketches do not depend on the choice.
+        int learned = -1;                   // policy under measurement in this call, -1: none
+        bool force_pack = false;
+        if (pipelined && (!ingest_env || std::strcmp(ingest_env, "auto") == 0)) {
+            bool pageable = false;
+            for (const ChunkRange& r : ranges) {
+                uint32_t i = r.c0;
+                while (i < r.c1 && contig_lens[i] < SKB_MIN_LENGTH_CONTIG) i++;
+                if (i == r.c1) continue;
+                cudaPointerAttributes at{};
+                if (cudaPointerGetAttributes(&at, contigs[i]) != cudaSuccess) { cudaGetLastError(); pageable = true; break; }
+                if (at.type == cudaMemoryTypeUnregistered) { pageable = true; break; }
+            }
+            if (pageable) force_pack = true;
+            else if (!ingest_env) {
+                int pick = -1;
+                for (int k = 0; k < 3 && pick < 0; k++) if (c.ingest_rate[k] == 0.0) pick = k;
+                if (pick < 0) {
+                    int best = 0;
+                    for (int k = 1; k < 3; k++) if (c.ingest_rate[k] > c.ingest_rate[best]) best = k;
+                    pick = best;
+                    if (c.ingest_calls % 16 == 15) pick = (best + 1 + (int)((c.ingest_calls / 16) % 2)) % 3;
+                }
+                c.ingest_calls++;
+                learned = pick;
+                if (pick == 2) pipelined = false;
+            }
+        }
+        auto ingest_t0 = std::chrono::steady_clock::now();      // restarted below, after one-time allocations
         float seed_ms = 0;
         uint64_t link_raw = 0, link_packed = 0;
         if (!pipelined) {
@@ -1154,37 +1192,7 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
             CU(cudaEventRecord(c.ev[5], st));
             CU(cudaStreamWaitEvent(cs, c.ev[5], 0));      // d_pk's allocation is ordered on `st` as well
             int policy = ingest_env && std::strcmp(ingest_env, "pack") == 0 ? Ingest::PACK_ONLY : Ingest::MIX;
-            if (policy == Ingest::MIX && (!ingest_env || std::strcmp(ingest_env, "auto") == 0)) {
-                // Pageable sources (Python bytes) never take the DMA route: the driver stages such a copy through its own
-                // buffers at a fraction of the link rate and holds the stream's lock meanwhile, which stalls the copies the
-                // packing threads enqueue (measured through the extension: 23 GB/s with the DMA route).  The
-                // packing threads read pageable memory as fast as pinned memory.
-                for (const ChunkRange& r : ranges) {
-                    uint32_t i = r.c0;
-                    while (i < r.c1 && contig_lens[i] < SKB_MIN_LENGTH_CONTIG) i++;
-                    if (i == r.c1) continue;
-                    cudaPointerAttributes at{};
-                    if (cudaPointerGetAttributes(&at, contigs[i]) != cudaSuccess) { cudaGetLastError(); policy = Ingest::PACK_ONLY; break; }
-                    if (at.type == cudaMemoryTypeUnregistered) { policy = Ingest::PACK_ONLY; break; }
-                }
-            }
-            // Pinned sources: both routes at once (MIX) or every chunk through the packing threads (PACK_ONLY)?  With enough
-            // threads the host's memory system, not PCIe, is the limit, and the DMA route's reads then only slow the packing
-            // threads down (16-CPU bench box: 13.2 ms mixed, 12.2 ms packed per 1.25 GB; with 4 threads 16.3 against 23.7 ms).
-            // Which one wins depends on the host, so it is measured: the first two large calls try one each, later calls take
-            // the faster and re-measure the other now and then.  The sketches do not depend on the choice.
-            bool learned_policy = false;
-            if (policy == Ingest::MIX && !ingest_env) {
-                learned_policy = true;
-                if (c.ingest_rate[0] == 0.0) policy = Ingest::MIX;
-                else if (c.ingest_rate[1] == 0.0) policy = Ingest::PACK_ONLY;
-                else {
-                    const int best = c.ingest_rate[1] > c.ingest_rate[0] ? Ingest::PACK_ONLY : Ingest::MIX;
-                    policy = (c.ingest_calls % 16 == 15) ? 1 - best : best;
-                }
-                c.ingest_calls++;
-            }
-            const auto ingest_t0 = std::chrono::steady_clock::now();
+            if (force_pack || learned == 1) policy = Ingest::PACK_ONLY;
             Ingest ing(c, contigs, contig_lens, offs.data(), d_seq, d_pk, (char*)c.pack_stage, stage_raw, policy);
             ing.chunks.resize(ranges.size());
             ing.remaining.assign(ranges.size(), 0);
@@ -1204,6 +1212,7 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
                 Ingest& ing; HostTeam& team; bool finished;
                 ~TeamGuard() { if (!finished) ing.abort.store(true); team.wait(); }
             };
+            ingest_t0 = std::chrono::steady_clock::now();
             c.team->launch([&ing](unsigned id) { ing.worker(id); });
             {
                 TeamGuard guard{ing, *c.team, false};
@@ -1217,13 +1226,7 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
             }
             if (ing.err) throw Fail{ing.err, ing.err_msg};
             link_raw = ing.raw_bytes; link_packed = ing.packed_bytes;
-            if (learned_policy) {
-                const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - ingest_t0).count();
-                const double rate = (double)kept_bytes / std::max(sec, 1e-6) / 1e9;
-                // disturbances only ever make a call slower: remember the best recent rate of each policy (slowly forgotten)
-                double& r = c.ingest_rate[policy];
-                r = std::max(0.97 * r, rate);
-            }
+
             if (tr.on) cudaEventRecord(ev_c1, cs);
             if (tr.on) std::fprintf(stderr, "[skb] sketch_batch: ingest by %u threads (%s): %.1f MB as ASCII, %.1f MB as 2-bit words (= %.1f MB of bases)\n",
                                     n_threads, host_pack_isa(), link_raw / 1048576.0, link_packed / 1048576.0, link_packed * 4 / 1048576.0);
@@ -1232,6 +1235,13 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
         CU(cudaEventRecord(c.ev[4], st));
         CU(cudaStreamSynchronize(st));
         tr.mark("final sync");
+        if (learned >= 0) {
+            const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - ingest_t0).count();
+            const double rate = (double)kept_bytes / std::max(sec, 1e-6) / 1e9;
+            // disturbances only ever make a call slower: remember the best recent rate of each policy (slowly forgotten)
+            double& r = c.ingest_rate[learned];
+            r = std::max(0.97 * r, rate);
+        }
         if (tr.on) {
             float cms = 0, lead = 0;
             cudaEventElapsedTime(&cms, ev_c0, ev_c1); cudaEventElapsedTime(&lead, c.ev[0], ev_c0);
