@@ -208,11 +208,38 @@ def main():
         # the one exchange step: packed device buffers, NCCL all-gather over NVLink, device-to-device unpack
         from pyskani_b200 import parallel
         be = parallel.CudaBackend.__new__(parallel.CudaBackend); be.capi = capi; be.ctx = ctx
-        dist.barrier(); torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        per_rank = parallel.exchange_sketches_device(be, sketches, dist, dev)
-        torch.cuda.synchronize()
-        t_exchange = tmax(time.perf_counter() - t0)
+        # twice: the first exchange pays for the fresh device memory of the block (new slabs from cudaMalloc), the second
+        # shows the steady state of a repeated job; then a bare NCCL all-gather of the same bytes for comparison
+        ex_log = []
+        for rep in range(2):
+            per_rank = None
+            dist.barrier(); torch.cuda.synchronize()
+            tm = {}
+            t0 = time.perf_counter()
+            per_rank = parallel.exchange_sketches_device(be, sketches, dist, dev, timings=tm)
+            t_host = time.perf_counter() - t0
+            torch.cuda.synchronize()
+            t_exchange = tmax(time.perf_counter() - t0)
+            ev = tm.pop("_exchange_events")
+            ag_ms = ev[0].elapsed_time(ev[1])
+            ex_log.append(dict(total_s=t_exchange, host_s=tmax(t_host), sizes_ms=tmax(tm["exchange_sizes_ms"]), pack_enqueue_ms=tmax(tm["exchange_pack_enqueue_ms"]),
+                               adopt_ms=tmax(tm["exchange_adopt_ms"]), allgather_ms=tmax(ag_ms), bytes_in=tm["exchange_bytes_in"], bytes_total=tm["exchange_bytes_total"],
+                               collective=tm["exchange_collective"]))
+        nbytes = int(ex_log[-1]["bytes_total"]) // world // 256 * 256
+        src = torch.empty(nbytes, dtype=torch.uint8, device=dev); dst = torch.empty(nbytes * world, dtype=torch.uint8, device=dev)
+        bare = []
+        for rep in range(3):
+            dist.barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); dist.all_gather_into_tensor(dst, src); e1.record(); torch.cuda.synchronize()
+            bare.append(tmax(e0.elapsed_time(e1)))
+        del src, dst
+        for i, e in enumerate(ex_log):
+            say("exchange %d: %.1f ms in all (host until usable %.1f ms: sizes %.2f + pack/enqueue %.2f + adopt %.2f); all-gathers %.2f ms for %.2f GB into "
+                "every GPU = %.0f GB/s busbw (%s)" % (i, 1e3 * e["total_s"], 1e3 * e["host_s"], e["sizes_ms"], e["pack_enqueue_ms"], e["adopt_ms"], e["allgather_ms"],
+                                                      e["bytes_in"] / 1e9, e["bytes_in"] / e["allgather_ms"] / 1e6, e["collective"]), flush=True)
+        say("exchange reference: a bare ncclAllGather of the same %.2f GB per rank: %s ms -> %.0f GB/s busbw" % (
+            nbytes / 1e9, ", ".join("%.2f" % b for b in bare), nbytes * (world - 1) / min(bare) / 1e6), flush=True)
         full = [None] * (F * M)
         for r in range(world):
             ids = [f * M + m for f in range(r, F, world) for m in range(M)]
@@ -307,7 +334,7 @@ def main():
         " (all ranks)" if world > 1 else "", intra and all_ok, ok_self and all_ok, mono and all_ok, worst))
     if args.json and rank == 0:
         json.dump({"gpus": world, "genomes": n, "queries": n_pairs // n, "bases": total_bases, "sketch_wall_s": t_sketch_wall,
-                   "exchange_s": t_exchange, "query_wall_s": t_wall, "screen_s": t_screen, "chain_s": t_chain, "pairs": n_pairs,
+                   "exchange_s": t_exchange, "exchange_log": ex_log if world > 1 else None, "query_wall_s": t_wall, "screen_s": t_screen, "chain_s": t_chain, "pairs": n_pairs,
                    "chained": n_in_all, "hits": n_hits_all, "properties_ok": all_ok, "max_abs_err_vs_divergence": worst},
                   open(args.json, "w"))
     if world > 1:
