@@ -64,7 +64,8 @@ __attribute__((target("avx2"))) inline __m256i codes_of_32(__m256i v) {
     return _mm256_madd_epi16(pairs, _mm256_set1_epi32(0x00010010));                   // p0 * 16 + p1
 }
 
-__attribute__((target("avx2"))) void pack_avx2(const uint8_t* src, size_t n_bases, uint32_t* words) {
+template <bool STREAM>
+__attribute__((target("avx2"))) void pack_avx2_t(const uint8_t* src, size_t n_bases, uint32_t* words) {
     const __m256i rev4 = _mm256_setr_epi8(3, 2, 1, 0, 7, 6, 5, 4, 11, 10, 9, 8, 15, 14, 13, 12, 3, 2, 1, 0, 7, 6, 5, 4, 11, 10, 9, 8, 15, 14, 13, 12);
     const __m256i order = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);
     size_t i = 0;
@@ -110,7 +111,8 @@ __attribute__((target("avx512f,avx512bw,avx512vbmi,avx512vl"))) inline __m128i w
     return _mm_shuffle_epi8(bytes, _mm_setr_epi8(3, 2, 1, 0, 7, 6, 5, 4, 11, 10, 9, 8, 15, 14, 13, 12));
 }
 
-__attribute__((target("avx512f,avx512bw,avx512vbmi,avx512vl"))) void pack_avx512(const uint8_t* src, size_t n_bases, uint32_t* words) {
+template <bool STREAM>
+__attribute__((target("avx512f,avx512bw,avx512vbmi,avx512vl"))) void pack_avx512_t(const uint8_t* src, size_t n_bases, uint32_t* words) {
     const __m512i lo = _mm512_load_si512((const void*)g_tab128.t), hi = _mm512_load_si512((const void*)(g_tab128.t + 64));
     size_t i = 0;
     while (((uintptr_t)(words + i / 16) & 31) && i + 16 <= n_bases) {
@@ -123,7 +125,9 @@ __attribute__((target("avx512f,avx512bw,avx512vbmi,avx512vl"))) void pack_avx512
         prefetch_ahead(src + i);
         const __m128i a = words_of_64(_mm512_loadu_si512((const void*)(src + i)), lo, hi);
         const __m128i b = words_of_64(_mm512_loadu_si512((const void*)(src + i + 64)), lo, hi);
-        _mm256_stream_si256((__m256i*)(words + i / 16), _mm256_inserti128_si256(_mm256_castsi128_si256(a), b, 1));
+        const __m256i q = _mm256_inserti128_si256(_mm256_castsi128_si256(a), b, 1);
+        if (STREAM) _mm256_stream_si256((__m256i*)(words + i / 16), q);
+        else _mm256_store_si256((__m256i*)(words + i / 16), q);
     }
     if (i < n_bases) pack_scalar(src + i, n_bases - i, words + i / 16);
     _mm_sfence();
@@ -141,9 +145,12 @@ bool have_avx2() {
 
 }  // namespace
 
-void host_pack_bases(const uint8_t* src, size_t n_bases, uint32_t* words) {
-    if (have_avx512()) pack_avx512(src, n_bases, words);
-    else if (have_avx2()) pack_avx2(src, n_bases, words);
+void pack_avx2(const uint8_t* src, size_t n, uint32_t* words, bool stream = true) { stream ? pack_avx2_t<true>(src, n, words) : pack_avx2_t<false>(src, n, words); }
+void pack_avx512(const uint8_t* src, size_t n, uint32_t* words, bool stream = true) { stream ? pack_avx512_t<true>(src, n, words) : pack_avx512_t<false>(src, n, words); }
+
+void host_pack_bases(const uint8_t* src, size_t n_bases, uint32_t* words, bool stream) {
+    if (have_avx512()) pack_avx512(src, n_bases, words, stream);
+    else if (have_avx2()) pack_avx2(src, n_bases, words, stream);
     else pack_scalar(src, n_bases, words);
 }
 const char* host_pack_isa() { return have_avx512() ? "avx512vbmi" : have_avx2() ? "avx2" : "scalar"; }

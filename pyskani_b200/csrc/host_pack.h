@@ -22,7 +22,9 @@ namespace skb {
 
 // words[i] = bases 16 i .. 16 i + 15 of src (missing bases of the last word encode as 0).  n_bases may be 0.
 // Results are globally visible when the call returns (the streaming stores are fenced).
-void host_pack_bases(const uint8_t* src, size_t n_bases, uint32_t* words);
+// stream = true: streaming (non-temporal) stores, for output that is written once and read by the copy engine much later;
+// stream = false: ordinary stores, for output blocks that are reused and should stay in the cache.
+void host_pack_bases(const uint8_t* src, size_t n_bases, uint32_t* words, bool stream = true);
 // which implementation host_pack_bases dispatches to on this CPU: "avx512vbmi", "avx2" or "scalar"
 const char* host_pack_isa();
 // CPUs this process may run on (sched_getaffinity), at least 1

@@ -7,12 +7,14 @@
 
 extern "C" {
 
-// packs n bases with the dispatching entry (isa = 0), the scalar body (1), the AVX2 body (2) or the AVX-512 body (3);
+// packs n bases with the dispatching entry (isa = 0), the scalar body (1), the AVX2 body (2), the AVX-512 body (3) or the
+// dispatching entry with ordinary stores (4);
 // returns the words written, or 0 if this CPU lacks the instruction set
 uint64_t shim_host_pack(const uint8_t* src, uint64_t n, uint32_t* words, int isa) {
     if (isa == 1) skb::pack_scalar(src, n, words);
     else if (isa == 2) { if (!skb::have_avx2()) return 0; skb::pack_avx2(src, n, words); }
     else if (isa == 3) { if (!skb::have_avx512()) return 0; skb::pack_avx512(src, n, words); }
+    else if (isa == 4) skb::host_pack_bases(src, n, words, false);       // ordinary instead of streaming stores
     else skb::host_pack_bases(src, n, words);
     return (n + 15) / 16 + 1;
 }

@@ -25,7 +25,7 @@ def shim(tmp_path_factory):
     return L
 
 
-ISAS = (0, 1, 2, 3)       # dispatching entry, scalar, AVX2, AVX-512 VBMI
+ISAS = (0, 1, 2, 3, 4)    # dispatching entry, scalar, AVX2, AVX-512 VBMI, dispatching entry with ordinary stores
 
 
 def messy(n, seed):
