@@ -96,7 +96,7 @@ void* skb_ctx_stream(skb_ctx_t* ctx);
  * once: the copy engine pulls chunks of ASCII out of the caller's memory while n - 1 threads compact other chunks to
  * 2-bit words (4:1) in pinned staging memory and one thread feeds the copy engine; the seeding kernel reads either form
  * and produces bit-identical sketches.  n = 0 or 1: every byte travels as ASCII; n < 0: default = SKB_HOST_THREADS, else
- * min(32, usable CPUs / LOCAL_WORLD_SIZE) - 1, and 0 when several ranks leave fewer than 8 CPUs to each; which of the two
+ * min(32, usable CPUs / LOCAL_WORLD_SIZE) - 1, and 0 from four ranks per host on or below 8 CPUs per rank; which of the two
  * policies (both routes, or every chunk compacted) a context uses for pinned sources is measured on its first large calls.  SKB_INGEST=raw|pack|mix
  * overrides the policy (test hook). */
 int  skb_ctx_set_host_threads(skb_ctx_t* ctx, int32_t n);

@@ -76,6 +76,7 @@ struct Core {
     // every chunk [1] and of plain copies [2]; the fastest is used, the others re-measured in turn every 16th large call
     double ingest_rate[3] = {0.0, 0.0, 0.0};
     uint32_t ingest_calls = 0;
+    int ingest_best = 0;
     cudaEvent_t pool_event(size_t i) {
         while (ev_pool.size() <= i) {
             cudaEvent_t e;
@@ -764,10 +765,12 @@ static unsigned resolve_host_threads(const Core& c) {
         const int w = std::atoi(e);
         if (w > 1) {
             cpus = std::max(1u, cpus / (unsigned)w);
-            // eight ranks on a 32-CPU host: 3 packing threads per rank beside 8 spinning callers and NCCL's proxies packed 5 % of
-            // the bytes and cost 4 % of the step (33.6 against 31.7 ms, gpurun_out/r2g_bench_n8*.json): below 8 CPUs per rank
-            // every byte travels as ASCII
-            if (cpus < 8) return 0;
+            // From four ranks per host on, the ranks' plain copies together already saturate the host's PCIe / memory fabric
+            // (copy floor per GPU on the bench boxes: 55 GB/s alone, 29 GB/s at 4, 23 GB/s at 8) and a packing team on every
+            // rank only adds load: 8 ranks 33.6 ms with the team against 31.7 ms without, 4 ranks 35.5-37 against 31.2 ms
+            // (profiles/r2_bench_line_n8_ingest_*.json).  A rank cannot see that from its own timings -
+            // its choice slows the OTHER ranks - so this is a rule, not something the context learns.
+            if (w >= 4 || cpus < 8) return 0;
         }
     }
     // the calling thread spins in its stream synchronisations: it keeps one CPU, the team gets the others (with 16 CPUs,
@@ -1119,9 +1122,9 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
         // routes at once [0], every chunk packed [1], or plain copies without the team [2].  With enough threads the host's
         // memory system, not PCIe, is the limit and the DMA route's reads only slow the packing threads down (16-CPU box,
         // 1.25 GB: 13.2 ms mixed, 12.2 ms packed, 24.5 ms copied); with 4 threads 16.3 / 23.7 / 24.5 ms; with several ranks on
-        // a host whose PCIe or memory fabric is already saturated by the copies, the team only costs.  The first three large
-        // calls try one policy each, later calls take the one with the best recent rate and re-measure the others in turn
-        // every 16th call.  The sketches do not depend on the choice.
+        // a host whose PCIe or memory fabric is already saturated by the copies, the team only costs.  The first six large
+        // calls try every policy twice, later calls stay with the best one (5 % hysteresis) and re-measure the others in turn
+        // every 32nd call.  The sketches do not depend on the choice.
         int learned = -1;                   // policy under measurement in this call, -1: none
         bool force_pack = false;
         if (pipelined && (!ingest_env || std::strcmp(ingest_env, "auto") == 0)) {
@@ -1136,13 +1139,16 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
             }
             if (pageable) force_pack = true;
             else if (!ingest_env) {
+                // two rounds over the three policies first (a single sample is too easily spoilt by what other ranks of the
+                // host happen to try at that moment), then the incumbent stays unless another policy is 5 % better
                 int pick = -1;
-                for (int k = 0; k < 3 && pick < 0; k++) if (c.ingest_rate[k] == 0.0) pick = k;
-                if (pick < 0) {
-                    int best = 0;
-                    for (int k = 1; k < 3; k++) if (c.ingest_rate[k] > c.ingest_rate[best]) best = k;
+                if (c.ingest_calls < 6) pick = (int)(c.ingest_calls % 3);
+                else {
+                    int best = c.ingest_best;
+                    for (int k = 0; k < 3; k++) if (c.ingest_rate[k] > 1.05 * c.ingest_rate[best]) best = k;
+                    c.ingest_best = best;
                     pick = best;
-                    if (c.ingest_calls % 16 == 15) pick = (best + 1 + (int)((c.ingest_calls / 16) % 2)) % 3;
+                    if (c.ingest_calls % 32 == 31) pick = (best + 1 + (int)((c.ingest_calls / 32) % 2)) % 3;
                 }
                 c.ingest_calls++;
                 learned = pick;

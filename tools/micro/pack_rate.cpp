@@ -9,10 +9,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <sys/mman.h>
 using namespace skb;
 int main(int argc, char** argv) {
     const size_t n = (size_t)(argc > 1 ? atol(argv[1]) : 1250) << 20;
-    uint8_t* src = (uint8_t*)aligned_alloc(4096, n);
+    uint8_t* src = (uint8_t*)aligned_alloc(2 << 20, n);
+    if (getenv("PACK_NOHUGE")) madvise(src, n, MADV_NOHUGEPAGE); else madvise(src, n, MADV_HUGEPAGE);     // 4 KB or 2 MB pages for the input
     uint32_t* dst = (uint32_t*)aligned_alloc(4096, n / 4 + 4096);
     uint64_t s = 88172645463325252ull;
     for (size_t i = 0; i < n; i += 8) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; uint64_t v = 0; for (int j = 0; j < 8; j++) v |= (uint64_t)"ACGT"[(s >> (2 * j)) & 3] << (8 * j); memcpy(src + i, &v, 8); }
