@@ -72,10 +72,16 @@ def test_sketch_ragged_batch(ctx):
     assert gs[0].info().n_seeds == 0 and gs[1].info().n_contigs == 0
 
 
-def test_sketch_tile_and_region_boundaries(ctx):
+@pytest.mark.parametrize("ingest", ["default", "pack"])
+def test_sketch_tile_and_region_boundaries(ctx, monkeypatch, ingest):
     """Contig lengths around the kernel's work units (16-base words, 2 048-base tiles, 16 384-base regions) with every
     position a seed (c = 1), so that a k-mer dropped or duplicated at any boundary changes the sketch; host pointers at
-    odd addresses."""
+    odd addresses.  Once through the ASCII input of the seeding kernel and once through its packed-word input (every
+    chunk compacted by the host threads, chunks of 16 KB so that launches start and end inside genomes' neighbourhoods)."""
+    if ingest == "pack":
+        monkeypatch.setenv("SKB_INGEST", "pack")
+        monkeypatch.setenv("SKB_CHUNK_KB", "16")
+        ctx.set_host_threads(3)
     lens = [500, 511, 512, 513, 2047, 2048, 2049, 2048 + 14, 2048 + 20, 4096, 16383, 16384, 16385, 16384 + 20, 32768 + 7,
             3 * 16384 - 1]
     big = np.frombuffer(rand(sum(lens) + 3 * len(lens) + 8, 41), np.uint8)
@@ -88,6 +94,10 @@ def test_sketch_tile_and_region_boundaries(ctx):
         want = [contigs, contigs[::-1], [contigs[5]], [contigs[11], contigs[12]]]
         for g, w in zip(gs, want):
             assert_sketch_equal(g, oracle.Sketch([x.tobytes() for x in w], c=c, marker_c=mc))
+        if ingest == "pack":
+            st = ctx.stats()
+            assert st.h2d_packed_bytes > 0 and st.h2d_raw_bytes == 0
+    ctx.set_host_threads(-1)
 
 
 def test_marker_sets_all_three_sort_paths(ctx):
@@ -136,6 +146,7 @@ def test_ingest_routes_give_the_same_sketch(ctx, monkeypatch):
     (host_pack.h); which chunk takes which route depends on timing.  Every policy - all ASCII, all compacted, mixed, the
     pipeline switched off - must give the oracle's sketches bit for bit: ragged genomes, contigs below the 500 bp gate, small
     contigs that go through staging, junk bytes, lower case, lengths that are not multiples of 16."""
+    from pyskani_b200 import capi
     monkeypatch.setenv("SKB_CHUNK_KB", "256")            # many chunks out of a few MB
     junk = bytearray(rand(600_000, 711))
     junk[1000:1400] = b"N" * 400
@@ -160,6 +171,15 @@ def test_ingest_routes_give_the_same_sketch(ctx, monkeypatch):
             seen_raw |= st.h2d_raw_bytes > 0
         (one,) = ctx.sketch_batch(genomes[4:5], c=30, marker_c=200)
         assert_sketch_equal(one, oracle.Sketch(genomes[4], c=30, marker_c=200))
+    # a call that fails while the team is at work (k > 16 is refused inside the first sub-batch) unwinds cleanly: the team
+    # is stopped before the call returns and the context keeps working
+    monkeypatch.setenv("SKB_INGEST", "mix")
+    ctx.set_host_threads(4)
+    for _ in range(3):
+        with pytest.raises(capi.SkbError):
+            ctx.sketch_batch(genomes, k=17)
+        (again,) = ctx.sketch_batch(genomes[:1])
+        assert_sketch_equal(again, want[0])
     # the automatic policy: pageable sources (these bytes objects) are left to the packing threads altogether, pinned ones
     # are shared between the copy engine and the packing threads
     monkeypatch.setenv("SKB_INGEST", "auto")
