@@ -636,7 +636,7 @@ struct RawCopier {
 
 struct Ingest {
     enum { MIX = 0, PACK_ONLY = 1 };
-    static constexpr size_t PIECE_BASES = (size_t)1 << 20;     // unit of work of a packing thread (a multiple of 16)
+    size_t PIECE_BASES = (size_t)512 << 10;                    // unit of work of a packing thread (a multiple of 16)
     static constexpr unsigned RAW_DEPTH = 2;                     // ASCII chunks the copy engine may have queued
     struct Chunk { uint32_t c0, c1; cudaEvent_t ev; int mode; bool done; };
     struct Piece { const uint8_t* src; size_t n; uint32_t* dst; uint32_t chunk; };
@@ -656,7 +656,9 @@ struct Ingest {
     uint64_t raw_bytes = 0, packed_bytes = 0;      // bytes that crossed the link in either form (guarded by mu)
 
     Ingest(Core& c_, const uint8_t* const* ct, const uint64_t* ln, const uint64_t* of, uint8_t* dseq, uint8_t* dpk, char* spk, char* sraw, int pol)
-        : c(c_), contigs(ct), lens(ln), offs(of), d_seq(dseq), d_pk(dpk), stage_pk(spk), stage_raw(sraw), policy(pol) {}
+        : c(c_), contigs(ct), lens(ln), offs(of), d_seq(dseq), d_pk(dpk), stage_pk(spk), stage_raw(sraw), policy(pol) {
+        if (const char* e = std::getenv("SKB_PIECE_KB")) PIECE_BASES = std::max<size_t>(16, ((size_t)std::atoll(e) << 10) & ~(size_t)15);   // tuning hook
+    }
 
     // calling thread: block until chunk ch is on its way (its event is recorded); returns the arrival form
     int wait(uint32_t ch) {
@@ -696,7 +698,12 @@ struct Ingest {
         }
     }
     // ---- route 2: 2-bit words through pinned staging (all other threads)
+    std::chrono::steady_clock::time_point t_start = std::chrono::steady_clock::now();
+    std::atomic<uint64_t> last_piece_ns{0};      // when the last piece was packed, from t_start
+    std::atomic<uint64_t> finish_ns{0}, lock_ns{0}, pack_ns{0};      // SKB_TRACE: time the workers spent in CUDA calls / waiting for mu / packing
     void finish_packed(uint32_t ch) {
+        const auto t_f0 = std::chrono::steady_clock::now();
+        struct Acc { std::atomic<uint64_t>& a; std::chrono::steady_clock::time_point t0; ~Acc() { a += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); } } acc{finish_ns, t_f0};
         uint32_t first = chunks[ch].c0, last = chunks[ch].c1;
         while (first < last && !kept(first)) first++;
         while (last > first && !kept(last - 1)) last--;
@@ -737,9 +744,15 @@ struct Ingest {
             }
             if (empty_chunk) { finish_packed(claimed); continue; }
             if (!have) continue;
+            const auto t_p0 = std::chrono::steady_clock::now();
             host_pack_bases(p.src, p.n, p.dst);
+            const auto t_p1 = std::chrono::steady_clock::now();
             bool last;
             { std::lock_guard<std::mutex> lk(mu); last = --remaining[p.chunk] == 0; }
+            const auto t_p2 = std::chrono::steady_clock::now();
+            pack_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_p1 - t_p0).count();
+            last_piece_ns.store((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_p1 - t_start).count());
+            lock_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_p2 - t_p1).count();
             if (last) finish_packed(p.chunk);
         }
     }
@@ -1058,11 +1071,20 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
         CU(cudaStreamWaitEvent(cs, c.ev[5], 0));          // d_seq's allocation is ordered on `st`
         cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr;
         if (tr.on) { cudaEventCreate(&ev_c0); cudaEventCreate(&ev_c1); cudaEventRecord(ev_c0, cs); }
-        uint64_t CHUNK = (uint64_t)16 << 20;                // granularity of copy -> seeding hand-over
+        // granularity of the copy -> seeding hand-over: 16 MB when this thread enqueues plain copies; 32 MB for batches that
+        // go through the ingest team, whose per-chunk costs (claim, copy + event by a worker, wake-up of this thread, launch)
+        // are larger: 1.25 GB packed by 15 threads takes 12.3 ms in 16 MB chunks, 10.4 ms in 32 MB chunks (with 512 KB pieces),
+        // 10.8 ms in 64 MB chunks (the last chunk's latency starts to show)
+        uint64_t kept_bytes = 0;
+        for (uint32_t i = 0; i < n_contigs; i++) if (contig_lens[i] >= SKB_MIN_LENGTH_CONTIG) kept_bytes += contig_lens[i];
+        const char* ingest_env = std::getenv("SKB_INGEST");      // raw | pack | mix | auto (= unset, but also for small batches)
+        const bool want_raw = ingest_env && std::strcmp(ingest_env, "raw") == 0;
+        const unsigned n_threads = want_raw ? 0 : resolve_host_threads(c);
+        constexpr uint64_t INGEST_MIN = (uint64_t)64 << 20; // smaller calls are not worth waking the thread team for
+        uint64_t CHUNK = (uint64_t)(n_threads >= 2 && kept_bytes >= INGEST_MIN ? 32 : 16) << 20;
         if (const char* e = std::getenv("SKB_CHUNK_KB")) CHUNK = std::max<uint64_t>(1, (uint64_t)std::atoll(e)) << 10;   // test hook
         constexpr uint64_t SUB = (uint64_t)192 << 20;       // genomes are indexed in sub-batches of about this size
         constexpr uint64_t SUB_MAX = (uint64_t)1536 << 20;  // upper bound of a sub-batch (the batch limit is 2^31 bases)
-        constexpr uint64_t INGEST_MIN = (uint64_t)64 << 20; // smaller calls are not worth waking the thread team for
         // The batch is processed in sub-batches (whole genomes): while the index of sub-batch i is built, the copies of
         // the later sub-batches keep the PCIe link busy, so only the last sub-batch's index build is exposed after the
         // final byte has arrived.
@@ -1070,8 +1092,6 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
         std::vector<SubBatch> subs;
         struct ChunkRange { uint32_t c0, c1; };
         std::vector<ChunkRange> ranges;                     // flat contig range of every chunk, in order
-        uint64_t kept_bytes = 0;
-        for (uint32_t i = 0; i < n_contigs; i++) if (contig_lens[i] >= SKB_MIN_LENGTH_CONTIG) kept_bytes += contig_lens[i];
         // cut points (cumulative bytes): equal parts of about SUB bytes (measured best on B200 among head/tail splits:
         // the index build runs ~2.5x slower while the copy engine is busy, so parts must stay small enough to keep up)
         std::vector<uint64_t> cuts;
@@ -1111,9 +1131,6 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
             }
         }
         // ---- how the bytes travel
-        const char* ingest_env = std::getenv("SKB_INGEST");      // raw | pack | mix | auto (= unset, but also for small batches)
-        const bool want_raw = ingest_env && std::strcmp(ingest_env, "raw") == 0;
-        const unsigned n_threads = want_raw ? 0 : resolve_host_threads(c);
         bool pipelined = n_threads >= 2 && ranges.size() >= 2 && (kept_bytes >= INGEST_MIN || ingest_env != nullptr);
         // Large batches without a forced policy: pageable sources (Python bytes) are left to the packing threads altogether -
         // the driver stages a pageable copy through its own buffers at a fraction of the link rate and holds the stream's lock
@@ -1234,8 +1251,10 @@ int skb_sketch_batch(skb_ctx_t* ctx, const skb_sketch_params_t* params, int32_t 
             link_raw = ing.raw_bytes; link_packed = ing.packed_bytes;
 
             if (tr.on) cudaEventRecord(ev_c1, cs);
-            if (tr.on) std::fprintf(stderr, "[skb] sketch_batch: ingest by %u threads (%s): %.1f MB as ASCII, %.1f MB as 2-bit words (= %.1f MB of bases)\n",
-                                    n_threads, host_pack_isa(), link_raw / 1048576.0, link_packed / 1048576.0, link_packed * 4 / 1048576.0);
+            if (tr.on) std::fprintf(stderr, "[skb] sketch_batch: ingest by %u threads (%s): %.1f MB as ASCII, %.1f MB as 2-bit words (= %.1f MB of bases); "
+                                    "workers: %.2f ms packing, %.2f ms in copy/event calls, %.2f ms at the queue lock (summed over threads), last piece packed %.2f ms after the team started\n",
+                                    n_threads, host_pack_isa(), link_raw / 1048576.0, link_packed / 1048576.0, link_packed * 4 / 1048576.0,
+                                    ing.pack_ns.load() / 1e6, ing.finish_ns.load() / 1e6, ing.lock_ns.load() / 1e6, ing.last_piece_ns.load() / 1e6);
         }
         tr.mark("sketch_core done");
         CU(cudaEventRecord(c.ev[4], st));
