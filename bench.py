@@ -589,7 +589,7 @@ def main():
             ("exchange_bytes_in", "max"), ("exchange_bytes_total", "max")]
     ph = phase_stats(tms, keys)
 
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(max(2, args.warmup)):          # also lets every context settle on its ingest policy (six large calls)
         step(sketch_host)
     e2e_ms, tms_h, table_h = timed(sketch_host, args.steps)
     ph_h = phase_stats(tms_h, [("sketch_ms", "max"), ("exchange_ms", "max"), ("query_ms", "max"), ("gather_ms", "max"),
