@@ -197,6 +197,7 @@ def sort_hits(table):
 
 
 _GATHER_ROWS = {}       # world size -> rows every rank sends per gather (grows when a rank had more)
+_GATHER_BUFS = {}       # (world size, capacity, device) -> pinned (send, receive) blocks
 
 
 def gather_hits(local_hits, dist, device="cpu", sort=True):
@@ -209,15 +210,34 @@ def gather_hits(local_hits, dist, device="cpu", sort=True):
     world = dist.get_world_size()
     rows = np.ascontiguousarray(np.asarray(local_hits, np.float64).reshape(-1, 5))
     cap = _GATHER_ROWS.get(world, 1024)
+    on_gpu = str(device).startswith("cuda")
     while True:
-        block = np.zeros((cap + 1, 5), np.float64)
+        if on_gpu:
+            # pinned host blocks (kept per world size and capacity): the small copies on either side of the collective then
+            # run at link speed instead of being staged through pageable memory
+            key = (world, cap, str(device))
+            bufs = _GATHER_BUFS.get(key)
+            if bufs is None:
+                _GATHER_BUFS.clear()
+                bufs = (torch.zeros((cap + 1, 5), dtype=torch.float64).pin_memory(),
+                        torch.zeros((world * (cap + 1), 5), dtype=torch.float64).pin_memory())
+                _GATHER_BUFS[key] = bufs
+            h_send, h_recv = bufs
+            block = h_send.numpy()
+        else:
+            block = np.zeros((cap + 1, 5), np.float64)
         block[0, 0] = len(rows)
         k = min(len(rows), cap)
         block[1:1 + k] = rows[:k]
-        send = torch.from_numpy(block).to(device)
+        send = h_send.to(device, non_blocking=True) if on_gpu else torch.from_numpy(block)
         allr = torch.empty((world * (cap + 1), 5), dtype=torch.float64, device=device)
         dist.all_gather_into_tensor(allr, send)
-        allr = allr.cpu().numpy().reshape(world, cap + 1, 5)
+        if on_gpu:
+            h_recv.copy_(allr, non_blocking=True)
+            torch.cuda.current_stream(device).synchronize()
+            allr = h_recv.numpy().reshape(world, cap + 1, 5)
+        else:
+            allr = allr.numpy().reshape(world, cap + 1, 5)
         counts = [int(allr[r, 0, 0]) for r in range(world)]
         if max(counts) <= cap:
             break
