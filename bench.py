@@ -687,12 +687,14 @@ def main():
             "issue_roofline": {
                 "bound": "integer ALU pipe", "kernel": "seed_scan_kernel", "unit": "Gbp/s",
                 "achieved": my_bases / (seed_ms / 1e3) / 1e9,
-                "peak": 148 * 4 * 32 / (42.0 * 2.0) * 1.965,
-                "frac": (my_bases / (seed_ms / 1e3) / 1e9) / (148 * 4 * 32 / (42.0 * 2.0) * 1.965),
-                "note": "two exact 64-bit mm_hash64 evaluations per base cost 42 ALU-pipe instructions per position in the hash "
-                        "loop (profiles/r2_seed_scan_sass_mix.txt, derived from the shipped cubin by tools/sass_mix.py); the pipe "
-                        "issues one warp instruction per 2 cycles per SM sub-partition: 148 SMs x 4 x 32 lanes / (42 x 2) x 1.965 GHz. "
-                        "ncu: ALU pipe 81 % busy over the whole kernel (74.7 instructions per position incl. pack, scan and write-out)"},
+                "peak": 148 * 4 * 32 / (40.25 * 2.0) * 1.965,
+                "frac": (my_bases / (seed_ms / 1e3) / 1e9) / (148 * 4 * 32 / (40.25 * 2.0) * 1.965),
+                "note": "two exact 64-bit mm_hash64 evaluations per base cost 37.25 ALU-pipe instructions per position in the hash "
+                        "loop plus 3 IMAD.WIDE that take an ALU slot each besides their two FMA slots (profiles/r2_seed_scan_sass_mix.txt, "
+                        "derived from the shipped cubin by tools/sass_mix.py; slot costs measured by tools/micro/int_pipes.cu, "
+                        "profiles/r2_int_pipes.txt); the pipe issues one warp instruction per 2 cycles per SM sub-partition: "
+                        "148 SMs x 4 x 32 lanes / (40.25 x 2) x 1.965 GHz. ncu: ALU pipe 75-81 % busy over the whole kernel "
+                        "(76 instructions per position incl. pack, scan and write-out)"},
             "clocks": clocks,
         }
         threads = args.cpu_threads or (os.cpu_count() or 1)

@@ -34,25 +34,40 @@ __device__ __forceinline__ uint4 ld_stream16(const uint8_t* p) {
 // ---- mm_hash64 in 32-bit halves (see kmer_bits.cuh::mm_hash64 for the reference form) -------------------
 struct U64 { uint32_t lo, hi; };
 
-__device__ __forceinline__ U64 mul_c(U64 x, uint32_t c) {            // x * c mod 2^64: IMAD.WIDE + IMAD (FMA pipe)
-    const uint64_t p = (uint64_t)x.lo * c;
+#ifndef SKB_MUL_SPLIT
+#define SKB_MUL_SPLIT 3
+#endif
+// x * c mod 2^64.  Plain: IMAD.WIDE + IMAD.  SPLIT: the low and high word of x.lo * c by separate multiplies (IMAD +
+// IMAD.HI + IMAD) - one more issue slot of the FMA pipe, but no 64-bit result: tools/micro/int_pipes.cu shows that an
+// IMAD.WIDE in a stream of ALU-pipe instructions costs that pipe about one slot as well (LOP3 + SHF + IMAD.WIDE + LOP3 takes
+// 3.9 ALU slots, not 3).  SKB_MUL_SPLIT: 1 = both hashes, 2 = the seed hash, 3 = the marker hash (the measured optimum: with
+// both split the FMA pipe becomes the busier one).
+// (c_again == c from constant memory, which the compiler cannot see through: given the same operand twice it fuses the two
+// multiplies back into a wide one.)
+__constant__ uint32_t c_hash_mul[3] = {(1u << 21) + 1u, 265u, 21u};
+template <bool SPLIT>
+__device__ __forceinline__ U64 mul_c(U64 x, uint32_t c, uint32_t c_again = 0) {
     U64 r;
-    r.lo = (uint32_t)p;
-    r.hi = x.hi * c + (uint32_t)(p >> 32);
+    if (SPLIT) {
+        r.lo = x.lo * c;
+        r.hi = x.hi * c + __umulhi(x.lo, c_again);
+    } else {
+        const uint64_t p = (uint64_t)x.lo * c;
+        r.lo = (uint32_t)p;
+        r.hi = x.hi * c + (uint32_t)(p >> 32);
+    }
     return r;
 }
 #ifndef SKB_XS_FMA
 #define SKB_XS_FMA 0
 #endif
-// x >> S for 0 < S < 32.  With SKB_XS_FMA the shifts are expressed as multiplies (IMAD.HI / IMAD) so that they
-// issue on the FMA pipe and leave the ALU pipe to the xors and compares.
-template <int S>
+// x >> S for 0 < S < 32.  With SKB_XS_FMA shifts are expressed as multiplies (IMAD.HI / IMAD) so that they issue on the FMA
+// pipe and leave the ALU pipe to the xors and compares: 1 = every shift of the xor-shift steps, 2 = the high-word shifts,
+// 3 = the high-word shifts of the seed hash only, 4 = those of the marker hash only.
+template <int S, bool FMA>
 __device__ __forceinline__ uint32_t shr_hi(uint32_t hi) {
-#if SKB_XS_FMA >= 1
-    return __umulhi(hi, 1u << (32 - S));
-#else
+    if (FMA) return __umulhi(hi, 1u << (32 - S));
     return hi >> S;
-#endif
 }
 template <int S>
 __device__ __forceinline__ uint32_t shr_lo(uint32_t lo, uint32_t hi) {
@@ -62,51 +77,74 @@ __device__ __forceinline__ uint32_t shr_lo(uint32_t lo, uint32_t hi) {
     return __funnelshift_r(lo, hi, S);
 #endif
 }
-template <int S>
+template <int S, bool FMA>
 __device__ __forceinline__ U64 xorshr(U64 x) {                        // x ^ (x >> S), 0 < S < 32
     U64 r;
     r.lo = x.lo ^ shr_lo<S>(x.lo, x.hi);
-    r.hi = x.hi ^ shr_hi<S>(x.hi);
+    r.hi = x.hi ^ shr_hi<S, FMA>(x.hi);
     return r;
 }
 // hash(x) < thr, x given in halves.  Step 1 is ~(x * (2^21 + 1)); the complement is folded into the first
 // xor-shift:  ~a ^ (~a >> 24) == a ^ (a >> 24) ^ 0xFFFFFF00_00000000.
+template <bool MARKER>
 __device__ __forceinline__ U64 hash_halves(U64 x) {
-    U64 a = mul_c(x, (1u << 21) + 1u);
+    constexpr bool FMA = SKB_XS_FMA == 1 || SKB_XS_FMA == 2 || (SKB_XS_FMA == 3 && !MARKER) || (SKB_XS_FMA == 4 && MARKER);
+    constexpr bool SPLIT = SKB_MUL_SPLIT == 1 || (SKB_MUL_SPLIT == 2 && !MARKER) || (SKB_MUL_SPLIT == 3 && MARKER);
+    U64 a = mul_c<SPLIT>(x, (1u << 21) + 1u, c_hash_mul[0]);
     U64 b;
     b.lo = a.lo ^ shr_lo<24>(a.lo, a.hi);
-    b.hi = a.hi ^ shr_hi<24>(a.hi) ^ 0xFFFFFF00u;
-    b = mul_c(b, 265u);
-    b = xorshr<14>(b);
-    b = mul_c(b, 21u);
-    b = xorshr<28>(b);
-    return mul_c(b, 0x80000001u);                                     // x + (x << 31)
+    b.hi = a.hi ^ shr_hi<24, FMA>(a.hi) ^ 0xFFFFFF00u;
+    b = mul_c<SPLIT>(b, 265u, c_hash_mul[1]);
+    b = xorshr<14, FMA>(b);
+    b = mul_c<SPLIT>(b, 21u, c_hash_mul[2]);
+    b = xorshr<28, FMA>(b);
+    return mul_c<false>(b, 0x80000001u);                                     // x + (x << 31)
 }
 // EXACT: the 64-bit comparison hash < thr.  Otherwise the comparison of the high words only, hash.hi <= thr.hi: one
 // ISETP instead of two per hash (4.5 % of the ALU-pipe work of the loop).  It accepts a superset: the extra elements are
 // the keys whose hash has hi == thr.hi and lo >= thr.lo, one position in ~6e9.  Every accepted position is re-checked
 // exactly when it is written out (1 % of the positions); a false positive raises the launch's `inexact` flag and the host
 // repeats the batch with EXACT = true, so results never depend on the shortcut.
-template <bool EXACT>
+template <bool EXACT, bool MARKER>
 __device__ __forceinline__ bool hash_below(U64 x, uint32_t thr_lo, uint32_t thr_hi) {
-    const U64 b = hash_halves(x);
+    const U64 b = hash_halves<MARKER>(x);
     if (EXACT) return (((uint64_t)b.hi << 32) | b.lo) < (((uint64_t)thr_hi << 32) | thr_lo);
     return b.hi <= thr_hi;
 }
 
 struct WordCtx { uint32_t w0, w1, w2, r0, r1, r2; };
 
+#ifndef SKB_MASK_FMA
+#define SKB_MASK_FMA 1
+#endif
+// The high-word comparison and the hit mask on the FMA pipe (the ALU pipe is the one that limits this kernel; ISETP + SEL
+// + IADD3 for the mask were 5 of its 42 instructions per position).  With M = 2^32 - 1 the high word of h * M is h - 1
+// (0 for h = 0), so the carry of  hi(h * M) + (2^32 - thr)  is exactly [h > thr] for thr >= 1: ONE multiply-add whose only
+// output is the carry predicate (IMAD.HI RZ, P, ...), and  miss = miss * 2 + carry  (IMAD.X) builds the mask of a word's 16
+// positions from the last position to the first.  M and 2 arrive as launch parameters so that the assembler cannot fold
+// the multiplies back into ALU-pipe instructions.  thr = 0 (no seeds wanted) has no such form: the host then asks for
+// the exact comparison.
+__device__ __forceinline__ uint32_t push_miss(uint32_t miss, uint32_t h, uint32_t m1, uint32_t comp, uint32_t two) {
+    uint32_t r;
+    asm("{ .reg .u32 t; mad.hi.cc.u32 t, %1, %2, %3; madc.lo.u32 %0, %4, %5, 0; }"
+        : "=r"(r) : "r"(h), "r"(m1), "r"(comp), "r"(miss), "r"(two));
+    return r;
+}
+
 // masks of the 16 positions of one word: bit e of *smask / *mmask = position e is a seed / marker
 template <bool EXACT>
 __device__ __forceinline__ void eval_word(const WordCtx& c, uint32_t kmask, uint32_t kshift, uint32_t ts_lo, uint32_t ts_hi,
-                                          uint32_t tm_lo, uint32_t tm_hi, uint32_t& smask, uint32_t& mmask) {
+                                          uint32_t tm_lo, uint32_t tm_hi, uint32_t m1, uint32_t two, uint32_t& smask, uint32_t& mmask) {
     smask = 0; mmask = 0;
+    constexpr bool FMA_MASK = !EXACT && SKB_MASK_FMA;
+    uint32_t miss_s = 0, miss_m = 0;                       // FMA_MASK: bit e = position e is NOT a seed / marker
+    const uint32_t comp_s = 0u - ts_hi, comp_m = 0u - tm_hi;
 #pragma unroll
-    for (int e = 0; e < 16; e++) {
+    for (int i = 0; i < 16; i++) {
+        const int e = FMA_MASK ? 15 - i : i;
         const uint32_t s = 30 - 2 * e;
         const uint32_t flo = __funnelshift_r(c.w0, c.w1, s);
         const uint32_t fhi = __funnelshift_r(c.w1, c.w2, s) & 0x3FFu;
-        constexpr int dummy = 0; (void)dummy;
         const uint32_t sr = 24 + 2 * e;
         uint32_t rlo, rhi;
         if (sr < 32) { rlo = __funnelshift_r(c.r2, c.r1, sr); rhi = __funnelshift_r(c.r1, c.r0, sr) & 0x3FFu; }
@@ -115,12 +153,18 @@ __device__ __forceinline__ void eval_word(const WordCtx& c, uint32_t kmask, uint
         const uint32_t fk = flo & kmask;
         const uint32_t rk = __funnelshift_r(rlo, rhi, kshift);
         const uint32_t km = min(fk, rk);
-        if (hash_below<EXACT>(U64{km, 0u}, ts_lo, ts_hi)) smask |= 1u << e;
         // marker 21-mer: canonical = min of the two 42-bit values
         const bool fsmall = (((uint64_t)fhi << 32) | flo) < (((uint64_t)rhi << 32) | rlo);
         const U64 mk{fsmall ? flo : rlo, fsmall ? fhi : rhi};
-        if (hash_below<EXACT>(mk, tm_lo, tm_hi)) mmask |= 1u << e;
+        if (FMA_MASK) {
+            miss_s = push_miss(miss_s, hash_halves<false>(U64{km, 0u}).hi, m1, comp_s, two);
+            miss_m = push_miss(miss_m, hash_halves<true>(mk).hi, m1, comp_m, two);
+        } else {
+            if (hash_below<EXACT, false>(U64{km, 0u}, ts_lo, ts_hi)) smask |= 1u << e;
+            if (hash_below<EXACT, true>(mk, tm_lo, tm_hi)) mmask |= 1u << e;
+        }
     }
+    if (FMA_MASK) { smask = ~miss_s & 0xFFFFu; mmask = ~miss_m & 0xFFFFu; }
 }
 
 #ifndef SKB_SEED_MINBLOCKS
@@ -257,7 +301,7 @@ __global__ void __launch_bounds__(SEED_THREADS, SKB_SEED_MINBLOCKS) seed_scan_ke
                     c.w2 = pk[w]; c.w1 = pk[w + 1]; c.w0 = pk[w + 2];
                     c.r2 = rc[w]; c.r1 = rc[w + 1]; c.r0 = rc[w + 2];
                     uint32_t sm, mm;
-                    eval_word<EXACT>(c, a.kmask, a.kshift, ts_lo, ts_hi, tm_lo, tm_hi, sm, mm);
+                    eval_word<EXACT>(c, a.kmask, a.kshift, ts_lo, ts_hi, tm_lo, tm_hi, a.fma_m1, a.fma_two, sm, mm);
                     const uint32_t left = n - 16u * w;
                     uint32_t valid = left >= 16 ? 0xFFFFu : ((1u << left) - 1u);
                     const uint32_t p0 = pos0 + 16u * w;

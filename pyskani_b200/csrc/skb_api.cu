@@ -445,7 +445,8 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
         // exact = 0: the seeding kernel compares only the high words of hash and threshold and re-checks every hit
         // exactly as it writes it; a position that slipped through (hash.hi == threshold.hi, lo above: one in ~6e9)
         // raises bit 1 of the flag and the batch is repeated with the exact 64-bit comparison (SKB_SEED_EXACT=1 forces it)
-        int exact = std::getenv("SKB_SEED_EXACT") ? 1 : 0;
+        // (also without seeds, threshold 0: the carry form of the high-word test in the kernel needs a threshold >= 1)
+        int exact = (std::getenv("SKB_SEED_EXACT") || !seed) ? 1 : 0;
         for (int attempt = 0; attempt < 2; attempt++) {
             const size_t seed_store = attempt == 0 ? (size_t)n_tiles * seed_tile_cap : (size_t)seed_start[n_genomes];
             const size_t marker_store = attempt == 0 ? (size_t)n_tiles * marker_tile_cap : (size_t)marker_start[n_genomes];
@@ -470,6 +471,7 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             a.genome_region = g_region; a.genome_seed_local = g_slocal; a.genome_marker_local = g_mlocal;
             a.overflow = d_overflow;
             a.exact_compare = (uint32_t)exact;
+            a.fma_m1 = 0xFFFFFFFFu; a.fma_two = 2;
             CU(cudaEventRecord(c.ev[1], st));
             for (size_t li = 0; li < launches.size(); li++) {
                 const Launch& L = launches[li];

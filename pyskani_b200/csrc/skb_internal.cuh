@@ -90,6 +90,8 @@ struct SeedScanArgs {
                                  // that the exact comparison rejects (the host repeats the batch with exact_compare = 1)
     uint32_t exact_compare;      // 0: compare the high words of hash and threshold, re-check hits when they are written
     uint32_t packed;             // 1: seq holds 2-bit words (contig at byte seq_off / 4) instead of ASCII (contig at byte seq_off)
+    uint32_t fma_m1, fma_two;    // the constants 2^32 - 1 and 2 as launch parameters: multipliers the assembler cannot fold, which
+                                 // keep the hit-mask arithmetic of the main loop on the FMA pipe (seed_kernels.cu, SKB_MASK_FMA)
 };
 
 // region_start[n_regions + 1] = exclusive scan of region_cnt (u64 lanes: seeds | markers << 32)

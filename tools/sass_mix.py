@@ -104,12 +104,14 @@ def main():
     for (p, op), c in sorted(ops.items(), key=lambda kv: (-kv[1], kv[0])):
         print("%-6s %-14s %6d %8.2f" % (p, op, c, c / units))
     alu, fma = counts["alu"], counts["fma"]
-    # issue model of one SM sub-partition: ALU pipe one warp instruction per 2 cycles; FMA pipe likewise for integer multiplies
-    # (IMAD.WIDE counted twice: two passes); the dispatch port issues one instruction per cycle
+    # issue model of one SM sub-partition: ALU pipe one warp instruction per 2 cycles; FMA pipe likewise for integer multiplies,
+    # with IMAD.WIDE and IMAD.HI taking two slots each (measured: tools/micro/int_pipes.cu, profiles/r2_int_pipes.txt), and an
+    # IMAD.WIDE costing the ALU pipe about one slot as well; the dispatch port issues one instruction per cycle
     wide = sum(c for (p, op), c in ops.items() if op == "IMAD.WIDE")
-    cyc = max(2 * alu, 2 * (fma + wide), total)
-    print("# issue model per iteration: ALU %d cycles, FMA %d cycles (IMAD.WIDE double), dispatch %d cycles -> bound %d cycles = %.2f cycles per unit per warp"
-          % (2 * alu, 2 * (fma + wide), total, cyc, cyc / units))
+    high = sum(c for (p, op), c in ops.items() if op == "IMAD.HI")
+    cyc = max(2 * (alu + wide), 2 * (fma + wide + high), total)
+    print("# issue model per iteration: ALU %d cycles (+ %d for IMAD.WIDE), FMA %d cycles (IMAD.WIDE and IMAD.HI double), dispatch %d cycles"
+          " -> bound %d cycles = %.2f cycles per unit per warp" % (2 * alu, 2 * wide, 2 * (fma + wide + high), total, cyc, cyc / units))
     print("# => %.1f G units/s per GPU at 148 SMs x 4 sub-partitions x 32 lanes x 1.965 GHz" % (148 * 4 * 32 * 1.965 / (cyc / units)))
 
 
