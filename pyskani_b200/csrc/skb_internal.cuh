@@ -43,7 +43,10 @@ struct GenomeView {
 };
 
 // ---------------------------------------------------------------- seeding
-constexpr int SEED_THREADS = 256;
+#ifndef SKB_SEED_THREADS
+#define SKB_SEED_THREADS 256
+#endif
+constexpr int SEED_THREADS = SKB_SEED_THREADS;
 constexpr int SEED_WARPS = SEED_THREADS / 32;
 constexpr int WORDS_PER_LANE = 4;                                     // 16-base words each lane evaluates per tile
 constexpr int TILE_WORDS = 32 * WORDS_PER_LANE;                       // 128 words per warp tile
