@@ -655,6 +655,25 @@ def test_anchor_capacity_rerun(ctx, monkeypatch):
     assert got == want and len(want[0]) == 2
 
 
+def test_anchor_join_with_unequal_genome_sizes(ctx):
+    """Anchor join of a query far smaller than its references (a tile of its k-mers spans many reference buckets) beside a
+    query of the references' size: hits, anchor, chain and window counts equal the oracle's."""
+    from pyskani_b200 import capi
+    base = synth.random_genome(1_200_000, 51)
+    small = synth.mutate(base[:150_000], 0.03, 52)
+    refs = [synth.mutate(base, d, 520 + i) for i, d in enumerate((0.01, 0.06))] + [synth.random_genome(400_000, 53)]
+    contigs = [[r.tobytes()] for r in refs] + [[small.tobytes()], [base.tobytes()]]
+    gs = ctx.sketch_batch(contigs)
+    db = capi.Database(ctx)
+    for g in gs[:3]:
+        db.add(g)
+    hits, _ = db.query(gs[3:])
+    assert len(hits) == 4                                         # both queries hit both relatives, not the stranger
+    osk = oracle.sketch_batch(contigs)
+    for qi in (0, 1):
+        check_hits([h for h in hits if h[0] == qi], osk[3 + qi], osk[:3])
+
+
 def test_large_genomes_take_the_global_memory_paths(ctx):
     """Genomes beyond the shared-memory fast paths: > 49 152 seeds (window walk falls back to global memory) and
     > ~20 000 markers (the screen falls back to the warp-per-pair kernel)."""
