@@ -530,7 +530,18 @@ void orc_sketch_contig_lengths(const orc_sketch_t* s, uint32_t* out) {
 // check_markers_quickly.  The cut-off is formed as  p21 * |small|  with
 // p21 = screen_val^21 computed once per query by repeated IEEE multiplication, so that the
 // product path can form the identical double (one rounding per multiply, no libm pow).
-static inline double pow21(double x) { double p = 1.0; for (int i = 0; i < MARKER_K; i++) p *= x; return p; }
+// x^21 in the order of Rust's f64::powi (LLVM's powi expansion and compiler-rt's __powidf2: square and multiply from the
+// lowest exponent bit, one IEEE rounding per product), so that the cut-off is the double skani forms if it calls powi
+static inline double pow21(double x) {
+    double r = 1.0;
+    for (int b = MARKER_K;;) {
+        if (b & 1) r *= x;
+        b >>= 1;
+        if (b == 0) break;
+        x *= x;
+    }
+    return r;
+}
 
 int32_t orc_screen(const orc_sketch_t* q, const orc_sketch_t* r, double screen_val, int32_t rescue_small,
                    uint64_t* shared) {

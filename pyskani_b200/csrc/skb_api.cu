@@ -1918,7 +1918,18 @@ struct ScreenOut {
     std::vector<uint32_t> pass_idx;   // q * n_refs + r, ascending
 };
 
-double pow21(double x) { double p = 1.0; for (int i = 0; i < SKB_MARKER_K; i++) p *= x; return p; }
+// x^21 in the order of Rust's f64::powi (LLVM's powi expansion and compiler-rt's __powidf2: square and multiply from the
+// lowest exponent bit, one IEEE rounding per product), so that the cut-off is the double skani forms if it calls powi
+double pow21(double x) {
+    double r = 1.0;
+    for (int b = SKB_MARKER_K;;) {
+        if (b & 1) r *= x;
+        b >>= 1;
+        if (b == 0) break;
+        x *= x;
+    }
+    return r;
+}
 
 // runs the screen for all (query, ref) pairs; optionally returns the dense arrays
 void run_screen(skb_db& db, const std::vector<std::shared_ptr<SketchImpl>>& queries, const GenomeView* d_q,
