@@ -445,8 +445,10 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
         // exact = 0: the seeding kernel compares only the high words of hash and threshold and re-checks every hit
         // exactly as it writes it; a position that slipped through (hash.hi == threshold.hi, lo above: one in ~6e9)
         // raises bit 1 of the flag and the batch is repeated with the exact 64-bit comparison (SKB_SEED_EXACT=1 forces it)
-        // (also without seeds, threshold 0: the carry form of the high-word test in the kernel needs a threshold >= 1)
-        int exact = (std::getenv("SKB_SEED_EXACT") || !seed) ? 1 : 0;
+        // (also when the high word of a threshold is 0 - no seeds wanted, or a compression factor >= 2^32: the carry form of the
+        // high-word test in the kernel needs a high word >= 1)
+        const uint64_t thr_seed = seed ? UINT64_MAX / (uint64_t)P.c : 0, thr_marker = UINT64_MAX / (uint64_t)P.marker_c;
+        int exact = (std::getenv("SKB_SEED_EXACT") || (thr_seed >> 32) == 0 || (thr_marker >> 32) == 0) ? 1 : 0;
         for (int attempt = 0; attempt < 2; attempt++) {
             const size_t seed_store = attempt == 0 ? (size_t)n_tiles * seed_tile_cap : (size_t)seed_start[n_genomes];
             const size_t marker_store = attempt == 0 ? (size_t)n_tiles * marker_tile_cap : (size_t)marker_start[n_genomes];
@@ -460,8 +462,8 @@ static void sketch_core(const std::shared_ptr<Core>& core, const skb_sketch_para
             a.seq = seq_dev;
             a.kmask = P.k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * P.k)) - 1u);
             a.kshift = 42 - 2 * P.k;
-            a.thr_seed = seed ? UINT64_MAX / (uint64_t)P.c : 0;     // seed=False keeps markers only (A.4)
-            a.thr_marker = UINT64_MAX / (uint64_t)P.marker_c;
+            a.thr_seed = thr_seed;                                   // seed=False keeps markers only (A.4)
+            a.thr_marker = thr_marker;
             a.chk_seed = a.thr_seed; a.chk_marker = a.thr_marker;
             if (std::getenv("SKB_SEED_TEST_INEXACT")) { a.chk_seed /= 2; a.chk_marker /= 2; }   // test hook: forces the exact repeat
             a.seed_tile_cap = seed_tile_cap; a.marker_tile_cap = marker_tile_cap;
