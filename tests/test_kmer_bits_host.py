@@ -94,3 +94,24 @@ def test_scan_ecoli_slice(shim, ecoli):
     o = np.lexsort((pos, kmer))
     assert np.array_equal(kmer[o].astype(np.uint64), ok) and np.array_equal(pos[o], op)
     assert np.array_equal(markers, O.markers())
+
+
+def test_carry_form_of_the_high_word_comparison():
+    """seed_kernels.cu::push_miss: with M = 2^32 - 1 the carry of hi(h * M) + (2^32 - thr) is [h > thr] for every
+    threshold >= 1 (the form that lets one IMAD.HI produce the comparison as its carry predicate), and shifting the carries
+    in from the last position to the first leaves bit e = position e missed."""
+    rng = np.random.default_rng(5)
+    M = (1 << 32) - 1
+    thrs = [1, 2, 34359738, (1 << 31) - 1, 1 << 31, (1 << 32) - 2, (1 << 32) - 1] + [int(t) for t in rng.integers(1, 1 << 32, 200)]
+    for thr in thrs:
+        comp = (-thr) & M
+        hs = [0, 1, thr - 1, thr, min(thr + 1, M), M] + [int(h) for h in rng.integers(0, 1 << 32, 300)]
+        for h in hs:
+            carry = (((h * M) >> 32) + comp) >> 32
+            assert carry == (1 if h > thr else 0), (thr, h)
+    thr, comp = 34359738, (-34359738) & M
+    hs = [int(h) for h in rng.integers(0, 1 << 27, 16)]               # one word: positions 0..15
+    miss = 0
+    for e in range(15, -1, -1):
+        miss = (miss * 2 + ((((hs[e] * M) >> 32) + comp) >> 32)) & M
+    assert (~miss) & 0xFFFF == sum(1 << e for e in range(16) if hs[e] <= thr)
