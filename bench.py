@@ -630,7 +630,8 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "r2_seed_scan_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            if int(tj.get("bases_per_launch", -1)) == int(host.lens[batches[0][0]:batches[0][1]].sum()):
+            # the capture describes one seeding launch of this workload: valid when one of this rank's launches covers exactly its bases
+            if int(tj.get("bases_per_launch", -1)) in [int(host.lens[b0:b1].sum()) for b0, b1 in batches]:
                 traffic, traffic_note = tj["dram_bytes_per_launch"], tj.get("source", tpath)
         ex_ms = ph.get("exchange_allgather_ms", 0.0)
         line = {
